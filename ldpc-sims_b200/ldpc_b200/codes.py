@@ -1,0 +1,294 @@
+"""Code library and Tanner-graph compiler (host side, numpy only).
+
+Replaces the reference's dense-mask graph compile (``pytorch/bp/masking.py:12-147``)
+and its default-code module (``pytorch/bp/parity.py:7-47``) with sparse edge tables:
+
+* ``EdgeTables``   - CSR by check / CSC by variable + the check-major <-> variable-major
+                     edge permutation.  Edge numbering is the reference's: check-major ids
+                     are the row-major non-zeros of H (``masking.py:85-88``), variable-major
+                     ids the column-major non-zeros (``masking.py:92-95``).
+* ``peg_64_32``    - the reference's default (64,32) PEG code, rebuilt from its sparse
+                     structure; returns H and the systematic generator G with the same
+                     shapes/dtypes as ``parity.H`` / ``parity.G``.
+* ``ieee80211n_1944_r12`` - IEEE 802.11n n=1944, R=1/2, Z=81 (not in the reference;
+                     prototype matrix from SURVEY.md appendix B).
+* encoders         - ``systematic_generator`` (dense GF(2) elimination, any H whose
+                     parity part is invertible) and ``QCCode.encode`` (linear-time
+                     dual-diagonal back-substitution).
+"""
+from __future__ import annotations
+
+import dataclasses
+import numpy as np
+
+# --------------------------------------------------------------------------------------
+# default code: (64,32) PEG, H = [P | I32].  Check r touches information bit r//2, one
+# information bit in 16..31 (table below) and parity bit 32+r (reference parity.py:7-40).
+# --------------------------------------------------------------------------------------
+_PEG_SECOND = (16, 17, 16, 18, 17, 19, 18, 20, 19, 21, 20, 22, 21, 23, 22, 24,
+               23, 25, 24, 26, 25, 27, 26, 28, 27, 29, 28, 30, 29, 31, 30, 31)
+
+
+def peg_64_32():
+    """Return (H int64 [32,64], G float64 [64,32]) identical to reference bp/parity.py."""
+    H = np.zeros((32, 64), dtype=np.int64)
+    for r in range(32):
+        H[r, r // 2] = 1
+        H[r, _PEG_SECOND[r]] = 1
+        H[r, 32 + r] = 1
+    P = H[:, 0:32]
+    # parity.py:44  G = [I ; P]  (64 x 32), codeword = G u, info bits first
+    G = np.concatenate((np.eye(32), P.astype(np.float64)), axis=0)
+    return H, G
+
+
+# --------------------------------------------------------------------------------------
+# IEEE 802.11n, n = 1944, R = 1/2, Z = 81.  -1 = zero block, s >= 0 = identity cyclically
+# shifted right by s (row i has its one in column (i + s) mod Z).
+# --------------------------------------------------------------------------------------
+_WIFI_1944_R12 = """
+57 -1 -1 -1 50 -1 11 -1 50 -1 79 -1  1  0 -1 -1 -1 -1 -1 -1 -1 -1 -1 -1
+ 3 -1 28 -1  0 -1 -1 -1 55  7 -1 -1 -1  0  0 -1 -1 -1 -1 -1 -1 -1 -1 -1
+30 -1 -1 -1 24 37 -1 -1 56 14 -1 -1 -1 -1  0  0 -1 -1 -1 -1 -1 -1 -1 -1
+62 53 -1 -1 53 -1 -1  3 35 -1 -1 -1 -1 -1 -1  0  0 -1 -1 -1 -1 -1 -1 -1
+40 -1 -1 20 66 -1 -1 22 28 -1 -1 -1 -1 -1 -1 -1  0  0 -1 -1 -1 -1 -1 -1
+ 0 -1 -1 -1  8 -1 42 -1 50 -1 -1  8 -1 -1 -1 -1 -1  0  0 -1 -1 -1 -1 -1
+69 79 79 -1 -1 -1 56 -1 52 -1 -1 -1  0 -1 -1 -1 -1 -1  0  0 -1 -1 -1 -1
+65 -1 -1 -1 38 57 -1 -1 72 -1 27 -1 -1 -1 -1 -1 -1 -1 -1  0  0 -1 -1 -1
+64 -1 -1 -1 14 52 -1 -1 30 -1 -1 32 -1 -1 -1 -1 -1 -1 -1 -1  0  0 -1 -1
+-1 45 -1 70  0 -1 -1 -1 77  9 -1 -1 -1 -1 -1 -1 -1 -1 -1 -1 -1  0  0 -1
+ 2 56 -1 57 35 -1 -1 -1 -1 -1 12 -1 -1 -1 -1 -1 -1 -1 -1 -1 -1 -1  0  0
+24 -1 61 -1 60 -1 -1 27 51 -1 -1 16  1 -1 -1 -1 -1 -1 -1 -1 -1 -1 -1  0
+"""
+
+
+def _parse_proto(text):
+    rows = [[int(t) for t in line.split()] for line in text.strip().splitlines()]
+    return np.array(rows, dtype=np.int16)
+
+
+def expand_qc(proto: np.ndarray, Z: int) -> np.ndarray:
+    """Expand a prototype matrix into the binary H (uint8 [mb*Z, nb*Z])."""
+    mb, nb = proto.shape
+    H = np.zeros((mb * Z, nb * Z), dtype=np.uint8)
+    idx = np.arange(Z)
+    for r in range(mb):
+        for c in range(nb):
+            s = int(proto[r, c])
+            if s >= 0:
+                H[r * Z + idx, c * Z + (idx + s) % Z] = 1
+    return H
+
+
+@dataclasses.dataclass
+class QCCode:
+    """A quasi-cyclic code given by its prototype (shift) matrix."""
+    name: str
+    proto: np.ndarray          # int16 [mb, nb], -1 = zero block
+    Z: int
+
+    @property
+    def mb(self): return int(self.proto.shape[0])
+
+    @property
+    def nb(self): return int(self.proto.shape[1])
+
+    @property
+    def n(self): return self.nb * self.Z
+
+    @property
+    def m(self): return self.mb * self.Z
+
+    @property
+    def k(self): return self.n - self.m
+
+    @property
+    def H(self) -> np.ndarray:
+        if not hasattr(self, "_H"):
+            self._H = expand_qc(self.proto, self.Z)
+        return self._H
+
+    # -- linear-time systematic encoder for the 802.11n dual-diagonal parity part -------
+    def encode(self, info_bits: np.ndarray) -> np.ndarray:
+        """info_bits uint8 [B, k] -> codewords uint8 [B, n] (information bits first).
+
+        Parity part is [h | T] with T dual-diagonal and column h having three entries
+        (top shift s0, one middle shift 0, bottom shift s0).  Summing all block rows
+        cancels T and the two equal h-shifts, leaving p0 = sum_r lambda_r.
+        """
+        u = np.asarray(info_bits, dtype=np.uint8)
+        B = u.shape[0]
+        Z, mb, nb = self.Z, self.mb, self.nb
+        kb = nb - mb
+        ub = u.reshape(B, kb, Z)
+        lam = np.zeros((B, mb, Z), dtype=np.uint8)
+        for r in range(mb):
+            for c in range(kb):
+                s = int(self.proto[r, c])
+                if s >= 0:
+                    # row i of the block reads u[(i+s) % Z]
+                    lam[:, r, :] ^= np.roll(ub[:, c, :], -s, axis=1)
+        hcol = self.proto[:, kb]
+        hrows = [r for r in range(mb) if hcol[r] >= 0]
+        assert len(hrows) == 3 and hrows[0] == 0 and hrows[-1] == mb - 1
+        assert hcol[hrows[0]] == hcol[hrows[-1]] and hcol[hrows[1]] == 0
+        p = np.zeros((B, mb, Z), dtype=np.uint8)
+        p0 = np.bitwise_xor.reduce(lam, axis=1)           # p0 (shift 0 of the middle entry)
+        p[:, 0, :] = p0
+        # forward substitution: row r:  lam_r + h_r(p0) + p_r' + p_{r+1}' = 0, with p_0' = 0
+        # where p_j' (j>=1) is parity block j.  Row 0: p_1 = lam_0 + shift(p0, s0)
+        for r in range(mb - 1):
+            acc = lam[:, r, :].copy()
+            if hcol[r] >= 0:
+                acc ^= np.roll(p0, -int(hcol[r]), axis=1)
+            if r >= 1:
+                acc ^= p[:, r, :]
+            p[:, r + 1, :] = acc
+        return np.concatenate([u, p.reshape(B, mb * Z)], axis=1)
+
+
+def ieee80211n_1944_r12() -> QCCode:
+    return QCCode("802.11n-1944-r1/2", _parse_proto(_WIFI_1944_R12), 81)
+
+
+# --------------------------------------------------------------------------------------
+# Edge tables
+# --------------------------------------------------------------------------------------
+@dataclasses.dataclass
+class EdgeTables:
+    """Sparse replacement for generate_masks(H) (reference masking.py:12-147).
+
+    cm = check-major edge id (row-major non-zeros), vm = variable-major edge id
+    (column-major non-zeros).  All arrays int32.
+    """
+    m: int
+    n: int
+    E: int
+    chk_ptr: np.ndarray     # [m+1]  cm ids of check c are chk_ptr[c]..chk_ptr[c+1]
+    chk_var: np.ndarray     # [E]    variable of cm edge
+    var_ptr: np.ndarray     # [n+1]  vm ids of variable v are var_ptr[v]..var_ptr[v+1]
+    var_chk: np.ndarray     # [E]    check of vm edge
+    cm_of_vm: np.ndarray    # [E]    cm id of a vm edge
+    vm_of_cm: np.ndarray    # [E]    vm id of a cm edge
+
+    @property
+    def max_dc(self): return int(np.diff(self.chk_ptr).max())
+
+    @property
+    def max_dv(self): return int(np.diff(self.var_ptr).max())
+
+    @staticmethod
+    def from_H(H) -> "EdgeTables":
+        H = np.asarray(H)
+        if H.ndim != 2:
+            raise ValueError("H must be a 2-D 0/1 matrix")
+        Hb = (H != 0)
+        m, n = Hb.shape
+        rows, cols = np.nonzero(Hb)                     # row-major = check-major order
+        E = int(rows.size)
+        chk_ptr = np.zeros(m + 1, dtype=np.int64)
+        np.add.at(chk_ptr, rows + 1, 1)
+        chk_ptr = np.cumsum(chk_ptr)
+        # variable-major: sort cm edges by (col, row); stable sort keeps rows ascending
+        order = np.lexsort((rows, cols))                # vm -> cm
+        var_ptr = np.zeros(n + 1, dtype=np.int64)
+        np.add.at(var_ptr, cols + 1, 1)
+        var_ptr = np.cumsum(var_ptr)
+        vm_of_cm = np.empty(E, dtype=np.int64)
+        vm_of_cm[order] = np.arange(E)
+        i32 = lambda a: np.ascontiguousarray(a, dtype=np.int32)
+        return EdgeTables(m=m, n=n, E=E, chk_ptr=i32(chk_ptr), chk_var=i32(cols),
+                          var_ptr=i32(var_ptr), var_chk=i32(rows[order]),
+                          cm_of_vm=i32(order), vm_of_cm=i32(vm_of_cm))
+
+    def dense_masks(self):
+        """The four dense arrays generate_masks(H) returns (masking.py:147); only for
+        API compatibility and tests - never used by the decoder."""
+        E, n = self.E, self.n
+        mask_c = np.zeros((E, E)); mask_v = np.zeros((E, E))
+        mask_v_final = np.zeros((n, E)); llr_expander = np.zeros((E, n))
+        llr_expander[np.arange(E), np.repeat(np.arange(n), np.diff(self.var_ptr))] = 1
+        mask_v_final[self.chk_var, np.arange(E)] = 1
+        for v in range(n):
+            vm = np.arange(self.var_ptr[v], self.var_ptr[v + 1])
+            cm = self.cm_of_vm[vm]
+            for a in range(vm.size):
+                for b in range(vm.size):
+                    if a != b:
+                        mask_v[vm[a], cm[b]] = 1       # out vm edge a <- in cm edge b
+        for c in range(self.m):
+            cm = np.arange(self.chk_ptr[c], self.chk_ptr[c + 1])
+            vm = self.vm_of_cm[cm]
+            for a in range(cm.size):
+                for b in range(cm.size):
+                    if a != b:
+                        mask_c[cm[a], vm[b]] = 1       # out cm edge a <- in vm edge b
+        return mask_c, mask_v, mask_v_final, llr_expander
+
+
+# --------------------------------------------------------------------------------------
+# QC detection and dense GF(2) helpers
+# --------------------------------------------------------------------------------------
+def detect_qc(H: np.ndarray, Z: int):
+    """Return the prototype matrix if H is block-circulant with circulant weight <= 1
+    for block size Z, else None."""
+    H = np.asarray(H)
+    m, n = H.shape
+    if Z <= 0 or m % Z or n % Z:
+        return None
+    mb, nb = m // Z, n // Z
+    proto = np.full((mb, nb), -1, dtype=np.int16)
+    idx = np.arange(Z)
+    for r in range(mb):
+        for c in range(nb):
+            blk = H[r * Z:(r + 1) * Z, c * Z:(c + 1) * Z]
+            w = int((blk != 0).sum())
+            if w == 0:
+                continue
+            if w != Z:
+                return None
+            s = int(np.nonzero(blk[0])[0][0])
+            if not np.all(blk[idx, (idx + s) % Z] != 0):
+                return None
+            proto[r, c] = s
+    return proto
+
+
+def gf2_rank(M: np.ndarray) -> int:
+    A = (np.asarray(M) != 0).astype(np.uint8).copy()
+    rows, cols = A.shape
+    r = 0
+    for c in range(cols):
+        piv = np.nonzero(A[r:, c])[0]
+        if piv.size == 0:
+            continue
+        p = r + piv[0]
+        if p != r:
+            A[[r, p]] = A[[p, r]]
+        sel = np.nonzero(A[:, c])[0]
+        sel = sel[sel != r]
+        A[sel] ^= A[r]
+        r += 1
+        if r == rows:
+            break
+    return r
+
+
+def systematic_generator(H: np.ndarray) -> np.ndarray:
+    """Dense G (uint8 [n,k], codeword = G u mod 2, information bits first) for any H
+    whose last m columns are invertible over GF(2):  H = [A | B]  ->  G = [I ; B^-1 A]."""
+    Hb = (np.asarray(H) != 0).astype(np.uint8)
+    m, n = Hb.shape
+    k = n - m
+    aug = np.concatenate([Hb[:, k:], Hb[:, :k]], axis=1)   # [B | A]
+    for c in range(m):
+        piv = np.nonzero(aug[c:, c])[0]
+        if piv.size == 0:
+            raise ValueError("parity part of H is singular")
+        p = c + piv[0]
+        if p != c:
+            aug[[c, p]] = aug[[p, c]]
+        sel = np.nonzero(aug[:, c])[0]
+        sel = sel[sel != c]
+        aug[sel] ^= aug[c]
+    return np.concatenate([np.eye(k, dtype=np.uint8), aug[:, m:]], axis=0)

@@ -1,0 +1,213 @@
+"""CPU ORACLE - TEST INFRASTRUCTURE ONLY (never imported by the product path).
+
+Sparse restatement of the reference's dense-masked belief-propagation decoder:
+
+    pytorch/bp/masking.py:75-138   edge numbering (check-major / variable-major)
+    pytorch/bp/bp_vc.py:16-32      V->C   0.5 * (llr' + sum of the other C->V messages)
+    pytorch/bp/bp.py:29            tanh
+    pytorch/bp/bp_cv.py:22-55      C->V   log((1+p)/(1-p)), p = clamp(prod of others, +-(1-1e-7))
+    pytorch/bp/bp.py:43-51         iteration loop, outer clamp, final marginal, 1 - sigmoid
+    pytorch/ofdm/ofdm_functions.py:131-163   decode_bits batching wrapper / np.round
+
+Arithmetic is fp32 throughout.  Transcendentals (tanh, log, sigmoid) go through the same
+PyTorch CPU ATen kernels the reference itself calls, so on the reference's default code
+(every sum / product has at most two non-trivial operands) this restatement is
+bit-identical to the dense reference.  For higher degrees the dense reference's
+association order is whatever sgemm / prod pick; this file FIXES it:
+
+    sum of others   S_k = P_k + Q_k,  P_k = ((x_0 + x_1) + ...) + x_{k-1}   (forward)
+                                      Q_k = x_{k+1} + (x_{k+2} + (... + x_{d-1}))  (backward)
+                    an empty side contributes nothing; both empty -> +0.0f
+    prod of others  same two-sweep association with *
+    marginal        ((x_0 + x_1) + ...) + x_{d-1}, then  0.5 * (llr' + that)
+
+Min-sum / normalized / offset min-sum do not exist in the reference; they are DEFINED
+here: V->C y = llr' + S_k (no 1/2, no tanh); C->V magnitude =
+min over the others of |y| (times alpha, or minus beta floored at 0), sign = xor of the
+others' IEEE sign bits; same outer clamp; same marginal 0.5*(llr' + sum) so prob / hard /
+posterior keep their meaning.  Only add / min / abs / sign ops => bit-exact CPU<->GPU.
+
+Pinned against the dense reference by oracle/make_golden.py (fixtures in tests/golden/).
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+F32 = np.float32
+P_CLAMP = np.float32(1.0 - 1e-7)      # rounds to 0.99999988 in fp32 (bp_cv.py:44-47)
+
+UPDATE_SP, UPDATE_MINSUM, UPDATE_NMS, UPDATE_OMS = 0, 1, 2, 3
+_UPDATE_IDS = {"sp": 0, "tanh": 0, "sum-product": 0, "minsum": 1, "min-sum": 1, "nms": 2, "oms": 3}
+
+
+class Graph:
+    """Edge enumeration exactly as masking.py does it."""
+
+    def __init__(self, H):
+        H = np.asarray(H) != 0
+        self.m, self.n = H.shape
+        rows, cols = np.nonzero(H)                      # check-major ids (masking.py:85-88)
+        self.E = rows.size
+        self.cm_row, self.cm_col = rows, cols
+        vcols, vrows = np.nonzero(H.T)                  # variable-major ids (masking.py:92-95)
+        self.vm_row, self.vm_col = vrows, vcols
+        cm_id = -np.ones(H.shape, dtype=np.int64); cm_id[rows, cols] = np.arange(self.E)
+        vm_id = -np.ones(H.shape, dtype=np.int64); vm_id[vrows, vcols] = np.arange(self.E)
+        self.cm_of_vm = cm_id[vrows, vcols]
+        self.vm_of_cm = vm_id[rows, cols]
+        self.dv = H.sum(0).astype(np.int64)
+        self.dc = H.sum(1).astype(np.int64)
+        self.var_ptr = np.concatenate([[0], np.cumsum(self.dv)])
+        self.chk_ptr = np.concatenate([[0], np.cumsum(self.dc)])
+        # degree groups: for every degree d, the nodes having it and their edge ids [nodes, d]
+        self.var_groups = []
+        for d in np.unique(self.dv):
+            vs = np.nonzero(self.dv == d)[0]
+            vm = self.var_ptr[vs][:, None] + np.arange(d)[None, :]      # vm ids, ascending check
+            self.var_groups.append((int(d), vs, vm, self.cm_of_vm[vm] if d else vm))
+        self.chk_groups = []
+        for d in np.unique(self.dc):
+            cs = np.nonzero(self.dc == d)[0]
+            cm = self.chk_ptr[cs][:, None] + np.arange(d)[None, :]      # cm ids, ascending variable
+            self.chk_groups.append((int(d), cs, cm, self.vm_of_cm[cm] if d else cm))
+
+
+def _others(vals, op):
+    """vals: list of d arrays. Returns list of d arrays: op over the others with the
+    documented two-sweep association (None where there are no others)."""
+    d = len(vals)
+    pre = [None] * d
+    acc = None
+    for k in range(d):
+        pre[k] = acc
+        acc = vals[k] if acc is None else op(acc, vals[k])
+    suf = [None] * d
+    acc = None
+    for k in range(d - 1, -1, -1):
+        suf[k] = acc
+        acc = vals[k] if acc is None else op(vals[k], acc)
+    out = []
+    for k in range(d):
+        if pre[k] is None:
+            out.append(suf[k])
+        elif suf[k] is None:
+            out.append(pre[k])
+        else:
+            out.append(op(pre[k], suf[k]))
+    return out
+
+
+def _t(a):
+    return torch.from_numpy(np.ascontiguousarray(a))
+
+
+def _tanh(a):
+    return torch.tanh(_t(a)).numpy()
+
+
+def _two_atanh(p):
+    tp = _t(p)
+    return torch.div(1 + tp, 1 - tp).log_().numpy()        # bp_cv.py:50
+
+
+def bp_decode(H, llr, iterations, clamp_value, update="sp", x0=None, alpha=1.0, beta=0.0,
+              graph=None, trace=False):
+    """Decode a batch.  llr: [B,n] (log P1/P0, the callers' convention, ofdm_functions.py:72).
+
+    Returns dict with
+      x      [B,E] f32  final C->V messages, check-major
+      t      [B,n] f32  pre-sigmoid marginal (bp.py:36-37); posterior log(P1/P0) = -2 t
+      prob   [B,n] f32  P(bit=1) = 1 - sigmoid(t)           (bp.py:51)
+      hard   [B,n] u8   np.round(prob)  (ties -> 0)         (ofdm_functions.py:161)
+      syndrome [B] i32  number of unsatisfied checks of `hard`
+    """
+    g = graph or Graph(H)
+    upd = _UPDATE_IDS[update] if isinstance(update, str) else int(update)
+    llr = np.ascontiguousarray(llr, dtype=F32)
+    B = llr.shape[0]
+    Lp = (-llr).astype(F32)                                 # bp.py:47  layer([x, -llr])
+    x = np.zeros((B, g.E), F32) if x0 is None else np.array(x0, dtype=F32)
+    y = np.zeros((B, g.E), F32)
+    cl = F32(clamp_value)
+    half = F32(0.5)
+    traces = []
+    for _ in range(int(iterations)):
+        # ---- V -> C (variable-major output) ----
+        for d, vs, vm, cm in g.var_groups:
+            if d == 0:
+                continue
+            xin = [x[:, cm[:, k]] for k in range(d)]
+            if d == 1:
+                S = [np.zeros((B, vs.size), F32)]
+            else:
+                S = _others(xin, np.add)
+            for k in range(d):
+                s = (Lp[:, vs] + S[k]).astype(F32)
+                y[:, vm[:, k]] = _tanh(half * s) if upd == UPDATE_SP else s
+        # ---- C -> V (check-major output) ----
+        for d, cs, cm, vm in g.chk_groups:
+            if d == 0:
+                continue
+            yin = [y[:, vm[:, j]] for j in range(d)]
+            if upd == UPDATE_SP:
+                if d == 1:
+                    P = [np.ones((B, cs.size), F32)]         # empty product (mask all ones)
+                else:
+                    P = _others(yin, np.multiply)
+                for j in range(d):
+                    p = np.clip(P[j], -P_CLAMP, P_CLAMP).astype(F32)
+                    x[:, cm[:, j]] = np.clip(_two_atanh(p), -cl, cl)
+            else:
+                mag = [np.abs(v) for v in yin]
+                sgn = [np.signbit(v) for v in yin]
+                if d == 1:
+                    M = [np.full((B, cs.size), np.inf, F32)]
+                    Sg = [np.zeros((B, cs.size), bool)]
+                else:
+                    M = _others(mag, np.minimum)
+                    Sg = _others(sgn, np.logical_xor)
+                for j in range(d):
+                    mj = M[j]
+                    if upd == UPDATE_NMS:
+                        mj = (F32(alpha) * mj).astype(F32)
+                    elif upd == UPDATE_OMS:
+                        mj = np.maximum((mj - F32(beta)).astype(F32), F32(0))
+                    mj = np.minimum(mj, cl)
+                    x[:, cm[:, j]] = np.where(Sg[j], -mj, mj)
+        if trace:
+            traces.append(x.copy())
+    # ---- marginal (bp.py:36-39,51) ----
+    t = np.zeros((B, g.n), F32)
+    for d, vs, vm, cm in g.var_groups:
+        acc = None
+        for k in range(d):
+            acc = x[:, cm[:, k]] if acc is None else (acc + x[:, cm[:, k]]).astype(F32)
+        if acc is None:
+            acc = np.zeros((B, vs.size), F32)
+        t[:, vs] = half * (Lp[:, vs] + acc)
+    prob = (-1 * torch.sigmoid(_t(t)) + 1).numpy()          # bp.py:51
+    hard = np.round(prob).astype(np.uint8)                  # ofdm_functions.py:161
+    synd = syndrome_weight(g, hard)
+    out = dict(x=x, t=t, prob=prob, hard=hard, syndrome=synd)
+    if trace:
+        out["trace"] = traces
+    return out
+
+
+def syndrome_weight(g, hard):
+    par = np.zeros((hard.shape[0], g.m), dtype=np.uint8)
+    np.bitwise_xor.at(par, (slice(None), g.cm_row), hard[:, g.cm_col])
+    return par.sum(1).astype(np.int32)
+
+
+def decode_bits(llrs, H, bp_iterations, batch_size, clamp_value, **kw):
+    """ofdm_functions.py:131-163 - batching wrapper: float64 0/1 output, ragged tail
+    (N % batch_size rows) left at zero because the reference silently skips it."""
+    llrs = np.asarray(llrs)
+    out = np.zeros(llrs.shape)
+    g = Graph(H)
+    for b in range(llrs.shape[0] // batch_size):
+        s, e = b * batch_size, (b + 1) * batch_size
+        out[s:e] = bp_decode(H, llrs[s:e].astype(F32), bp_iterations, clamp_value, graph=g, **kw)["hard"]
+    return out
