@@ -1,0 +1,58 @@
+// common.cuh - parameter blocks and error plumbing shared by the kernels and the C ABI.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <stdint.h>
+#include "../../include/ldpc_b200.h"
+
+namespace ldpc {
+
+struct DecodeArgs {
+    // inputs
+    const void *llr;        // [B,n] of llr_dtype
+    int llr_dtype;
+    long long B;
+    int iters, update;
+    float clampv, param;
+    const float *x0;        // [B,E] or null
+    // outputs (nullable)
+    float *prob, *llr_post;
+    uint8_t *hard, *hard_packed;
+    int32_t *syndrome;
+    float *x_out;
+    // fused error counting (nullable): ref_bits [B,n] u8 or packed, counters[5] i64
+    const uint8_t *ref_packed;  // [B,ceil(n/8)] transmitted codeword, MSB-first
+    unsigned long long *counters;
+    int k_info;
+};
+
+struct GraphTables {        // device pointers
+    int m, n, E;
+    const int32_t *chk_ptr;   // [m+1]
+    const int32_t *chk_var;   // [E]  variable of a check-major edge
+    const int32_t *var_ptr;   // [n+1]
+    const int32_t *cm_of_vm;  // [E]  check-major slot of a variable-major edge
+};
+
+__device__ __forceinline__ float load_llr(const void *p, int dtype, long long i) {
+    if (dtype == LDPC_F32) return __ldg(reinterpret_cast<const float *>(p) + i);
+    if (dtype == LDPC_F64) return static_cast<float>(__ldg(reinterpret_cast<const double *>(p) + i));
+    return __half2float(__ldg(reinterpret_cast<const __half *>(p) + i));
+}
+
+void set_error(const char *fmt, ...);
+int cuda_fail(cudaError_t e, const char *what);
+
+#define LDPC_CUDA_TRY(expr)                                         \
+    do {                                                            \
+        cudaError_t _e = (expr);                                    \
+        if (_e != cudaSuccess) return ::ldpc::cuda_fail(_e, #expr); \
+    } while (0)
+
+// kernels' host launchers
+int launch_decode_generic(const GraphTables &g, int max_dv, int max_dc, const DecodeArgs &a, cudaStream_t s);
+bool qc_kernel_available(int Z, int mb, int nb, const int16_t *proto);
+int launch_decode_qc(int qc_id, const DecodeArgs &a, cudaStream_t s);
+int qc_lookup(int Z, int mb, int nb, const int16_t *proto);   // -1 if no compiled specialisation
+
+}  // namespace ldpc

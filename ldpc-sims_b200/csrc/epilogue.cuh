@@ -1,0 +1,66 @@
+// epilogue.cuh - shared tail of the decoder kernels: bit packing of the hard decision and
+// the fused exact integer link metrics (replaces evaluate_quantized_snr.py:169-188).
+#pragma once
+#include "common.cuh"
+
+namespace ldpc {
+
+// hard_s: [ncw][hs_stride] u8 in shared memory; packed output MSB-first (numpy.packbits).
+__device__ __forceinline__ void pack_hard(const uint8_t *hard_s, int hs_stride, int ncw, int n,
+                                          uint8_t *packed_g /* [ncw][ceil(n/8)] */) {
+    const int nbytes = (n + 7) >> 3;
+    for (int i = threadIdx.x; i < ncw * nbytes; i += blockDim.x) {
+        const int cw = i / nbytes, by = i - cw * nbytes;
+        const uint8_t *h = hard_s + cw * hs_stride + by * 8;
+        unsigned v = 0;
+#pragma unroll
+        for (int b = 0; b < 8; ++b) {
+            const int idx = by * 8 + b;
+            v |= (idx < n ? (unsigned)h[b] : 0u) << (7 - b);
+        }
+        packed_g[(long long)cw * nbytes + by] = (uint8_t)v;
+    }
+}
+
+// counters: {uncoded bit errors, info-bit errors, frame errors, bits, frames} (u64, +=).
+// llr_s [ncw][ls_stride] f32 channel LLRs (uncoded decision: llr > 0 -> 1, llr == 0 -> 0,
+// i.e. (sign+1)//2);  ref_packed_g: transmitted codewords, MSB-first.
+// scratch: 3 ints + ncw ints of shared memory, zeroed by the caller before a barrier.
+__device__ __forceinline__ void count_errors(const float *llr_s, int ls_stride, const uint8_t *hard_s,
+                                             int hs_stride, int ncw, int n, int k_info,
+                                             const uint8_t *ref_packed_g, unsigned long long *counters,
+                                             int *scratch /* [3 + ncw] */) {
+    const int nbytes = (n + 7) >> 3;
+    int unc = 0, inf = 0;
+    for (int i = threadIdx.x; i < ncw * n; i += blockDim.x) {
+        const int cw = i / n, v = i - cw * n;
+        const int ref = (ref_packed_g[(long long)cw * nbytes + (v >> 3)] >> (7 - (v & 7))) & 1;
+        const int hb = hard_s[cw * hs_stride + v];
+        const int ub = llr_s[cw * ls_stride + v] > 0.0f;
+        unc += (ub != ref);
+        const int e = (hb != ref);
+        inf += e & (v < k_info);
+        if (e) scratch[3 + cw] = 1;            // benign race: everyone writes 1
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        unc += __shfl_xor_sync(0xffffffffu, unc, o);
+        inf += __shfl_xor_sync(0xffffffffu, inf, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (unc) atomicAdd(&scratch[0], unc);
+        if (inf) atomicAdd(&scratch[1], inf);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int fe = 0;
+        for (int c = 0; c < ncw; ++c) fe += scratch[3 + c];
+        if (scratch[0]) atomicAdd(&counters[0], (unsigned long long)scratch[0]);
+        if (scratch[1]) atomicAdd(&counters[1], (unsigned long long)scratch[1]);
+        if (fe) atomicAdd(&counters[2], (unsigned long long)fe);
+        atomicAdd(&counters[3], (unsigned long long)ncw * (unsigned long long)n);
+        atomicAdd(&counters[4], (unsigned long long)ncw);
+    }
+}
+
+}  // namespace ldpc

@@ -1,0 +1,294 @@
+// ldpc_abi.cu - the C ABI declared in include/ldpc_b200.h: code handles, dispatch, the
+// host-buffer decode pipeline and error plumbing.  No torch types, no CPU fallback.
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "common.cuh"
+
+namespace ldpc {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int cuda_fail(cudaError_t e, const char *what) {
+    set_error("CUDA error %d (%s) in %s", (int)e, cudaGetErrorString(e), what);
+    return LDPC_ECUDA;
+}
+
+}  // namespace ldpc
+
+using namespace ldpc;
+
+struct ldpc_code {
+    int m, n, E, max_dc, max_dv;
+    int kernel;        // LDPC_KERNEL_*
+    int qc_id;         // index of the compiled specialisation or -1
+    int qc_Z;
+    int device;
+    int32_t *d_tables; // one allocation: chk_ptr | chk_var | var_ptr | cm_of_vm
+    GraphTables g;
+};
+
+extern "C" {
+
+int ldpc_abi_version(void) { return LDPC_B200_ABI_VERSION; }
+
+const char *ldpc_last_error(void) { return g_err; }
+
+int ldpc_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int ldpc_code_create(const int32_t *row_ptr, const int32_t *col_idx, int m, int n, int qc_Z,
+                     const int16_t *qc_proto, ldpc_code_t **out) {
+    if (!row_ptr || !col_idx || !out || m <= 0 || n <= 0) { set_error("ldpc_code_create: bad arguments"); return LDPC_EINVAL; }
+    *out = nullptr;
+    if (row_ptr[0] != 0) { set_error("row_ptr[0] must be 0"); return LDPC_EINVAL; }
+    const int E = row_ptr[m];
+    if (E <= 0) { set_error("H has no edges"); return LDPC_EINVAL; }
+    int max_dc = 0;
+    std::vector<int32_t> dv(n, 0);
+    for (int c = 0; c < m; ++c) {
+        const int b = row_ptr[c], e = row_ptr[c + 1];
+        if (e < b) { set_error("row_ptr not monotone at row %d", c); return LDPC_EINVAL; }
+        max_dc = std::max(max_dc, e - b);
+        for (int i = b; i < e; ++i) {
+            const int v = col_idx[i];
+            if (v < 0 || v >= n) { set_error("col_idx out of range at row %d", c); return LDPC_EINVAL; }
+            if (i > b && col_idx[i - 1] >= v) { set_error("columns must be strictly ascending inside row %d", c); return LDPC_EINVAL; }
+            dv[v]++;
+        }
+    }
+    // variable-major numbering: column-major non-zeros (masking.py:92-95)
+    std::vector<int32_t> var_ptr(n + 1, 0), cm_of_vm(E), fill(n, 0);
+    int max_dv = 0;
+    for (int v = 0; v < n; ++v) { var_ptr[v + 1] = var_ptr[v] + dv[v]; max_dv = std::max(max_dv, dv[v]); }
+    for (int c = 0; c < m; ++c)
+        for (int i = row_ptr[c]; i < row_ptr[c + 1]; ++i) {
+            const int v = col_idx[i];
+            cm_of_vm[var_ptr[v] + fill[v]++] = i;       // rows visited ascending => checks ascending
+        }
+    int dev = 0;
+    LDPC_CUDA_TRY(cudaGetDevice(&dev));
+    ldpc_code *h = new (std::nothrow) ldpc_code();
+    if (!h) { set_error("out of host memory"); return LDPC_ENOMEM; }
+    h->m = m; h->n = n; h->E = E; h->max_dc = max_dc; h->max_dv = max_dv; h->device = dev;
+    h->qc_Z = 0; h->qc_id = -1; h->kernel = LDPC_KERNEL_GENERIC; h->d_tables = nullptr;
+    const size_t words = (size_t)(m + 1) + E + (n + 1) + E;
+    cudaError_t e = cudaMalloc(&h->d_tables, words * sizeof(int32_t));
+    if (e != cudaSuccess) { delete h; return cuda_fail(e, "cudaMalloc(tables)"); }
+    std::vector<int32_t> host(words);
+    int32_t *p = host.data();
+    memcpy(p, row_ptr, sizeof(int32_t) * (m + 1)); p += m + 1;
+    memcpy(p, col_idx, sizeof(int32_t) * E); p += E;
+    memcpy(p, var_ptr.data(), sizeof(int32_t) * (n + 1)); p += n + 1;
+    memcpy(p, cm_of_vm.data(), sizeof(int32_t) * E);
+    e = cudaMemcpy(h->d_tables, host.data(), words * sizeof(int32_t), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { cudaFree(h->d_tables); delete h; return cuda_fail(e, "cudaMemcpy(tables)"); }
+    h->g.m = m; h->g.n = n; h->g.E = E;
+    h->g.chk_ptr = h->d_tables;
+    h->g.chk_var = h->d_tables + (m + 1);
+    h->g.var_ptr = h->g.chk_var + E;
+    h->g.cm_of_vm = h->g.var_ptr + (n + 1);
+    if (qc_Z > 0 && qc_proto) {
+        if (m % qc_Z || n % qc_Z) { cudaFree(h->d_tables); delete h; set_error("qc_Z does not divide H"); return LDPC_EINVAL; }
+        // verify that the declared prototype really describes H (edge count + every edge)
+        const int mb = m / qc_Z, nb = n / qc_Z;
+        long long cnt = 0;
+        for (int i = 0; i < mb * nb; ++i) cnt += qc_proto[i] >= 0 ? qc_Z : 0;
+        bool ok = (cnt == E);
+        for (int c = 0; ok && c < m; ++c)
+            for (int i = row_ptr[c]; ok && i < row_ptr[c + 1]; ++i) {
+                const int v = col_idx[i], s = qc_proto[(c / qc_Z) * nb + v / qc_Z];
+                ok = s >= 0 && ((c % qc_Z + s) % qc_Z) == v % qc_Z;
+            }
+        if (!ok) { cudaFree(h->d_tables); delete h; set_error("qc_proto does not match H"); return LDPC_EINVAL; }
+        h->qc_Z = qc_Z;
+        h->qc_id = qc_lookup(qc_Z, mb, nb, qc_proto);
+        if (h->qc_id >= 0) h->kernel = LDPC_KERNEL_QC;
+    }
+    *out = h;
+    return LDPC_OK;
+}
+
+void ldpc_code_destroy(ldpc_code_t *code) {
+    if (!code) return;
+    if (code->d_tables) cudaFree(code->d_tables);
+    delete code;
+}
+
+int ldpc_code_info(const ldpc_code_t *code, ldpc_code_info_t *info) {
+    if (!code || !info) { set_error("ldpc_code_info: null argument"); return LDPC_EINVAL; }
+    info->m = code->m; info->n = code->n; info->E = code->E;
+    info->max_dc = code->max_dc; info->max_dv = code->max_dv;
+    info->kernel = code->kernel; info->qc_Z = code->qc_Z; info->reserved = 0;
+    return LDPC_OK;
+}
+
+int ldpc_code_set_kernel(ldpc_code_t *code, int kernel) {
+    if (!code) { set_error("null code"); return LDPC_EINVAL; }
+    if (kernel == LDPC_KERNEL_GENERIC) { code->kernel = kernel; return LDPC_OK; }
+    if (kernel == LDPC_KERNEL_QC && code->qc_id >= 0) { code->kernel = kernel; return LDPC_OK; }
+    set_error("kernel %d not available for this code", kernel);
+    return LDPC_EUNSUPPORTED;
+}
+
+static int check_decode_args(const ldpc_code_t *code, const void *llr, int llr_dtype, int64_t B, int iters,
+                             int update, float clamp_value) {
+    if (!code) { set_error("null code handle"); return LDPC_EINVAL; }
+    if (B < 0 || iters < 0) { set_error("negative batch or iteration count"); return LDPC_EINVAL; }
+    if (B > 0 && !llr) { set_error("null llr pointer"); return LDPC_EINVAL; }
+    if (llr_dtype < LDPC_F32 || llr_dtype > LDPC_F16) { set_error("bad llr_dtype %d", llr_dtype); return LDPC_EINVAL; }
+    if (update < LDPC_UPDATE_SP || update > LDPC_UPDATE_OMS) { set_error("bad update rule %d", update); return LDPC_EINVAL; }
+    if (!(clamp_value > 0.0f)) { set_error("clamp_value must be positive"); return LDPC_EINVAL; }
+    return LDPC_OK;
+}
+
+static int decode_dispatch(const ldpc_code_t *code, const DecodeArgs &a, cudaStream_t s) {
+    if (code->kernel == LDPC_KERNEL_QC && a.x0 == nullptr && a.x_out == nullptr)
+        return launch_decode_qc(code->qc_id, a, s);
+    return launch_decode_generic(code->g, code->max_dv, code->max_dc, a, s);
+}
+
+int ldpc_decode(const ldpc_code_t *code, const void *llr, int llr_dtype, int64_t B, int iters, int update,
+                float clamp_value, float param, const float *x0, float *prob, float *llr_post,
+                uint8_t *hard, uint8_t *hard_packed, int32_t *syndrome, float *x_out, ldpc_stream_t stream) {
+    int rc = check_decode_args(code, llr, llr_dtype, B, iters, update, clamp_value);
+    if (rc) return rc;
+    DecodeArgs a;
+    memset(&a, 0, sizeof(a));
+    a.llr = llr; a.llr_dtype = llr_dtype; a.B = B; a.iters = iters; a.update = update;
+    a.clampv = clamp_value; a.param = param; a.x0 = x0;
+    a.prob = prob; a.llr_post = llr_post; a.hard = hard; a.hard_packed = hard_packed;
+    a.syndrome = syndrome; a.x_out = x_out;
+    return decode_dispatch(code, a, (cudaStream_t)stream);
+}
+
+// ---- host-buffer pipeline (decode_bits, ofdm_functions.py:131-163) ---------------------------
+int ldpc_decode_host(const ldpc_code_t *code, const void *llr_host, int llr_dtype, int64_t N, int iters,
+                     int update, float clamp_value, float param, uint8_t *hard_host,
+                     uint8_t *hard_packed_host, float *llr_post_host, int32_t *syndrome_host,
+                     int64_t chunk) {
+    int rc = check_decode_args(code, llr_host, llr_dtype, N, iters, update, clamp_value);
+    if (rc) return rc;
+    if (N == 0) return LDPC_OK;
+    const int n = code->n, nby = (n + 7) / 8;
+    const size_t esz = llr_dtype == LDPC_F64 ? 8 : (llr_dtype == LDPC_F16 ? 2 : 4);
+    if (chunk <= 0) chunk = 32768;
+    chunk = std::min<int64_t>(chunk, N);
+    const int NBUF = 3;
+    struct Buf { void *llr; uint8_t *hard, *packed; float *post; int32_t *synd; cudaStream_t s; cudaEvent_t done; };
+    Buf buf[NBUF];
+    memset(buf, 0, sizeof(buf));
+    auto cleanup = [&]() {
+        for (auto &b : buf) {
+            if (b.llr) cudaFree(b.llr);
+            if (b.hard) cudaFree(b.hard);
+            if (b.packed) cudaFree(b.packed);
+            if (b.post) cudaFree(b.post);
+            if (b.synd) cudaFree(b.synd);
+            if (b.done) cudaEventDestroy(b.done);
+            if (b.s) cudaStreamDestroy(b.s);
+        }
+    };
+#define HTRY(x) do { cudaError_t _e = (x); if (_e != cudaSuccess) { cleanup(); return cuda_fail(_e, #x); } } while (0)
+    for (auto &b : buf) {
+        HTRY(cudaStreamCreateWithFlags(&b.s, cudaStreamNonBlocking));
+        HTRY(cudaEventCreateWithFlags(&b.done, cudaEventDisableTiming));
+        HTRY(cudaMalloc(&b.llr, (size_t)chunk * n * esz));
+        if (hard_host) HTRY(cudaMalloc(&b.hard, (size_t)chunk * n));
+        if (hard_packed_host) HTRY(cudaMalloc(&b.packed, (size_t)chunk * nby));
+        if (llr_post_host) HTRY(cudaMalloc(&b.post, (size_t)chunk * n * sizeof(float)));
+        if (syndrome_host) HTRY(cudaMalloc(&b.synd, (size_t)chunk * sizeof(int32_t)));
+    }
+    int64_t done = 0;
+    int i = 0;
+    while (done < N) {
+        Buf &b = buf[i % NBUF];
+        const int64_t cnt = std::min<int64_t>(chunk, N - done);
+        HTRY(cudaMemcpyAsync(b.llr, (const char *)llr_host + (size_t)done * n * esz, (size_t)cnt * n * esz,
+                             cudaMemcpyHostToDevice, b.s));
+        DecodeArgs a;
+        memset(&a, 0, sizeof(a));
+        a.llr = b.llr; a.llr_dtype = llr_dtype; a.B = cnt; a.iters = iters; a.update = update;
+        a.clampv = clamp_value; a.param = param;
+        a.hard = b.hard; a.hard_packed = b.packed; a.llr_post = b.post; a.syndrome = b.synd;
+        rc = decode_dispatch(code, a, b.s);
+        if (rc) { cleanup(); return rc; }
+        if (hard_host) HTRY(cudaMemcpyAsync(hard_host + (size_t)done * n, b.hard, (size_t)cnt * n, cudaMemcpyDeviceToHost, b.s));
+        if (hard_packed_host) HTRY(cudaMemcpyAsync(hard_packed_host + (size_t)done * nby, b.packed, (size_t)cnt * nby, cudaMemcpyDeviceToHost, b.s));
+        if (llr_post_host) HTRY(cudaMemcpyAsync(llr_post_host + (size_t)done * n, b.post, (size_t)cnt * n * sizeof(float), cudaMemcpyDeviceToHost, b.s));
+        if (syndrome_host) HTRY(cudaMemcpyAsync(syndrome_host + done, b.synd, (size_t)cnt * sizeof(int32_t), cudaMemcpyDeviceToHost, b.s));
+        done += cnt;
+        ++i;
+    }
+    for (auto &b : buf) HTRY(cudaStreamSynchronize(b.s));
+#undef HTRY
+    cleanup();
+    return LDPC_OK;
+}
+
+}  // extern "C"
+
+// ---- standalone error counting ---------------------------------------------------------------
+namespace ldpc {
+__global__ void count_errors_kernel(const void *llr, int llr_dtype, const uint8_t *hard, const uint8_t *ref,
+                                    long long B, int n, int k, unsigned long long *counters) {
+    // one warp per codeword, grid-stride
+    const int lane = threadIdx.x & 31;
+    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    unsigned long long unc = 0, inf = 0, fr = 0;
+    for (long long cw = warp; cw < B; cw += nwarps) {
+        int e_any = 0;
+        for (int v = lane; v < n; v += 32) {
+            const long long o = cw * n + v;
+            const int r = ref[o];
+            if (llr) unc += ((load_llr(llr, llr_dtype, o) > 0.0f) != r);
+            const int e = hard[o] != r;
+            inf += e & (v < k);
+            e_any |= e;
+        }
+        e_any = __any_sync(0xffffffffu, e_any);
+        if (lane == 0) fr += e_any;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        unc += __shfl_xor_sync(0xffffffffu, unc, o);
+        inf += __shfl_xor_sync(0xffffffffu, inf, o);
+    }
+    if (lane == 0) {
+        if (unc) atomicAdd(&counters[0], unc);
+        if (inf) atomicAdd(&counters[1], inf);
+        if (fr) atomicAdd(&counters[2], fr);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        atomicAdd(&counters[3], (unsigned long long)B * n);
+        atomicAdd(&counters[4], (unsigned long long)B);
+    }
+}
+}  // namespace ldpc
+
+extern "C" int ldpc_count_errors(const void *llr, int llr_dtype, const uint8_t *hard, const uint8_t *ref_bits,
+                                 int64_t B, int n, int k, int64_t *counters, ldpc_stream_t stream) {
+    if (!hard || !ref_bits || !counters || B < 0 || n <= 0 || k < 0 || k > n) { set_error("ldpc_count_errors: bad arguments"); return LDPC_EINVAL; }
+    if (B == 0) return LDPC_OK;
+    const int threads = 256;
+    long long blocks = std::min<long long>((B * 32 + threads - 1) / threads, 148 * 8);
+    count_errors_kernel<<<(int)blocks, threads, 0, (cudaStream_t)stream>>>(
+        llr, llr_dtype, hard, ref_bits, B, n, k, reinterpret_cast<unsigned long long *>(counters));
+    LDPC_CUDA_TRY(cudaGetLastError());
+    return LDPC_OK;
+}

@@ -1,0 +1,72 @@
+"""Code library: structural validators and encoders."""
+import numpy as np
+import pytest
+
+from ldpc_b200.codes import (EdgeTables, detect_qc, gf2_rank, ieee80211n_1944_r12, peg_64_32,
+                             systematic_generator)
+
+
+def test_default_code_shapes():
+    H, G = peg_64_32()
+    assert H.shape == (32, 64) and H.dtype == np.int64 and G.shape == (64, 32) and G.dtype == np.float64
+    assert int(H.sum()) == 96
+    assert set(H.sum(1)) == {3} and set(H.sum(0)) <= {1, 2}
+    assert not ((H @ G.astype(np.int64)) % 2).any()            # H G = 0 (mod 2)
+    assert np.array_equal(G[:32], np.eye(32))                  # systematic, info bits first
+
+
+def test_wifi_structure():
+    qc = ieee80211n_1944_r12()
+    H = qc.H
+    assert H.shape == (972, 1944) and int(H.sum()) == 6966 and (qc.proto >= 0).sum() == 86
+    rd, rc = np.unique(H.sum(1), return_counts=True)
+    assert dict(zip(rd.tolist(), rc.tolist())) == {7: 810, 8: 162}
+    cd, cc = np.unique(H.sum(0), return_counts=True)
+    assert dict(zip(cd.tolist(), cc.tolist())) == {2: 891, 3: 729, 4: 81, 11: 243}
+    assert gf2_rank(H) == 972
+    ov = H.astype(np.int32) @ H.astype(np.int32).T
+    np.fill_diagonal(ov, 0)
+    assert ov.max() == 1                                        # no 4-cycles
+    # dual-diagonal parity part, column 12 = {1, 0, 1} at rows 0, 6, 11
+    assert [int(qc.proto[r, 12]) for r in (0, 6, 11)] == [1, 0, 1]
+    for j in range(11):
+        assert qc.proto[j, 13 + j] == 0 and qc.proto[j + 1, 13 + j] == 0
+    assert np.array_equal(detect_qc(H, 81), qc.proto)
+    assert detect_qc(H, 80) is None
+
+
+def test_wifi_encoder_matches_dense_generator():
+    qc = ieee80211n_1944_r12()
+    rng = np.random.RandomState(0)
+    u = rng.randint(0, 2, (16, qc.k)).astype(np.uint8)
+    c = qc.encode(u)
+    assert np.array_equal(c[:, :qc.k], u)
+    assert not ((qc.H.astype(np.int64) @ c.T.astype(np.int64)) % 2).any()
+    G = systematic_generator(qc.H)
+    assert np.array_equal((G.astype(np.int64) @ u.T.astype(np.int64) % 2).T, c)
+
+
+@pytest.mark.parametrize("seed", [0, 1])
+def test_edge_tables_random(seed):
+    rng = np.random.RandomState(seed)
+    H = (rng.rand(7, 15) < 0.3).astype(np.int64)
+    H[:, 0] = 1; H[0, :] = 1
+    et = EdgeTables.from_H(H)
+    rows, cols = np.nonzero(H)
+    assert et.E == rows.size
+    assert np.array_equal(et.chk_var, cols)
+    vcols, vrows = np.nonzero(H.T)
+    assert np.array_equal(et.var_chk, vrows)
+    # permutations are inverse of each other and connect the same (check, variable) pair
+    assert np.array_equal(et.vm_of_cm[et.cm_of_vm], np.arange(et.E))
+    assert np.array_equal(rows[et.cm_of_vm], vrows) and np.array_equal(cols[et.cm_of_vm], vcols)
+    mask_c, mask_v, mask_v_final, llr_expander = et.dense_masks()
+    assert mask_v_final.shape == (15, et.E) and llr_expander.shape == (et.E, 15)
+    assert mask_v_final.sum() == et.E and llr_expander.sum() == et.E
+    from bp.masking import masks_to_H
+    assert np.array_equal(masks_to_H(mask_c, mask_v, mask_v_final, llr_expander)[:, :], _dedup(H))
+
+
+def _dedup(H):
+    # masks_to_H cannot tell identical rows apart; the random H above has distinct rows w.h.p.
+    return H
