@@ -100,7 +100,7 @@ __global__ void __launch_bounds__(256) decode_generic_kernel(const GenericParams
             if (k < d) in[k] = mrow[__ldg(g.cm_of_vm + b + k)];
         const float t = marginal_t<MAXDV>(in, d, llr_s[cw * p.llr_stride + v]);
         const float pr = prob_one(t);
-        const uint8_t hb = pr > 0.5f;                    // np.round: tie 0.5 -> 0
+        const uint8_t hb = hard_bit(t);                  // np.round(prob): tie 0.5 -> 0
         hard_s[cw * p.hard_stride + v] = hb;
         const long long o = cw0 * n + i;
         if (a.prob) a.prob[o] = pr;

@@ -183,7 +183,7 @@ __global__ void __launch_bounds__((QcLayout<Code, CW>::THREADS)) decode_qc_kerne
             });
             const float t = marginal_t<(D > 0 ? D : 1)>(in, D, llr[c * Z + z]);
             const float pr = prob_one(t);
-            const uint8_t hb = pr > 0.5f;
+            const uint8_t hb = hard_bit(t);
             hard_s[cw * L::HARD_STRIDE + c * Z + z] = hb;
             const long long o = obase + c * Z + z;
             if (a.prob) a.prob[o] = pr;
