@@ -118,6 +118,94 @@ int ldpc_decode_host(const ldpc_code_t *code, const void *llr_host, int llr_dtyp
 int ldpc_count_errors(const void *llr, int llr_dtype, const uint8_t *hard, const uint8_t *ref_bits,
                       int64_t B, int n, int k, int64_t *counters, ldpc_stream_t stream);
 
+/* ==== link-simulator front end (K2).  Complex arrays are interleaved (re, im) pairs of
+ * real_dtype (LDPC_F64 = numpy complex128, LDPC_F32 = complex64); an array of L complex values
+ * is a sequence of OFDM symbols, symbol j occupying [j*N, (j+1)*N) - the reference's flat
+ * (1, L) layout (it reshapes to (-1, N).T and back).  ofdm_size N in {32, 64, 128, 256};
+ * transforms are unitary (1/sqrt(N)) like DFT(N), ofdm/ofdm_functions.py:86-93. ==== */
+
+/* encode_bits (ofdm/ofdm_functions.py:11-15): out[c, :] = G bits[c, :] mod 2.
+ *   bits [ncw,k] u8 0/1; G_packed [n, ceil(k/32)] u32, bit j of word w = G[r][32 w + j];
+ *   out [ncw,n] u8. */
+int ldpc_encode_bits(const uint8_t *bits, const uint32_t *G_packed, int n, int k, int64_t ncw,
+                     uint8_t *out, ldpc_stream_t stream);
+
+/* modulate_bits (ofdm/ofdm_functions.py:17-22): bit pairs (b0,b1) -> ((1-2 b0) + j(1-2 b1))/sqrt(2).
+ *   bits [2*n_symbols] u8; out [n_symbols] complex. */
+int ldpc_modulate_bits(const uint8_t *bits, int64_t n_symbols, int real_dtype, void *out,
+                       ldpc_stream_t stream);
+
+/* transmit_symbols (ofdm/ofdm_functions.py:25-35): tx = W^H s per OFDM symbol, rx = tx + noise.
+ *   noise: [n_ofdm*N] complex, ALREADY scaled (the reference's (N(0,1/sqrt(snr)) + j N(..))/sqrt(2)),
+ *   or NULL to draw it on the device from Philox4x32-10(seed) with that variance.
+ *   tx may be NULL. */
+int ldpc_ofdm_transmit(const void *symbols, int64_t n_ofdm, int ofdm_size, int real_dtype,
+                       const void *noise, double snr, uint64_t seed, void *rx, void *tx,
+                       ldpc_stream_t stream);
+
+/* quantizer (ofdm/ofdm_functions.py:37-51) applied to n_real real values (a complex array is
+ * 2 reals per element): step = 2 clip/(L-1); q = step*floor(x/step + .5);
+ * clip(q, -(L/2) step + 1, (L/2) step - 1) - the +-1 in SIGNAL units is the reference's
+ * behaviour and is reproduced.  num_levels = 2^num_bits. */
+int ldpc_quantize(const void *in, int64_t n_real, int real_dtype, double num_levels, double clip,
+                  void *out, ldpc_stream_t stream);
+
+/* demodulate_signal (ofdm/ofdm_functions.py:63-78): R = W r per OFDM symbol;
+ *   llrs [2*n_ofdm*N] real, interleaved (b0,b1) per subcarrier,
+ *   llr = ((R - a)^2 - (R + a)^2) / (2 * 0.5/snr_est), a = 1/sqrt(2)  (log P1/P0);
+ *   symbols [n_ofdm*N] complex.  Either output may be NULL. */
+int ldpc_ofdm_demodulate(const void *signal, int64_t n_ofdm, int ofdm_size, int real_dtype,
+                         double snr_est, void *llrs, void *symbols, ldpc_stream_t stream);
+
+/* ==== fused Monte-Carlo link simulation (replaces the per-SNR loop body of
+ * evaluate_quantized_snr.py:91-188: create_bits, encode_bits, modulate_bits, gen_data, the
+ * inline AGC quantizer, decode_bits and the BER/BLER means) ==== */
+
+/* Philox4x32-10 block function exactly as the simulator's kernels use it (host-callable, for
+ * known-answer tests): counter = {low32(codeword), high32(codeword), stream, block},
+ * streams: 0 = information bits, 1 = channel noise. */
+void ldpc_philox4x32(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
+
+/* Attach the systematic encoder: parity rows of G (rows k..n-1 of the [n,k] generator,
+ * ofdm/ofdm_functions.py:11-15 / bp/parity.py:44), bit-packed [n-k, ceil(k/32)] u32 on the HOST. */
+int ldpc_code_set_generator(ldpc_code_t *code, const uint32_t *parity_rows_packed_host, int k);
+
+typedef struct {
+    int32_t struct_size;    /* = sizeof(ldpc_sim_params_t) */
+    int32_t ofdm_size;      /* 32 (every reference script), 64, 128, 256 */
+    int32_t qbits;          /* 0 = unquantized (gen_data path); > 0 = low-resolution ADC */
+    int32_t agc_mode;       /* 1 = factor = agc_clip/(0.5(1+1/snr))*clip_ratio, clip = agc_clip
+                               (evaluate_quantized_snr.py:103-111);
+                               2 = clip = sqrt(1+1/snr)*clip_ratio, the analytic value of gen_qdata's
+                               std(rx_signal)*clip_ratio (ofdm/ofdm_functions.py:121-123) */
+    float agc_clip;         /* 10 in the reference scripts */
+    float clip_ratio;
+    float snr_db;           /* per-subcarrier Es/N0 in dB (ofdm/ofdm_functions.py:110) */
+    int32_t iters;          /* BP iterations */
+    int32_t update;         /* LDPC_UPDATE_* */
+    float clamp_value;
+    float param;
+    int32_t reserved;
+    uint64_t seed;          /* Philox key */
+    int64_t first_codeword; /* global index of the first codeword (Philox subsequence) */
+    int64_t n_codewords;
+} ldpc_sim_params_t;
+
+/* Run the link for codewords [first_codeword, first_codeword + n_codewords) and ADD the exact
+ * integer metrics into counters[5] (i64, device): {uncoded bit errors, info-bit errors, frame
+ * errors, bits, frames} (evaluate_quantized_snr.py:169-188).  Each codeword is framed into
+ * ceil((n/2)/N) OFDM symbols (null subcarriers after its last QPSK symbol; identical to the
+ * reference when n = 2N).  workspace: device scratch for the LLR tile, >= 1024 codewords of
+ * (4 n + ceil(n/8)) bytes; the run is chunked to fit.  Results depend only on (seed, global
+ * codeword index), never on the sharding. */
+int ldpc_sim_run(const ldpc_code_t *code, const ldpc_sim_params_t *params, void *workspace,
+                 size_t workspace_bytes, int64_t *counters, ldpc_stream_t stream);
+
+/* The front end alone (K2): transmitted codewords, MSB-first packed [n_codewords, ceil(n/8)],
+ * and channel LLRs f32 [n_codewords, n], for tests and for feeding ldpc_decode directly. */
+int ldpc_sim_generate(const ldpc_code_t *code, const ldpc_sim_params_t *params, uint8_t *cw_packed,
+                      float *llr, ldpc_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

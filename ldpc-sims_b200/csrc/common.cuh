@@ -40,7 +40,25 @@ __device__ __forceinline__ float load_llr(const void *p, int dtype, long long i)
     return __half2float(__ldg(reinterpret_cast<const __half *>(p) + i));
 }
 
+}  // namespace ldpc
+
+// the opaque handle of include/ldpc_b200.h
+struct ldpc_code {
+    int m, n, E, max_dc, max_dv;
+    int kernel;         // LDPC_KERNEL_*
+    int qc_id;          // index of the compiled specialisation or -1
+    int qc_Z;
+    int device;
+    int32_t *d_tables;  // one allocation: chk_ptr | chk_var | var_ptr | cm_of_vm
+    ldpc::GraphTables g;
+    uint32_t *d_gen;    // bit-packed parity rows of the systematic generator [m][ceil(k/32)] or null
+    int k_info;
+};
+
+namespace ldpc {
+
 void set_error(const char *fmt, ...);
+int decode_dispatch(const ldpc_code *code, const DecodeArgs &a, cudaStream_t s);
 int cuda_fail(cudaError_t e, const char *what);
 
 #define LDPC_CUDA_TRY(expr)                                         \

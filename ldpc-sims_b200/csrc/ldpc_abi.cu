@@ -29,16 +29,6 @@ int cuda_fail(cudaError_t e, const char *what) {
 
 using namespace ldpc;
 
-struct ldpc_code {
-    int m, n, E, max_dc, max_dv;
-    int kernel;        // LDPC_KERNEL_*
-    int qc_id;         // index of the compiled specialisation or -1
-    int qc_Z;
-    int device;
-    int32_t *d_tables; // one allocation: chk_ptr | chk_var | var_ptr | cm_of_vm
-    GraphTables g;
-};
-
 extern "C" {
 
 int ldpc_abi_version(void) { return LDPC_B200_ABI_VERSION; }
@@ -86,6 +76,7 @@ int ldpc_code_create(const int32_t *row_ptr, const int32_t *col_idx, int m, int 
     if (!h) { set_error("out of host memory"); return LDPC_ENOMEM; }
     h->m = m; h->n = n; h->E = E; h->max_dc = max_dc; h->max_dv = max_dv; h->device = dev;
     h->qc_Z = 0; h->qc_id = -1; h->kernel = LDPC_KERNEL_GENERIC; h->d_tables = nullptr;
+    h->d_gen = nullptr; h->k_info = 0;
     const size_t words = (size_t)(m + 1) + E + (n + 1) + E;
     cudaError_t e = cudaMalloc(&h->d_tables, words * sizeof(int32_t));
     if (e != cudaSuccess) { delete h; return cuda_fail(e, "cudaMalloc(tables)"); }
@@ -126,6 +117,7 @@ int ldpc_code_create(const int32_t *row_ptr, const int32_t *col_idx, int m, int 
 void ldpc_code_destroy(ldpc_code_t *code) {
     if (!code) return;
     if (code->d_tables) cudaFree(code->d_tables);
+    if (code->d_gen) cudaFree(code->d_gen);
     delete code;
 }
 
@@ -156,11 +148,17 @@ static int check_decode_args(const ldpc_code_t *code, const void *llr, int llr_d
     return LDPC_OK;
 }
 
-static int decode_dispatch(const ldpc_code_t *code, const DecodeArgs &a, cudaStream_t s) {
+}  // extern "C"
+
+namespace ldpc {
+int decode_dispatch(const ldpc_code *code, const DecodeArgs &a, cudaStream_t s) {
     if (code->kernel == LDPC_KERNEL_QC && a.x0 == nullptr && a.x_out == nullptr)
         return launch_decode_qc(code->qc_id, a, s);
     return launch_decode_generic(code->g, code->max_dv, code->max_dc, a, s);
 }
+}  // namespace ldpc
+
+extern "C" {
 
 int ldpc_decode(const ldpc_code_t *code, const void *llr, int llr_dtype, int64_t B, int iters, int update,
                 float clamp_value, float param, const float *x0, float *prob, float *llr_post,

@@ -1,0 +1,236 @@
+// sim.cu - the Monte-Carlo link simulator: random bits -> encode -> QPSK -> OFDM -> AWGN ->
+// low-resolution ADC -> de-OFDM -> LLR -> BP decode -> exact error counters, all on the GPU.
+//
+// Replaces the per-SNR loop body of the evaluate scripts (evaluate_quantized_snr.py:91-188:
+// create_bits / encode_bits / modulate_bits / gen_data / inline AGC quantizer / decode_bits /
+// BER-BLER means).  Three launches per chunk of codewords, chained on one stream:
+//   K2a gen_codewords   Philox info bits, systematic encode (bit-packed generator)
+//   K2b linksim_llr     QPSK, per-codeword OFDM framing, warp IFFT, Philox AWGN, AGC+quantizer,
+//                       warp FFT, exact LLR -> f32 [chunk, n] (stays L2-resident between K2b and K1)
+//   K1+K3 decode        flooding BP + fused integer counters (epilogue.cuh)
+// Every random draw is keyed by the GLOBAL codeword index, so counters do not depend on how the
+// codewords are sharded over GPUs or chunks.
+#include <algorithm>
+#include <cstring>
+
+#include "common.cuh"
+#include "frontend.cuh"
+
+namespace ldpc {
+
+// ---- K2a ----------------------------------------------------------------------------------------------
+// One CTA per codeword (grid-stride).  Info bits: Philox(cw, RNG_BITS, block) -> 128 bits per call.
+__global__ void __launch_bounds__(256) gen_codewords_kernel(const uint32_t *Pp /*[m][kw]*/, int n, int k, long long cw_first,
+                                                            long long ncw, unsigned long long seed, uint8_t *cw_packed) {
+    extern __shared__ uint32_t sm[];
+    const int kw = (k + 31) / 32, m = n - k, nby = (n + 7) / 8;
+    uint32_t *u_s = sm;                                   // [kw] info words, bit j of word w = bit 32w+j
+    uint8_t *bits_s = reinterpret_cast<uint8_t *>(sm + kw);   // [n] one byte per code bit
+    const Philox rng(seed);
+    for (long long c = blockIdx.x; c < ncw; c += gridDim.x) {
+        const unsigned long long gcw = (unsigned long long)(cw_first + c);
+        for (int blk = threadIdx.x; blk * 4 < kw; blk += blockDim.x) {
+            uint32_t r[4];
+            rng((uint32_t)gcw, (uint32_t)(gcw >> 32), RNG_BITS, (uint32_t)blk, r);
+            for (int j = 0; j < 4; ++j) {
+                const int w = blk * 4 + j;
+                if (w < kw) {
+                    uint32_t v = r[j];
+                    if (32 * (w + 1) > k) v &= (k - 32 * w >= 32) ? 0xffffffffu : ((1u << (k - 32 * w)) - 1u);
+                    u_s[w] = v;
+                }
+            }
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < k; i += blockDim.x) bits_s[i] = (u_s[i >> 5] >> (i & 31)) & 1u;
+        for (int r = threadIdx.x; r < m; r += blockDim.x) {
+            uint32_t acc = 0;
+            for (int w = 0; w < kw; ++w) acc ^= __ldg(Pp + (long long)r * kw + w) & u_s[w];
+            bits_s[k + r] = (uint8_t)(__popc(acc) & 1);
+        }
+        __syncthreads();
+        for (int by = threadIdx.x; by < nby; by += blockDim.x) {
+            unsigned v = 0;
+            for (int b = 0; b < 8; ++b) {
+                const int i = by * 8 + b;
+                v |= (i < n ? (unsigned)bits_s[i] : 0u) << (7 - b);
+            }
+            cw_packed[c * nby + by] = (uint8_t)v;
+        }
+        __syncthreads();
+    }
+}
+
+// ---- K2b ----------------------------------------------------------------------------------------------
+struct LinkParams {
+    int n;                 // code length (bits)
+    int n_ofdm_per_cw;     // ceil((n/2) / N)
+    float snr;             // linear per-subcarrier Es/N0 (ofdm_functions.py:110)
+    int qbits;             // 0 = no ADC model
+    int agc_mode;          // 1 = script AGC (evaluate_quantized_snr.py:103-111), 2 = gen_qdata-style clip
+    float agc_clip, clip_ratio;
+    unsigned long long seed;
+    long long cw_first;
+};
+
+__device__ __forceinline__ int cw_bit(const uint8_t *row, int i) { return (row[i >> 3] >> (7 - (i & 7))) & 1; }
+
+template <int N>
+__global__ void __launch_bounds__(256) linksim_llr_kernel(const uint8_t *cw_packed, long long ncw, LinkParams p, float *llr) {
+    constexpr int P = N / 32, LOGN = ilog2(N);
+    __shared__ cplx<float> tw[N / 2];
+    for (int j = threadIdx.x; j < N / 2; j += blockDim.x) {
+        double s, c;
+        sincospi(-2.0 * (double)j / (double)N, &s, &c);
+        tw[j] = {(float)c, (float)s};
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    const long long total = ncw * p.n_ofdm_per_cw;
+    const int nby = (p.n + 7) / 8, nsym = p.n / 2;
+    const float scale = rsqrtf((float)N), a = 0.70710678118654752f;
+    const float nstd = sqrtf(0.5f / p.snr);                 // per real dimension
+    const float two_np = 1.0f / p.snr;                      // 2 * (0.5 / snr)
+    float factor = 1.0f, clip = 1.0f;
+    if (p.qbits > 0) {
+        if (p.agc_mode == 1) { clip = p.agc_clip; factor = p.agc_clip / (0.5f * (1.0f + 1.0f / p.snr)) * p.clip_ratio; }
+        else { clip = sqrtf(1.0f + 1.0f / p.snr) * p.clip_ratio; factor = 1.0f; }
+    }
+    const Quantizer<float> quant((float)(1 << (p.qbits > 0 ? p.qbits : 1)), clip);
+    const Philox rng(p.seed);
+    for (long long o = warp; o < total; o += nwarps) {
+        const long long c = o / p.n_ofdm_per_cw;
+        const int os = (int)(o - c * p.n_ofdm_per_cw);
+        const uint8_t *row = cw_packed + c * nby;
+        const unsigned long long gcw = (unsigned long long)(p.cw_first + c);
+        cplx<float> x[P];
+#pragma unroll
+        for (int r = 0; r < P; ++r) {                         // QPSK, null subcarriers past the codeword
+            const int sidx = os * N + r * 32 + lane;
+            if (sidx < nsym) x[r] = {a * (float)(1 - 2 * cw_bit(row, 2 * sidx)), a * (float)(1 - 2 * cw_bit(row, 2 * sidx + 1))};
+            else x[r] = {0.0f, 0.0f};
+        }
+        warp_fft<N, float, true>(x, lane, tw, scale);         // time sample t = bitrev(r*32+lane)
+#pragma unroll
+        for (int r = 0; r < P; ++r) {
+            const int t = bitrev(r * 32 + lane, LOGN);
+            uint32_t rnd[4];
+            rng((uint32_t)gcw, (uint32_t)(gcw >> 32), RNG_NOISE, (uint32_t)(os * N + t), rnd);
+            float z0, z1;
+            box_muller<float>(rnd[0], rnd[1], z0, z1);
+            float re = x[r].re + nstd * z0, im = x[r].im + nstd * z1;
+            if (p.qbits > 0) { re = quant(factor * re) / factor; im = quant(factor * im) / factor; }
+            x[r] = {re, im};
+        }
+        warp_fft_dit<N, float, false>(x, lane, tw, scale);    // back to natural subcarrier order
+#pragma unroll
+        for (int r = 0; r < P; ++r) {
+            const int sidx = os * N + r * 32 + lane;
+            if (sidx < nsym) {
+                float2 v = make_float2(qpsk_llr<float>(x[r].re, a, two_np), qpsk_llr<float>(x[r].im, a, two_np));
+                *reinterpret_cast<float2 *>(llr + c * p.n + 2 * sidx) = v;
+            }
+        }
+    }
+}
+
+}  // namespace ldpc
+
+using namespace ldpc;
+
+extern "C" {
+
+void ldpc_philox4x32(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) {
+    Philox rng(((uint64_t)key[1] << 32) | key[0]);
+    uint32_t o[4];
+    rng(ctr[0], ctr[1], ctr[2], ctr[3], o);
+    for (int i = 0; i < 4; ++i) out[i] = o[i];
+}
+
+int ldpc_code_set_generator(ldpc_code_t *code, const uint32_t *parity_rows_packed_host, int k) {
+    if (!code || !parity_rows_packed_host || k <= 0 || k >= code->n) { set_error("ldpc_code_set_generator: bad arguments"); return LDPC_EINVAL; }
+    const int m = code->n - k, kw = (k + 31) / 32;
+    if (code->d_gen) { cudaFree(code->d_gen); code->d_gen = nullptr; }
+    LDPC_CUDA_TRY(cudaMalloc(&code->d_gen, (size_t)m * kw * sizeof(uint32_t)));
+    LDPC_CUDA_TRY(cudaMemcpy(code->d_gen, parity_rows_packed_host, (size_t)m * kw * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    code->k_info = k;
+    return LDPC_OK;
+}
+
+static int check_sim(const ldpc_code_t *code, const ldpc_sim_params_t *sp) {
+    if (!code || !sp) { set_error("ldpc_sim: null argument"); return LDPC_EINVAL; }
+    if (sp->struct_size != (int32_t)sizeof(ldpc_sim_params_t)) { set_error("ldpc_sim_params_t size mismatch (%d vs %d)", sp->struct_size, (int)sizeof(ldpc_sim_params_t)); return LDPC_EINVAL; }
+    if (!code->d_gen) { set_error("code has no generator: call ldpc_code_set_generator first"); return LDPC_EINVAL; }
+    if (code->n % 2) { set_error("QPSK needs an even code length"); return LDPC_EUNSUPPORTED; }
+    if (sp->ofdm_size != 32 && sp->ofdm_size != 64 && sp->ofdm_size != 128 && sp->ofdm_size != 256) { set_error("ofdm_size must be 32, 64, 128 or 256"); return LDPC_EUNSUPPORTED; }
+    if (sp->n_codewords < 0 || sp->qbits < 0 || sp->qbits > 16) { set_error("bad n_codewords / qbits"); return LDPC_EINVAL; }
+    if (sp->qbits > 0 && sp->agc_mode != 1 && sp->agc_mode != 2) { set_error("agc_mode must be 1 (script AGC) or 2 (gen_qdata) when qbits > 0"); return LDPC_EINVAL; }
+    return LDPC_OK;
+}
+
+static int launch_frontend(const ldpc_code_t *code, const ldpc_sim_params_t *sp, long long first, long long cnt,
+                           uint8_t *cw_packed, float *llr, cudaStream_t s) {
+    const int n = code->n, k = code->k_info, kw = (k + 31) / 32;
+    const size_t sm = (size_t)kw * 4 + ((n + 3) & ~3);
+    const int g1 = (int)std::min<long long>(cnt, 148LL * 8);
+    gen_codewords_kernel<<<g1, 256, sm, s>>>(code->d_gen, n, k, first, cnt, sp->seed, cw_packed);
+    LDPC_CUDA_TRY(cudaGetLastError());
+    LinkParams lp;
+    lp.n = n; lp.n_ofdm_per_cw = (n / 2 + sp->ofdm_size - 1) / sp->ofdm_size;
+    lp.snr = powf(10.0f, sp->snr_db / 10.0f);
+    lp.qbits = sp->qbits; lp.agc_mode = sp->agc_mode; lp.agc_clip = sp->agc_clip; lp.clip_ratio = sp->clip_ratio;
+    lp.seed = sp->seed; lp.cw_first = first;
+    const long long warps = cnt * lp.n_ofdm_per_cw;
+    const int g2 = (int)std::min<long long>((warps + 7) / 8, 148LL * 16);
+    switch (sp->ofdm_size) {
+        case 32: linksim_llr_kernel<32><<<g2, 256, 0, s>>>(cw_packed, cnt, lp, llr); break;
+        case 64: linksim_llr_kernel<64><<<g2, 256, 0, s>>>(cw_packed, cnt, lp, llr); break;
+        case 128: linksim_llr_kernel<128><<<g2, 256, 0, s>>>(cw_packed, cnt, lp, llr); break;
+        default: linksim_llr_kernel<256><<<g2, 256, 0, s>>>(cw_packed, cnt, lp, llr); break;
+    }
+    LDPC_CUDA_TRY(cudaGetLastError());
+    return LDPC_OK;
+}
+
+int ldpc_sim_generate(const ldpc_code_t *code, const ldpc_sim_params_t *sp, uint8_t *cw_packed, float *llr,
+                      ldpc_stream_t stream) {
+    int rc = check_sim(code, sp);
+    if (rc) return rc;
+    if (!cw_packed || !llr) { set_error("ldpc_sim_generate: null output"); return LDPC_EINVAL; }
+    if (sp->n_codewords == 0) return LDPC_OK;
+    return launch_frontend(code, sp, sp->first_codeword, sp->n_codewords, cw_packed, llr, (cudaStream_t)stream);
+}
+
+int ldpc_sim_run(const ldpc_code_t *code, const ldpc_sim_params_t *sp, void *workspace, size_t workspace_bytes,
+                 int64_t *counters, ldpc_stream_t stream) {
+    int rc = check_sim(code, sp);
+    if (rc) return rc;
+    if (!counters) { set_error("ldpc_sim_run: null counters"); return LDPC_EINVAL; }
+    if (sp->iters < 0 || sp->update < LDPC_UPDATE_SP || sp->update > LDPC_UPDATE_OMS || !(sp->clamp_value > 0.0f)) { set_error("ldpc_sim_run: bad decoder parameters"); return LDPC_EINVAL; }
+    const int n = code->n, nby = (n + 7) / 8;
+    const size_t per_cw = (size_t)n * sizeof(float) + ((nby + 15) & ~15);
+    if (!workspace || workspace_bytes < per_cw * 1024) { set_error("ldpc_sim_run: workspace must hold at least 1024 codewords (%zu bytes)", per_cw * 1024); return LDPC_EINVAL; }
+    long long chunk = (long long)(workspace_bytes / per_cw);
+    chunk = std::min<long long>(chunk, 1 << 20);
+    chunk &= ~1023LL;
+    float *llr = reinterpret_cast<float *>(workspace);
+    uint8_t *cwp = reinterpret_cast<uint8_t *>(workspace) + (size_t)chunk * n * sizeof(float);
+    cudaStream_t s = (cudaStream_t)stream;
+    for (long long done = 0; done < sp->n_codewords; done += chunk) {
+        const long long cnt = std::min<long long>(chunk, sp->n_codewords - done);
+        rc = launch_frontend(code, sp, sp->first_codeword + done, cnt, cwp, llr, s);
+        if (rc) return rc;
+        DecodeArgs a;
+        memset(&a, 0, sizeof(a));
+        a.llr = llr; a.llr_dtype = LDPC_F32; a.B = cnt; a.iters = sp->iters; a.update = sp->update;
+        a.clampv = sp->clamp_value; a.param = sp->param;
+        a.ref_packed = cwp; a.counters = reinterpret_cast<unsigned long long *>(counters); a.k_info = code->k_info;
+        rc = decode_dispatch(code, a, s);
+        if (rc) return rc;
+    }
+    return LDPC_OK;
+}
+
+}  // extern "C"

@@ -64,6 +64,24 @@ def lib():
     L.ldpc_decode_host.argtypes = [vp, vp, i32, i64, i32, i32, f32, f32, vp, vp, vp, vp, i64]
     L.ldpc_count_errors.restype = ctypes.c_int
     L.ldpc_count_errors.argtypes = [vp, i32, vp, vp, i64, i32, i32, vp, vp]
+    u64, sz = ctypes.c_uint64, ctypes.c_size_t
+    f64 = ctypes.c_double
+    L.ldpc_encode_bits.restype = ctypes.c_int
+    L.ldpc_encode_bits.argtypes = [vp, vp, i32, i32, i64, vp, vp]
+    L.ldpc_modulate_bits.restype = ctypes.c_int
+    L.ldpc_modulate_bits.argtypes = [vp, i64, i32, vp, vp]
+    L.ldpc_ofdm_transmit.restype = ctypes.c_int
+    L.ldpc_ofdm_transmit.argtypes = [vp, i64, i32, i32, vp, f64, u64, vp, vp, vp]
+    L.ldpc_quantize.restype = ctypes.c_int
+    L.ldpc_quantize.argtypes = [vp, i64, i32, f64, f64, vp, vp]
+    L.ldpc_ofdm_demodulate.restype = ctypes.c_int
+    L.ldpc_ofdm_demodulate.argtypes = [vp, i64, i32, i32, f64, vp, vp, vp]
+    L.ldpc_code_set_generator.restype = ctypes.c_int
+    L.ldpc_code_set_generator.argtypes = [vp, vp, i32]
+    L.ldpc_sim_run.restype = ctypes.c_int
+    L.ldpc_sim_run.argtypes = [vp, vp, vp, sz, vp, vp]
+    L.ldpc_sim_generate.restype = ctypes.c_int
+    L.ldpc_sim_generate.argtypes = [vp, vp, vp, vp, vp]
     if L.ldpc_abi_version() != ABI_VERSION:
         raise ImportError(f"libldpc_b200.so ABI {L.ldpc_abi_version()} != binding {ABI_VERSION}; rebuild")
     _lib = L

@@ -213,7 +213,7 @@ def test_full_size_properties_minsum(wcode):
     B = 65536
     gen = torch.Generator(device="cuda").manual_seed(123)
     noise = torch.randn(B, qc.n, device="cuda", generator=gen)
-    sigma = 0.9
+    sigma = 0.62                                                        # Eb/N0 = 4.2 dB
     llr0 = -2.0 * (1.0 + sigma * noise) / sigma ** 2                   # all-zero codeword
     a = wcode.decode(llr0, 10, 20, update="minsum", want=("hard", "llr_post", "syndrome"))
     rng = np.random.RandomState(0)

@@ -1,0 +1,128 @@
+"""Fused link simulation (K2a + K2b + K1 + K3): structure, sharding invariance (exact integer
+equality), and Monte-Carlo agreement with the oracle / the reference's published BER pickle."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import bp_oracle as O
+import linksim_oracle as LO
+from ldpc_b200.codes import ieee80211n_1944_r12, peg_64_32
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dsim():
+    from ldpc_b200.decoder import LdpcCode
+    from ldpc_b200.linksim import attach_generator
+    H, G = peg_64_32()
+    return attach_generator(LdpcCode(H), G)
+
+
+@pytest.fixture(scope="module")
+def wsim():
+    from ldpc_b200.decoder import LdpcCode
+    from ldpc_b200.linksim import attach_generator
+    qc = ieee80211n_1944_r12()
+    return attach_generator(LdpcCode(qc.H, qc_Z=81, qc_proto=qc.proto))
+
+
+def test_generated_codewords_and_noiseless_llrs(wsim):
+    from ldpc_b200.linksim import LinkConfig, sim_generate
+    qc = ieee80211n_1944_r12()
+    for N in (64, 128, 256, 32):
+        cwp, llr = sim_generate(wsim, LinkConfig(snr_db=60.0, ofdm_size=N, seed=3), 1000, 256)
+        cw = np.unpackbits(cwp.cpu().numpy(), axis=1)[:, :qc.n]
+        assert not ((qc.H.astype(np.int64) @ cw.T.astype(np.int64)) % 2).any()       # valid codewords
+        assert 0.45 < cw[:, :qc.k].mean() < 0.55
+        L = llr.cpu().numpy()
+        snr = 10.0 ** 6
+        # noiseless limit: llr = -2*sqrt(2)*snr*Re(R) = 2*snr*(2b-1)
+        assert np.allclose(L / (2 * snr), 2.0 * cw - 1.0, atol=2e-2), N
+    # same global index -> same codeword, whatever the OFDM size or the call it came from
+    a, _ = sim_generate(wsim, LinkConfig(snr_db=3.0, ofdm_size=64, seed=3), 1000, 8)
+    b, _ = sim_generate(wsim, LinkConfig(snr_db=9.0, ofdm_size=128, seed=3), 1004, 4)
+    assert torch.equal(a[4:], b)
+
+
+def test_sim_equals_generate_plus_decode_plus_count(wsim):
+    from ldpc_b200.linksim import LinkConfig, sim_generate, sim_run
+    qc = ieee80211n_1944_r12()
+    cfg = LinkConfig(snr_db=1.5, ofdm_size=64, iters=10, update="minsum", clamp_value=20.0, seed=11)
+    cnt = sim_run(wsim, cfg, 5000, 3000).cpu().numpy()
+    cwp, llr = sim_generate(wsim, cfg, 5000, 3000)
+    out = wsim.decode(llr, 10, 20.0, update="minsum", want=("hard",))
+    cw = torch.as_tensor(np.unpackbits(cwp.cpu().numpy(), axis=1)[:, :qc.n]).cuda()
+    ref = wsim.count_errors(out["hard"], cw, qc.k, llr=llr).cpu().numpy()
+    assert cnt.tolist() == ref.tolist()
+    assert cnt[3] == 3000 * qc.n and cnt[4] == 3000 and 0 < cnt[0] < cnt[3] // 4
+
+
+def test_sharding_invariance_exact(dsim):
+    """Counters depend only on (seed, global codeword index): 1 shard == 3 ragged shards,
+    whatever the workspace chunking."""
+    from ldpc_b200.linksim import LinkConfig, shard_range, sim_run
+    cfg = LinkConfig(snr_db=4.0, ofdm_size=32, qbits=3, agc_mode=1, iters=5, update="sp", clamp_value=20.0, seed=99)
+    total = 20000
+    one = sim_run(dsim, cfg, 0, total).cpu().numpy()
+    acc = torch.zeros(5, dtype=torch.int64, device="cuda")
+    ws = torch.empty(1024 * (4 * 64 + 16), dtype=torch.uint8, device="cuda")      # forces 1024-codeword chunks
+    for r in range(3):
+        first, count = shard_range(total, r, 3)
+        sim_run(dsim, cfg, first, count, acc, ws)
+    assert acc.cpu().numpy().tolist() == one.tolist()
+    assert shard_range(10, 0, 4) == (0, 3) and shard_range(10, 3, 4) == (8, 2)
+
+
+def test_default_code_matches_published_ber_and_oracle(dsim, golden_dir):
+    """Config 1: (64,32) code, QPSK/OFDM-32/AWGN, 3 iterations, clamp 20 - the reference's
+    shipped BER pickle is the acceptance band (binomial 4 sigma)."""
+    from ldpc_b200.linksim import LinkConfig, rates, sim_run
+    pub = json.load(open(os.path.join(golden_dir, "published_ber.json")))
+    Ncw = 1 << 17
+    for snr in (0, 2, 4, 6):
+        c = sim_run(dsim, LinkConfig(snr_db=float(snr), ofdm_size=32, iters=3, update="sp", clamp_value=20.0, seed=7), 0, Ncw).cpu().numpy()
+        r = rates(c, 64, 32)
+        i = pub["snrdb"].index(float(snr))
+        pub_n = 1 << 15
+        for key, nbits in (("uncoded_ber", 64), ("coded_ber", 32), ("coded_bler", 1)):
+            p = pub[key][i]
+            # independent-trial sigma of both estimates; info-bit errors are bursty per frame -> x4 slack
+            sig = np.sqrt(p * (1 - p) * (1.0 / (Ncw * nbits) + 1.0 / (pub_n * nbits))) * (4 if key == "coded_ber" else 1)
+            assert abs(float(r[key]) - p) < 4 * sig + 1e-6, (snr, key, float(r[key]), p)
+
+
+def test_quantized_link_matches_oracle_statistics(dsim):
+    """Config 2: 3-bit ADC with the script AGC (evaluate_quantized_snr.py:96-133), 15 dB,
+    10 iterations, clamp 100: GPU simulation vs the oracle chain on fresh random data."""
+    from ldpc_b200.linksim import LinkConfig, rates, sim_run
+    H, G = peg_64_32()
+    np.random.seed(4321)
+    Ncw = 1 << 14
+    enc = LO.encode_bits(LO.create_bits(Ncw * 32), G)
+    rx_signal, _, _, _ = LO.gen_data(LO.modulate_bits(enc), 15.0, 32)
+    qllr, _ = LO.agc_quantized_frontend(rx_signal, 15.0, 3, 1.0, 32, agc_clip=10)
+    L = qllr.reshape(-1, 64); E = enc.reshape(-1, 64)
+    dec = O.decode_bits(L, H, 10, 1024, 100)
+    m = LO.error_metrics(L, dec, E, 32)
+    o_unc, o_bler = m["uncoded_errs"] / m["bits"], m["frame_errs"] / m["frames"]
+    Ng = 1 << 18
+    c = sim_run(dsim, LinkConfig(snr_db=15.0, ofdm_size=32, qbits=3, agc_mode=1, agc_clip=10.0, clip_ratio=1.0,
+                                 iters=10, update="sp", clamp_value=100.0, seed=5), 0, Ng).cpu().numpy()
+    r = rates(c, 64, 32)
+    assert abs(float(r["uncoded_ber"]) - o_unc) < 5 * np.sqrt(o_unc / (Ncw * 64)) + 5 * np.sqrt(o_unc / (Ng * 64))
+    assert abs(float(r["coded_bler"]) - o_bler) < 5 * np.sqrt(o_bler / Ncw) + 5 * np.sqrt(o_bler / Ng)
+    assert 0.008 < float(r["uncoded_ber"]) < 0.02                      # survey probe: 1.35e-2
+
+
+def test_sweep_single_rank(wsim):
+    from ldpc_b200.linksim import LinkConfig, rates, sweep
+    cfgs = [LinkConfig(snr_db=s, ofdm_size=64, iters=10, update="minsum", clamp_value=20.0, seed=1) for s in (0.0, 2.0, 4.0)]
+    c = sweep(wsim, cfgs, 4096)
+    assert c.shape == (3, 5) and (c[:, 4] == 4096).all()
+    r = rates(c, 1944, 972)
+    assert r["coded_bler"][0] >= r["coded_bler"][1] >= r["coded_bler"][2]
+    assert r["uncoded_ber"][0] > r["uncoded_ber"][2] > 0
