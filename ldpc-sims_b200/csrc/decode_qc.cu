@@ -92,9 +92,10 @@ struct QcLayout {
                                    sizeof(int) * (8 + CW);
 };
 
-template <class Code, int CW, bool IS_SP>
+template <class Code, int CW, int UPD>
 __global__ void __launch_bounds__((QcLayout<Code, CW>::THREADS)) decode_qc_kernel(const DecodeArgs a) {
     using L = QcLayout<Code, CW>;
+    constexpr bool IS_SP = (UPD == UPD_SP);
     constexpr int Z = Code::Z, NB = Code::NB, MB = Code::MB, N = L::N, M = L::M;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float *llr_s = reinterpret_cast<float *>(smem_raw);
@@ -156,7 +157,7 @@ __global__ void __launch_bounds__((QcLayout<Code, CW>::THREADS)) decode_qc_kerne
                         in[j] = msg[off + z];
                     });
                     if constexpr (IS_SP) check_node_sp<D>(in, D, a.clampv, out);
-                    else check_node_ms<D>(in, D, a.update, a.clampv, a.param, out);
+                    else check_node_ms_ct<D, UPD>(in, a.clampv, a.param, out);
                     static_for<D>([&](auto jj) {
                         constexpr int j = decltype(jj)::value;
                         constexpr int off = kQc<Code>.row_blk[r][j] * Z;
@@ -248,15 +249,15 @@ static int launch_qc_t(const DecodeArgs &a, cudaStream_t s) {
     using L = QcLayout<Code, CW>;
     const long long grid = (a.B + CW - 1) / CW;
     if (grid > 0x7fffffffLL) { set_error("batch too large"); return LDPC_EINVAL; }
-    if (a.update == UPD_SP) {
-        auto k = decode_qc_kernel<Code, CW, true>;
-        LDPC_CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::SMEM));
-        k<<<(int)grid, L::THREADS, L::SMEM, s>>>(a);
-    } else {
-        auto k = decode_qc_kernel<Code, CW, false>;
-        LDPC_CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::SMEM));
-        k<<<(int)grid, L::THREADS, L::SMEM, s>>>(a);
+    void (*k)(const DecodeArgs) = nullptr;
+    switch (a.update) {
+        case UPD_SP: k = decode_qc_kernel<Code, CW, UPD_SP>; break;
+        case UPD_MINSUM: k = decode_qc_kernel<Code, CW, UPD_MINSUM>; break;
+        case UPD_NMS: k = decode_qc_kernel<Code, CW, UPD_NMS>; break;
+        default: k = decode_qc_kernel<Code, CW, UPD_OMS>; break;
     }
+    LDPC_CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::SMEM));
+    k<<<(int)grid, L::THREADS, L::SMEM, s>>>(a);
     LDPC_CUDA_TRY(cudaGetLastError());
     return LDPC_OK;
 }
