@@ -101,7 +101,7 @@ __global__ void __launch_bounds__(256) decode_generic_kernel(const GenericParams
         const float t = marginal_t<MAXDV>(in, d, llr_s[cw * p.llr_stride + v]);
         const float pr = prob_one(t);
         const uint8_t hb = hard_bit(t);                  // np.round(prob): tie 0.5 -> 0
-        hard_s[cw * p.hard_stride + v] = hb;
+        hard_s[cw * p.hard_stride + v] = hb | ((llr_s[cw * p.llr_stride + v] > 0.0f) ? 2 : 0);
         const long long o = cw0 * n + i;
         if (a.prob) a.prob[o] = pr;
         if (a.llr_post) a.llr_post[o] = __fmul_rn(-2.0f, t);
@@ -120,7 +120,7 @@ __global__ void __launch_bounds__(256) decode_generic_kernel(const GenericParams
             const int cw = i / m, c = i - cw * m;
             unsigned par = 0;
             for (int e = __ldg(g.chk_ptr + c); e < __ldg(g.chk_ptr + c + 1); ++e)
-                par ^= hard_s[cw * p.hard_stride + __ldg(g.chk_var + e)];
+                par ^= hard_s[cw * p.hard_stride + __ldg(g.chk_var + e)] & 1u;
             if (par) atomicAdd(&scratch[4 + cw], 1);
         }
         __syncthreads();
@@ -131,7 +131,7 @@ __global__ void __launch_bounds__(256) decode_generic_kernel(const GenericParams
     if (a.hard_packed) pack_hard(hard_s, p.hard_stride, ncw, n, a.hard_packed + cw0 * ((n + 7) >> 3));
     if (a.counters) {
         __syncthreads();
-        count_errors(llr_s, p.llr_stride, hard_s, p.hard_stride, ncw, n, a.k_info,
+        count_errors(hard_s, p.hard_stride, ncw, n, a.k_info,
                      a.ref_packed + cw0 * ((n + 7) >> 3), a.counters, scratch + 1);
     }
 }

@@ -6,13 +6,16 @@
 // inner loops carry no index loads at all (the reference multiplies by dense E x E masks,
 // bp/masking.py:12-147, bp/bp_vc.py:19, bp/bp_cv.py:24-42).
 //
-// Mapping: thread = (codeword cw of the CTA's tile, lane z in [0,Z)).  Messages live in
-// shared memory for all iterations, one fp32 slot per edge at  blk*Z + zc  (zc = the
-// CHECK's lane), so the check phase is a pure linear access and the variable phase reads
-// a rotated window (z - shift mod Z).  Channel LLRs sit beside them in natural order.
+// Mapping: thread = (codeword cw of the CTA's tile, lane t in [0,Z)); see QcPlan for which
+// check / variable of each block row / column a lane computes.  Channel LLRs (NB per thread)
+// and the messages of the thread-local blocks stay in REGISTERS for the whole decode; the
+// other blocks keep one fp32 slot per edge in shared memory at  blk*Z + tc  (tc = the check's
+// thread), so the check phase is a pure linear access and the variable phase reads a rotated
+// window ((t - s') mod Z).  HBM traffic is the LLR load and the result store only.
 // Per iteration: variable phase (NB unrolled block columns per thread), barrier, check
 // phase (MB unrolled block rows per thread), barrier.  Arithmetic = node_math.cuh, so the
 // results are bit-identical to the generic kernel and to the CPU oracle's definition.
+#include <cstdlib>
 #include <utility>
 
 #include "common.cuh"
@@ -39,33 +42,70 @@ struct Wifi1944R12 {
         {24, -1, 61, -1, 60, -1, -1, 27, 51, -1, -1, 16, 1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, 0}};
 };
 
-// Derived tables, all evaluated at compile time.
+// ---- compile-time plan ------------------------------------------------------------------------------
+// Lane relabelling.  Thread t of a codeword processes check (r, (t + sigma_r) mod Z) of every
+// block row r and variable (c, (t + rho_c) mod Z) of every block column c.  An edge of block
+// (r, c, shift s) then joins check-thread tc with variable-thread tc + s', where
+//     s' = (s + sigma_r - rho_c) mod Z.
+// Blocks with s' == 0 connect a thread to ITSELF: their messages never leave the register
+// file.  A spanning tree of the (block row, block column) graph fixes sigma/rho so that
+// MB + NB - 1 blocks (35 of the 86 for 802.11n n=1944) become thread-local; only the remaining
+// blocks are exchanged through shared memory.  Which node a thread computes does not change
+// the node's arithmetic, so results stay bit-identical to the generic kernel.
 template <class Code>
-struct QcTables {
+struct QcPlan {
     static constexpr int Z = Code::Z, MB = Code::MB, NB = Code::NB;
-    int nblk = 0;
-    int row_deg[MB] = {}, row_col[MB][NB] = {}, row_shift[MB][NB] = {}, row_blk[MB][NB] = {};
-    int col_deg[NB] = {}, col_row[NB][MB] = {}, col_shift[NB][MB] = {}, col_blk[NB][MB] = {};
-    int max_dv = 0, max_dc = 0;
-    constexpr QcTables() {
-        int id = 0;
+    int sigma[MB] = {}, rho[NB] = {};
+    int nblk = 0, n_local = 0, n_smem = 0;
+    int row_deg[MB] = {}, row_col[MB][NB] = {}, row_eff[MB][NB] = {}, row_slot[MB][NB] = {}, row_shift[MB][NB] = {};
+    int col_deg[NB] = {}, col_row[NB][MB] = {}, col_eff[NB][MB] = {}, col_slot[NB][MB] = {};
+    bool row_loc[MB][NB] = {}, col_loc[NB][MB] = {};
+    constexpr QcPlan() {
+        // breadth-first spanning tree over block rows / block columns
+        bool row_seen[MB] = {}, col_seen[NB] = {};
+        int queue[MB + NB] = {}, head = 0, tail = 0;     // entries: r (>=0) or -(c+1)
+        for (int root = 0; root < MB; ++root) {
+            if (row_seen[root]) continue;
+            row_seen[root] = true; sigma[root] = 0; queue[tail++] = root;
+            while (head < tail) {
+                const int q = queue[head++];
+                if (q >= 0) {
+                    const int r = q;
+                    for (int c = 0; c < NB; ++c)
+                        if (Code::proto[r][c] >= 0 && !col_seen[c]) {
+                            col_seen[c] = true;
+                            rho[c] = (Code::proto[r][c] + sigma[r]) % Z;
+                            queue[tail++] = -(c + 1);
+                        }
+                } else {
+                    const int c = -q - 1;
+                    for (int r = 0; r < MB; ++r)
+                        if (Code::proto[r][c] >= 0 && !row_seen[r]) {
+                            row_seen[r] = true;
+                            sigma[r] = ((rho[c] - Code::proto[r][c]) % Z + Z) % Z;
+                            queue[tail++] = r;
+                        }
+                }
+            }
+        }
         for (int r = 0; r < MB; ++r)
             for (int c = 0; c < NB; ++c)
                 if (Code::proto[r][c] >= 0) {
+                    const int eff = ((Code::proto[r][c] + sigma[r] - rho[c]) % Z + Z) % Z;
+                    const bool loc = (eff == 0);
+                    const int slot = loc ? n_local++ : n_smem++;
                     const int j = row_deg[r]++;
-                    row_col[r][j] = c; row_shift[r][j] = Code::proto[r][c]; row_blk[r][j] = id;
+                    row_col[r][j] = c; row_eff[r][j] = eff; row_slot[r][j] = slot; row_loc[r][j] = loc;
+                    row_shift[r][j] = Code::proto[r][c];
                     const int k = col_deg[c]++;
-                    col_row[c][k] = r; col_shift[c][k] = Code::proto[r][c]; col_blk[c][k] = id;
-                    ++id;
+                    col_row[c][k] = r; col_eff[c][k] = eff; col_slot[c][k] = slot; col_loc[c][k] = loc;
+                    ++nblk;
                 }
-        nblk = id;
-        for (int r = 0; r < MB; ++r) if (row_deg[r] > max_dc) max_dc = row_deg[r];
-        for (int c = 0; c < NB; ++c) if (col_deg[c] > max_dv) max_dv = col_deg[c];
     }
 };
 
 template <class Code>
-inline constexpr QcTables<Code> kQc{};
+inline constexpr QcPlan<Code> kQc{};
 
 template <class F, int... I>
 __device__ __forceinline__ void static_for_impl(F &&f, std::integer_sequence<int, I...>) {
@@ -81,50 +121,53 @@ struct QcLayout {
     static constexpr int Z = Code::Z;
     static constexpr int N = Code::NB * Z;
     static constexpr int M = Code::MB * Z;
-    static constexpr int E = kQc<Code>.nblk * Z;
+    static constexpr int NLOC = kQc<Code>.n_local, NSM = kQc<Code>.n_smem;
     // codeword strides == Z (mod 32): lanes of two codewords sharing a warp stay on distinct banks
     static constexpr int pad_to(int v) { return v + ((Z % 32) - (v % 32) + 32) % 32; }
-    static constexpr int LLR_STRIDE = pad_to(N);
-    static constexpr int MSG_STRIDE = pad_to(E);
+    static constexpr int MSG_STRIDE = pad_to(NSM * Z);
     static constexpr int HARD_STRIDE = (N + 15) & ~15;
     static constexpr int THREADS = ((CW * Z + 31) / 32) * 32;
-    static constexpr size_t SMEM = sizeof(float) * CW * (LLR_STRIDE + MSG_STRIDE) + (size_t)CW * HARD_STRIDE +
-                                   sizeof(int) * (8 + CW);
+    static constexpr size_t SMEM = sizeof(float) * CW * MSG_STRIDE + (size_t)CW * HARD_STRIDE + sizeof(int) * (8 + CW);
 };
 
 template <class Code, int CW, int UPD>
 __global__ void __launch_bounds__((QcLayout<Code, CW>::THREADS)) decode_qc_kernel(const DecodeArgs a) {
     using L = QcLayout<Code, CW>;
     constexpr bool IS_SP = (UPD == UPD_SP);
-    constexpr int Z = Code::Z, NB = Code::NB, MB = Code::MB, N = L::N, M = L::M;
+    constexpr int Z = Code::Z, NB = Code::NB, MB = Code::MB, N = L::N;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    float *llr_s = reinterpret_cast<float *>(smem_raw);
-    float *msg_s = llr_s + CW * L::LLR_STRIDE;
+    float *msg_s = reinterpret_cast<float *>(smem_raw);
     uint8_t *hard_s = reinterpret_cast<uint8_t *>(msg_s + CW * L::MSG_STRIDE);
     int *scratch = reinterpret_cast<int *>(hard_s + CW * L::HARD_STRIDE);       // [4 + CW]
 
     const int tid = threadIdx.x, T = blockDim.x;
     const long long cw0 = (long long)blockIdx.x * CW;
     const int ncw = (int)min((long long)CW, a.B - cw0);
-    const int cw = tid / Z, z = tid - cw * Z;
+    const int cw = tid / Z, t = tid - cw * Z;
     const bool active = cw < ncw;            // also false for the padding threads (cw >= CW)
-
-    // ---- load LLR tile, clear messages --------------------------------------------------------
-    for (int i = tid; i < ncw * N; i += T) {
-        const int c = i / N, v = i - c * N;
-        llr_s[c * L::LLR_STRIDE + v] = load_llr(a.llr, a.llr_dtype, cw0 * N + i);
-    }
-    for (int i = tid; i < CW * L::MSG_STRIDE; i += T) msg_s[i] = 0.0f;
     for (int i = tid; i < 4 + CW; i += T) scratch[i] = 0;
-    __syncthreads();
 
     float *const msg = msg_s + (active ? cw : 0) * L::MSG_STRIDE;
-    const float *const llr = llr_s + (active ? cw : 0) * L::LLR_STRIDE;
-    // rotated window bases: slot (blk, (z - s) mod Z) = (z < s ? hi : lo)[blk*Z - s]
-    float *const lo = msg + z;
-    float *const hi = msg + z + Z;
+    // rotated window bases: slot (blk, (t - s') mod Z) = (t < s' ? hi : lo)[blk*Z - s']
+    float *const lo = msg + t;
+    float *const hi = msg + t + Z;
+
+    // ---- channel LLRs of this thread's NB variables live in registers for the whole decode ----------
+    float llr[NB];
+    float loc[L::NLOC > 0 ? L::NLOC : 1];
+    const long long gbase = (cw0 + (active ? cw : 0)) * N;
+    if (active) {
+        static_for<NB>([&](auto cc) {
+            constexpr int c = decltype(cc)::value;
+            constexpr int rho = kQc<Code>.rho[c];
+            int zv = t + rho;
+            if (zv >= Z) zv -= Z;
+            llr[c] = load_llr(a.llr, a.llr_dtype, gbase + c * Z + zv);
+        });
+    }
 
     for (int it = 0; it < a.iters; ++it) {
+        // ---- V -> C -----------------------------------------------------------------------------------
         if (active) {
             static_for<NB>([&](auto cc) {
                 constexpr int c = decltype(cc)::value;
@@ -134,17 +177,31 @@ __global__ void __launch_bounds__((QcLayout<Code, CW>::THREADS)) decode_qc_kerne
                     float *ptr[D];
                     static_for<D>([&](auto kk) {
                         constexpr int k = decltype(kk)::value;
-                        constexpr int s = kQc<Code>.col_shift[c][k];
-                        constexpr int off = kQc<Code>.col_blk[c][k] * Z - s;
-                        ptr[k] = (z < s ? hi : lo) + off;
-                        in[k] = *ptr[k];
+                        constexpr bool is_loc = kQc<Code>.col_loc[c][k];
+                        constexpr int slot = kQc<Code>.col_slot[c][k];
+                        if constexpr (is_loc) {
+                            ptr[k] = nullptr;
+                            in[k] = (it == 0) ? 0.0f : loc[slot];
+                        } else {
+                            constexpr int s = kQc<Code>.col_eff[c][k];
+                            constexpr int off = slot * Z - s;
+                            ptr[k] = (t < s ? hi : lo) + off;
+                            in[k] = (it == 0) ? 0.0f : *ptr[k];          // first iteration: x = 0 (ofdm_functions.py:157)
+                        }
                     });
-                    var_node<D, IS_SP>(in, D, llr[c * Z + z], out);
-                    static_for<D>([&](auto kk) { *ptr[decltype(kk)::value] = out[decltype(kk)::value]; });
+                    var_node<D, IS_SP>(in, D, llr[c], out);
+                    static_for<D>([&](auto kk) {
+                        constexpr int k = decltype(kk)::value;
+                        constexpr bool is_loc = kQc<Code>.col_loc[c][k];
+                        constexpr int slot = kQc<Code>.col_slot[c][k];
+                        if constexpr (is_loc) loc[slot] = out[k];
+                        else *ptr[k] = out[k];
+                    });
                 }
             });
         }
         __syncthreads();
+        // ---- C -> V -----------------------------------------------------------------------------------
         if (active) {
             static_for<MB>([&](auto rr) {
                 constexpr int r = decltype(rr)::value;
@@ -153,15 +210,19 @@ __global__ void __launch_bounds__((QcLayout<Code, CW>::THREADS)) decode_qc_kerne
                     float in[D], out[D];
                     static_for<D>([&](auto jj) {
                         constexpr int j = decltype(jj)::value;
-                        constexpr int off = kQc<Code>.row_blk[r][j] * Z;
-                        in[j] = msg[off + z];
+                        constexpr bool is_loc = kQc<Code>.row_loc[r][j];
+                        constexpr int slot = kQc<Code>.row_slot[r][j];
+                        if constexpr (is_loc) in[j] = loc[slot];
+                        else in[j] = msg[slot * Z + t];
                     });
                     if constexpr (IS_SP) check_node_sp<D>(in, D, a.clampv, out);
                     else check_node_ms_ct<D, UPD>(in, a.clampv, a.param, out);
                     static_for<D>([&](auto jj) {
                         constexpr int j = decltype(jj)::value;
-                        constexpr int off = kQc<Code>.row_blk[r][j] * Z;
-                        msg[off + z] = out[j];
+                        constexpr bool is_loc = kQc<Code>.row_loc[r][j];
+                        constexpr int slot = kQc<Code>.row_slot[r][j];
+                        if constexpr (is_loc) loc[slot] = out[j];
+                        else msg[slot * Z + t] = out[j];
                     });
                 }
             });
@@ -171,24 +232,30 @@ __global__ void __launch_bounds__((QcLayout<Code, CW>::THREADS)) decode_qc_kerne
 
     // ---- marginal, P(bit=1), hard decision --------------------------------------------------------
     if (active) {
-        const long long obase = (cw0 + cw) * N;
         static_for<NB>([&](auto cc) {
             constexpr int c = decltype(cc)::value;
             constexpr int D = kQc<Code>.col_deg[c];
+            constexpr int rho = kQc<Code>.rho[c];
             float in[D > 0 ? D : 1];
             static_for<D>([&](auto kk) {
                 constexpr int k = decltype(kk)::value;
-                constexpr int s = kQc<Code>.col_shift[c][k];
-                constexpr int off = kQc<Code>.col_blk[c][k] * Z - s;
-                in[k] = ((z < s ? hi : lo) + off)[0];
+                constexpr bool is_loc = kQc<Code>.col_loc[c][k];
+                constexpr int slot = kQc<Code>.col_slot[c][k];
+                if constexpr (is_loc) in[k] = (a.iters == 0) ? 0.0f : loc[slot];
+                else {
+                    constexpr int s = kQc<Code>.col_eff[c][k];
+                    constexpr int off = slot * Z - s;
+                    in[k] = (a.iters == 0) ? 0.0f : ((t < s ? hi : lo) + off)[0];
+                }
             });
-            const float t = marginal_t<(D > 0 ? D : 1)>(in, D, llr[c * Z + z]);
-            const float pr = prob_one(t);
-            const uint8_t hb = hard_bit(t);
-            hard_s[cw * L::HARD_STRIDE + c * Z + z] = hb;
-            const long long o = obase + c * Z + z;
-            if (a.prob) a.prob[o] = pr;
-            if (a.llr_post) a.llr_post[o] = __fmul_rn(-2.0f, t);
+            const float tm = marginal_t<(D > 0 ? D : 1)>(in, D, llr[c]);
+            const uint8_t hb = hard_bit(tm);
+            int zv = t + rho;
+            if (zv >= Z) zv -= Z;
+            hard_s[cw * L::HARD_STRIDE + c * Z + zv] = hb | ((llr[c] > 0.0f) ? 2 : 0);
+            const long long o = gbase + c * Z + zv;
+            if (a.prob) a.prob[o] = prob_one(tm);
+            if (a.llr_post) a.llr_post[o] = __fmul_rn(-2.0f, tm);
             if (a.hard) a.hard[o] = hb;
         });
     }
@@ -202,14 +269,17 @@ __global__ void __launch_bounds__((QcLayout<Code, CW>::THREADS)) decode_qc_kerne
             static_for<MB>([&](auto rr) {
                 constexpr int r = decltype(rr)::value;
                 constexpr int D = kQc<Code>.row_deg[r];
+                constexpr int sg = kQc<Code>.sigma[r];
+                int zc = t + sg;
+                if (zc >= Z) zc -= Z;
                 unsigned par = 0;
                 static_for<D>([&](auto jj) {
                     constexpr int j = decltype(jj)::value;
                     constexpr int s = kQc<Code>.row_shift[r][j];
-                    int zv = z + s;
-                    if (zv >= Z) zv -= Z;
                     constexpr int cbase = kQc<Code>.row_col[r][j] * Z;
-                    par ^= h[cbase + zv];
+                    int zv = zc + s;
+                    if (zv >= Z) zv -= Z;
+                    par ^= h[cbase + zv] & 1u;
                 });
                 w += (int)par;
             });
@@ -223,10 +293,9 @@ __global__ void __launch_bounds__((QcLayout<Code, CW>::THREADS)) decode_qc_kerne
     if (a.hard_packed) pack_hard(hard_s, L::HARD_STRIDE, ncw, N, a.hard_packed + cw0 * ((N + 7) >> 3));
     if (a.counters) {
         __syncthreads();
-        count_errors(llr_s, L::LLR_STRIDE, hard_s, L::HARD_STRIDE, ncw, N, a.k_info,
-                     a.ref_packed + cw0 * ((N + 7) >> 3), a.counters, scratch + 1);
+        count_errors(hard_s, L::HARD_STRIDE, ncw, N, a.k_info, a.ref_packed + cw0 * ((N + 7) >> 3), a.counters,
+                     scratch + 1);
     }
-    (void)M;
 }
 
 // ---- registry of compiled specialisations ----------------------------------------------------------
@@ -265,7 +334,15 @@ static int launch_qc_t(const DecodeArgs &a, cudaStream_t s) {
 int launch_decode_qc(int qc_id, const DecodeArgs &a, cudaStream_t s) {
     if (a.B <= 0) return LDPC_OK;
     switch (qc_id) {
-        case 0: return launch_qc_t<Wifi1944R12, 3>(a, s);
+        case 0: {
+            static const int cw = [] { const char *e = getenv("LDPC_QC_CW"); return e ? atoi(e) : 3; }();
+            if (a.update != UPD_SP) {
+                if (cw == 6) return launch_qc_t<Wifi1944R12, 6>(a, s);
+                if (cw == 2) return launch_qc_t<Wifi1944R12, 2>(a, s);
+                if (cw == 1) return launch_qc_t<Wifi1944R12, 1>(a, s);
+            }
+            return launch_qc_t<Wifi1944R12, 3>(a, s);
+        }
         default: set_error("unknown QC specialisation %d", qc_id); return LDPC_EINVAL;
     }
 }

@@ -5,7 +5,8 @@
 
 namespace ldpc {
 
-// hard_s: [ncw][hs_stride] u8 in shared memory; packed output MSB-first (numpy.packbits).
+// hard_s: [ncw][hs_stride] u8 in shared memory, bit 0 = decoded bit, bit 1 = uncoded channel
+// decision (llr > 0); packed output MSB-first (numpy.packbits).
 __device__ __forceinline__ void pack_hard(const uint8_t *hard_s, int hs_stride, int ncw, int n,
                                           uint8_t *packed_g /* [ncw][ceil(n/8)] */) {
     const int nbytes = (n + 7) >> 3;
@@ -16,18 +17,17 @@ __device__ __forceinline__ void pack_hard(const uint8_t *hard_s, int hs_stride, 
 #pragma unroll
         for (int b = 0; b < 8; ++b) {
             const int idx = by * 8 + b;
-            v |= (idx < n ? (unsigned)h[b] : 0u) << (7 - b);
+            v |= (idx < n ? (unsigned)(h[b] & 1) : 0u) << (7 - b);
         }
         packed_g[(long long)cw * nbytes + by] = (uint8_t)v;
     }
 }
 
 // counters: {uncoded bit errors, info-bit errors, frame errors, bits, frames} (u64, +=).
-// llr_s [ncw][ls_stride] f32 channel LLRs (uncoded decision: llr > 0 -> 1, llr == 0 -> 0,
-// i.e. (sign+1)//2);  ref_packed_g: transmitted codewords, MSB-first.
+// Uncoded decision = bit 1 of hard_s (llr > 0 -> 1, llr == 0 -> 0, i.e. (sign+1)//2);
+// ref_packed_g: transmitted codewords, MSB-first.
 // scratch: 3 ints + ncw ints of shared memory, zeroed by the caller before a barrier.
-__device__ __forceinline__ void count_errors(const float *llr_s, int ls_stride, const uint8_t *hard_s,
-                                             int hs_stride, int ncw, int n, int k_info,
+__device__ __forceinline__ void count_errors(const uint8_t *hard_s, int hs_stride, int ncw, int n, int k_info,
                                              const uint8_t *ref_packed_g, unsigned long long *counters,
                                              int *scratch /* [3 + ncw] */) {
     const int nbytes = (n + 7) >> 3;
@@ -35,8 +35,8 @@ __device__ __forceinline__ void count_errors(const float *llr_s, int ls_stride, 
     for (int i = threadIdx.x; i < ncw * n; i += blockDim.x) {
         const int cw = i / n, v = i - cw * n;
         const int ref = (ref_packed_g[(long long)cw * nbytes + (v >> 3)] >> (7 - (v & 7))) & 1;
-        const int hb = hard_s[cw * hs_stride + v];
-        const int ub = llr_s[cw * ls_stride + v] > 0.0f;
+        const int hv = hard_s[cw * hs_stride + v];
+        const int hb = hv & 1, ub = hv >> 1;
         unc += (ub != ref);
         const int e = (hb != ref);
         inf += e & (v < k_info);
