@@ -166,67 +166,78 @@ __global__ void __launch_bounds__((QcLayout<Code, CW>::THREADS)) decode_qc_kerne
         });
     }
 
-    for (int it = 0; it < a.iters; ++it) {
-        // ---- V -> C -----------------------------------------------------------------------------------
-        if (active) {
-            static_for<NB>([&](auto cc) {
-                constexpr int c = decltype(cc)::value;
-                constexpr int D = kQc<Code>.col_deg[c];
-                if constexpr (D > 0) {
-                    float in[D], out[D];
-                    float *ptr[D];
-                    static_for<D>([&](auto kk) {
-                        constexpr int k = decltype(kk)::value;
-                        constexpr bool is_loc = kQc<Code>.col_loc[c][k];
-                        constexpr int slot = kQc<Code>.col_slot[c][k];
-                        if constexpr (is_loc) {
-                            ptr[k] = nullptr;
-                            in[k] = (it == 0) ? 0.0f : loc[slot];
-                        } else {
-                            constexpr int s = kQc<Code>.col_eff[c][k];
-                            constexpr int off = slot * Z - s;
-                            ptr[k] = (t < s ? hi : lo) + off;
-                            in[k] = (it == 0) ? 0.0f : *ptr[k];          // first iteration: x = 0 (ofdm_functions.py:157)
-                        }
-                    });
-                    var_node<D, IS_SP>(in, D, llr[c], out);
-                    static_for<D>([&](auto kk) {
-                        constexpr int k = decltype(kk)::value;
-                        constexpr bool is_loc = kQc<Code>.col_loc[c][k];
-                        constexpr int slot = kQc<Code>.col_slot[c][k];
-                        if constexpr (is_loc) loc[slot] = out[k];
-                        else *ptr[k] = out[k];
-                    });
-                }
-            });
-        }
+    // V -> C for all NB block columns of this thread.  FIRST: the C->V messages are still the
+    // zeros every reference caller passes (ofdm_functions.py:157) - nothing is loaded.
+    auto var_phase = [&](auto first_tag) {
+        constexpr bool FIRST = decltype(first_tag)::value;
+        static_for<NB>([&](auto cc) {
+            constexpr int c = decltype(cc)::value;
+            constexpr int D = kQc<Code>.col_deg[c];
+            if constexpr (D > 0) {
+                float in[D], out[D];
+                float *ptr[D];
+                static_for<D>([&](auto kk) {
+                    constexpr int k = decltype(kk)::value;
+                    constexpr bool is_loc = kQc<Code>.col_loc[c][k];
+                    constexpr int slot = kQc<Code>.col_slot[c][k];
+                    if constexpr (is_loc) {
+                        ptr[k] = nullptr;
+                        in[k] = FIRST ? 0.0f : loc[slot];
+                    } else {
+                        constexpr int s = kQc<Code>.col_eff[c][k];
+                        constexpr int off = slot * Z - s;
+                        ptr[k] = (t < s ? hi : lo) + off;
+                        in[k] = FIRST ? 0.0f : *ptr[k];
+                    }
+                });
+                var_node<D, IS_SP>(in, D, llr[c], out);
+                static_for<D>([&](auto kk) {
+                    constexpr int k = decltype(kk)::value;
+                    constexpr bool is_loc = kQc<Code>.col_loc[c][k];
+                    constexpr int slot = kQc<Code>.col_slot[c][k];
+                    if constexpr (is_loc) loc[slot] = out[k];
+                    else *ptr[k] = out[k];
+                });
+            }
+        });
+    };
+    auto check_phase = [&]() {
+        static_for<MB>([&](auto rr) {
+            constexpr int r = decltype(rr)::value;
+            constexpr int D = kQc<Code>.row_deg[r];
+            if constexpr (D > 0) {
+                float in[D], out[D];
+                static_for<D>([&](auto jj) {
+                    constexpr int j = decltype(jj)::value;
+                    constexpr bool is_loc = kQc<Code>.row_loc[r][j];
+                    constexpr int slot = kQc<Code>.row_slot[r][j];
+                    if constexpr (is_loc) in[j] = loc[slot];
+                    else in[j] = msg[slot * Z + t];
+                });
+                if constexpr (IS_SP) check_node_sp<D>(in, D, a.clampv, out);
+                else check_node_ms_ct<D, UPD>(in, a.clampv, a.param, out);
+                static_for<D>([&](auto jj) {
+                    constexpr int j = decltype(jj)::value;
+                    constexpr bool is_loc = kQc<Code>.row_loc[r][j];
+                    constexpr int slot = kQc<Code>.row_slot[r][j];
+                    if constexpr (is_loc) loc[slot] = out[j];
+                    else msg[slot * Z + t] = out[j];
+                });
+            }
+        });
+    };
+
+    if (a.iters > 0) {
+        if (active) var_phase(std::true_type{});
         __syncthreads();
-        // ---- C -> V -----------------------------------------------------------------------------------
-        if (active) {
-            static_for<MB>([&](auto rr) {
-                constexpr int r = decltype(rr)::value;
-                constexpr int D = kQc<Code>.row_deg[r];
-                if constexpr (D > 0) {
-                    float in[D], out[D];
-                    static_for<D>([&](auto jj) {
-                        constexpr int j = decltype(jj)::value;
-                        constexpr bool is_loc = kQc<Code>.row_loc[r][j];
-                        constexpr int slot = kQc<Code>.row_slot[r][j];
-                        if constexpr (is_loc) in[j] = loc[slot];
-                        else in[j] = msg[slot * Z + t];
-                    });
-                    if constexpr (IS_SP) check_node_sp<D>(in, D, a.clampv, out);
-                    else check_node_ms_ct<D, UPD>(in, a.clampv, a.param, out);
-                    static_for<D>([&](auto jj) {
-                        constexpr int j = decltype(jj)::value;
-                        constexpr bool is_loc = kQc<Code>.row_loc[r][j];
-                        constexpr int slot = kQc<Code>.row_slot[r][j];
-                        if constexpr (is_loc) loc[slot] = out[j];
-                        else msg[slot * Z + t] = out[j];
-                    });
-                }
-            });
-        }
+        if (active) check_phase();
+        __syncthreads();
+    }
+#pragma unroll 1
+    for (int it = 1; it < a.iters; ++it) {
+        if (active) var_phase(std::false_type{});
+        __syncthreads();
+        if (active) check_phase();
         __syncthreads();
     }
 
