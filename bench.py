@@ -11,6 +11,7 @@ workload of BASELINE.json: IEEE 802.11n n=1944 R=1/2, 10 fixed min-sum iteration
 One "step" = one pass of the decoder over one batch of synthetic LLRs.  Prints ONE JSON line.
 """
 import argparse
+import ctypes
 import json
 import os
 import sys
@@ -193,7 +194,6 @@ def main():
     packed = torch.empty(B, code.packed_bytes, dtype=torch.uint8, device=dev)
     stream = torch.cuda.current_stream(dev)
     upd = N.UPDATE_IDS[a.update]
-    import ctypes
     lib = N.lib()
 
     def step():
@@ -242,8 +242,17 @@ def main():
     sm_mhz = clocks["sm_mhz"] or peaks.get("sm_max_mhz", 1965.0)
     upd_per_cw = 2 * E_CODE * a.iters
     upd_s = B / (k_ms * 1e-3) * upd_per_cw
-    smem_bytes_per_update = (4 * E_CODE + N_CODE) * 4 / (2 * E_CODE)          # fp32 slots: 2 LDS + 2 STS per edge + LLR
+    plan = (ctypes.c_int32 * 4)()
+    N.check(lib.ldpc_code_plan_info(code._h, plan))
+    n_loc, n_sm, thr_cta, cw_cta = [int(v) for v in plan]
+    # shared-memory ceiling of the storage format actually used: 2 LDS + 2 STS of 4 B per edge of the
+    # n_sm blocks exchanged through shared memory (the other n_loc blocks and the LLRs are registers)
+    smem_bytes_per_update = 4 * n_sm * 81 * 4 / (2 * E_CODE) if n_sm else (4 * E_CODE + N_CODE) * 4 / (2 * E_CODE)
     smem_peak = 148 * 128 * sm_mhz * 1e6 / smem_bytes_per_update
+    # issue ceiling of the instruction stream: 932 SASS instructions per thread-iteration
+    # (profiles/sass_loop_r01.txt), thr_cta/cw_cta thread slots per codeword, 2*E updates per iteration
+    lane_instr_per_update = 932 * (thr_cta / max(cw_cta, 1)) / (2 * E_CODE) if n_sm else None
+    issue_peak = 148 * 4 * 32 * sm_mhz * 1e6 / lane_instr_per_update if lane_instr_per_update else None
     out = {
         "metric": METRIC, "value": value, "unit": "Gbit/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -257,9 +266,13 @@ def main():
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                      "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
                      "note": "decoder is shared-memory/issue bound, not HBM bound: see roofline_decoder"},
-        "roofline_decoder": {"bound": "smem", "achieved": upd_s, "peak": smem_peak, "unit": "edge-updates/s",
-                             "frac": upd_s / smem_peak,
-                             "peak_source": f"148 SMs x 128 B/clk x {sm_mhz:.0f} MHz / {smem_bytes_per_update:.2f} B per directed edge-update (fp32 message slots)"},
+        "roofline_decoder": {"bound": "issue" if (issue_peak and issue_peak < smem_peak) else "smem",
+                             "achieved": upd_s, "peak": min(smem_peak, issue_peak or smem_peak),
+                             "unit": "edge-updates/s", "frac": upd_s / min(smem_peak, issue_peak or smem_peak),
+                             "smem_peak": smem_peak, "issue_peak": issue_peak,
+                             "plan": {"register_blocks": n_loc, "smem_blocks": n_sm, "threads_per_cta": thr_cta, "codewords_per_cta": cw_cta},
+                             "peak_source": f"smem: 148 SMs x 128 B/clk x {sm_mhz:.0f} MHz / {smem_bytes_per_update:.2f} B per directed edge-update; "
+                                            f"issue: 148 SMs x 4 SMSP x 32 lanes x {sm_mhz:.0f} MHz / {lane_instr_per_update or 0:.2f} lane-instr per update"},
     }
 
     # ---- e2e: the C-ABI host call (decode_bits path): pinned host LLRs in, packed bits out ---------
@@ -272,6 +285,14 @@ def main():
         def e2e_step():
             N.check(lib.ldpc_decode_host(code._h, h_llr.data_ptr(), N.F32, Be, a.iters, upd, a.clamp, 1.0,
                                          None, h_packed.data_ptr(), None, None, 16384))
+        # raw pinned H2D bandwidth of this box, for context
+        d_tmp = torch.empty_like(h_llr, device=dev)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        d_tmp.copy_(h_llr, non_blocking=True)
+        torch.cuda.synchronize()
+        h2d_gbs = h_llr.numel() * 4 / (time.perf_counter() - t0) / 1e9
+        del d_tmp
         for _ in range(2):
             e2e_step()
         barrier()
@@ -284,7 +305,7 @@ def main():
             dist.all_reduce(dt, op=dist.ReduceOp.MAX)
         e2e = Be * world * a.steps * K_CODE / float(dt.item()) / 1e9
         out["e2e"] = {"value": e2e, "unit": "Gbit/s", "h2d_bytes_per_step": Be * qc.n * 4,
-                      "d2h_bytes_per_step": Be * code.packed_bytes, "codewords_per_step": Be,
+                      "d2h_bytes_per_step": Be * code.packed_bytes, "codewords_per_step": Be, "pinned_h2d_gbs": h2d_gbs,
                       "api": "ldpc_decode_host (C ABI behind ofdm_functions.decode_bits), pinned f32 LLRs in, packed bits out"}
         assert torch.equal(h_packed.to(dev), packed[:Be]), "e2e result differs from the device path"
 

@@ -73,6 +73,11 @@ typedef struct {
 } ldpc_code_info_t;
 int ldpc_code_info(const ldpc_code_t *code, ldpc_code_info_t *info);
 
+/* Execution plan of the code-specialised kernel (zeros for the generic kernel):
+ * out = {blocks whose messages stay in registers, blocks exchanged through shared memory,
+ *        threads per CTA, codewords per CTA}.  Used by bench.py for the roofline arithmetic. */
+int ldpc_code_plan_info(const ldpc_code_t *code, int32_t out[4]);
+
 /* Force the generic kernel for a handle (testing / A-B comparison). */
 int ldpc_code_set_kernel(ldpc_code_t *code, int kernel);
 

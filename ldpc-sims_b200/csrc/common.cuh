@@ -24,6 +24,7 @@ struct DecodeArgs {
     const uint8_t *ref_packed;  // [B,ceil(n/8)] transmitted codeword, MSB-first
     unsigned long long *counters;
     int k_info;
+    void *host_pipe;    // lazily created staging state of ldpc_decode_host
 };
 
 struct GraphTables {        // device pointers
@@ -53,6 +54,7 @@ struct ldpc_code {
     ldpc::GraphTables g;
     uint32_t *d_gen;    // bit-packed parity rows of the systematic generator [m][ceil(k/32)] or null
     int k_info;
+    void *host_pipe;    // lazily created staging state of ldpc_decode_host
 };
 
 namespace ldpc {
@@ -72,5 +74,6 @@ int launch_decode_generic(const GraphTables &g, int max_dv, int max_dc, const De
 bool qc_kernel_available(int Z, int mb, int nb, const int16_t *proto);
 int launch_decode_qc(int qc_id, const DecodeArgs &a, cudaStream_t s);
 int qc_lookup(int Z, int mb, int nb, const int16_t *proto);   // -1 if no compiled specialisation
+void qc_plan_info(int qc_id, int out[4]);                     // {register-resident blocks, shared-memory blocks, threads/CTA, codewords/CTA}
 
 }  // namespace ldpc

@@ -319,9 +319,29 @@ static bool proto_matches(int Z, int mb, int nb, const int16_t *proto) {
     return true;
 }
 
+void qc_plan_info(int qc_id, int out[4]) {
+    out[0] = out[1] = out[2] = out[3] = 0;
+    if (qc_id == 0) {
+        using L = QcLayout<Wifi1944R12, 3>;
+        out[0] = L::NLOC; out[1] = L::NSM; out[2] = L::THREADS; out[3] = 3;
+    }
+}
+
 int qc_lookup(int Z, int mb, int nb, const int16_t *proto) {
     if (proto_matches<Wifi1944R12>(Z, mb, nb, proto)) return 0;
     return -1;
+}
+
+template <class Code, int CW, int UPD>
+static int launch_qc_one(const DecodeArgs &a, cudaStream_t s) {
+    using L = QcLayout<Code, CW>;
+    const long long grid = (a.B + CW - 1) / CW;
+    if (grid > 0x7fffffffLL) { set_error("batch too large"); return LDPC_EINVAL; }
+    auto k = decode_qc_kernel<Code, CW, UPD>;
+    LDPC_CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::SMEM));
+    k<<<(int)grid, L::THREADS, L::SMEM, s>>>(a);
+    LDPC_CUDA_TRY(cudaGetLastError());
+    return LDPC_OK;
 }
 
 template <class Code, int CW>
@@ -347,10 +367,9 @@ int launch_decode_qc(int qc_id, const DecodeArgs &a, cudaStream_t s) {
     switch (qc_id) {
         case 0: {
             static const int cw = [] { const char *e = getenv("LDPC_QC_CW"); return e ? atoi(e) : 3; }();
-            if (a.update != UPD_SP) {
-                if (cw == 6) return launch_qc_t<Wifi1944R12, 6>(a, s);
-                if (cw == 2) return launch_qc_t<Wifi1944R12, 2>(a, s);
-                if (cw == 1) return launch_qc_t<Wifi1944R12, 1>(a, s);
+            if (a.update == UPD_MINSUM) {
+                if (cw == 6) return launch_qc_one<Wifi1944R12, 6, UPD_MINSUM>(a, s);
+                if (cw == 1) return launch_qc_one<Wifi1944R12, 1, UPD_MINSUM>(a, s);
             }
             return launch_qc_t<Wifi1944R12, 3>(a, s);
         }

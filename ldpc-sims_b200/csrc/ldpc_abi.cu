@@ -4,6 +4,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <mutex>
 #include <new>
 #include <vector>
 
@@ -28,6 +29,8 @@ int cuda_fail(cudaError_t e, const char *what) {
 }  // namespace ldpc
 
 using namespace ldpc;
+
+extern "C" void ldpc_host_pipe_free(void *p);
 
 extern "C" {
 
@@ -76,7 +79,7 @@ int ldpc_code_create(const int32_t *row_ptr, const int32_t *col_idx, int m, int 
     if (!h) { set_error("out of host memory"); return LDPC_ENOMEM; }
     h->m = m; h->n = n; h->E = E; h->max_dc = max_dc; h->max_dv = max_dv; h->device = dev;
     h->qc_Z = 0; h->qc_id = -1; h->kernel = LDPC_KERNEL_GENERIC; h->d_tables = nullptr;
-    h->d_gen = nullptr; h->k_info = 0;
+    h->d_gen = nullptr; h->k_info = 0; h->host_pipe = nullptr;
     const size_t words = (size_t)(m + 1) + E + (n + 1) + E;
     cudaError_t e = cudaMalloc(&h->d_tables, words * sizeof(int32_t));
     if (e != cudaSuccess) { delete h; return cuda_fail(e, "cudaMalloc(tables)"); }
@@ -118,6 +121,7 @@ void ldpc_code_destroy(ldpc_code_t *code) {
     if (!code) return;
     if (code->d_tables) cudaFree(code->d_tables);
     if (code->d_gen) cudaFree(code->d_gen);
+    if (code->host_pipe) ldpc_host_pipe_free(code->host_pipe);
     delete code;
 }
 
@@ -126,6 +130,14 @@ int ldpc_code_info(const ldpc_code_t *code, ldpc_code_info_t *info) {
     info->m = code->m; info->n = code->n; info->E = code->E;
     info->max_dc = code->max_dc; info->max_dv = code->max_dv;
     info->kernel = code->kernel; info->qc_Z = code->qc_Z; info->reserved = 0;
+    return LDPC_OK;
+}
+
+int ldpc_code_plan_info(const ldpc_code_t *code, int32_t out[4]) {
+    if (!code || !out) { set_error("ldpc_code_plan_info: null argument"); return LDPC_EINVAL; }
+    int v[4] = {0, 0, 0, 0};
+    if (code->qc_id >= 0) qc_plan_info(code->qc_id, v);
+    for (int i = 0; i < 4; ++i) out[i] = v[i];
     return LDPC_OK;
 }
 
@@ -175,6 +187,36 @@ int ldpc_decode(const ldpc_code_t *code, const void *llr, int llr_dtype, int64_t
 }
 
 // ---- host-buffer pipeline (decode_bits, ofdm_functions.py:131-163) ---------------------------
+// Staging buffers, streams and events are created once per code handle and reused by later
+// calls (a mutex serialises host-buffer decodes on one handle).
+namespace {
+struct HostPipe {
+    static const int NBUF = 3;
+    struct Buf { void *llr = nullptr; uint8_t *hard = nullptr, *packed = nullptr; float *post = nullptr; int32_t *synd = nullptr; cudaStream_t s = nullptr; } buf[NBUF];
+    size_t llr_bytes = 0, hard_bytes = 0, packed_bytes = 0, post_bytes = 0, synd_bytes = 0;
+    std::mutex mu;
+    void release() {
+        for (auto &b : buf) {
+            if (b.llr) cudaFree(b.llr);
+            if (b.hard) cudaFree(b.hard);
+            if (b.packed) cudaFree(b.packed);
+            if (b.post) cudaFree(b.post);
+            if (b.synd) cudaFree(b.synd);
+            if (b.s) cudaStreamDestroy(b.s);
+            b = Buf();
+        }
+        llr_bytes = hard_bytes = packed_bytes = post_bytes = synd_bytes = 0;
+    }
+};
+}  // namespace
+
+extern "C" void ldpc_host_pipe_free(void *p) {
+    HostPipe *hp = static_cast<HostPipe *>(p);
+    if (!hp) return;
+    hp->release();
+    delete hp;
+}
+
 int ldpc_decode_host(const ldpc_code_t *code, const void *llr_host, int llr_dtype, int64_t N, int iters,
                      int update, float clamp_value, float param, uint8_t *hard_host,
                      uint8_t *hard_packed_host, float *llr_post_host, int32_t *syndrome_host,
@@ -184,37 +226,40 @@ int ldpc_decode_host(const ldpc_code_t *code, const void *llr_host, int llr_dtyp
     if (N == 0) return LDPC_OK;
     const int n = code->n, nby = (n + 7) / 8;
     const size_t esz = llr_dtype == LDPC_F64 ? 8 : (llr_dtype == LDPC_F16 ? 2 : 4);
-    if (chunk <= 0) chunk = 32768;
+    if (chunk <= 0) chunk = 16384;
     chunk = std::min<int64_t>(chunk, N);
-    const int NBUF = 3;
-    struct Buf { void *llr; uint8_t *hard, *packed; float *post; int32_t *synd; cudaStream_t s; cudaEvent_t done; };
-    Buf buf[NBUF];
-    memset(buf, 0, sizeof(buf));
-    auto cleanup = [&]() {
-        for (auto &b : buf) {
-            if (b.llr) cudaFree(b.llr);
-            if (b.hard) cudaFree(b.hard);
-            if (b.packed) cudaFree(b.packed);
-            if (b.post) cudaFree(b.post);
-            if (b.synd) cudaFree(b.synd);
-            if (b.done) cudaEventDestroy(b.done);
-            if (b.s) cudaStreamDestroy(b.s);
+    ldpc_code *mc = const_cast<ldpc_code *>(code);
+    {
+        static std::mutex create_mu;
+        std::lock_guard<std::mutex> g(create_mu);
+        if (!mc->host_pipe) mc->host_pipe = new (std::nothrow) HostPipe();
+        if (!mc->host_pipe) { set_error("out of host memory"); return LDPC_ENOMEM; }
+    }
+    HostPipe *hp = static_cast<HostPipe *>(mc->host_pipe);
+    std::lock_guard<std::mutex> lock(hp->mu);
+#define HTRY(x) do { cudaError_t _e = (x); if (_e != cudaSuccess) { hp->release(); return cuda_fail(_e, #x); } } while (0)
+    const size_t need_llr = (size_t)chunk * n * esz, need_hard = hard_host ? (size_t)chunk * n : 0,
+                 need_packed = hard_packed_host ? (size_t)chunk * nby : 0,
+                 need_post = llr_post_host ? (size_t)chunk * n * sizeof(float) : 0,
+                 need_synd = syndrome_host ? (size_t)chunk * sizeof(int32_t) : 0;
+    if (need_llr > hp->llr_bytes || need_hard > hp->hard_bytes || need_packed > hp->packed_bytes ||
+        need_post > hp->post_bytes || need_synd > hp->synd_bytes || !hp->buf[0].s) {
+        hp->release();
+        for (auto &b : hp->buf) {
+            HTRY(cudaStreamCreateWithFlags(&b.s, cudaStreamNonBlocking));
+            HTRY(cudaMalloc(&b.llr, need_llr));
+            if (need_hard) HTRY(cudaMalloc(&b.hard, need_hard));
+            if (need_packed) HTRY(cudaMalloc(&b.packed, need_packed));
+            if (need_post) HTRY(cudaMalloc(&b.post, need_post));
+            if (need_synd) HTRY(cudaMalloc(&b.synd, need_synd));
         }
-    };
-#define HTRY(x) do { cudaError_t _e = (x); if (_e != cudaSuccess) { cleanup(); return cuda_fail(_e, #x); } } while (0)
-    for (auto &b : buf) {
-        HTRY(cudaStreamCreateWithFlags(&b.s, cudaStreamNonBlocking));
-        HTRY(cudaEventCreateWithFlags(&b.done, cudaEventDisableTiming));
-        HTRY(cudaMalloc(&b.llr, (size_t)chunk * n * esz));
-        if (hard_host) HTRY(cudaMalloc(&b.hard, (size_t)chunk * n));
-        if (hard_packed_host) HTRY(cudaMalloc(&b.packed, (size_t)chunk * nby));
-        if (llr_post_host) HTRY(cudaMalloc(&b.post, (size_t)chunk * n * sizeof(float)));
-        if (syndrome_host) HTRY(cudaMalloc(&b.synd, (size_t)chunk * sizeof(int32_t)));
+        hp->llr_bytes = need_llr; hp->hard_bytes = need_hard; hp->packed_bytes = need_packed;
+        hp->post_bytes = need_post; hp->synd_bytes = need_synd;
     }
     int64_t done = 0;
     int i = 0;
     while (done < N) {
-        Buf &b = buf[i % NBUF];
+        HostPipe::Buf &b = hp->buf[i % HostPipe::NBUF];
         const int64_t cnt = std::min<int64_t>(chunk, N - done);
         HTRY(cudaMemcpyAsync(b.llr, (const char *)llr_host + (size_t)done * n * esz, (size_t)cnt * n * esz,
                              cudaMemcpyHostToDevice, b.s));
@@ -222,9 +267,10 @@ int ldpc_decode_host(const ldpc_code_t *code, const void *llr_host, int llr_dtyp
         memset(&a, 0, sizeof(a));
         a.llr = b.llr; a.llr_dtype = llr_dtype; a.B = cnt; a.iters = iters; a.update = update;
         a.clampv = clamp_value; a.param = param;
-        a.hard = b.hard; a.hard_packed = b.packed; a.llr_post = b.post; a.syndrome = b.synd;
+        a.hard = hard_host ? b.hard : nullptr; a.hard_packed = hard_packed_host ? b.packed : nullptr;
+        a.llr_post = llr_post_host ? b.post : nullptr; a.syndrome = syndrome_host ? b.synd : nullptr;
         rc = decode_dispatch(code, a, b.s);
-        if (rc) { cleanup(); return rc; }
+        if (rc) { hp->release(); return rc; }
         if (hard_host) HTRY(cudaMemcpyAsync(hard_host + (size_t)done * n, b.hard, (size_t)cnt * n, cudaMemcpyDeviceToHost, b.s));
         if (hard_packed_host) HTRY(cudaMemcpyAsync(hard_packed_host + (size_t)done * nby, b.packed, (size_t)cnt * nby, cudaMemcpyDeviceToHost, b.s));
         if (llr_post_host) HTRY(cudaMemcpyAsync(llr_post_host + (size_t)done * n, b.post, (size_t)cnt * n * sizeof(float), cudaMemcpyDeviceToHost, b.s));
@@ -232,9 +278,8 @@ int ldpc_decode_host(const ldpc_code_t *code, const void *llr_host, int llr_dtyp
         done += cnt;
         ++i;
     }
-    for (auto &b : buf) HTRY(cudaStreamSynchronize(b.s));
+    for (auto &b : hp->buf) HTRY(cudaStreamSynchronize(b.s));
 #undef HTRY
-    cleanup();
     return LDPC_OK;
 }
 

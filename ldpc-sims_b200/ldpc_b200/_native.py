@@ -56,6 +56,8 @@ def lib():
     L.ldpc_code_destroy.argtypes = [vp]
     L.ldpc_code_info.restype = ctypes.c_int
     L.ldpc_code_info.argtypes = [vp, ctypes.POINTER(CodeInfo)]
+    L.ldpc_code_plan_info.restype = ctypes.c_int
+    L.ldpc_code_plan_info.argtypes = [vp, vp]
     L.ldpc_code_set_kernel.restype = ctypes.c_int
     L.ldpc_code_set_kernel.argtypes = [vp, i32]
     L.ldpc_decode.restype = ctypes.c_int
