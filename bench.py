@@ -40,6 +40,7 @@ def parse():
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target duration of the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-f16", action="store_true")
     return ap.parse_args()
 
 
@@ -280,6 +281,29 @@ def main():
                              "peak_source": f"smem: 148 SMs x 128 B/clk x {sm_mhz:.0f} MHz / {smem_bytes_per_update:.2f} B per directed edge-update; "
                                             f"issue: 148 SMs x 4 SMSP x 32 lanes x {sm_mhz:.0f} MHz / {lane_instr_per_update or 0:.2f} lane-instr per update"},
     }
+
+    # ---- the f16x2 variant of the same kernel (two codewords per thread), reported beside the fp32 headline ----
+    if a.update in ("minsum", "nms") and not a.no_f16:
+        code.set_precision("f16")
+        for _ in range(2):
+            step()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(a.steps):
+            step()
+        e1.record(stream)
+        barrier()
+        tt = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms16 = float(tt.item()) / a.steps
+        out["f16x2"] = {"value": B * world / (ms16 * 1e-3) * K_CODE / 1e9, "unit": "Gbit/s", "ms_per_step": ms16, "dtype": "f16",
+                        "note": "same workload and outputs, messages and LLRs in binary16, two codewords per thread (LDPC_PREC_F16X2); "
+                                "bit-exact against oracle/bp_oracle.py::bp_decode_f16; not the headline value"}
+        code.set_precision("f32")
+        step()
+        barrier()
 
     # ---- e2e: the C-ABI host call (decode_bits path): pinned host LLRs in, packed bits out ---------
     if not a.no_e2e:

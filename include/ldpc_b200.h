@@ -78,6 +78,14 @@ int ldpc_code_info(const ldpc_code_t *code, ldpc_code_info_t *info);
  *        threads per CTA, codewords per CTA}.  Used by bench.py for the roofline arithmetic. */
 int ldpc_code_plan_info(const ldpc_code_t *code, int32_t out[4]);
 
+/* Message precision of the code-specialised min-sum kernels.  LDPC_PREC_F32 (default) is the
+ * reference's arithmetic type (bp/bp.py runs in torch.float, ofdm_functions.py:156).
+ * LDPC_PREC_F16X2 packs two codewords per thread in half2 registers / shared-memory words
+ * (min-sum and normalized min-sum only; sum-product, offset min-sum and warm starts keep fp32);
+ * its results are defined bit-exactly by oracle/bp_oracle.py::bp_decode_f16. */
+enum { LDPC_PREC_F32 = 0, LDPC_PREC_F16X2 = 1 };
+int ldpc_code_set_precision(ldpc_code_t *code, int precision);
+
 /* Force the generic kernel for a handle (testing / A-B comparison). */
 int ldpc_code_set_kernel(ldpc_code_t *code, int kernel);
 

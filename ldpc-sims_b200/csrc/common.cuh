@@ -25,6 +25,7 @@ struct DecodeArgs {
     unsigned long long *counters;
     int k_info;
     void *host_pipe;    // lazily created staging state of ldpc_decode_host
+    int precision;      // LDPC_PREC_*
 };
 
 struct GraphTables {        // device pointers
@@ -55,6 +56,7 @@ struct ldpc_code {
     uint32_t *d_gen;    // bit-packed parity rows of the systematic generator [m][ceil(k/32)] or null
     int k_info;
     void *host_pipe;    // lazily created staging state of ldpc_decode_host
+    int precision;      // LDPC_PREC_*
 };
 
 namespace ldpc {
@@ -73,6 +75,7 @@ int cuda_fail(cudaError_t e, const char *what);
 int launch_decode_generic(const GraphTables &g, int max_dv, int max_dc, const DecodeArgs &a, cudaStream_t s);
 bool qc_kernel_available(int Z, int mb, int nb, const int16_t *proto);
 int launch_decode_qc(int qc_id, const DecodeArgs &a, cudaStream_t s);
+int launch_decode_qc_h2(int qc_id, const DecodeArgs &a, cudaStream_t s);
 int qc_lookup(int Z, int mb, int nb, const int16_t *proto);   // -1 if no compiled specialisation
 void qc_plan_info(int qc_id, int out[4]);                     // {register-resident blocks, shared-memory blocks, threads/CTA, codewords/CTA}
 

@@ -21,114 +21,9 @@
 #include "common.cuh"
 #include "epilogue.cuh"
 #include "node_math.cuh"
+#include "qc_plan.cuh"
 
 namespace ldpc {
-
-// ---- compile-time prototype matrices ---------------------------------------------------------
-struct Wifi1944R12 {
-    static constexpr int Z = 81, MB = 12, NB = 24;
-    static constexpr int16_t proto[MB][NB] = {
-        {57, -1, -1, -1, 50, -1, 11, -1, 50, -1, 79, -1, 1, 0, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1},
-        {3, -1, 28, -1, 0, -1, -1, -1, 55, 7, -1, -1, -1, 0, 0, -1, -1, -1, -1, -1, -1, -1, -1, -1},
-        {30, -1, -1, -1, 24, 37, -1, -1, 56, 14, -1, -1, -1, -1, 0, 0, -1, -1, -1, -1, -1, -1, -1, -1},
-        {62, 53, -1, -1, 53, -1, -1, 3, 35, -1, -1, -1, -1, -1, -1, 0, 0, -1, -1, -1, -1, -1, -1, -1},
-        {40, -1, -1, 20, 66, -1, -1, 22, 28, -1, -1, -1, -1, -1, -1, -1, 0, 0, -1, -1, -1, -1, -1, -1},
-        {0, -1, -1, -1, 8, -1, 42, -1, 50, -1, -1, 8, -1, -1, -1, -1, -1, 0, 0, -1, -1, -1, -1, -1},
-        {69, 79, 79, -1, -1, -1, 56, -1, 52, -1, -1, -1, 0, -1, -1, -1, -1, -1, 0, 0, -1, -1, -1, -1},
-        {65, -1, -1, -1, 38, 57, -1, -1, 72, -1, 27, -1, -1, -1, -1, -1, -1, -1, -1, 0, 0, -1, -1, -1},
-        {64, -1, -1, -1, 14, 52, -1, -1, 30, -1, -1, 32, -1, -1, -1, -1, -1, -1, -1, -1, 0, 0, -1, -1},
-        {-1, 45, -1, 70, 0, -1, -1, -1, 77, 9, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, 0, 0, -1},
-        {2, 56, -1, 57, 35, -1, -1, -1, -1, -1, 12, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, 0, 0},
-        {24, -1, 61, -1, 60, -1, -1, 27, 51, -1, -1, 16, 1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, 0}};
-};
-
-// ---- compile-time plan ------------------------------------------------------------------------------
-// Lane relabelling.  Thread t of a codeword processes check (r, (t + sigma_r) mod Z) of every
-// block row r and variable (c, (t + rho_c) mod Z) of every block column c.  An edge of block
-// (r, c, shift s) then joins check-thread tc with variable-thread tc + s', where
-//     s' = (s + sigma_r - rho_c) mod Z.
-// Blocks with s' == 0 connect a thread to ITSELF: their messages never leave the register
-// file.  A spanning tree of the (block row, block column) graph fixes sigma/rho so that
-// MB + NB - 1 blocks (35 of the 86 for 802.11n n=1944) become thread-local; only the remaining
-// blocks are exchanged through shared memory.  Which node a thread computes does not change
-// the node's arithmetic, so results stay bit-identical to the generic kernel.
-template <class Code>
-struct QcPlan {
-    static constexpr int Z = Code::Z, MB = Code::MB, NB = Code::NB;
-    int sigma[MB] = {}, rho[NB] = {};
-    int nblk = 0, n_local = 0, n_smem = 0;
-    int row_deg[MB] = {}, row_col[MB][NB] = {}, row_eff[MB][NB] = {}, row_slot[MB][NB] = {}, row_shift[MB][NB] = {};
-    int col_deg[NB] = {}, col_row[NB][MB] = {}, col_eff[NB][MB] = {}, col_slot[NB][MB] = {};
-    bool row_loc[MB][NB] = {}, col_loc[NB][MB] = {};
-    constexpr QcPlan() {
-        // breadth-first spanning tree over block rows / block columns
-        bool row_seen[MB] = {}, col_seen[NB] = {};
-        int queue[MB + NB] = {}, head = 0, tail = 0;     // entries: r (>=0) or -(c+1)
-        for (int root = 0; root < MB; ++root) {
-            if (row_seen[root]) continue;
-            row_seen[root] = true; sigma[root] = 0; queue[tail++] = root;
-            while (head < tail) {
-                const int q = queue[head++];
-                if (q >= 0) {
-                    const int r = q;
-                    for (int c = 0; c < NB; ++c)
-                        if (Code::proto[r][c] >= 0 && !col_seen[c]) {
-                            col_seen[c] = true;
-                            rho[c] = (Code::proto[r][c] + sigma[r]) % Z;
-                            queue[tail++] = -(c + 1);
-                        }
-                } else {
-                    const int c = -q - 1;
-                    for (int r = 0; r < MB; ++r)
-                        if (Code::proto[r][c] >= 0 && !row_seen[r]) {
-                            row_seen[r] = true;
-                            sigma[r] = ((rho[c] - Code::proto[r][c]) % Z + Z) % Z;
-                            queue[tail++] = r;
-                        }
-                }
-            }
-        }
-        for (int r = 0; r < MB; ++r)
-            for (int c = 0; c < NB; ++c)
-                if (Code::proto[r][c] >= 0) {
-                    const int eff = ((Code::proto[r][c] + sigma[r] - rho[c]) % Z + Z) % Z;
-                    const bool loc = (eff == 0);
-                    const int slot = loc ? n_local++ : n_smem++;
-                    const int j = row_deg[r]++;
-                    row_col[r][j] = c; row_eff[r][j] = eff; row_slot[r][j] = slot; row_loc[r][j] = loc;
-                    row_shift[r][j] = Code::proto[r][c];
-                    const int k = col_deg[c]++;
-                    col_row[c][k] = r; col_eff[c][k] = eff; col_slot[c][k] = slot; col_loc[c][k] = loc;
-                    ++nblk;
-                }
-    }
-};
-
-template <class Code>
-inline constexpr QcPlan<Code> kQc{};
-
-template <class F, int... I>
-__device__ __forceinline__ void static_for_impl(F &&f, std::integer_sequence<int, I...>) {
-    (f(std::integral_constant<int, I>{}), ...);
-}
-template <int N, class F>
-__device__ __forceinline__ void static_for(F &&f) {
-    static_for_impl(static_cast<F &&>(f), std::make_integer_sequence<int, N>{});
-}
-
-template <class Code, int CW>
-struct QcLayout {
-    static constexpr int Z = Code::Z;
-    static constexpr int N = Code::NB * Z;
-    static constexpr int M = Code::MB * Z;
-    static constexpr int NLOC = kQc<Code>.n_local, NSM = kQc<Code>.n_smem;
-    // codeword strides == Z (mod 32): lanes of two codewords sharing a warp stay on distinct banks
-    static constexpr int pad_to(int v) { return v + ((Z % 32) - (v % 32) + 32) % 32; }
-    static constexpr int MSG_STRIDE = pad_to(NSM * Z);
-    static constexpr int HARD_STRIDE = (N + 15) & ~15;
-    static constexpr int THREADS = ((CW * Z + 31) / 32) * 32;
-    static constexpr size_t SMEM = sizeof(float) * CW * MSG_STRIDE + (size_t)CW * HARD_STRIDE + sizeof(int) * (8 + CW);
-};
 
 template <class Code, int CW, int UPD>
 __global__ void __launch_bounds__((QcLayout<Code, CW>::THREADS)) decode_qc_kernel(const DecodeArgs a) {

@@ -1,0 +1,293 @@
+// decode_qc_h2.cu - f16x2 variant of the code-specialised min-sum decoder: every thread
+// carries TWO codewords packed in one 32-bit register (half2), so each shared-memory word,
+// each HADD2 and each HMNMX2.XORSIGN serves two codewords.  Same plan (qc_plan.cuh), same
+// schedule and phases as decode_qc.cu; only the number format differs.
+//
+// Arithmetic ("min-sum f16", defined bit-exactly by oracle/bp_oracle.py::bp_decode_f16 - the
+// reference has neither min-sum nor half precision, bp/bp.py:27-31):
+//   Lh   = fp16_rn(clip(llr, +-32768)),  L' = -Lh
+//   V->C y_k = fp16(L' + S_k), S_k = P_k + Q_k two-sweep, every add rounded to fp16 (RN)
+//   C->V x_j = c (+) (+)_{i!=j} g(y_i), a (+) b = sign(a)sign(b) min(|a|,|b|), c = fp16_rn(clamp),
+//        g = identity (min-sum) | fp16(alpha_h * y) (normalized min-sum)
+//   t    = fp16(0.5 * fp16(L' + ((x_0 + x_1) + ...)));  outputs from float(t) exactly as fp32 path.
+#include <cuda_fp16.h>
+
+#include "common.cuh"
+#include "epilogue.cuh"
+#include "node_math.cuh"
+#include "qc_plan.cuh"
+
+namespace ldpc {
+
+__device__ __forceinline__ __half2 h2_add(__half2 a, __half2 b) { return __hadd2_rn(a, b); }
+
+__device__ __forceinline__ __half2 h2_boxmin(__half2 a, __half2 b) {
+    unsigned d;
+    asm("min.xorsign.abs.f16x2 %0, %1, %2;" : "=r"(d) : "r"(*reinterpret_cast<unsigned *>(&a)), "r"(*reinterpret_cast<unsigned *>(&b)));
+    return *reinterpret_cast<__half2 *>(&d);
+}
+
+template <int D>
+__device__ __forceinline__ void h2_sum_others(const __half2 (&in)[D], __half2 (&out)[D]) {
+    if constexpr (D == 1) { out[0] = __float2half2_rn(0.0f); return; }
+    __half2 pre[D];
+    __half2 acc = in[0];
+#pragma unroll
+    for (int k = 1; k < D; ++k) { pre[k] = acc; acc = h2_add(acc, in[k]); }
+    acc = in[D - 1];
+    out[D - 1] = pre[D - 1];
+#pragma unroll
+    for (int k = D - 2; k >= 1; --k) { out[k] = h2_add(pre[k], acc); acc = h2_add(in[k], acc); }
+    out[0] = acc;
+}
+
+template <int D>
+__device__ __forceinline__ void h2_boxmin_others_clamped(const __half2 (&v)[D], __half2 c, __half2 (&out)[D]) {
+    if constexpr (D == 8) {
+        const __half2 p01 = h2_boxmin(v[0], v[1]), p23 = h2_boxmin(v[2], v[3]), p45 = h2_boxmin(v[4], v[5]), p67 = h2_boxmin(v[6], v[7]);
+        const __half2 qL = h2_boxmin(h2_boxmin(p01, p23), c), qR = h2_boxmin(h2_boxmin(p45, p67), c);
+        out[0] = h2_boxmin(h2_boxmin(v[1], p23), qR); out[1] = h2_boxmin(h2_boxmin(v[0], p23), qR);
+        out[2] = h2_boxmin(h2_boxmin(v[3], p01), qR); out[3] = h2_boxmin(h2_boxmin(v[2], p01), qR);
+        out[4] = h2_boxmin(h2_boxmin(v[5], p67), qL); out[5] = h2_boxmin(h2_boxmin(v[4], p67), qL);
+        out[6] = h2_boxmin(h2_boxmin(v[7], p45), qL); out[7] = h2_boxmin(h2_boxmin(v[6], p45), qL);
+    } else if constexpr (D == 7) {
+        const __half2 p01 = h2_boxmin(v[0], v[1]), p23 = h2_boxmin(v[2], v[3]), p45 = h2_boxmin(v[4], v[5]);
+        const __half2 qL = h2_boxmin(h2_boxmin(p01, p23), c), qR = h2_boxmin(h2_boxmin(p45, v[6]), c);
+        out[0] = h2_boxmin(h2_boxmin(v[1], p23), qR); out[1] = h2_boxmin(h2_boxmin(v[0], p23), qR);
+        out[2] = h2_boxmin(h2_boxmin(v[3], p01), qR); out[3] = h2_boxmin(h2_boxmin(v[2], p01), qR);
+        out[4] = h2_boxmin(h2_boxmin(v[5], v[6]), qL); out[5] = h2_boxmin(h2_boxmin(v[4], v[6]), qL);
+        out[6] = h2_boxmin(p45, qL);
+    } else {
+        __half2 pre[D];
+        __half2 acc = c;
+#pragma unroll
+        for (int j = 0; j < D; ++j) { pre[j] = acc; acc = h2_boxmin(acc, v[j]); }
+        acc = c;
+#pragma unroll
+        for (int j = D - 1; j >= 0; --j) { out[j] = h2_boxmin(pre[j], acc); acc = h2_boxmin(acc, v[j]); }
+    }
+}
+
+__device__ __forceinline__ float sat_llr(float v) { return fminf(fmaxf(v, -32768.0f), 32768.0f); }
+
+template <class Code, int CW /* codeword PAIRS per CTA */, int UPD>
+__global__ void __launch_bounds__((QcLayout<Code, CW>::THREADS)) decode_qc_h2_kernel(const DecodeArgs a) {
+    using L = QcLayout<Code, CW>;
+    constexpr int Z = Code::Z, NB = Code::NB, MB = Code::MB, N = L::N;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __half2 *msg_s = reinterpret_cast<__half2 *>(smem_raw);
+    uint8_t *hard_s = reinterpret_cast<uint8_t *>(msg_s + CW * L::MSG_STRIDE);           // [2*CW][HARD_STRIDE]
+    int *scratch = reinterpret_cast<int *>(hard_s + 2 * CW * L::HARD_STRIDE);              // [4 + 2*CW]
+
+    const int tid = threadIdx.x, T = blockDim.x;
+    const long long cw0 = (long long)blockIdx.x * (2 * CW);
+    const int ncw = (int)min((long long)(2 * CW), a.B - cw0);            // codewords in this tile
+    const int pr = tid / Z, t = tid - pr * Z;                             // pair slot, lane
+    const bool active = 2 * pr < ncw;                                     // false for padding threads too
+    const bool second = 2 * pr + 1 < ncw;                                 // .y lane holds a real codeword
+    for (int i = tid; i < 4 + 2 * CW; i += T) scratch[i] = 0;
+
+    __half2 *const msg = msg_s + (active ? pr : 0) * L::MSG_STRIDE;
+    __half2 *const lo = msg + t;
+    __half2 *const hi = msg + t + Z;
+
+    __half2 llr[NB];
+    __half2 loc[L::NLOC > 0 ? L::NLOC : 1];
+    const long long gbase = (cw0 + (active ? 2 * pr : 0)) * N;
+    if (active) {
+        static_for<NB>([&](auto cc) {
+            constexpr int c = decltype(cc)::value;
+            constexpr int rho = kQc<Code>.rho[c];
+            int zv = t + rho;
+            if (zv >= Z) zv -= Z;
+            const float l0 = sat_llr(load_llr(a.llr, a.llr_dtype, gbase + c * Z + zv));
+            const float l1 = second ? sat_llr(load_llr(a.llr, a.llr_dtype, gbase + N + c * Z + zv)) : 0.0f;
+            llr[c] = __floats2half2_rn(l0, l1);
+        });
+    }
+    const __half2 clamp_h = __float2half2_rn(a.clampv);
+    const __half2 alpha_h = __float2half2_rn(a.param);
+
+    auto var_phase = [&](auto first_tag) {
+        constexpr bool FIRST = decltype(first_tag)::value;
+        static_for<NB>([&](auto cc) {
+            constexpr int c = decltype(cc)::value;
+            constexpr int D = kQc<Code>.col_deg[c];
+            if constexpr (D > 0) {
+                __half2 in[D], s[D];
+                __half2 *ptr[D];
+                static_for<D>([&](auto kk) {
+                    constexpr int k = decltype(kk)::value;
+                    constexpr bool is_loc = kQc<Code>.col_loc[c][k];
+                    constexpr int slot = kQc<Code>.col_slot[c][k];
+                    if constexpr (is_loc) {
+                        ptr[k] = nullptr;
+                        in[k] = FIRST ? __float2half2_rn(0.0f) : loc[slot];
+                    } else {
+                        constexpr int sh = kQc<Code>.col_eff[c][k];
+                        constexpr int off = slot * Z - sh;
+                        ptr[k] = (t < sh ? hi : lo) + off;
+                        in[k] = FIRST ? __float2half2_rn(0.0f) : *ptr[k];
+                    }
+                });
+                h2_sum_others<D>(in, s);
+                const __half2 Lp = __hneg2(llr[c]);
+                static_for<D>([&](auto kk) {
+                    constexpr int k = decltype(kk)::value;
+                    constexpr bool is_loc = kQc<Code>.col_loc[c][k];
+                    constexpr int slot = kQc<Code>.col_slot[c][k];
+                    const __half2 y = h2_add(Lp, s[k]);
+                    if constexpr (is_loc) loc[slot] = y;
+                    else *ptr[k] = y;
+                });
+            }
+        });
+    };
+    auto check_phase = [&]() {
+        static_for<MB>([&](auto rr) {
+            constexpr int r = decltype(rr)::value;
+            constexpr int D = kQc<Code>.row_deg[r];
+            if constexpr (D > 0) {
+                __half2 in[D], out[D];
+                static_for<D>([&](auto jj) {
+                    constexpr int j = decltype(jj)::value;
+                    constexpr bool is_loc = kQc<Code>.row_loc[r][j];
+                    constexpr int slot = kQc<Code>.row_slot[r][j];
+                    __half2 v;
+                    if constexpr (is_loc) v = loc[slot];
+                    else v = msg[slot * Z + t];
+                    in[j] = (UPD == UPD_NMS) ? __hmul2_rn(alpha_h, v) : v;
+                });
+                h2_boxmin_others_clamped<D>(in, clamp_h, out);
+                static_for<D>([&](auto jj) {
+                    constexpr int j = decltype(jj)::value;
+                    constexpr bool is_loc = kQc<Code>.row_loc[r][j];
+                    constexpr int slot = kQc<Code>.row_slot[r][j];
+                    if constexpr (is_loc) loc[slot] = out[j];
+                    else msg[slot * Z + t] = out[j];
+                });
+            }
+        });
+    };
+
+    if (a.iters > 0) {
+        if (active) var_phase(std::true_type{});
+        __syncthreads();
+        if (active) check_phase();
+        __syncthreads();
+    }
+#pragma unroll 1
+    for (int it = 1; it < a.iters; ++it) {
+        if (active) var_phase(std::false_type{});
+        __syncthreads();
+        if (active) check_phase();
+        __syncthreads();
+    }
+
+    // ---- marginal, P(bit=1), hard decision ------------------------------------------------------------
+    if (active) {
+        const __half2 half_h = __float2half2_rn(0.5f);
+        static_for<NB>([&](auto cc) {
+            constexpr int c = decltype(cc)::value;
+            constexpr int D = kQc<Code>.col_deg[c];
+            constexpr int rho = kQc<Code>.rho[c];
+            __half2 acc = __float2half2_rn(0.0f);
+            static_for<D>([&](auto kk) {
+                constexpr int k = decltype(kk)::value;
+                constexpr bool is_loc = kQc<Code>.col_loc[c][k];
+                constexpr int slot = kQc<Code>.col_slot[c][k];
+                __half2 v;
+                if constexpr (is_loc) v = loc[slot];
+                else {
+                    constexpr int sh = kQc<Code>.col_eff[c][k];
+                    constexpr int off = slot * Z - sh;
+                    v = ((t < sh ? hi : lo) + off)[0];
+                }
+                if (a.iters == 0) v = __float2half2_rn(0.0f);
+                acc = (k == 0) ? v : h2_add(acc, v);
+            });
+            const __half2 th = __hmul2_rn(half_h, h2_add(__hneg2(llr[c]), acc));
+            const float2 tf = __half22float2(th);
+            const float2 lf = __half22float2(llr[c]);
+            int zv = t + rho;
+            if (zv >= Z) zv -= Z;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                if (h == 1 && !second) break;
+                const float tm = h ? tf.y : tf.x;
+                const float lv = h ? lf.y : lf.x;
+                const uint8_t hb = hard_bit(tm);
+                hard_s[(2 * pr + h) * L::HARD_STRIDE + c * Z + zv] = hb | ((lv > 0.0f) ? 2 : 0);
+                const long long o = gbase + (long long)h * N + c * Z + zv;
+                if (a.prob) a.prob[o] = prob_one(tm);
+                if (a.llr_post) a.llr_post[o] = __fmul_rn(-2.0f, tm);
+                if (a.hard) a.hard[o] = hb;
+            }
+        });
+    }
+    __syncthreads();
+
+    // ---- syndrome weight --------------------------------------------------------------------------------
+    if (a.syndrome) {
+        if (active) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                if (h == 1 && !second) break;
+                int w = 0;
+                const uint8_t *hs = hard_s + (2 * pr + h) * L::HARD_STRIDE;
+                static_for<MB>([&](auto rr) {
+                    constexpr int r = decltype(rr)::value;
+                    constexpr int D = kQc<Code>.row_deg[r];
+                    constexpr int sg = kQc<Code>.sigma[r];
+                    int zc = t + sg;
+                    if (zc >= Z) zc -= Z;
+                    unsigned par = 0;
+                    static_for<D>([&](auto jj) {
+                        constexpr int j = decltype(jj)::value;
+                        constexpr int s = kQc<Code>.row_shift[r][j];
+                        constexpr int cbase = kQc<Code>.row_col[r][j] * Z;
+                        int zv = zc + s;
+                        if (zv >= Z) zv -= Z;
+                        par ^= hs[cbase + zv] & 1u;
+                    });
+                    w += (int)par;
+                });
+                if (w) atomicAdd(&scratch[4 + 2 * pr + h], w);
+            }
+        }
+        __syncthreads();
+        for (int i = tid; i < ncw; i += T) a.syndrome[cw0 + i] = scratch[4 + i];
+        __syncthreads();
+        for (int i = tid; i < 2 * CW; i += T) scratch[4 + i] = 0;
+    }
+    if (a.hard_packed) pack_hard(hard_s, L::HARD_STRIDE, ncw, N, a.hard_packed + cw0 * ((N + 7) >> 3));
+    if (a.counters) {
+        __syncthreads();
+        count_errors(hard_s, L::HARD_STRIDE, ncw, N, a.k_info, a.ref_packed + cw0 * ((N + 7) >> 3), a.counters,
+                     scratch + 1);
+    }
+}
+
+template <class Code, int CW, int UPD>
+static int launch_h2_one(const DecodeArgs &a, cudaStream_t s) {
+    using L = QcLayout<Code, CW>;
+    const size_t smem = sizeof(__half2) * CW * L::MSG_STRIDE + (size_t)2 * CW * L::HARD_STRIDE + sizeof(int) * (8 + 2 * CW);
+    const long long grid = (a.B + 2 * CW - 1) / (2 * CW);
+    if (grid > 0x7fffffffLL) { set_error("batch too large"); return LDPC_EINVAL; }
+    auto k = decode_qc_h2_kernel<Code, CW, UPD>;
+    LDPC_CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k<<<(int)grid, L::THREADS, smem, s>>>(a);
+    LDPC_CUDA_TRY(cudaGetLastError());
+    return LDPC_OK;
+}
+
+int launch_decode_qc_h2(int qc_id, const DecodeArgs &a, cudaStream_t s) {
+    if (a.B <= 0) return LDPC_OK;
+    if (qc_id != 0) { set_error("unknown QC specialisation %d", qc_id); return LDPC_EINVAL; }
+    if (a.update == UPD_MINSUM) return launch_h2_one<Wifi1944R12, 3, UPD_MINSUM>(a, s);
+    if (a.update == UPD_NMS) return launch_h2_one<Wifi1944R12, 3, UPD_NMS>(a, s);
+    set_error("the f16x2 kernel implements min-sum and normalized min-sum only");
+    return LDPC_EUNSUPPORTED;
+}
+
+}  // namespace ldpc

@@ -79,7 +79,7 @@ int ldpc_code_create(const int32_t *row_ptr, const int32_t *col_idx, int m, int 
     if (!h) { set_error("out of host memory"); return LDPC_ENOMEM; }
     h->m = m; h->n = n; h->E = E; h->max_dc = max_dc; h->max_dv = max_dv; h->device = dev;
     h->qc_Z = 0; h->qc_id = -1; h->kernel = LDPC_KERNEL_GENERIC; h->d_tables = nullptr;
-    h->d_gen = nullptr; h->k_info = 0; h->host_pipe = nullptr;
+    h->d_gen = nullptr; h->k_info = 0; h->host_pipe = nullptr; h->precision = LDPC_PREC_F32;
     const size_t words = (size_t)(m + 1) + E + (n + 1) + E;
     cudaError_t e = cudaMalloc(&h->d_tables, words * sizeof(int32_t));
     if (e != cudaSuccess) { delete h; return cuda_fail(e, "cudaMalloc(tables)"); }
@@ -141,6 +141,14 @@ int ldpc_code_plan_info(const ldpc_code_t *code, int32_t out[4]) {
     return LDPC_OK;
 }
 
+int ldpc_code_set_precision(ldpc_code_t *code, int precision) {
+    if (!code) { set_error("null code"); return LDPC_EINVAL; }
+    if (precision == LDPC_PREC_F32) { code->precision = precision; return LDPC_OK; }
+    if (precision == LDPC_PREC_F16X2 && code->qc_id >= 0) { code->precision = precision; return LDPC_OK; }
+    set_error("precision %d not available for this code (f16x2 needs a code-specialised kernel)", precision);
+    return LDPC_EUNSUPPORTED;
+}
+
 int ldpc_code_set_kernel(ldpc_code_t *code, int kernel) {
     if (!code) { set_error("null code"); return LDPC_EINVAL; }
     if (kernel == LDPC_KERNEL_GENERIC) { code->kernel = kernel; return LDPC_OK; }
@@ -164,8 +172,11 @@ static int check_decode_args(const ldpc_code_t *code, const void *llr, int llr_d
 
 namespace ldpc {
 int decode_dispatch(const ldpc_code *code, const DecodeArgs &a, cudaStream_t s) {
-    if (code->kernel == LDPC_KERNEL_QC && a.x0 == nullptr && a.x_out == nullptr)
+    if (code->kernel == LDPC_KERNEL_QC && a.x0 == nullptr && a.x_out == nullptr) {
+        if (code->precision == LDPC_PREC_F16X2 && (a.update == LDPC_UPDATE_MINSUM || a.update == LDPC_UPDATE_NMS))
+            return launch_decode_qc_h2(code->qc_id, a, s);
         return launch_decode_qc(code->qc_id, a, s);
+    }
     return launch_decode_generic(code->g, code->max_dv, code->max_dc, a, s);
 }
 }  // namespace ldpc

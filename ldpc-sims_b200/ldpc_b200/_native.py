@@ -17,6 +17,7 @@ OK, EINVAL, ECUDA, ENOMEM, EUNSUPPORTED = 0, -1, -2, -3, -4
 UPDATE_SP, UPDATE_MINSUM, UPDATE_NMS, UPDATE_OMS = 0, 1, 2, 3
 F32, F64, F16 = 0, 1, 2
 KERNEL_GENERIC, KERNEL_QC = 0, 1
+PREC_F32, PREC_F16X2 = 0, 1
 ABI_VERSION = 1
 
 UPDATE_IDS = {"sp": 0, "tanh": 0, "sum-product": 0, "sumproduct": 0,
@@ -58,6 +59,8 @@ def lib():
     L.ldpc_code_info.argtypes = [vp, ctypes.POINTER(CodeInfo)]
     L.ldpc_code_plan_info.restype = ctypes.c_int
     L.ldpc_code_plan_info.argtypes = [vp, vp]
+    L.ldpc_code_set_precision.restype = ctypes.c_int
+    L.ldpc_code_set_precision.argtypes = [vp, i32]
     L.ldpc_code_set_kernel.restype = ctypes.c_int
     L.ldpc_code_set_kernel.argtypes = [vp, i32]
     L.ldpc_decode.restype = ctypes.c_int

@@ -70,6 +70,13 @@ class LdpcCode:
         N.check(N.lib().ldpc_code_set_kernel(self._h, int(kid)))
         self.kernel = int(kid)
 
+    def set_precision(self, precision):
+        """'f32' (default, the reference's dtype) or 'f16' (two codewords per thread in half2;
+        min-sum / normalized min-sum on code-specialised kernels only)."""
+        pid = {"f32": N.PREC_F32, "f16": N.PREC_F16X2, "f16x2": N.PREC_F16X2}.get(precision, precision)
+        N.check(N.lib().ldpc_code_set_precision(self._h, int(pid)))
+        self.precision = int(pid)
+
     @property
     def packed_bytes(self):
         return (self.n + 7) // 8

@@ -211,3 +211,68 @@ def decode_bits(llrs, H, bp_iterations, batch_size, clamp_value, **kw):
         s, e = b * batch_size, (b + 1) * batch_size
         out[s:e] = bp_decode(H, llrs[s:e].astype(F32), bp_iterations, clamp_value, graph=g, **kw)["hard"]
     return out
+
+
+# ------------------------------------------------------------------------------------------
+# "min-sum f16": the definition of the f16x2 fast path (csrc/decode_qc_h2.cu).  NOT in the
+# reference (no min-sum, no half precision there: bp/bp.py:27-31) - this function IS the spec.
+# Every operation is an IEEE binary16 operation with round-to-nearest-even, emulated exactly:
+# operands are binary16 values held in float64 (sum / product of two binary16 values is exact
+# in float64), rounded ONCE by float64 -> float16.
+# ------------------------------------------------------------------------------------------
+def _r16(x):
+    return np.asarray(x, dtype=np.float64).astype(np.float16).astype(np.float64)
+
+
+def _boxmin(a, b):
+    """sign(a) sign(b) min(|a|,|b|) with IEEE sign bits (min.xorsign.abs)."""
+    m = np.minimum(np.abs(a), np.abs(b))
+    return np.where(np.logical_xor(np.signbit(a), np.signbit(b)), -m, m)
+
+
+def bp_decode_f16(H, llr, iterations, clamp_value, update="minsum", alpha=1.0, graph=None):
+    """Returns dict t [B,n] f32 (binary16 values), hard u8, syndrome i32, prob f32."""
+    g = graph or Graph(H)
+    upd = _UPDATE_IDS[update] if isinstance(update, str) else int(update)
+    assert upd in (UPDATE_MINSUM, UPDATE_NMS)
+    llr = np.ascontiguousarray(llr, dtype=F32)
+    B = llr.shape[0]
+    Lh = _r16(np.clip(llr, -32768.0, 32768.0))
+    Lp = -Lh
+    c_h = float(_r16(np.float32(clamp_value)))
+    a_h = float(_r16(np.float32(alpha)))
+    x = np.zeros((B, g.E), np.float64)
+    y = np.zeros((B, g.E), np.float64)
+    add = lambda p, q: _r16(p + q)
+    for _ in range(int(iterations)):
+        for d, vs, vm, cm in g.var_groups:
+            if d == 0:
+                continue
+            xin = [x[:, cm[:, k]] for k in range(d)]
+            S = [np.zeros((B, vs.size))] if d == 1 else _others(xin, add)
+            for k in range(d):
+                y[:, vm[:, k]] = add(Lp[:, vs], S[k])
+        for d, cs, cm, vm in g.chk_groups:
+            if d == 0:
+                continue
+            yin = [y[:, vm[:, j]] for j in range(d)]
+            if upd == UPDATE_NMS:
+                yin = [_r16(a_h * v) for v in yin]
+            if d == 1:
+                O_ = [np.full((B, cs.size), np.inf)]
+            else:
+                O_ = _others(yin, _boxmin)
+            for j in range(d):
+                x[:, cm[:, j]] = _boxmin(O_[j], c_h)
+    t = np.zeros((B, g.n), np.float64)
+    for d, vs, vm, cm in g.var_groups:
+        acc = None
+        for k in range(d):
+            acc = x[:, cm[:, k]] if acc is None else add(acc, x[:, cm[:, k]])
+        if acc is None:
+            acc = np.zeros((B, vs.size))
+        t[:, vs] = _r16(0.5 * add(Lp[:, vs], acc))
+    t32 = t.astype(F32)
+    prob = (-1 * torch.sigmoid(_t(t32)) + 1).numpy()
+    hard = np.round(prob).astype(np.uint8)
+    return dict(t=t32, prob=prob, hard=hard, syndrome=syndrome_weight(g, hard))

@@ -237,3 +237,30 @@ def test_full_size_properties_minsum(wcode):
     # noiseless round trip
     clean = wcode.decode(-8.0 * (1.0 - 2.0 * cwt[:4096].float()), 10, 20, update="minsum", want=("hard",))
     assert torch.equal(clean["hard"], cwt[:4096])
+
+
+@pytest.mark.parametrize("update,param,B", [("minsum", 1.0, 131), ("nms", 0.8125, 64), ("minsum", 1.0, 1)])
+def test_f16x2_fast_path_bit_exact_vs_its_oracle(update, param, B):
+    """The two-codewords-per-thread half2 kernel against oracle/bp_oracle.py::bp_decode_f16
+    (binary16 arithmetic emulated exactly): marginals, hard bits, syndromes bit-exact.
+    Odd batch sizes exercise the half-empty last pair."""
+    from ldpc_b200.decoder import LdpcCode
+    qc = ieee80211n_1944_r12()
+    code = LdpcCode(qc.H, qc_Z=81, qc_proto=qc.proto)
+    code.set_precision("f16")
+    rng = np.random.RandomState(21 + B)
+    c = qc.encode(rng.randint(0, 2, (B, qc.k)).astype(np.uint8))
+    sigma = 0.78
+    llr = (-2.0 * ((1.0 - 2.0 * c) + sigma * rng.randn(B, qc.n)) / sigma ** 2).astype(np.float32)
+    llr[0, :7] = [0.0, 1e6, -1e6, 1e-9, -70000.0, 65504.0, 3.0]           # saturation / zero / tiny inputs
+    a = O.bp_decode_f16(qc.H, llr, 10, 20, update=update, alpha=param)
+    o = dec(code, llr, 10, 20, update, param, want=("llr_post", "hard", "hard_packed", "syndrome", "prob"))
+    assert np.array_equal(o["llr_post"], -2.0 * a["t"])
+    assert np.array_equal(o["hard"], a["hard"]) and np.array_equal(o["syndrome"], a["syndrome"])
+    assert np.array_equal(o["hard_packed"], np.packbits(a["hard"], axis=1))
+    # and it decodes as well as fp32 min-sum on this sample
+    code.set_precision("f32")
+    f = dec(code, llr, 10, 20, update, param, want=("hard",))
+    assert abs(int((f["hard"] != c).sum()) - int((o["hard"] != c).sum())) <= max(8, 0.02 * int((f["hard"] != c).sum()))
+    with pytest.raises(Exception):
+        LdpcCode(peg_64_32()[0]).set_precision("f16")                     # generic kernel: fp32 only
