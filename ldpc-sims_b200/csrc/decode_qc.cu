@@ -52,13 +52,18 @@ __global__ void __launch_bounds__((QcLayout<Code, CW>::THREADS)) decode_qc_kerne
     float loc[L::NLOC > 0 ? L::NLOC : 1];
     const long long gbase = (cw0 + (active ? cw : 0)) * N;
     if (active) {
-        static_for<NB>([&](auto cc) {
-            constexpr int c = decltype(cc)::value;
-            constexpr int rho = kQc<Code>.rho[c];
-            int zv = t + rho;
-            if (zv >= Z) zv -= Z;
-            llr[c] = load_llr(a.llr, a.llr_dtype, gbase + c * Z + zv);
-        });
+        auto load_all = [&](auto ld) {                                    // one uniform dtype branch, then NB straight loads
+            static_for<NB>([&](auto cc) {
+                constexpr int c = decltype(cc)::value;
+                constexpr int rho = kQc<Code>.rho[c];
+                int zv = t + rho;
+                if (zv >= Z) zv -= Z;
+                llr[c] = ld(gbase + c * Z + zv);
+            });
+        };
+        if (a.llr_dtype == LDPC_F32) load_all([&](long long i) { return __ldg(reinterpret_cast<const float *>(a.llr) + i); });
+        else if (a.llr_dtype == LDPC_F64) load_all([&](long long i) { return (float)__ldg(reinterpret_cast<const double *>(a.llr) + i); });
+        else load_all([&](long long i) { return __half2float(__ldg(reinterpret_cast<const __half *>(a.llr) + i)); });
     }
 
     // V -> C for all NB block columns of this thread.  FIRST: the C->V messages are still the

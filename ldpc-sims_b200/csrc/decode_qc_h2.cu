@@ -12,6 +12,8 @@
 //   t    = fp16(0.5 * fp16(L' + ((x_0 + x_1) + ...)));  outputs from float(t) exactly as fp32 path.
 #include <cuda_fp16.h>
 
+#include <cstdlib>
+
 #include "common.cuh"
 #include "epilogue.cuh"
 #include "node_math.cuh"
@@ -95,14 +97,25 @@ __global__ void __launch_bounds__((QcLayout<Code, CW>::THREADS)) decode_qc_h2_ke
     __half2 loc[L::NLOC > 0 ? L::NLOC : 1];
     const long long gbase = (cw0 + (active ? 2 * pr : 0)) * N;
     if (active) {
+        // issue all 2*NB independent global loads first (they overlap in flight), convert afterwards
+        float raw0[NB], raw1[NB];
+        const long long g1 = second ? gbase + N : gbase;                 // half-empty last pair: re-read row 0, discard
+        auto load_all = [&](auto ld) {                                    // one uniform dtype branch, then 2*NB straight loads
+            static_for<NB>([&](auto cc) {
+                constexpr int c = decltype(cc)::value;
+                constexpr int rho = kQc<Code>.rho[c];
+                int zv = t + rho;
+                if (zv >= Z) zv -= Z;
+                raw0[c] = ld(gbase + c * Z + zv);
+                raw1[c] = ld(g1 + c * Z + zv);
+            });
+        };
+        if (a.llr_dtype == LDPC_F32) load_all([&](long long i) { return __ldg(reinterpret_cast<const float *>(a.llr) + i); });
+        else if (a.llr_dtype == LDPC_F64) load_all([&](long long i) { return (float)__ldg(reinterpret_cast<const double *>(a.llr) + i); });
+        else load_all([&](long long i) { return __half2float(__ldg(reinterpret_cast<const __half *>(a.llr) + i)); });
         static_for<NB>([&](auto cc) {
             constexpr int c = decltype(cc)::value;
-            constexpr int rho = kQc<Code>.rho[c];
-            int zv = t + rho;
-            if (zv >= Z) zv -= Z;
-            const float l0 = sat_llr(load_llr(a.llr, a.llr_dtype, gbase + c * Z + zv));
-            const float l1 = second ? sat_llr(load_llr(a.llr, a.llr_dtype, gbase + N + c * Z + zv)) : 0.0f;
-            llr[c] = __floats2half2_rn(l0, l1);
+            llr[c] = __floats2half2_rn(sat_llr(raw0[c]), second ? sat_llr(raw1[c]) : 0.0f);
         });
     }
     const __half2 clamp_h = __float2half2_rn(a.clampv);
@@ -284,6 +297,8 @@ static int launch_h2_one(const DecodeArgs &a, cudaStream_t s) {
 int launch_decode_qc_h2(int qc_id, const DecodeArgs &a, cudaStream_t s) {
     if (a.B <= 0) return LDPC_OK;
     if (qc_id != 0) { set_error("unknown QC specialisation %d", qc_id); return LDPC_EINVAL; }
+    static const int cw = [] { const char *e = getenv("LDPC_QC_H2_CW"); return e ? atoi(e) : 3; }();
+    if (a.update == UPD_MINSUM && cw == 6) return launch_h2_one<Wifi1944R12, 6, UPD_MINSUM>(a, s);
     if (a.update == UPD_MINSUM) return launch_h2_one<Wifi1944R12, 3, UPD_MINSUM>(a, s);
     if (a.update == UPD_NMS) return launch_h2_one<Wifi1944R12, 3, UPD_NMS>(a, s);
     set_error("the f16x2 kernel implements min-sum and normalized min-sum only");
