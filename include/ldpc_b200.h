@@ -198,7 +198,7 @@ typedef struct {
     int32_t update;         /* LDPC_UPDATE_* */
     float clamp_value;
     float param;
-    int32_t reserved;
+    int32_t reserved;       /* bit 0: force the three-launch chain (A/B test of the single-launch kernel) */
     uint64_t seed;          /* Philox key */
     int64_t first_codeword; /* global index of the first codeword (Philox subsequence) */
     int64_t n_codewords;
@@ -208,9 +208,12 @@ typedef struct {
  * integer metrics into counters[5] (i64, device): {uncoded bit errors, info-bit errors, frame
  * errors, bits, frames} (evaluate_quantized_snr.py:169-188).  Each codeword is framed into
  * ceil((n/2)/N) OFDM symbols (null subcarriers after its last QPSK symbol; identical to the
- * reference when n = 2N).  workspace: device scratch for the LLR tile, >= 1024 codewords of
- * (4 n + ceil(n/8)) bytes; the run is chunked to fit.  Results depend only on (seed, global
- * codeword index), never on the sharding. */
+ * reference when n = 2N).  For a code with a compiled specialisation the whole chain runs in ONE
+ * kernel launch (front end fused in front of the decoder, nothing touches HBM but the counters);
+ * otherwise three launches per chunk (generate, link, decode+count) with `workspace` as device
+ * scratch for the LLR tile (>= 1024 codewords of 4 n + ceil(n/8) bytes; the run is chunked to
+ * fit).  Both paths give identical counters; they depend only on (seed, global codeword index),
+ * never on the sharding. */
 int ldpc_sim_run(const ldpc_code_t *code, const ldpc_sim_params_t *params, void *workspace,
                  size_t workspace_bytes, int64_t *counters, ldpc_stream_t stream);
 

@@ -76,6 +76,8 @@ int launch_decode_generic(const GraphTables &g, int max_dv, int max_dc, const De
 bool qc_kernel_available(int Z, int mb, int nb, const int16_t *proto);
 int launch_decode_qc(int qc_id, const DecodeArgs &a, cudaStream_t s);
 int launch_decode_qc_h2(int qc_id, const DecodeArgs &a, cudaStream_t s);
+struct LinkParams;
+int launch_sim_fused_qc(int qc_id, const DecodeArgs &a, const LinkParams &lp, cudaStream_t s);   // LDPC_EUNSUPPORTED -> use the 3-launch chain
 int qc_lookup(int Z, int mb, int nb, const int16_t *proto);   // -1 if no compiled specialisation
 void qc_plan_info(int qc_id, int out[4]);                     // {register-resident blocks, shared-memory blocks, threads/CTA, codewords/CTA}
 

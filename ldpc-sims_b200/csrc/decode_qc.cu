@@ -21,12 +21,20 @@
 #include "common.cuh"
 #include "epilogue.cuh"
 #include "node_math.cuh"
+#include "linksim_device.cuh"
 #include "qc_plan.cuh"
 
 namespace ldpc {
 
-template <class Code, int CW, int UPD>
-__global__ void __launch_bounds__((QcLayout<Code, CW>::THREADS)) decode_qc_kernel(const DecodeArgs a) {
+// SIM = 0: channel LLRs come from global memory (ldpc_decode).
+// SIM = N_ofdm (32/64/128/256): the link front end runs INSIDE this kernel - Philox information
+// bits, linear-time dual-diagonal encoder, QPSK, per-codeword OFDM framing, warp IFFT, Philox
+// AWGN, AGC + quantizer, warp FFT, exact LLR (linksim_device.cuh) - and writes the LLR tile into
+// the (still unused) message region of shared memory; the error counters compare against the
+// transmitted bits kept in shared memory.  One launch takes random bits to BER counts
+// (replaces the per-SNR loop body of evaluate_quantized_snr.py:91-188).
+template <class Code, int CW, int UPD, int SIM>
+__global__ void __launch_bounds__((QcLayout<Code, CW>::THREADS)) decode_qc_kernel(const DecodeArgs a, const LinkParams lp) {
     using L = QcLayout<Code, CW>;
     constexpr bool IS_SP = (UPD == UPD_SP);
     constexpr int Z = Code::Z, NB = Code::NB, MB = Code::MB, N = L::N;
@@ -51,6 +59,7 @@ __global__ void __launch_bounds__((QcLayout<Code, CW>::THREADS)) decode_qc_kerne
     float llr[NB];
     float loc[L::NLOC > 0 ? L::NLOC : 1];
     const long long gbase = (cw0 + (active ? cw : 0)) * N;
+    if constexpr (SIM == 0) {
     if (active) {
         auto load_all = [&](auto ld) {                                    // one uniform dtype branch, then NB straight loads
             static_for<NB>([&](auto cc) {
@@ -64,6 +73,88 @@ __global__ void __launch_bounds__((QcLayout<Code, CW>::THREADS)) decode_qc_kerne
         if (a.llr_dtype == LDPC_F32) load_all([&](long long i) { return __ldg(reinterpret_cast<const float *>(a.llr) + i); });
         else if (a.llr_dtype == LDPC_F64) load_all([&](long long i) { return (float)__ldg(reinterpret_cast<const double *>(a.llr) + i); });
         else load_all([&](long long i) { return __half2float(__ldg(reinterpret_cast<const __half *>(a.llr) + i)); });
+    }
+    } else {
+        static_assert(SIM == 0 || kQc<Code>.dual_diagonal, "the fused simulator needs the dual-diagonal encoder structure");
+        static_assert(SIM == 0 || CW * L::MSG_STRIDE >= CW * N + CW * 32 + SIM, "LLR staging does not fit the message region");
+        constexpr int K = (NB - MB) * Z, KW = (K + 31) / 32, KB = NB - MB;
+        float *stage = msg_s;                                              // [CW][N] channel LLRs
+        uint32_t *u_s = reinterpret_cast<uint32_t *>(msg_s + CW * N);       // [CW][32] packed information words
+        cplx<float> *tw = reinterpret_cast<cplx<float> *>(u_s + CW * 32);   // [SIM/2] twiddles
+        const Philox rng(lp.seed);
+        // -- information bits (same Philox blocks as sim.cu gen_codewords_kernel)
+        for (int i = tid; i < ncw * ((KW + 3) / 4); i += T) {
+            const int c = i / ((KW + 3) / 4), blk = i - c * ((KW + 3) / 4);
+            info_words_block(rng, (unsigned long long)(lp.cw_first + cw0 + c), blk, K, u_s + c * 32);
+        }
+        fill_twiddles_f<float>(tw, SIM);
+        __syncthreads();
+        // -- systematic encode, natural lane z = t: lambda_r = sum_c rot(u_c, s_rc); p0 = sum_r lambda_r;
+        //    p_1 = lambda_0 + rot(p0, h_0); p_{r+1} = lambda_r + [h_r] rot(p0, h_r) + p_r
+        uint8_t *bits = hard_s + (active ? cw : 0) * L::HARD_STRIDE;       // bit 2 of the byte = transmitted bit
+        const uint32_t *u = u_s + (active ? cw : 0) * 32;
+        auto ubit = [&](int i) { return (u[i >> 5] >> (i & 31)) & 1u; };
+        unsigned lam = 0;                                                  // bit r = lambda_r[t]
+        if (active) {
+            static_for<MB>([&](auto rr) {
+                constexpr int r = decltype(rr)::value;
+                unsigned acc = 0;
+                static_for<kQc<Code>.enc_deg[r]>([&](auto jj) {
+                    constexpr int j = decltype(jj)::value;
+                    constexpr int c = kQc<Code>.enc_col[r][j], sh = kQc<Code>.enc_shift[r][j];
+                    int z = t + sh;
+                    if (z >= Z) z -= Z;
+                    acc ^= ubit(c * Z + z);
+                });
+                lam |= acc << r;
+            });
+            static_for<KB>([&](auto cc) {
+                constexpr int c = decltype(cc)::value;
+                bits[c * Z + t] = (uint8_t)(ubit(c * Z + t) << 2);
+            });
+            bits[KB * Z + t] = (uint8_t)((__popc(lam) & 1) << 2);          // p0
+        }
+        __syncthreads();
+        if (active) {
+            unsigned prev = 0;
+            static_for<MB - 1>([&](auto rr) {
+                constexpr int r = decltype(rr)::value;
+                unsigned v = (lam >> r) & 1u;
+                if constexpr (kQc<Code>.hcol[r] >= 0) {
+                    int z = t + kQc<Code>.hcol[r];
+                    if (z >= Z) z -= Z;
+                    v ^= (bits[KB * Z + z] >> 2) & 1u;
+                }
+                if constexpr (r >= 1) v ^= prev;
+                prev = v;
+                bits[(KB + r + 1) * Z + t] = (uint8_t)(v << 2);
+            });
+        }
+        __syncthreads();
+        // -- OFDM link, one warp per OFDM symbol
+        {
+            const LinkConsts kc(lp, SIM);
+            const int lane = tid & 31, nsym = N / 2;
+            for (int o = tid >> 5; o < ncw * lp.n_ofdm_per_cw; o += T >> 5) {
+                const int c = o / lp.n_ofdm_per_cw, os = o - c * lp.n_ofdm_per_cw;
+                const uint8_t *brow = hard_s + c * L::HARD_STRIDE;
+                float *orow = stage + c * N;
+                ofdm_symbol_llr<(SIM > 0 ? SIM : 32)>(lane, os, nsym, (unsigned long long)(lp.cw_first + cw0 + c), lp, kc, tw,
+                                                      [&](int i) { return (int)((brow[i] >> 2) & 1); },
+                                                      [&](int sidx, float l0, float l1) { *reinterpret_cast<float2 *>(orow + 2 * sidx) = make_float2(l0, l1); });
+            }
+        }
+        __syncthreads();
+        if (active) {
+            static_for<NB>([&](auto cc) {
+                constexpr int c = decltype(cc)::value;
+                constexpr int rho = kQc<Code>.rho[c];
+                int zv = t + rho;
+                if (zv >= Z) zv -= Z;
+                llr[c] = stage[cw * N + c * Z + zv];
+            });
+        }
+        __syncthreads();                                                   // the message region is free again
     }
 
     // V -> C for all NB block columns of this thread.  FIRST: the C->V messages are still the
@@ -143,10 +234,11 @@ __global__ void __launch_bounds__((QcLayout<Code, CW>::THREADS)) decode_qc_kerne
 
     // ---- marginal, P(bit=1), hard decision --------------------------------------------------------
     if (active) {
+        float tm[NB];
+        float tmin = CUDART_INF_F;
         static_for<NB>([&](auto cc) {
             constexpr int c = decltype(cc)::value;
             constexpr int D = kQc<Code>.col_deg[c];
-            constexpr int rho = kQc<Code>.rho[c];
             float in[D > 0 ? D : 1];
             static_for<D>([&](auto kk) {
                 constexpr int k = decltype(kk)::value;
@@ -159,15 +251,25 @@ __global__ void __launch_bounds__((QcLayout<Code, CW>::THREADS)) decode_qc_kerne
                     in[k] = (a.iters == 0) ? 0.0f : ((t < s ? hi : lo) + off)[0];
                 }
             });
-            const float tm = marginal_t<(D > 0 ? D : 1)>(in, D, llr[c]);
-            const uint8_t hb = hard_bit(tm);
+            tm[c] = marginal_t<(D > 0 ? D : 1)>(in, D, llr[c]);
+            tmin = fminf(tmin, fabsf(tm[c]));
+        });
+        // hard decision = (t < 0) outside the tie band; one rarely-taken branch per thread
+        // re-evaluates the band cases the way the reference rounds them (node_math.cuh: hard_bit)
+        const bool band = !(tmin > 1e-5f);
+        const float *base_post = a.llr_post ? a.llr_post + gbase : nullptr;
+        static_for<NB>([&](auto cc) {
+            constexpr int c = decltype(cc)::value;
+            constexpr int rho = kQc<Code>.rho[c];
+            uint8_t hb = tm[c] < 0.0f;
+            if (band) hb = hard_bit(tm[c]);
             int zv = t + rho;
             if (zv >= Z) zv -= Z;
-            hard_s[cw * L::HARD_STRIDE + c * Z + zv] = hb | ((llr[c] > 0.0f) ? 2 : 0);
-            const long long o = gbase + c * Z + zv;
-            if (a.prob) a.prob[o] = prob_one(tm);
-            if (a.llr_post) a.llr_post[o] = __fmul_rn(-2.0f, tm);
-            if (a.hard) a.hard[o] = hb;
+            uint8_t *hp = hard_s + cw * L::HARD_STRIDE + c * Z + zv;
+            *hp = (SIM ? (*hp & 4) : 0) | hb | ((llr[c] > 0.0f) ? 2 : 0);
+            if (a.llr_post) const_cast<float *>(base_post)[c * Z + zv] = __fmul_rn(-2.0f, tm[c]);
+            if (a.prob) a.prob[gbase + c * Z + zv] = prob_one(tm[c]);
+            if (a.hard) a.hard[gbase + c * Z + zv] = hb;
         });
     }
     __syncthreads();
@@ -204,8 +306,8 @@ __global__ void __launch_bounds__((QcLayout<Code, CW>::THREADS)) decode_qc_kerne
     if (a.hard_packed) pack_hard(hard_s, L::HARD_STRIDE, ncw, N, a.hard_packed + cw0 * ((N + 7) >> 3));
     if (a.counters) {
         __syncthreads();
-        count_errors(hard_s, L::HARD_STRIDE, ncw, N, a.k_info, a.ref_packed + cw0 * ((N + 7) >> 3), a.counters,
-                     scratch + 1);
+        count_errors(hard_s, L::HARD_STRIDE, ncw, N, a.k_info, SIM ? nullptr : a.ref_packed + cw0 * ((N + 7) >> 3),
+                     a.counters, scratch + 1);
     }
 }
 
@@ -237,9 +339,9 @@ static int launch_qc_one(const DecodeArgs &a, cudaStream_t s) {
     using L = QcLayout<Code, CW>;
     const long long grid = (a.B + CW - 1) / CW;
     if (grid > 0x7fffffffLL) { set_error("batch too large"); return LDPC_EINVAL; }
-    auto k = decode_qc_kernel<Code, CW, UPD>;
+    auto k = decode_qc_kernel<Code, CW, UPD, 0>;
     LDPC_CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::SMEM));
-    k<<<(int)grid, L::THREADS, L::SMEM, s>>>(a);
+    k<<<(int)grid, L::THREADS, L::SMEM, s>>>(a, LinkParams());
     LDPC_CUDA_TRY(cudaGetLastError());
     return LDPC_OK;
 }
@@ -249,15 +351,15 @@ static int launch_qc_t(const DecodeArgs &a, cudaStream_t s) {
     using L = QcLayout<Code, CW>;
     const long long grid = (a.B + CW - 1) / CW;
     if (grid > 0x7fffffffLL) { set_error("batch too large"); return LDPC_EINVAL; }
-    void (*k)(const DecodeArgs) = nullptr;
+    void (*k)(const DecodeArgs, const LinkParams) = nullptr;
     switch (a.update) {
-        case UPD_SP: k = decode_qc_kernel<Code, CW, UPD_SP>; break;
-        case UPD_MINSUM: k = decode_qc_kernel<Code, CW, UPD_MINSUM>; break;
-        case UPD_NMS: k = decode_qc_kernel<Code, CW, UPD_NMS>; break;
-        default: k = decode_qc_kernel<Code, CW, UPD_OMS>; break;
+        case UPD_SP: k = decode_qc_kernel<Code, CW, UPD_SP, 0>; break;
+        case UPD_MINSUM: k = decode_qc_kernel<Code, CW, UPD_MINSUM, 0>; break;
+        case UPD_NMS: k = decode_qc_kernel<Code, CW, UPD_NMS, 0>; break;
+        default: k = decode_qc_kernel<Code, CW, UPD_OMS, 0>; break;
     }
     LDPC_CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::SMEM));
-    k<<<(int)grid, L::THREADS, L::SMEM, s>>>(a);
+    k<<<(int)grid, L::THREADS, L::SMEM, s>>>(a, LinkParams());
     LDPC_CUDA_TRY(cudaGetLastError());
     return LDPC_OK;
 }
@@ -275,6 +377,44 @@ int launch_decode_qc(int qc_id, const DecodeArgs &a, cudaStream_t s) {
         }
         default: set_error("unknown QC specialisation %d", qc_id); return LDPC_EINVAL;
     }
+}
+
+}  // namespace ldpc
+
+namespace ldpc {
+
+// Single-launch simulator: supported for the compiled QC codes, ofdm_size 64 (all update rules)
+// and 32 / 128 / 256 (min-sum); returns LDPC_EUNSUPPORTED otherwise and the caller falls back to
+// the three-launch chain.
+template <class Code, int CW, int UPD, int SIM>
+static int launch_sim_one(const DecodeArgs &a, const LinkParams &lp, cudaStream_t s) {
+    using L = QcLayout<Code, CW>;
+    const long long grid = (a.B + CW - 1) / CW;
+    if (grid > 0x7fffffffLL) { set_error("batch too large"); return LDPC_EINVAL; }
+    auto k = decode_qc_kernel<Code, CW, UPD, SIM>;
+    LDPC_CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::SMEM));
+    k<<<(int)grid, L::THREADS, L::SMEM, s>>>(a, lp);
+    LDPC_CUDA_TRY(cudaGetLastError());
+    return LDPC_OK;
+}
+
+int launch_sim_fused_qc(int qc_id, const DecodeArgs &a, const LinkParams &lp, cudaStream_t s) {
+    if (qc_id != 0) return LDPC_EUNSUPPORTED;
+    if (a.B <= 0) return LDPC_OK;
+    if (lp.ofdm_size == 64) {
+        switch (a.update) {
+            case UPD_SP: return launch_sim_one<Wifi1944R12, 3, UPD_SP, 64>(a, lp, s);
+            case UPD_MINSUM: return launch_sim_one<Wifi1944R12, 3, UPD_MINSUM, 64>(a, lp, s);
+            case UPD_NMS: return launch_sim_one<Wifi1944R12, 3, UPD_NMS, 64>(a, lp, s);
+            default: return launch_sim_one<Wifi1944R12, 3, UPD_OMS, 64>(a, lp, s);
+        }
+    }
+    if (a.update == UPD_MINSUM) {
+        if (lp.ofdm_size == 32) return launch_sim_one<Wifi1944R12, 3, UPD_MINSUM, 32>(a, lp, s);
+        if (lp.ofdm_size == 128) return launch_sim_one<Wifi1944R12, 3, UPD_MINSUM, 128>(a, lp, s);
+        if (lp.ofdm_size == 256) return launch_sim_one<Wifi1944R12, 3, UPD_MINSUM, 256>(a, lp, s);
+    }
+    return LDPC_EUNSUPPORTED;
 }
 
 }  // namespace ldpc

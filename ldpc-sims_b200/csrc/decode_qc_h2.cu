@@ -229,7 +229,8 @@ __global__ void __launch_bounds__((QcLayout<Code, CW>::THREADS)) decode_qc_h2_ke
                 if (h == 1 && !second) break;
                 const float tm = h ? tf.y : tf.x;
                 const float lv = h ? lf.y : lf.x;
-                const uint8_t hb = hard_bit(tm);
+                uint8_t hb = tm < 0.0f;
+                if (!(fabsf(tm) > 1e-5f)) hb = hard_bit(tm);              // tie band (rare)
                 hard_s[(2 * pr + h) * L::HARD_STRIDE + c * Z + zv] = hb | ((lv > 0.0f) ? 2 : 0);
                 const long long o = gbase + (long long)h * N + c * Z + zv;
                 if (a.prob) a.prob[o] = prob_one(tm);

@@ -34,9 +34,10 @@ __device__ __forceinline__ void count_errors(const uint8_t *hard_s, int hs_strid
     int unc = 0, inf = 0;
     for (int i = threadIdx.x; i < ncw * n; i += blockDim.x) {
         const int cw = i / n, v = i - cw * n;
-        const int ref = (ref_packed_g[(long long)cw * nbytes + (v >> 3)] >> (7 - (v & 7))) & 1;
         const int hv = hard_s[cw * hs_stride + v];
-        const int hb = hv & 1, ub = hv >> 1;
+        // transmitted bit: packed global array, or bit 2 of the shared byte (single-launch simulator)
+        const int ref = ref_packed_g ? (ref_packed_g[(long long)cw * nbytes + (v >> 3)] >> (7 - (v & 7))) & 1 : (hv >> 2) & 1;
+        const int hb = hv & 1, ub = (hv >> 1) & 1;
         unc += (ub != ref);
         const int e = (hb != ref);
         inf += e & (v < k_info);

@@ -1,0 +1,101 @@
+// linksim_device.cuh - the per-OFDM-symbol link chain of the simulator as ONE device function,
+// shared by the standalone front-end kernel (sim.cu, K2b) and the single-launch fused
+// simulator (decode_qc.cu): QPSK -> warp IFFT -> Philox AWGN -> AGC + quantizer -> warp FFT ->
+// exact LLR.  Both translation units are compiled with -fmad=false so the two paths produce
+// the same float bits and therefore the same integer counters.
+// Reference chain: ofdm/ofdm_functions.py:17-35,63-78 and evaluate_quantized_snr.py:96-133.
+#pragma once
+#include "frontend.cuh"
+
+namespace ldpc {
+
+struct LinkParams {
+    int n;                 // code length (bits)
+    int n_ofdm_per_cw;     // ceil((n/2) / N)
+    int ofdm_size;
+    float snr;             // linear per-subcarrier Es/N0 (ofdm_functions.py:110)
+    int qbits;             // 0 = no ADC model
+    int agc_mode;          // 1 = script AGC (evaluate_quantized_snr.py:103-111), 2 = gen_qdata-style clip
+    float agc_clip, clip_ratio;
+    unsigned long long seed;
+    long long cw_first;
+};
+
+struct LinkConsts {
+    float scale, a, nstd, two_np, factor, clip, levels;
+    __device__ __forceinline__ LinkConsts(const LinkParams &p, int N) {
+        scale = rsqrtf((float)N);
+        a = 0.70710678118654752f;
+        nstd = sqrtf(0.5f / p.snr);                      // per real dimension
+        two_np = 1.0f / p.snr;                           // 2 * (0.5 / snr)
+        factor = 1.0f; clip = 1.0f;
+        if (p.qbits > 0) {
+            if (p.agc_mode == 1) { clip = p.agc_clip; factor = p.agc_clip / (0.5f * (1.0f + 1.0f / p.snr)) * p.clip_ratio; }
+            else { clip = sqrtf(1.0f + 1.0f / p.snr) * p.clip_ratio; }
+        }
+        levels = (float)(1 << (p.qbits > 0 ? p.qbits : 1));
+    }
+};
+
+template <typename T>
+__device__ __forceinline__ void fill_twiddles_f(cplx<T> *tw, int N) {
+    for (int j = threadIdx.x; j < N / 2; j += blockDim.x) {
+        double s, c;
+        sincospi(-2.0 * (double)j / (double)N, &s, &c);
+        tw[j] = {(T)c, (T)s};
+    }
+}
+
+// One warp, one OFDM symbol `os` of global codeword `gcw`.  bit(i) -> 0/1 code bit i of that
+// codeword; out(sidx, llr_b0, llr_b1) receives the LLR pair of QPSK symbol sidx < nsym.
+template <int N, class BitFn, class OutFn>
+__device__ __forceinline__ void ofdm_symbol_llr(int lane, int os, int nsym, unsigned long long gcw, const LinkParams &p,
+                                                const LinkConsts &k, const cplx<float> *tw, BitFn bit, OutFn out) {
+    constexpr int P = N / 32, LOGN = ilog2(N);
+    const Quantizer<float> quant(k.levels, k.clip);
+    const Philox rng(p.seed);
+    cplx<float> x[P];
+#pragma unroll
+    for (int r = 0; r < P; ++r) {                         // QPSK, null subcarriers past the codeword
+        const int sidx = os * N + r * 32 + lane;
+        if (sidx < nsym) x[r] = {k.a * (float)(1 - 2 * bit(2 * sidx)), k.a * (float)(1 - 2 * bit(2 * sidx + 1))};
+        else x[r] = {0.0f, 0.0f};
+    }
+    warp_fft<N, float, true>(x, lane, tw, k.scale);       // time sample t = bitrev(r*32+lane)
+#pragma unroll
+    for (int r = 0; r < P; ++r) {
+        const int t = bitrev(r * 32 + lane, LOGN);
+        uint32_t rnd[4];
+        rng((uint32_t)gcw, (uint32_t)(gcw >> 32), RNG_NOISE, (uint32_t)(os * N + t), rnd);
+        float z0, z1;
+        box_muller<float>(rnd[0], rnd[1], z0, z1);
+        float re = x[r].re + k.nstd * z0, im = x[r].im + k.nstd * z1;
+        if (p.qbits > 0) { re = quant(k.factor * re) / k.factor; im = quant(k.factor * im) / k.factor; }
+        x[r] = {re, im};
+    }
+    warp_fft_dit<N, float, false>(x, lane, tw, k.scale);  // back to natural subcarrier order
+#pragma unroll
+    for (int r = 0; r < P; ++r) {
+        const int sidx = os * N + r * 32 + lane;
+        if (sidx < nsym) out(sidx, qpsk_llr<float>(x[r].re, k.a, k.two_np), qpsk_llr<float>(x[r].im, k.a, k.two_np));
+    }
+}
+
+// Philox information words of one codeword: word w (bit j = information bit 32 w + j) comes
+// from block w/4, lane w%4 of stream RNG_BITS; bits at or beyond k are cleared.
+__device__ __forceinline__ void info_words_block(const Philox &rng, unsigned long long gcw, int blk, int k, uint32_t *u /* [kw] */) {
+    const int kw = (k + 31) / 32;
+    uint32_t r[4];
+    rng((uint32_t)gcw, (uint32_t)(gcw >> 32), RNG_BITS, (uint32_t)blk, r);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int w = blk * 4 + j;
+        if (w < kw) {
+            uint32_t v = r[j];
+            if (32 * (w + 1) > k) v &= (k - 32 * w >= 32) ? 0xffffffffu : ((1u << (k - 32 * w)) - 1u);
+            u[w] = v;
+        }
+    }
+}
+
+}  // namespace ldpc

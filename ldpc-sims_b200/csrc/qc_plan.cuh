@@ -42,7 +42,26 @@ struct QcPlan {
     int row_deg[MB] = {}, row_col[MB][NB] = {}, row_eff[MB][NB] = {}, row_slot[MB][NB] = {}, row_shift[MB][NB] = {};
     int col_deg[NB] = {}, col_row[NB][MB] = {}, col_eff[NB][MB] = {}, col_slot[NB][MB] = {};
     bool row_loc[MB][NB] = {}, col_loc[NB][MB] = {};
+    // systematic encoder (802.11n style): H = [A | h | T], T dual-diagonal (shift 0), column h with the
+    // same shift at its top and bottom entries and shift 0 at the middle one
+    int kb = NB - MB, enc_deg[MB] = {}, enc_col[MB][NB] = {}, enc_shift[MB][NB] = {}, hcol[MB] = {};
+    bool dual_diagonal = true;
     constexpr QcPlan() {
+        for (int r = 0; r < MB; ++r) {
+            for (int c = 0; c < NB - MB; ++c)
+                if (Code::proto[r][c] >= 0) { enc_col[r][enc_deg[r]] = c; enc_shift[r][enc_deg[r]] = Code::proto[r][c]; ++enc_deg[r]; }
+            hcol[r] = Code::proto[r][NB - MB];
+            for (int j = 1; j < MB; ++j) {
+                const bool want = (r == j - 1) || (r == j);
+                const int v = Code::proto[r][NB - MB + j];
+                if (want ? (v != 0) : (v >= 0)) dual_diagonal = false;
+            }
+        }
+        {
+            int cnt = 0, mid = -1;
+            for (int r = 0; r < MB; ++r) if (hcol[r] >= 0) { ++cnt; if (r != 0 && r != MB - 1) mid = r; }
+            if (cnt != 3 || hcol[0] < 0 || hcol[MB - 1] < 0 || hcol[0] != hcol[MB - 1] || mid < 0 || hcol[mid] != 0) dual_diagonal = false;
+        }
         // breadth-first spanning tree over block rows / block columns
         bool row_seen[MB] = {}, col_seen[NB] = {};
         int queue[MB + NB] = {}, head = 0, tail = 0;     // entries: r (>=0) or -(c+1)

@@ -14,7 +14,7 @@
 #include <cstring>
 
 #include "common.cuh"
-#include "frontend.cuh"
+#include "linksim_device.cuh"
 
 namespace ldpc {
 
@@ -29,18 +29,7 @@ __global__ void __launch_bounds__(256) gen_codewords_kernel(const uint32_t *Pp /
     const Philox rng(seed);
     for (long long c = blockIdx.x; c < ncw; c += gridDim.x) {
         const unsigned long long gcw = (unsigned long long)(cw_first + c);
-        for (int blk = threadIdx.x; blk * 4 < kw; blk += blockDim.x) {
-            uint32_t r[4];
-            rng((uint32_t)gcw, (uint32_t)(gcw >> 32), RNG_BITS, (uint32_t)blk, r);
-            for (int j = 0; j < 4; ++j) {
-                const int w = blk * 4 + j;
-                if (w < kw) {
-                    uint32_t v = r[j];
-                    if (32 * (w + 1) > k) v &= (k - 32 * w >= 32) ? 0xffffffffu : ((1u << (k - 32 * w)) - 1u);
-                    u_s[w] = v;
-                }
-            }
-        }
+        for (int blk = threadIdx.x; blk * 4 < kw; blk += blockDim.x) info_words_block(rng, gcw, blk, k, u_s);
         __syncthreads();
         for (int i = threadIdx.x; i < k; i += blockDim.x) bits_s[i] = (u_s[i >> 5] >> (i & 31)) & 1u;
         for (int r = threadIdx.x; r < m; r += blockDim.x) {
@@ -62,77 +51,27 @@ __global__ void __launch_bounds__(256) gen_codewords_kernel(const uint32_t *Pp /
 }
 
 // ---- K2b ----------------------------------------------------------------------------------------------
-struct LinkParams {
-    int n;                 // code length (bits)
-    int n_ofdm_per_cw;     // ceil((n/2) / N)
-    float snr;             // linear per-subcarrier Es/N0 (ofdm_functions.py:110)
-    int qbits;             // 0 = no ADC model
-    int agc_mode;          // 1 = script AGC (evaluate_quantized_snr.py:103-111), 2 = gen_qdata-style clip
-    float agc_clip, clip_ratio;
-    unsigned long long seed;
-    long long cw_first;
-};
-
 __device__ __forceinline__ int cw_bit(const uint8_t *row, int i) { return (row[i >> 3] >> (7 - (i & 7))) & 1; }
 
 template <int N>
 __global__ void __launch_bounds__(256) linksim_llr_kernel(const uint8_t *cw_packed, long long ncw, LinkParams p, float *llr) {
-    constexpr int P = N / 32, LOGN = ilog2(N);
     __shared__ cplx<float> tw[N / 2];
-    for (int j = threadIdx.x; j < N / 2; j += blockDim.x) {
-        double s, c;
-        sincospi(-2.0 * (double)j / (double)N, &s, &c);
-        tw[j] = {(float)c, (float)s};
-    }
+    fill_twiddles_f<float>(tw, N);
     __syncthreads();
     const int lane = threadIdx.x & 31;
     const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
     const long long total = ncw * p.n_ofdm_per_cw;
     const int nby = (p.n + 7) / 8, nsym = p.n / 2;
-    const float scale = rsqrtf((float)N), a = 0.70710678118654752f;
-    const float nstd = sqrtf(0.5f / p.snr);                 // per real dimension
-    const float two_np = 1.0f / p.snr;                      // 2 * (0.5 / snr)
-    float factor = 1.0f, clip = 1.0f;
-    if (p.qbits > 0) {
-        if (p.agc_mode == 1) { clip = p.agc_clip; factor = p.agc_clip / (0.5f * (1.0f + 1.0f / p.snr)) * p.clip_ratio; }
-        else { clip = sqrtf(1.0f + 1.0f / p.snr) * p.clip_ratio; factor = 1.0f; }
-    }
-    const Quantizer<float> quant((float)(1 << (p.qbits > 0 ? p.qbits : 1)), clip);
-    const Philox rng(p.seed);
+    const LinkConsts k(p, N);
     for (long long o = warp; o < total; o += nwarps) {
         const long long c = o / p.n_ofdm_per_cw;
         const int os = (int)(o - c * p.n_ofdm_per_cw);
         const uint8_t *row = cw_packed + c * nby;
-        const unsigned long long gcw = (unsigned long long)(p.cw_first + c);
-        cplx<float> x[P];
-#pragma unroll
-        for (int r = 0; r < P; ++r) {                         // QPSK, null subcarriers past the codeword
-            const int sidx = os * N + r * 32 + lane;
-            if (sidx < nsym) x[r] = {a * (float)(1 - 2 * cw_bit(row, 2 * sidx)), a * (float)(1 - 2 * cw_bit(row, 2 * sidx + 1))};
-            else x[r] = {0.0f, 0.0f};
-        }
-        warp_fft<N, float, true>(x, lane, tw, scale);         // time sample t = bitrev(r*32+lane)
-#pragma unroll
-        for (int r = 0; r < P; ++r) {
-            const int t = bitrev(r * 32 + lane, LOGN);
-            uint32_t rnd[4];
-            rng((uint32_t)gcw, (uint32_t)(gcw >> 32), RNG_NOISE, (uint32_t)(os * N + t), rnd);
-            float z0, z1;
-            box_muller<float>(rnd[0], rnd[1], z0, z1);
-            float re = x[r].re + nstd * z0, im = x[r].im + nstd * z1;
-            if (p.qbits > 0) { re = quant(factor * re) / factor; im = quant(factor * im) / factor; }
-            x[r] = {re, im};
-        }
-        warp_fft_dit<N, float, false>(x, lane, tw, scale);    // back to natural subcarrier order
-#pragma unroll
-        for (int r = 0; r < P; ++r) {
-            const int sidx = os * N + r * 32 + lane;
-            if (sidx < nsym) {
-                float2 v = make_float2(qpsk_llr<float>(x[r].re, a, two_np), qpsk_llr<float>(x[r].im, a, two_np));
-                *reinterpret_cast<float2 *>(llr + c * p.n + 2 * sidx) = v;
-            }
-        }
+        float *orow = llr + c * p.n;
+        ofdm_symbol_llr<N>(lane, os, nsym, (unsigned long long)(p.cw_first + c), p, k, tw,
+                           [&](int i) { return cw_bit(row, i); },
+                           [&](int sidx, float l0, float l1) { *reinterpret_cast<float2 *>(orow + 2 * sidx) = make_float2(l0, l1); });
     }
 }
 
@@ -178,7 +117,7 @@ static int launch_frontend(const ldpc_code_t *code, const ldpc_sim_params_t *sp,
     gen_codewords_kernel<<<g1, 256, sm, s>>>(code->d_gen, n, k, first, cnt, sp->seed, cw_packed);
     LDPC_CUDA_TRY(cudaGetLastError());
     LinkParams lp;
-    lp.n = n; lp.n_ofdm_per_cw = (n / 2 + sp->ofdm_size - 1) / sp->ofdm_size;
+    lp.n = n; lp.n_ofdm_per_cw = (n / 2 + sp->ofdm_size - 1) / sp->ofdm_size; lp.ofdm_size = sp->ofdm_size;
     lp.snr = powf(10.0f, sp->snr_db / 10.0f);
     lp.qbits = sp->qbits; lp.agc_mode = sp->agc_mode; lp.agc_clip = sp->agc_clip; lp.clip_ratio = sp->clip_ratio;
     lp.seed = sp->seed; lp.cw_first = first;
@@ -210,6 +149,23 @@ int ldpc_sim_run(const ldpc_code_t *code, const ldpc_sim_params_t *sp, void *wor
     if (!counters) { set_error("ldpc_sim_run: null counters"); return LDPC_EINVAL; }
     if (sp->iters < 0 || sp->update < LDPC_UPDATE_SP || sp->update > LDPC_UPDATE_OMS || !(sp->clamp_value > 0.0f)) { set_error("ldpc_sim_run: bad decoder parameters"); return LDPC_EINVAL; }
     const int n = code->n, nby = (n + 7) / 8;
+    cudaStream_t s = (cudaStream_t)stream;
+    // ---- single launch: front end fused into the code-specialised decoder kernel -------------------
+    if (code->kernel == LDPC_KERNEL_QC && code->precision == LDPC_PREC_F32 && !(sp->reserved & 1)) {
+        DecodeArgs a;
+        memset(&a, 0, sizeof(a));
+        a.llr_dtype = LDPC_F32; a.B = sp->n_codewords; a.iters = sp->iters; a.update = sp->update;
+        a.clampv = sp->clamp_value; a.param = sp->param;
+        a.counters = reinterpret_cast<unsigned long long *>(counters); a.k_info = code->k_info;
+        LinkParams lp;
+        lp.n = n; lp.n_ofdm_per_cw = (n / 2 + sp->ofdm_size - 1) / sp->ofdm_size; lp.ofdm_size = sp->ofdm_size;
+        lp.snr = powf(10.0f, sp->snr_db / 10.0f);
+        lp.qbits = sp->qbits; lp.agc_mode = sp->agc_mode; lp.agc_clip = sp->agc_clip; lp.clip_ratio = sp->clip_ratio;
+        lp.seed = sp->seed; lp.cw_first = sp->first_codeword;
+        rc = launch_sim_fused_qc(code->qc_id, a, lp, s);
+        if (rc != LDPC_EUNSUPPORTED) return rc;
+    }
+    // ---- three launches per chunk -----------------------------------------------------------------------
     const size_t per_cw = (size_t)n * sizeof(float) + ((nby + 15) & ~15);
     if (!workspace || workspace_bytes < per_cw * 1024) { set_error("ldpc_sim_run: workspace must hold at least 1024 codewords (%zu bytes)", per_cw * 1024); return LDPC_EINVAL; }
     long long chunk = (long long)(workspace_bytes / per_cw);
@@ -217,7 +173,6 @@ int ldpc_sim_run(const ldpc_code_t *code, const ldpc_sim_params_t *sp, void *wor
     chunk &= ~1023LL;
     float *llr = reinterpret_cast<float *>(workspace);
     uint8_t *cwp = reinterpret_cast<uint8_t *>(workspace) + (size_t)chunk * n * sizeof(float);
-    cudaStream_t s = (cudaStream_t)stream;
     for (long long done = 0; done < sp->n_codewords; done += chunk) {
         const long long cnt = std::min<long long>(chunk, sp->n_codewords - done);
         rc = launch_frontend(code, sp, sp->first_codeword + done, cnt, cwp, llr, s);

@@ -154,12 +154,13 @@ class LinkConfig:
     clamp_value: float = 20.0
     param: float = 1.0
     seed: int = 1234
+    force_unfused: bool = False      # A/B: three-launch chain instead of the single-launch kernel
 
     def to_struct(self, first, count):
         from .decoder import _update_id
         return SimParams(ctypes.sizeof(SimParams), self.ofdm_size, self.qbits, self.agc_mode, self.agc_clip,
                          self.clip_ratio, self.snr_db, self.iters, _update_id(self.update), self.clamp_value,
-                         self.param, 0, self.seed, first, count)
+                         self.param, 1 if self.force_unfused else 0, self.seed, first, count)
 
 
 COUNTER_NAMES = ("uncoded_bit_errors", "info_bit_errors", "frame_errors", "bits", "frames")

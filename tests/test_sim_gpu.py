@@ -126,3 +126,17 @@ def test_sweep_single_rank(wsim):
     r = rates(c, 1944, 972)
     assert r["coded_bler"][0] >= r["coded_bler"][1] >= r["coded_bler"][2]
     assert r["uncoded_ber"][0] > r["uncoded_ber"][2] > 0
+
+
+@pytest.mark.parametrize("N,update,qbits", [(64, "minsum", 0), (64, "sp", 3), (64, "nms", 0), (32, "minsum", 3), (128, "minsum", 0), (256, "minsum", 2)])
+def test_single_launch_simulator_equals_three_launch_chain(wsim, N, update, qbits):
+    """The fused kernel (bits -> encode -> OFDM -> AWGN -> ADC -> LLR -> BP -> counters in ONE launch)
+    must reproduce the three-launch chain's integer counters exactly: same Philox draws, same
+    encoder output, same float bits (both paths compile the link chain without FMA contraction)."""
+    from ldpc_b200.linksim import LinkConfig, sim_run
+    kw = dict(snr_db=2.5, ofdm_size=N, qbits=qbits, agc_mode=1, iters=6, update=update, clamp_value=20.0,
+              param=0.8125 if update == "nms" else 1.0, seed=77)
+    fused = sim_run(wsim, LinkConfig(**kw), 12345, 1000).cpu().numpy()          # 1000: ragged vs the 3-codeword tile
+    chain = sim_run(wsim, LinkConfig(force_unfused=True, **kw), 12345, 1000).cpu().numpy()
+    assert fused.tolist() == chain.tolist()
+    assert fused[4] == 1000 and fused[0] > 0
