@@ -111,6 +111,29 @@ int ldpc_decode(const ldpc_code_t *code, const void *llr, int llr_dtype, int64_t
                 float *prob, float *llr_post, uint8_t *hard, uint8_t *hard_packed,
                 int32_t *syndrome, float *x_out, ldpc_stream_t stream);
 
+/* ldpc_decode_ex - ldpc_decode with the extensible parameter block; adds syndrome-based early
+ * termination (north star; NOT in the reference, whose iteration count is fixed, bp/bp.py:46-47,
+ * so it is off in every parity run).  With early_exit != 0 a codeword is frozen after the first
+ * iteration whose hard decision satisfies every check; its outputs are those of that iteration.
+ * iters_used [B] i32 (nullable) receives the iterations run per codeword.  The f16x2 kernel does
+ * not implement early termination (the fp32 kernel is used). */
+typedef struct {
+    int32_t struct_size;      /* = sizeof(ldpc_decode_params_t) */
+    int32_t llr_dtype;
+    const void *llr;
+    int64_t B;
+    int32_t iters, update;
+    float clamp_value, param;
+    const float *x0;
+    float *prob, *llr_post;
+    uint8_t *hard, *hard_packed;
+    int32_t *syndrome;
+    float *x_out;
+    int32_t early_exit, reserved;
+    int32_t *iters_used;
+} ldpc_decode_params_t;
+int ldpc_decode_ex(const ldpc_code_t *code, const ldpc_decode_params_t *params, ldpc_stream_t stream);
+
 /* ldpc_decode_host - the decode_bits batching loop (ofdm/ofdm_functions.py:131-163) with
  * HOST buffers: chunked, double-buffered H2D copy -> ldpc_decode -> D2H copy on internal
  * streams; synchronous.  llr_host [N,n] of llr_dtype; outputs (each nullable):

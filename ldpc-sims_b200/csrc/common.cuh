@@ -24,6 +24,11 @@ struct DecodeArgs {
     const uint8_t *ref_packed;  // [B,ceil(n/8)] transmitted codeword, MSB-first
     unsigned long long *counters;
     int k_info;
+    // syndrome-based early termination (off in every reference-parity run: the reference has a fixed
+    // iteration count, bp/bp.py:46-47): a codeword whose hard decision satisfies all checks after an
+    // iteration is frozen; iters_used [B] i32 (nullable) receives the iterations actually run
+    int early_exit;
+    int32_t *iters_used;
     void *host_pipe;    // lazily created staging state of ldpc_decode_host
     int precision;      // LDPC_PREC_*
 };

@@ -52,78 +52,106 @@ __global__ void __launch_bounds__(256) decode_generic_kernel(const GenericParams
     for (int i = tid; i < 4 + p.CW; i += T) scratch[i] = 0;
     __syncthreads();
 
-    for (int it = 0; it < a.iters; ++it) {
-        // ---- V -> C ---------------------------------------------------------------------------
+    int *frozen_s = scratch + 4 + p.CW;                                  // [CW] iteration of convergence, 0 = running
+    for (int i = tid; i < p.CW; i += T) frozen_s[i] = 0;
+    __syncthreads();
+    bool finished = false;
+    int it = 0;
+    for (;;) {
+        const bool do_iter = (it < a.iters) && !finished;
+        if (do_iter) {
+            // ---- V -> C -----------------------------------------------------------------------
+            for (int i = tid; i < ncw * n; i += T) {
+                const int cw = i / n, v = i - cw * n;
+                if (a.early_exit && frozen_s[cw]) continue;
+                const int b = __ldg(g.var_ptr + v), d = __ldg(g.var_ptr + v + 1) - b;
+                if (d == 0) continue;
+                float *mrow = msg + cw * p.msg_stride;
+                int slot[MAXDV];
+                float in[MAXDV], out[MAXDV];
+#pragma unroll
+                for (int k = 0; k < MAXDV; ++k)
+                    if (k < d) { slot[k] = __ldg(g.cm_of_vm + b + k); in[k] = mrow[slot[k]]; }
+                var_node<MAXDV, IS_SP>(in, d, llr_s[cw * p.llr_stride + v], out);
+#pragma unroll
+                for (int k = 0; k < MAXDV; ++k)
+                    if (k < d) mrow[slot[k]] = out[k];
+            }
+            __syncthreads();
+            // ---- C -> V -----------------------------------------------------------------------
+            for (int i = tid; i < ncw * m; i += T) {
+                const int cw = i / m, c = i - cw * m;
+                if (a.early_exit && frozen_s[cw]) continue;
+                const int b = __ldg(g.chk_ptr + c), d = __ldg(g.chk_ptr + c + 1) - b;
+                if (d == 0) continue;
+                float *mrow = msg + cw * p.msg_stride + b;
+                float in[MAXDC], out[MAXDC];
+#pragma unroll
+                for (int j = 0; j < MAXDC; ++j)
+                    if (j < d) in[j] = mrow[j];
+                if (IS_SP) check_node_sp<MAXDC>(in, d, a.clampv, out);
+                else check_node_ms<MAXDC>(in, d, a.update, a.clampv, a.param, out);
+#pragma unroll
+                for (int j = 0; j < MAXDC; ++j)
+                    if (j < d) mrow[j] = out[j];
+            }
+            __syncthreads();
+            ++it;
+        }
+        const bool last = !do_iter || it >= a.iters;
+        if (!last && !a.early_exit) continue;
+
+        // ---- marginal, P(bit=1), hard decision (outputs only on the last pass) ---------------------
         for (int i = tid; i < ncw * n; i += T) {
             const int cw = i / n, v = i - cw * n;
+            if (!last && frozen_s[cw]) continue;
             const int b = __ldg(g.var_ptr + v), d = __ldg(g.var_ptr + v + 1) - b;
-            if (d == 0) continue;
-            float *mrow = msg + cw * p.msg_stride;
-            int slot[MAXDV];
-            float in[MAXDV], out[MAXDV];
+            const float *mrow = msg + cw * p.msg_stride;
+            float in[MAXDV];
 #pragma unroll
             for (int k = 0; k < MAXDV; ++k)
-                if (k < d) { slot[k] = __ldg(g.cm_of_vm + b + k); in[k] = mrow[slot[k]]; }
-            var_node<MAXDV, IS_SP>(in, d, llr_s[cw * p.llr_stride + v], out);
-#pragma unroll
-            for (int k = 0; k < MAXDV; ++k)
-                if (k < d) mrow[slot[k]] = out[k];
+                if (k < d) in[k] = mrow[__ldg(g.cm_of_vm + b + k)];
+            const float t = marginal_t<MAXDV>(in, d, llr_s[cw * p.llr_stride + v]);
+            const uint8_t hb = hard_bit(t);                  // np.round(prob): tie 0.5 -> 0
+            hard_s[cw * p.hard_stride + v] = hb | ((llr_s[cw * p.llr_stride + v] > 0.0f) ? 2 : 0);
+            if (last) {
+                const long long o = cw0 * n + i;
+                if (a.prob) a.prob[o] = prob_one(t);
+                if (a.llr_post) a.llr_post[o] = __fmul_rn(-2.0f, t);
+                if (a.hard) a.hard[o] = hb;
+            }
         }
         __syncthreads();
-        // ---- C -> V ---------------------------------------------------------------------------
-        for (int i = tid; i < ncw * m; i += T) {
-            const int cw = i / m, c = i - cw * m;
-            const int b = __ldg(g.chk_ptr + c), d = __ldg(g.chk_ptr + c + 1) - b;
-            if (d == 0) continue;
-            float *mrow = msg + cw * p.msg_stride + b;
-            float in[MAXDC], out[MAXDC];
-#pragma unroll
-            for (int j = 0; j < MAXDC; ++j)
-                if (j < d) in[j] = mrow[j];
-            if (IS_SP) check_node_sp<MAXDC>(in, d, a.clampv, out);
-            else check_node_ms<MAXDC>(in, d, a.update, a.clampv, a.param, out);
-#pragma unroll
-            for (int j = 0; j < MAXDC; ++j)
-                if (j < d) mrow[j] = out[j];
+        // ---- syndrome weight of the hard decision ---------------------------------------------------
+        if (!last || a.syndrome) {
+            for (int i = tid; i < ncw * m; i += T) {
+                const int cw = i / m, c = i - cw * m;
+                if (!last && frozen_s[cw]) continue;
+                unsigned par = 0;
+                for (int e = __ldg(g.chk_ptr + c); e < __ldg(g.chk_ptr + c + 1); ++e)
+                    par ^= hard_s[cw * p.hard_stride + __ldg(g.chk_var + e)] & 1u;
+                if (par) atomicAdd(&scratch[4 + cw], 1);
+            }
+            __syncthreads();
+        }
+        if (last) break;
+        for (int i = tid; i < p.CW; i += T) {
+            if (i < ncw && frozen_s[i] == 0 && scratch[4 + i] == 0) frozen_s[i] = it;
+            scratch[4 + i] = 0;
         }
         __syncthreads();
+        bool all = true;
+        for (int c = 0; c < ncw; ++c) all = all && (frozen_s[c] != 0);
+        finished = all;
     }
-
-    // ---- marginal, P(bit=1), hard decision --------------------------------------------------------
-    for (int i = tid; i < ncw * n; i += T) {
-        const int cw = i / n, v = i - cw * n;
-        const int b = __ldg(g.var_ptr + v), d = __ldg(g.var_ptr + v + 1) - b;
-        const float *mrow = msg + cw * p.msg_stride;
-        float in[MAXDV];
-#pragma unroll
-        for (int k = 0; k < MAXDV; ++k)
-            if (k < d) in[k] = mrow[__ldg(g.cm_of_vm + b + k)];
-        const float t = marginal_t<MAXDV>(in, d, llr_s[cw * p.llr_stride + v]);
-        const float pr = prob_one(t);
-        const uint8_t hb = hard_bit(t);                  // np.round(prob): tie 0.5 -> 0
-        hard_s[cw * p.hard_stride + v] = hb | ((llr_s[cw * p.llr_stride + v] > 0.0f) ? 2 : 0);
-        const long long o = cw0 * n + i;
-        if (a.prob) a.prob[o] = pr;
-        if (a.llr_post) a.llr_post[o] = __fmul_rn(-2.0f, t);
-        if (a.hard) a.hard[o] = hb;
-    }
+    if (a.iters_used)
+        for (int i = tid; i < ncw; i += T) a.iters_used[cw0 + i] = (a.early_exit && frozen_s[i]) ? frozen_s[i] : a.iters;
     if (a.x_out)
         for (int i = tid; i < ncw * E; i += T) {
             const int cw = i / E, e = i - cw * E;
             a.x_out[cw0 * E + i] = msg[cw * p.msg_stride + e];
         }
-    __syncthreads();
-
-    // ---- syndrome weight of the hard decision -----------------------------------------------------
     if (a.syndrome) {
-        for (int i = tid; i < ncw * m; i += T) {
-            const int cw = i / m, c = i - cw * m;
-            unsigned par = 0;
-            for (int e = __ldg(g.chk_ptr + c); e < __ldg(g.chk_ptr + c + 1); ++e)
-                par ^= hard_s[cw * p.hard_stride + __ldg(g.chk_var + e)] & 1u;
-            if (par) atomicAdd(&scratch[4 + cw], 1);
-        }
-        __syncthreads();
         for (int i = tid; i < ncw; i += T) a.syndrome[cw0 + i] = scratch[4 + i];
         __syncthreads();
         for (int i = tid; i < p.CW; i += T) scratch[4 + i] = 0;
@@ -161,7 +189,7 @@ int launch_decode_generic(const GraphTables &g, int max_dv, int max_dc, const De
     const size_t per_cw = sizeof(float) * (p.llr_stride + p.msg_stride) + p.hard_stride;
     const size_t fixed = sizeof(int) * 8 + 64;
     const size_t budget_small = 100 * 1024, budget_max = 227 * 1024;
-    if (per_cw + fixed + 32 * sizeof(int) > budget_max) {
+    if (per_cw + fixed + 64 * sizeof(int) > budget_max) {
         set_error("code too large for shared-memory residency: %zu bytes per codeword", per_cw);
         return LDPC_EUNSUPPORTED;
     }
@@ -172,7 +200,7 @@ int launch_decode_generic(const GraphTables &g, int max_dv, int max_dc, const De
     // do not starve the grid for small batches
     while (CW > 1 && (a.B + CW - 1) / CW < 2 * 148) CW >>= 1;
     p.CW = CW;
-    const size_t smem = CW * per_cw + sizeof(int) * (8 + CW) + 16;
+    const size_t smem = CW * per_cw + sizeof(int) * (8 + 2 * CW) + 16;
     const long long grid = (a.B + CW - 1) / CW;
     if (grid > 0x7fffffffLL) { set_error("batch too large"); return LDPC_EINVAL; }
     if (max_dv <= 4 && max_dc <= 4) return launch_t<4, 4>(p, smem, (int)grid, s);

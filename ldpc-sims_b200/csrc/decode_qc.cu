@@ -33,8 +33,8 @@ namespace ldpc {
 // the (still unused) message region of shared memory; the error counters compare against the
 // transmitted bits kept in shared memory.  One launch takes random bits to BER counts
 // (replaces the per-SNR loop body of evaluate_quantized_snr.py:91-188).
-template <class Code, int CW, int UPD, int SIM>
-__global__ void __launch_bounds__((QcLayout<Code, CW>::THREADS)) decode_qc_kernel(const DecodeArgs a, const LinkParams lp) {
+template <class Code, int CW, int UPD, int SIM, bool EE>
+__global__ void __launch_bounds__((QcLayout<Code, CW>::THREADS), (QcLayout<Code, CW>::MIN_CTAS)) decode_qc_kernel(const DecodeArgs a, const LinkParams lp) {
     using L = QcLayout<Code, CW>;
     constexpr bool IS_SP = (UPD == UPD_SP);
     constexpr int Z = Code::Z, NB = Code::NB, MB = Code::MB, N = L::N;
@@ -218,22 +218,9 @@ __global__ void __launch_bounds__((QcLayout<Code, CW>::THREADS)) decode_qc_kerne
         });
     };
 
-    if (a.iters > 0) {
-        if (active) var_phase(std::true_type{});
-        __syncthreads();
-        if (active) check_phase();
-        __syncthreads();
-    }
-#pragma unroll 1
-    for (int it = 1; it < a.iters; ++it) {
-        if (active) var_phase(std::false_type{});
-        __syncthreads();
-        if (active) check_phase();
-        __syncthreads();
-    }
-
-    // ---- marginal, P(bit=1), hard decision --------------------------------------------------------
-    if (active) {
+    int *frozen_s = scratch + 4 + CW;                                   // [CW] iteration at which a codeword converged, 0 = running
+    // forward declarations of the two tail phases (also used by the early-termination test)
+    auto marginal_phase = [&](const bool final_pass) {
         float tm[NB];
         float tmin = CUDART_INF_F;
         static_for<NB>([&](auto cc) {
@@ -267,38 +254,97 @@ __global__ void __launch_bounds__((QcLayout<Code, CW>::THREADS)) decode_qc_kerne
             if (zv >= Z) zv -= Z;
             uint8_t *hp = hard_s + cw * L::HARD_STRIDE + c * Z + zv;
             *hp = (SIM ? (*hp & 4) : 0) | hb | ((llr[c] > 0.0f) ? 2 : 0);
-            if (a.llr_post) const_cast<float *>(base_post)[c * Z + zv] = __fmul_rn(-2.0f, tm[c]);
-            if (a.prob) a.prob[gbase + c * Z + zv] = prob_one(tm[c]);
-            if (a.hard) a.hard[gbase + c * Z + zv] = hb;
+            if (final_pass) {
+                if (a.llr_post) const_cast<float *>(base_post)[c * Z + zv] = __fmul_rn(-2.0f, tm[c]);
+                if (a.prob) a.prob[gbase + c * Z + zv] = prob_one(tm[c]);
+                if (a.hard) a.hard[gbase + c * Z + zv] = hb;
+            }
         });
-    }
-    __syncthreads();
-
-    // ---- syndrome weight ------------------------------------------------------------------------
-    if (a.syndrome) {
-        if (active) {
-            int w = 0;
-            const uint8_t *h = hard_s + cw * L::HARD_STRIDE;
-            static_for<MB>([&](auto rr) {
-                constexpr int r = decltype(rr)::value;
-                constexpr int D = kQc<Code>.row_deg[r];
-                constexpr int sg = kQc<Code>.sigma[r];
-                int zc = t + sg;
-                if (zc >= Z) zc -= Z;
-                unsigned par = 0;
-                static_for<D>([&](auto jj) {
-                    constexpr int j = decltype(jj)::value;
-                    constexpr int s = kQc<Code>.row_shift[r][j];
-                    constexpr int cbase = kQc<Code>.row_col[r][j] * Z;
-                    int zv = zc + s;
-                    if (zv >= Z) zv -= Z;
-                    par ^= h[cbase + zv] & 1u;
-                });
-                w += (int)par;
+    };
+    auto syndrome_phase = [&]() {                                        // adds this thread's unsatisfied checks
+        int w = 0;
+        const uint8_t *h = hard_s + cw * L::HARD_STRIDE;
+        static_for<MB>([&](auto rr) {
+            constexpr int r = decltype(rr)::value;
+            constexpr int D = kQc<Code>.row_deg[r];
+            constexpr int sg = kQc<Code>.sigma[r];
+            int zc = t + sg;
+            if (zc >= Z) zc -= Z;
+            unsigned par = 0;
+            static_for<D>([&](auto jj) {
+                constexpr int j = decltype(jj)::value;
+                constexpr int s = kQc<Code>.row_shift[r][j];
+                constexpr int cbase = kQc<Code>.row_col[r][j] * Z;
+                int zv = zc + s;
+                if (zv >= Z) zv -= Z;
+                par ^= h[cbase + zv] & 1u;
             });
-            if (w) atomicAdd(&scratch[4 + cw], w);
+            w += (int)par;
+        });
+        if (w) atomicAdd(&scratch[4 + cw], w);
+    };
+    for (int i = tid; i < CW; i += T) frozen_s[i] = 0;                  // (visible after the first barrier below)
+    if constexpr (!EE) {
+        // fixed iteration count (the reference's schedule, bp/bp.py:46-47); first iteration peeled
+        if (a.iters > 0) {
+            if (active) var_phase(std::true_type{});
+            __syncthreads();
+            if (active) check_phase();
+            __syncthreads();
         }
+#pragma unroll 1
+        for (int it = 1; it < a.iters; ++it) {
+            if (active) var_phase(std::false_type{});
+            __syncthreads();
+            if (active) check_phase();
+            __syncthreads();
+        }
+        if (active) marginal_phase(true);
         __syncthreads();
+        if (a.syndrome) {
+            if (active) syndrome_phase();
+            __syncthreads();
+        }
+    } else {
+        // Early termination.  One loop in which every phase appears once (so each lambda is inlined
+        // exactly once): iteration, then marginal + hard decision + syndrome; a codeword is frozen as
+        // soon as its hard decision satisfies every check; the last pass writes the outputs.
+        bool finished = false;
+        int it = 0;
+#pragma unroll 1
+        for (;;) {
+            const bool do_iter = (it < a.iters) && !finished;
+            if (do_iter) {
+                const bool run = active && (it == 0 || frozen_s[cw] == 0);
+                if (it == 0) { if (run) var_phase(std::true_type{}); }
+                else { if (run) var_phase(std::false_type{}); }
+                __syncthreads();
+                if (run) check_phase();
+                __syncthreads();
+                ++it;
+            }
+            const bool last = !do_iter || it >= a.iters;                // no further iteration will run
+            const bool run2 = active && (last || frozen_s[cw] == 0);
+            if (run2) marginal_phase(last);
+            __syncthreads();
+            if (!last || a.syndrome) {
+                if (run2) syndrome_phase();
+                __syncthreads();
+            }
+            if (last) break;
+            if (tid < CW) {
+                if (tid < ncw && frozen_s[tid] == 0 && scratch[4 + tid] == 0) frozen_s[tid] = it;
+                scratch[4 + tid] = 0;
+            }
+            __syncthreads();
+            bool all = true;
+            for (int c = 0; c < ncw; ++c) all = all && (frozen_s[c] != 0);
+            finished = all;
+        }
+    }
+    if (a.iters_used)
+        for (int i = tid; i < ncw; i += T) a.iters_used[cw0 + i] = (EE && frozen_s[i]) ? frozen_s[i] : a.iters;
+    if (a.syndrome) {
         for (int i = tid; i < ncw; i += T) a.syndrome[cw0 + i] = scratch[4 + i];
         __syncthreads();
         for (int i = tid; i < CW; i += T) scratch[4 + i] = 0;
@@ -339,7 +385,7 @@ static int launch_qc_one(const DecodeArgs &a, cudaStream_t s) {
     using L = QcLayout<Code, CW>;
     const long long grid = (a.B + CW - 1) / CW;
     if (grid > 0x7fffffffLL) { set_error("batch too large"); return LDPC_EINVAL; }
-    auto k = decode_qc_kernel<Code, CW, UPD, 0>;
+    auto k = decode_qc_kernel<Code, CW, UPD, 0, false>;
     LDPC_CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::SMEM));
     k<<<(int)grid, L::THREADS, L::SMEM, s>>>(a, LinkParams());
     LDPC_CUDA_TRY(cudaGetLastError());
@@ -353,10 +399,10 @@ static int launch_qc_t(const DecodeArgs &a, cudaStream_t s) {
     if (grid > 0x7fffffffLL) { set_error("batch too large"); return LDPC_EINVAL; }
     void (*k)(const DecodeArgs, const LinkParams) = nullptr;
     switch (a.update) {
-        case UPD_SP: k = decode_qc_kernel<Code, CW, UPD_SP, 0>; break;
-        case UPD_MINSUM: k = decode_qc_kernel<Code, CW, UPD_MINSUM, 0>; break;
-        case UPD_NMS: k = decode_qc_kernel<Code, CW, UPD_NMS, 0>; break;
-        default: k = decode_qc_kernel<Code, CW, UPD_OMS, 0>; break;
+        case UPD_SP: k = a.early_exit ? decode_qc_kernel<Code, CW, UPD_SP, 0, true> : decode_qc_kernel<Code, CW, UPD_SP, 0, false>; break;
+        case UPD_MINSUM: k = a.early_exit ? decode_qc_kernel<Code, CW, UPD_MINSUM, 0, true> : decode_qc_kernel<Code, CW, UPD_MINSUM, 0, false>; break;
+        case UPD_NMS: k = a.early_exit ? decode_qc_kernel<Code, CW, UPD_NMS, 0, true> : decode_qc_kernel<Code, CW, UPD_NMS, 0, false>; break;
+        default: k = a.early_exit ? decode_qc_kernel<Code, CW, UPD_OMS, 0, true> : decode_qc_kernel<Code, CW, UPD_OMS, 0, false>; break;
     }
     LDPC_CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::SMEM));
     k<<<(int)grid, L::THREADS, L::SMEM, s>>>(a, LinkParams());
@@ -369,7 +415,7 @@ int launch_decode_qc(int qc_id, const DecodeArgs &a, cudaStream_t s) {
     switch (qc_id) {
         case 0: {
             static const int cw = [] { const char *e = getenv("LDPC_QC_CW"); return e ? atoi(e) : 3; }();
-            if (a.update == UPD_MINSUM) {
+            if (a.update == UPD_MINSUM && !a.early_exit) {
                 if (cw == 6) return launch_qc_one<Wifi1944R12, 6, UPD_MINSUM>(a, s);
                 if (cw == 1) return launch_qc_one<Wifi1944R12, 1, UPD_MINSUM>(a, s);
             }
@@ -391,7 +437,7 @@ static int launch_sim_one(const DecodeArgs &a, const LinkParams &lp, cudaStream_
     using L = QcLayout<Code, CW>;
     const long long grid = (a.B + CW - 1) / CW;
     if (grid > 0x7fffffffLL) { set_error("batch too large"); return LDPC_EINVAL; }
-    auto k = decode_qc_kernel<Code, CW, UPD, SIM>;
+    auto k = decode_qc_kernel<Code, CW, UPD, SIM, false>;
     LDPC_CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::SMEM));
     k<<<(int)grid, L::THREADS, L::SMEM, s>>>(a, lp);
     LDPC_CUDA_TRY(cudaGetLastError());

@@ -173,7 +173,8 @@ static int check_decode_args(const ldpc_code_t *code, const void *llr, int llr_d
 namespace ldpc {
 int decode_dispatch(const ldpc_code *code, const DecodeArgs &a, cudaStream_t s) {
     if (code->kernel == LDPC_KERNEL_QC && a.x0 == nullptr && a.x_out == nullptr) {
-        if (code->precision == LDPC_PREC_F16X2 && (a.update == LDPC_UPDATE_MINSUM || a.update == LDPC_UPDATE_NMS))
+        if (code->precision == LDPC_PREC_F16X2 && (a.update == LDPC_UPDATE_MINSUM || a.update == LDPC_UPDATE_NMS) &&
+            !a.early_exit && !a.iters_used)
             return launch_decode_qc_h2(code->qc_id, a, s);
         return launch_decode_qc(code->qc_id, a, s);
     }
@@ -194,6 +195,20 @@ int ldpc_decode(const ldpc_code_t *code, const void *llr, int llr_dtype, int64_t
     a.clampv = clamp_value; a.param = param; a.x0 = x0;
     a.prob = prob; a.llr_post = llr_post; a.hard = hard; a.hard_packed = hard_packed;
     a.syndrome = syndrome; a.x_out = x_out;
+    return decode_dispatch(code, a, (cudaStream_t)stream);
+}
+
+int ldpc_decode_ex(const ldpc_code_t *code, const ldpc_decode_params_t *p, ldpc_stream_t stream) {
+    if (!p || p->struct_size != (int32_t)sizeof(ldpc_decode_params_t)) { set_error("ldpc_decode_ex: bad params struct"); return LDPC_EINVAL; }
+    int rc = check_decode_args(code, p->llr, p->llr_dtype, p->B, p->iters, p->update, p->clamp_value);
+    if (rc) return rc;
+    DecodeArgs a;
+    memset(&a, 0, sizeof(a));
+    a.llr = p->llr; a.llr_dtype = p->llr_dtype; a.B = p->B; a.iters = p->iters; a.update = p->update;
+    a.clampv = p->clamp_value; a.param = p->param; a.x0 = p->x0;
+    a.prob = p->prob; a.llr_post = p->llr_post; a.hard = p->hard; a.hard_packed = p->hard_packed;
+    a.syndrome = p->syndrome; a.x_out = p->x_out;
+    a.early_exit = p->early_exit ? 1 : 0; a.iters_used = p->iters_used;
     return decode_dispatch(code, a, (cudaStream_t)stream);
 }
 

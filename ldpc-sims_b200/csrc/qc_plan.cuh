@@ -128,7 +128,8 @@ struct QcLayout {
     static constexpr int MSG_STRIDE = pad_to(NSM * Z);
     static constexpr int HARD_STRIDE = (N + 15) & ~15;
     static constexpr int THREADS = ((CW * Z + 31) / 32) * 32;
-    static constexpr size_t SMEM = sizeof(float) * CW * MSG_STRIDE + (size_t)CW * HARD_STRIDE + sizeof(int) * (8 + CW);
+    static constexpr int MIN_CTAS = THREADS <= 96 ? 5 : (THREADS <= 256 ? 2 : 1);   // register budget: 64K / (THREADS * MIN_CTAS)
+    static constexpr size_t SMEM = sizeof(float) * CW * MSG_STRIDE + (size_t)CW * HARD_STRIDE + sizeof(int) * (8 + 2 * CW);
 };
 
 }  // namespace ldpc

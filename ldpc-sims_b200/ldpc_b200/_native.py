@@ -30,6 +30,15 @@ class LdpcError(RuntimeError):
         self.code = code
 
 
+class DecodeParams(ctypes.Structure):
+    _fields_ = [("struct_size", ctypes.c_int32), ("llr_dtype", ctypes.c_int32), ("llr", ctypes.c_void_p),
+                ("B", ctypes.c_int64), ("iters", ctypes.c_int32), ("update", ctypes.c_int32),
+                ("clamp_value", ctypes.c_float), ("param", ctypes.c_float), ("x0", ctypes.c_void_p),
+                ("prob", ctypes.c_void_p), ("llr_post", ctypes.c_void_p), ("hard", ctypes.c_void_p),
+                ("hard_packed", ctypes.c_void_p), ("syndrome", ctypes.c_void_p), ("x_out", ctypes.c_void_p),
+                ("early_exit", ctypes.c_int32), ("reserved", ctypes.c_int32), ("iters_used", ctypes.c_void_p)]
+
+
 class CodeInfo(ctypes.Structure):
     _fields_ = [(k, ctypes.c_int32) for k in ("m", "n", "E", "max_dc", "max_dv", "kernel", "qc_Z", "reserved")]
 
@@ -65,6 +74,8 @@ def lib():
     L.ldpc_code_set_kernel.argtypes = [vp, i32]
     L.ldpc_decode.restype = ctypes.c_int
     L.ldpc_decode.argtypes = [vp, vp, i32, i64, i32, i32, f32, f32, vp, vp, vp, vp, vp, vp, vp, vp]
+    L.ldpc_decode_ex.restype = ctypes.c_int
+    L.ldpc_decode_ex.argtypes = [vp, ctypes.POINTER(DecodeParams), vp]
     L.ldpc_decode_host.restype = ctypes.c_int
     L.ldpc_decode_host.argtypes = [vp, vp, i32, i64, i32, i32, f32, f32, vp, vp, vp, vp, i64]
     L.ldpc_count_errors.restype = ctypes.c_int

@@ -82,9 +82,10 @@ class LdpcCode:
         return (self.n + 7) // 8
 
     def decode(self, llr, iterations, clamp_value, update="sp", param=1.0, x0=None,
-               want=("prob", "hard"), stream=None):
+               want=("prob", "hard"), stream=None, early_exit=False):
         """llr: CUDA tensor [B,n] (f32/f64/f16), log(P1/P0).  Returns a dict of CUDA tensors
-        for the names in `want`: prob, llr_post, hard, hard_packed, syndrome, x."""
+        for the names in `want`: prob, llr_post, hard, hard_packed, syndrome, x, iters_used.
+        early_exit=True freezes a codeword once its hard decision satisfies every check."""
         if not llr.is_cuda:
             raise ValueError("llr must be a CUDA tensor (no CPU fallback); use decode_host for numpy input")
         if llr.dim() != 2 or llr.shape[1] != self.n:
@@ -102,18 +103,26 @@ class LdpcCode:
         packed = mk((B, self.packed_bytes), torch.uint8) if "hard_packed" in want else None
         synd = mk((B,), torch.int32) if "syndrome" in want else None
         xo = mk((B, self.E), torch.float32) if "x" in want else None
+        used = mk((B,), torch.int32) if "iters_used" in want else None
         if x0 is not None:
             if tuple(x0.shape) != (B, self.E):
                 raise ValueError(f"x0 must be [B,{self.E}]")
             x0 = x0.to(device=dev, dtype=torch.float32).contiguous()
         with torch.cuda.device(dev):
             s = torch.cuda.current_stream(dev).cuda_stream if stream is None else stream
-            N.check(N.lib().ldpc_decode(
-                self._h, _ptr(llr), _DTYPES[llr.dtype], B, int(iterations), _update_id(update),
-                float(clamp_value), float(param), _ptr(x0), _ptr(prob), _ptr(post), _ptr(hard),
-                _ptr(packed), _ptr(synd), _ptr(xo), ctypes.c_void_p(s)))
+            if early_exit or used is not None:
+                dp = N.DecodeParams(ctypes.sizeof(N.DecodeParams), _DTYPES[llr.dtype], llr.data_ptr(), B, int(iterations),
+                                    _update_id(update), float(clamp_value), float(param),
+                                    *[None if v is None else v.data_ptr() for v in (x0, prob, post, hard, packed, synd, xo)],
+                                    1 if early_exit else 0, 0, None if used is None else used.data_ptr())
+                N.check(N.lib().ldpc_decode_ex(self._h, ctypes.byref(dp), ctypes.c_void_p(s)))
+            else:
+                N.check(N.lib().ldpc_decode(
+                    self._h, _ptr(llr), _DTYPES[llr.dtype], B, int(iterations), _update_id(update),
+                    float(clamp_value), float(param), _ptr(x0), _ptr(prob), _ptr(post), _ptr(hard),
+                    _ptr(packed), _ptr(synd), _ptr(xo), ctypes.c_void_p(s)))
         for k, v in (("prob", prob), ("llr_post", post), ("hard", hard), ("hard_packed", packed),
-                     ("syndrome", synd), ("x", xo)):
+                     ("syndrome", synd), ("x", xo), ("iters_used", used)):
             if v is not None:
                 out[k] = v
         return out

@@ -112,7 +112,7 @@ def _two_atanh(p):
 
 
 def bp_decode(H, llr, iterations, clamp_value, update="sp", x0=None, alpha=1.0, beta=0.0,
-              graph=None, trace=False):
+              graph=None, trace=False, early_exit=False):
     """Decode a batch.  llr: [B,n] (log P1/P0, the callers' convention, ofdm_functions.py:72).
 
     Returns dict with
@@ -121,7 +121,12 @@ def bp_decode(H, llr, iterations, clamp_value, update="sp", x0=None, alpha=1.0, 
       prob   [B,n] f32  P(bit=1) = 1 - sigmoid(t)           (bp.py:51)
       hard   [B,n] u8   np.round(prob)  (ties -> 0)         (ofdm_functions.py:161)
       syndrome [B] i32  number of unsatisfied checks of `hard`
+    early_exit (NOT in the reference, bp.py:46-47 runs a fixed count): after every iteration but
+    the last, rows whose hard decision satisfies every check are frozen (their messages stop
+    changing); out["iters_used"] [B] i32 is the number of iterations each row ran.
     """
+    if early_exit:
+        return _bp_decode_early_exit(H, llr, iterations, clamp_value, update, alpha, beta, graph)
     g = graph or Graph(H)
     upd = _UPDATE_IDS[update] if isinstance(update, str) else int(update)
     llr = np.ascontiguousarray(llr, dtype=F32)
@@ -192,6 +197,27 @@ def bp_decode(H, llr, iterations, clamp_value, update="sp", x0=None, alpha=1.0, 
     out = dict(x=x, t=t, prob=prob, hard=hard, syndrome=synd)
     if trace:
         out["trace"] = traces
+    return out
+
+
+def _bp_decode_early_exit(H, llr, iterations, clamp_value, update, alpha, beta, graph):
+    g = graph or Graph(H)
+    llr = np.ascontiguousarray(llr, dtype=F32)
+    B = llr.shape[0]
+    x = np.zeros((B, g.E), F32)
+    used = np.full(B, int(iterations), np.int32)
+    running = np.arange(B)
+    for it in range(1, int(iterations) + 1):
+        if running.size == 0:
+            break
+        o = bp_decode(H, llr[running], 1, clamp_value, update=update, x0=x[running], alpha=alpha, beta=beta, graph=g)
+        x[running] = o["x"]
+        if it < iterations:
+            done = o["syndrome"] == 0
+            used[running[done]] = it
+            running = running[~done]
+    out = bp_decode(H, llr, 0, clamp_value, update=update, x0=x, alpha=alpha, beta=beta, graph=g)   # marginal of the frozen messages
+    out["iters_used"] = used
     return out
 
 

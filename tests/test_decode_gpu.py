@@ -264,3 +264,35 @@ def test_f16x2_fast_path_bit_exact_vs_its_oracle(update, param, B):
     assert abs(int((f["hard"] != c).sum()) - int((o["hard"] != c).sum())) <= max(8, 0.02 * int((f["hard"] != c).sum()))
     with pytest.raises(Exception):
         LdpcCode(peg_64_32()[0]).set_precision("f16")                     # generic kernel: fp32 only
+
+
+def test_early_termination_matches_oracle(wcode, wcode_generic, dcode):
+    """Syndrome-based early exit (not in the reference; off in every parity run): frozen
+    codewords keep the outputs of the iteration that converged; iters_used is exact."""
+    qc = ieee80211n_1944_r12()
+    rng = np.random.RandomState(31)
+    B = 100
+    c = qc.encode(rng.randint(0, 2, (B, qc.k)).astype(np.uint8))
+    sigma = 0.72
+    llr = (-2.0 * ((1.0 - 2.0 * c) + sigma * rng.randn(B, qc.n)) / sigma ** 2).astype(np.float32)
+    llr[7] *= 0.05                                                        # one codeword that never converges
+    a = O.bp_decode(qc.H, llr, 10, 20, update="minsum", early_exit=True)
+    assert 1 < a["iters_used"].min() < a["iters_used"].max() == 10
+    for code in (wcode, wcode_generic):
+        o = code.decode(torch.as_tensor(llr).cuda(), 10, 20, update="minsum", early_exit=True,
+                        want=("llr_post", "hard", "syndrome", "iters_used"))
+        o = {k: v.cpu().numpy() for k, v in o.items()}
+        assert np.array_equal(o["iters_used"], a["iters_used"])
+        assert np.array_equal(o["llr_post"], -2.0 * a["t"])
+        assert np.array_equal(o["hard"], a["hard"]) and np.array_equal(o["syndrome"], a["syndrome"])
+    # without early exit iters_used is the fixed count and results equal the plain call
+    p = wcode.decode(torch.as_tensor(llr).cuda(), 10, 20, update="minsum", want=("hard", "iters_used"))
+    q = wcode.decode(torch.as_tensor(llr).cuda(), 10, 20, update="minsum", want=("hard",))
+    assert (p["iters_used"] == 10).all() and torch.equal(p["hard"], q["hard"])
+    # default code, sum-product, generic kernel
+    H = peg_64_32()[0]
+    l2 = (rng.randn(300, 64) * 3 + 1.0).astype(np.float32)
+    a2 = O.bp_decode(H, l2, 8, 20, early_exit=True)
+    o2 = dcode.decode(torch.as_tensor(l2).cuda(), 8, 20, early_exit=True, want=("hard", "iters_used", "syndrome"))
+    assert np.array_equal(o2["iters_used"].cpu().numpy(), a2["iters_used"])
+    assert np.array_equal(o2["hard"].cpu().numpy(), a2["hard"])
