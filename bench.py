@@ -252,9 +252,9 @@ def main():
     # n_sm blocks exchanged through shared memory (the other n_loc blocks and the LLRs are registers)
     smem_bytes_per_update = 4 * n_sm * 81 * 4 / (2 * E_CODE) if n_sm else (4 * E_CODE + N_CODE) * 4 / (2 * E_CODE)
     smem_peak = 148 * 128 * sm_mhz * 1e6 / smem_bytes_per_update
-    # issue ceiling of the instruction stream: 843 SASS instructions per thread-iteration
+    # issue ceiling of the instruction stream: 739 SASS instructions per thread-iteration
     # (profiles/r01_sass_loop.txt), thr_cta/cw_cta thread slots per codeword, 2*E updates per iteration
-    lane_instr_per_update = 843 * (thr_cta / max(cw_cta, 1)) / (2 * E_CODE) if n_sm else None
+    lane_instr_per_update = 739 * (thr_cta / max(cw_cta, 1)) / (2 * E_CODE) if n_sm else None
     issue_peak = 148 * 4 * 32 * sm_mhz * 1e6 / lane_instr_per_update if lane_instr_per_update else None
     out = {
         "metric": METRIC, "value": value, "unit": "Gbit/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
@@ -269,8 +269,8 @@ def main():
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                      "frac": achieved / hbm_peak,
                      # dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture of this launch
-                     # shape (profiles/r01_decode_qc_ncu_summary.txt): 15 752.5 B per codeword
-                     "traffic": (15752.5 * B / 1e9) if (code.kernel and a.update != "sp") else None, "traffic_unit": "GB per launch",
+                     # shape (profiles/r01_decode_qc_ncu_summary.txt): 15 756 B per codeword
+                     "traffic": (15756.0 * B / 1e9) if (code.kernel and a.update != "sp") else None, "traffic_unit": "GB per launch",
                      "algorithmic_bytes_per_launch_gb": alg_bytes / 1e9, "peak_source": peak_src,
                      "note": "decoder is shared-memory/issue bound, not HBM bound: see roofline_decoder"},
         "roofline_decoder": {"bound": "issue" if (issue_peak and issue_peak < smem_peak) else "smem",
