@@ -135,13 +135,27 @@ __global__ void __launch_bounds__((QcLayout<Code, CW>::THREADS), (QcLayout<Code,
         {
             const LinkConsts kc(lp, SIM);
             const int lane = tid & 31, nsym = N / 2;
-            for (int o = tid >> 5; o < ncw * lp.n_ofdm_per_cw; o += T >> 5) {
-                const int c = o / lp.n_ofdm_per_cw, os = o - c * lp.n_ofdm_per_cw;
-                const uint8_t *brow = hard_s + c * L::HARD_STRIDE;
-                float *orow = stage + c * N;
-                ofdm_symbol_llr<(SIM > 0 ? SIM : 32)>(lane, os, nsym, (unsigned long long)(lp.cw_first + cw0 + c), lp, kc, tw,
-                                                      [&](int i) { return (int)((brow[i] >> 2) & 1); },
-                                                      [&](int sidx, float l0, float l1) { *reinterpret_cast<float2 *>(orow + 2 * sidx) = make_float2(l0, l1); });
+            constexpr int S = 1;                                         // OFDM symbols in flight per warp (2 measured no faster)
+            const int total = ncw * lp.n_ofdm_per_cw;
+            for (int o0 = (tid >> 5) * S; o0 < total; o0 += (T >> 5) * S) {
+                int osv[S];
+                unsigned long long gcw[S];
+                bool valid[S];
+                const uint8_t *brow[S];
+                float *orow[S];
+#pragma unroll
+                for (int q = 0; q < S; ++q) {
+                    const int o = o0 + q;
+                    valid[q] = o < total;
+                    const int c = valid[q] ? o / lp.n_ofdm_per_cw : 0;
+                    osv[q] = valid[q] ? o - c * lp.n_ofdm_per_cw : 0;
+                    gcw[q] = (unsigned long long)(lp.cw_first + cw0 + c);
+                    brow[q] = hard_s + c * L::HARD_STRIDE;
+                    orow[q] = stage + c * N;
+                }
+                ofdm_symbols_llr<(SIM > 0 ? SIM : 32), S>(lane, osv, gcw, valid, nsym, lp, kc, tw,
+                                                          [&](int q, int i) { return (int)((brow[q][i] >> 2) & 1); },
+                                                          [&](int q, int sidx, float l0, float l1) { *reinterpret_cast<float2 *>(orow[q] + 2 * sidx) = make_float2(l0, l1); });
             }
         }
         __syncthreads();

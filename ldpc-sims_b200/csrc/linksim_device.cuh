@@ -46,39 +46,71 @@ __device__ __forceinline__ void fill_twiddles_f(cplx<T> *tw, int N) {
     }
 }
 
-// One warp, one OFDM symbol `os` of global codeword `gcw`.  bit(i) -> 0/1 code bit i of that
-// codeword; out(sidx, llr_b0, llr_b1) receives the LLR pair of QPSK symbol sidx < nsym.
-template <int N, class BitFn, class OutFn>
-__device__ __forceinline__ void ofdm_symbol_llr(int lane, int os, int nsym, unsigned long long gcw, const LinkParams &p,
-                                                const LinkConsts &k, const cplx<float> *tw, BitFn bit, OutFn out) {
+// One warp, S independent OFDM symbols at once (the S dependency chains of shuffles interleave and
+// hide each other's latency).  Symbol slot s: OFDM symbol os[s] of global codeword gcw[s];
+// valid[s] = false skips its output.  bit(s, i) -> 0/1 code bit i of that codeword;
+// out(s, sidx, llr_b0, llr_b1) receives the LLR pair of QPSK symbol sidx < nsym.
+// Per-symbol arithmetic does not depend on S.
+template <int N, int S, class BitFn, class OutFn>
+__device__ __forceinline__ void ofdm_symbols_llr(int lane, const int (&os)[S], const unsigned long long (&gcw)[S],
+                                                 const bool (&valid)[S], int nsym, const LinkParams &p, const LinkConsts &k,
+                                                 const cplx<float> *tw, BitFn bit, OutFn out) {
     constexpr int P = N / 32, LOGN = ilog2(N);
     const Quantizer<float> quant(k.levels, k.clip);
     const Philox rng(p.seed);
-    cplx<float> x[P];
+    cplx<float> x[S][P];
 #pragma unroll
-    for (int r = 0; r < P; ++r) {                         // QPSK, null subcarriers past the codeword
-        const int sidx = os * N + r * 32 + lane;
-        if (sidx < nsym) x[r] = {k.a * (float)(1 - 2 * bit(2 * sidx)), k.a * (float)(1 - 2 * bit(2 * sidx + 1))};
-        else x[r] = {0.0f, 0.0f};
-    }
-    warp_fft<N, float, true>(x, lane, tw, k.scale);       // time sample t = bitrev(r*32+lane)
+    for (int s = 0; s < S; ++s)
 #pragma unroll
-    for (int r = 0; r < P; ++r) {
-        const int t = bitrev(r * 32 + lane, LOGN);
-        uint32_t rnd[4];
-        rng((uint32_t)gcw, (uint32_t)(gcw >> 32), RNG_NOISE, (uint32_t)(os * N + t), rnd);
-        float z0, z1;
-        box_muller<float>(rnd[0], rnd[1], z0, z1);
-        float re = x[r].re + k.nstd * z0, im = x[r].im + k.nstd * z1;
-        if (p.qbits > 0) { re = quant(k.factor * re) / k.factor; im = quant(k.factor * im) / k.factor; }
-        x[r] = {re, im};
-    }
-    warp_fft_dit<N, float, false>(x, lane, tw, k.scale);  // back to natural subcarrier order
+        for (int r = 0; r < P; ++r) {                     // QPSK, null subcarriers past the codeword
+            const int sidx = os[s] * N + r * 32 + lane;
+            if (valid[s] && sidx < nsym) x[s][r] = {k.a * (float)(1 - 2 * bit(s, 2 * sidx)), k.a * (float)(1 - 2 * bit(s, 2 * sidx + 1))};
+            else x[s][r] = {0.0f, 0.0f};
+        }
 #pragma unroll
-    for (int r = 0; r < P; ++r) {
-        const int sidx = os * N + r * 32 + lane;
-        if (sidx < nsym) out(sidx, qpsk_llr<float>(x[r].re, k.a, k.two_np), qpsk_llr<float>(x[r].im, k.a, k.two_np));
+    for (int s = 0; s < S; ++s) warp_fft<N, float, true>(x[s], lane, tw, k.scale);   // time sample t = bitrev(r*32+lane)
+    // AWGN: one Philox block serves the two time samples 2j, 2j+1 (counter = j, words {0,1} / {2,3}).
+    // With i = r*32 + lane the sample index t = bitrev(i) has bit 0 = bit LOGN-1 of i, so for N >= 64
+    // registers r and r + P/2 of a lane hold exactly such a pair and share one Philox call.
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+        if constexpr (P >= 2) {
+#pragma unroll
+            for (int r = 0; r < P / 2; ++r) {
+                const int t0 = bitrev(r * 32 + lane, LOGN);                   // even
+                uint32_t rnd[4];
+                rng((uint32_t)gcw[s], (uint32_t)(gcw[s] >> 32), RNG_NOISE, (uint32_t)((os[s] * N + t0) >> 1), rnd);
+                float z[4];
+                box_muller<float>(rnd[0], rnd[1], z[0], z[1]);
+                box_muller<float>(rnd[2], rnd[3], z[2], z[3]);
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int rr = r + h * (P / 2);
+                    float re = x[s][rr].re + k.nstd * z[2 * h], im = x[s][rr].im + k.nstd * z[2 * h + 1];
+                    if (p.qbits > 0) { re = quant(k.factor * re) / k.factor; im = quant(k.factor * im) / k.factor; }
+                    x[s][rr] = {re, im};
+                }
+            }
+        } else {
+            const int t = bitrev(lane, LOGN);
+            uint32_t rnd[4];
+            rng((uint32_t)gcw[s], (uint32_t)(gcw[s] >> 32), RNG_NOISE, (uint32_t)((os[s] * N + t) >> 1), rnd);
+            float z0, z1;
+            box_muller<float>(rnd[2 * (t & 1)], rnd[2 * (t & 1) + 1], z0, z1);
+            float re = x[s][0].re + k.nstd * z0, im = x[s][0].im + k.nstd * z1;
+            if (p.qbits > 0) { re = quant(k.factor * re) / k.factor; im = quant(k.factor * im) / k.factor; }
+            x[s][0] = {re, im};
+        }
     }
+#pragma unroll
+    for (int s = 0; s < S; ++s) warp_fft_dit<N, float, false>(x[s], lane, tw, k.scale);  // back to natural subcarrier order
+#pragma unroll
+    for (int s = 0; s < S; ++s)
+#pragma unroll
+        for (int r = 0; r < P; ++r) {
+            const int sidx = os[s] * N + r * 32 + lane;
+            if (valid[s] && sidx < nsym) out(s, sidx, qpsk_llr<float>(x[s][r].re, k.a, k.two_np), qpsk_llr<float>(x[s][r].im, k.a, k.two_np));
+        }
 }
 
 // Philox information words of one codeword: word w (bit j = information bit 32 w + j) comes

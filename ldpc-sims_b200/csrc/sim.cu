@@ -64,14 +64,26 @@ __global__ void __launch_bounds__(256) linksim_llr_kernel(const uint8_t *cw_pack
     const long long total = ncw * p.n_ofdm_per_cw;
     const int nby = (p.n + 7) / 8, nsym = p.n / 2;
     const LinkConsts k(p, N);
-    for (long long o = warp; o < total; o += nwarps) {
-        const long long c = o / p.n_ofdm_per_cw;
-        const int os = (int)(o - c * p.n_ofdm_per_cw);
-        const uint8_t *row = cw_packed + c * nby;
-        float *orow = llr + c * p.n;
-        ofdm_symbol_llr<N>(lane, os, nsym, (unsigned long long)(p.cw_first + c), p, k, tw,
-                           [&](int i) { return cw_bit(row, i); },
-                           [&](int sidx, float l0, float l1) { *reinterpret_cast<float2 *>(orow + 2 * sidx) = make_float2(l0, l1); });
+    constexpr int S = 1;                                     // OFDM symbols in flight per warp (2 measured no faster)
+    for (long long o0 = warp * S; o0 < total; o0 += nwarps * S) {
+        int os[S];
+        unsigned long long gcw[S];
+        bool valid[S];
+        const uint8_t *row[S];
+        float *orow[S];
+#pragma unroll
+        for (int s = 0; s < S; ++s) {
+            const long long o = o0 + s;
+            valid[s] = o < total;
+            const long long c = valid[s] ? o / p.n_ofdm_per_cw : 0;
+            os[s] = valid[s] ? (int)(o - c * p.n_ofdm_per_cw) : 0;
+            gcw[s] = (unsigned long long)(p.cw_first + c);
+            row[s] = cw_packed + c * nby;
+            orow[s] = llr + c * p.n;
+        }
+        ofdm_symbols_llr<N, S>(lane, os, gcw, valid, nsym, p, k, tw,
+                               [&](int s, int i) { return cw_bit(row[s], i); },
+                               [&](int s, int sidx, float l0, float l1) { *reinterpret_cast<float2 *>(orow[s] + 2 * sidx) = make_float2(l0, l1); });
     }
 }
 
