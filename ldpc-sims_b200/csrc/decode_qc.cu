@@ -46,14 +46,18 @@ __global__ void __launch_bounds__((QcLayout<Code, CW>::THREADS), (QcLayout<Code,
     const int tid = threadIdx.x, T = blockDim.x;
     const long long cw0 = (long long)blockIdx.x * CW;
     const int ncw = (int)min((long long)CW, a.B - cw0);
-    const int cw = tid / Z, t = tid - cw * Z;
-    const bool active = cw < ncw;            // also false for the padding threads (cw >= CW)
+    // codewords interleaved by lane: thread = t * CW + cw, message slot (blk, z) of codeword cw at
+    // (blk * Z + z) * CW + cw.  A block's CW rings form ONE ring of CW * Z words, so the linear access
+    // of the check phase is conflict-free and the rotated window of the variable phase wraps once per
+    // block and CTA (one two-wavefront warp) instead of once per block and codeword.
+    const int t = tid / CW, cw = tid - t * CW;
+    const bool active = cw < ncw && t < Z;   // false for the padding threads (t >= Z) too
     for (int i = tid; i < 4 + CW; i += T) scratch[i] = 0;
 
-    float *const msg = msg_s + (active ? cw : 0) * L::MSG_STRIDE;
-    // rotated window bases: slot (blk, (t - s') mod Z) = (t < s' ? hi : lo)[blk*Z - s']
-    float *const lo = msg + t;
-    float *const hi = msg + t + Z;
+    float *const msg = msg_s + (active ? tid : 0);                         // slot (blk, t): msg[blk * Z * CW]
+    // rotated window bases: slot (blk, (t - s') mod Z) = (t < s' ? hi : lo)[(blk*Z - s') * CW]
+    float *const lo = msg;
+    float *const hi = msg + Z * CW;
 
     // ---- channel LLRs of this thread's NB variables live in registers for the whole decode ----------
     float llr[NB];
@@ -190,7 +194,7 @@ __global__ void __launch_bounds__((QcLayout<Code, CW>::THREADS), (QcLayout<Code,
                         in[k] = FIRST ? 0.0f : loc[slot];
                     } else {
                         constexpr int s = kQc<Code>.col_eff[c][k];
-                        constexpr int off = slot * Z - s;
+                        constexpr int off = (slot * Z - s) * CW;
                         ptr[k] = (t < s ? hi : lo) + off;
                         in[k] = FIRST ? 0.0f : *ptr[k];
                     }
@@ -217,7 +221,7 @@ __global__ void __launch_bounds__((QcLayout<Code, CW>::THREADS), (QcLayout<Code,
                     constexpr bool is_loc = kQc<Code>.row_loc[r][j];
                     constexpr int slot = kQc<Code>.row_slot[r][j];
                     if constexpr (is_loc) in[j] = loc[slot];
-                    else in[j] = msg[slot * Z + t];
+                    else in[j] = msg[slot * Z * CW];
                 });
                 if constexpr (IS_SP) check_node_sp<D>(in, D, a.clampv, out);
                 else check_node_ms_ct<D, UPD>(in, a.clampv, a.param, out);
@@ -226,7 +230,7 @@ __global__ void __launch_bounds__((QcLayout<Code, CW>::THREADS), (QcLayout<Code,
                     constexpr bool is_loc = kQc<Code>.row_loc[r][j];
                     constexpr int slot = kQc<Code>.row_slot[r][j];
                     if constexpr (is_loc) loc[slot] = out[j];
-                    else msg[slot * Z + t] = out[j];
+                    else msg[slot * Z * CW] = out[j];
                 });
             }
         });
@@ -248,7 +252,7 @@ __global__ void __launch_bounds__((QcLayout<Code, CW>::THREADS), (QcLayout<Code,
                 if constexpr (is_loc) in[k] = (a.iters == 0) ? 0.0f : loc[slot];
                 else {
                     constexpr int s = kQc<Code>.col_eff[c][k];
-                    constexpr int off = slot * Z - s;
+                    constexpr int off = (slot * Z - s) * CW;
                     in[k] = (a.iters == 0) ? 0.0f : ((t < s ? hi : lo) + off)[0];
                 }
             });

@@ -84,14 +84,14 @@ __global__ void __launch_bounds__((QcLayout<Code, CW>::THREADS)) decode_qc_h2_ke
     const int tid = threadIdx.x, T = blockDim.x;
     const long long cw0 = (long long)blockIdx.x * (2 * CW);
     const int ncw = (int)min((long long)(2 * CW), a.B - cw0);            // codewords in this tile
-    const int pr = tid / Z, t = tid - pr * Z;                             // pair slot, lane
-    const bool active = 2 * pr < ncw;                                     // false for padding threads too
+    const int t = tid / CW, pr = tid - t * CW;                            // lane, pair slot (pairs interleaved by lane, see decode_qc.cu)
+    const bool active = 2 * pr < ncw && t < Z;                            // false for padding threads too
     const bool second = 2 * pr + 1 < ncw;                                 // .y lane holds a real codeword
     for (int i = tid; i < 4 + 2 * CW; i += T) scratch[i] = 0;
 
-    __half2 *const msg = msg_s + (active ? pr : 0) * L::MSG_STRIDE;
-    __half2 *const lo = msg + t;
-    __half2 *const hi = msg + t + Z;
+    __half2 *const msg = msg_s + (active ? tid : 0);
+    __half2 *const lo = msg;
+    __half2 *const hi = msg + Z * CW;
 
     __half2 llr[NB];
     __half2 loc[L::NLOC > 0 ? L::NLOC : 1];
@@ -138,7 +138,7 @@ __global__ void __launch_bounds__((QcLayout<Code, CW>::THREADS)) decode_qc_h2_ke
                         in[k] = FIRST ? __float2half2_rn(0.0f) : loc[slot];
                     } else {
                         constexpr int sh = kQc<Code>.col_eff[c][k];
-                        constexpr int off = slot * Z - sh;
+                        constexpr int off = (slot * Z - sh) * CW;
                         ptr[k] = (t < sh ? hi : lo) + off;
                         in[k] = FIRST ? __float2half2_rn(0.0f) : *ptr[k];
                     }
@@ -168,7 +168,7 @@ __global__ void __launch_bounds__((QcLayout<Code, CW>::THREADS)) decode_qc_h2_ke
                     constexpr int slot = kQc<Code>.row_slot[r][j];
                     __half2 v;
                     if constexpr (is_loc) v = loc[slot];
-                    else v = msg[slot * Z + t];
+                    else v = msg[slot * Z * CW];
                     in[j] = (UPD == UPD_NMS) ? __hmul2_rn(alpha_h, v) : v;
                 });
                 h2_boxmin_others_clamped<D>(in, clamp_h, out);
@@ -177,7 +177,7 @@ __global__ void __launch_bounds__((QcLayout<Code, CW>::THREADS)) decode_qc_h2_ke
                     constexpr bool is_loc = kQc<Code>.row_loc[r][j];
                     constexpr int slot = kQc<Code>.row_slot[r][j];
                     if constexpr (is_loc) loc[slot] = out[j];
-                    else msg[slot * Z + t] = out[j];
+                    else msg[slot * Z * CW] = out[j];
                 });
             }
         });
@@ -213,7 +213,7 @@ __global__ void __launch_bounds__((QcLayout<Code, CW>::THREADS)) decode_qc_h2_ke
                 if constexpr (is_loc) v = loc[slot];
                 else {
                     constexpr int sh = kQc<Code>.col_eff[c][k];
-                    constexpr int off = slot * Z - sh;
+                    constexpr int off = (slot * Z - sh) * CW;
                     v = ((t < sh ? hi : lo) + off)[0];
                 }
                 if (a.iters == 0) v = __float2half2_rn(0.0f);

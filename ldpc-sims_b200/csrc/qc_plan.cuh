@@ -123,9 +123,7 @@ struct QcLayout {
     static constexpr int N = Code::NB * Z;
     static constexpr int M = Code::MB * Z;
     static constexpr int NLOC = kQc<Code>.n_local, NSM = kQc<Code>.n_smem;
-    // codeword strides == Z (mod 32): lanes of two codewords sharing a warp stay on distinct banks
-    static constexpr int pad_to(int v) { return v + ((Z % 32) - (v % 32) + 32) % 32; }
-    static constexpr int MSG_STRIDE = pad_to(NSM * Z);
+    static constexpr int MSG_STRIDE = NSM * Z;       // message words per codeword (codewords interleaved by lane)
     static constexpr int HARD_STRIDE = (N + 15) & ~15;
     static constexpr int THREADS = ((CW * Z + 31) / 32) * 32;
     static constexpr int MIN_CTAS = THREADS <= 96 ? 5 : (THREADS <= 256 ? 2 : 1);   // register budget: 64K / (THREADS * MIN_CTAS)
