@@ -40,7 +40,7 @@ __global__ void __launch_bounds__((QcLayout<Code, CW>::THREADS), (QcLayout<Code,
     constexpr int Z = Code::Z, NB = Code::NB, MB = Code::MB, N = L::N;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float *msg_s = reinterpret_cast<float *>(smem_raw);
-    uint8_t *hard_s = reinterpret_cast<uint8_t *>(msg_s + CW * L::MSG_STRIDE);
+    uint8_t *hard_s = smem_raw + L::MSG_BYTES;
     int *scratch = reinterpret_cast<int *>(hard_s + CW * L::HARD_STRIDE);       // [4 + CW]
 
     const int tid = threadIdx.x, T = blockDim.x;
@@ -238,6 +238,8 @@ __global__ void __launch_bounds__((QcLayout<Code, CW>::THREADS), (QcLayout<Code,
 
     int *frozen_s = scratch + 4 + CW;                                   // [CW] iteration at which a codeword converged, 0 = running
     // forward declarations of the two tail phases (also used by the early-termination test)
+    // Marginal, hard decision, outputs.  The output pointers are tested ONCE (uniform branches around
+    // compact store loops); an iteration count of 0 is handled by zero-filling the messages up front.
     auto marginal_phase = [&](const bool final_pass) {
         float tm[NB];
         float tmin = CUDART_INF_F;
@@ -249,11 +251,11 @@ __global__ void __launch_bounds__((QcLayout<Code, CW>::THREADS), (QcLayout<Code,
                 constexpr int k = decltype(kk)::value;
                 constexpr bool is_loc = kQc<Code>.col_loc[c][k];
                 constexpr int slot = kQc<Code>.col_slot[c][k];
-                if constexpr (is_loc) in[k] = (a.iters == 0) ? 0.0f : loc[slot];
+                if constexpr (is_loc) in[k] = loc[slot];
                 else {
                     constexpr int s = kQc<Code>.col_eff[c][k];
                     constexpr int off = (slot * Z - s) * CW;
-                    in[k] = (a.iters == 0) ? 0.0f : ((t < s ? hi : lo) + off)[0];
+                    in[k] = ((t < s ? hi : lo) + off)[0];
                 }
             });
             tm[c] = marginal_t<(D > 0 ? D : 1)>(in, D, llr[c]);
@@ -261,23 +263,56 @@ __global__ void __launch_bounds__((QcLayout<Code, CW>::THREADS), (QcLayout<Code,
         });
         // hard decision = (t < 0) outside the tie band; one rarely-taken branch per thread
         // re-evaluates the band cases the way the reference rounds them (node_math.cuh: hard_bit)
-        const bool band = !(tmin > 1e-5f);
-        const float *base_post = a.llr_post ? a.llr_post + gbase : nullptr;
+        unsigned hbits = 0;
+        static_for<NB>([&](auto cc) {
+            constexpr int c = decltype(cc)::value;
+            hbits |= (tm[c] < 0.0f ? 1u : 0u) << c;
+        });
+        if (!(tmin > 1e-5f)) {
+            hbits = 0;
+            static_for<NB>([&](auto cc) {
+                constexpr int c = decltype(cc)::value;
+                hbits |= (unsigned)hard_bit(tm[c]) << c;
+            });
+        }
+        uint8_t *const hrow = hard_s + cw * L::HARD_STRIDE;
         static_for<NB>([&](auto cc) {
             constexpr int c = decltype(cc)::value;
             constexpr int rho = kQc<Code>.rho[c];
-            uint8_t hb = tm[c] < 0.0f;
-            if (band) hb = hard_bit(tm[c]);
             int zv = t + rho;
             if (zv >= Z) zv -= Z;
-            uint8_t *hp = hard_s + cw * L::HARD_STRIDE + c * Z + zv;
-            *hp = (SIM ? (*hp & 4) : 0) | hb | ((llr[c] > 0.0f) ? 2 : 0);
-            if (final_pass) {
-                if (a.llr_post) const_cast<float *>(base_post)[c * Z + zv] = __fmul_rn(-2.0f, tm[c]);
-                if (a.prob) a.prob[gbase + c * Z + zv] = prob_one(tm[c]);
-                if (a.hard) a.hard[gbase + c * Z + zv] = hb;
-            }
+            const unsigned v = ((hbits >> c) & 1u) | ((llr[c] > 0.0f) ? 2u : 0u);
+            uint8_t *hp = hrow + c * Z + zv;
+            *hp = (uint8_t)(SIM ? ((*hp & 4u) | v) : v);
         });
+        if (final_pass) {
+            if (a.llr_post) {
+                float *const post = a.llr_post + gbase;
+                static_for<NB>([&](auto cc) {
+                    constexpr int c = decltype(cc)::value;
+                    constexpr int rho = kQc<Code>.rho[c];
+                    int zv = t + rho;
+                    if (zv >= Z) zv -= Z;
+                    post[c * Z + zv] = __fmul_rn(-2.0f, tm[c]);
+                });
+            }
+            if (a.prob || a.hard) {                                          // byte / probability outputs: cold path
+#pragma unroll 1
+                for (int c = 0; c < NB; ++c) {
+                    float tc = 0.0f;
+                    int rho = 0;
+                    static_for<NB>([&](auto cc) {
+                        constexpr int c2 = decltype(cc)::value;
+                        constexpr int rho2 = kQc<Code>.rho[c2];
+                        if (c == c2) { tc = tm[c2]; rho = rho2; }
+                    });
+                    int zv = t + rho;
+                    if (zv >= Z) zv -= Z;
+                    if (a.prob) a.prob[gbase + c * Z + zv] = prob_one(tc);
+                    if (a.hard) a.hard[gbase + c * Z + zv] = (uint8_t)((hbits >> c) & 1u);
+                }
+            }
+        }
     };
     auto syndrome_phase = [&]() {                                        // adds this thread's unsatisfied checks
         int w = 0;
@@ -302,6 +337,12 @@ __global__ void __launch_bounds__((QcLayout<Code, CW>::THREADS), (QcLayout<Code,
         if (w) atomicAdd(&scratch[4 + cw], w);
     };
     for (int i = tid; i < CW; i += T) frozen_s[i] = 0;                  // (visible after the first barrier below)
+    if (a.iters <= 0) {                                                 // no iteration: the messages are the zeros every caller passes
+        for (int i = tid; i < CW * L::MSG_STRIDE; i += T) msg_s[i] = 0.0f;
+#pragma unroll
+        for (int i = 0; i < (L::NLOC > 0 ? L::NLOC : 1); ++i) loc[i] = 0.0f;
+        __syncthreads();
+    }
     if constexpr (!EE) {
         // fixed iteration count (the reference's schedule, bp/bp.py:46-47); first iteration peeled
         if (a.iters > 0) {

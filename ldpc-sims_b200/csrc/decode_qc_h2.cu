@@ -78,7 +78,7 @@ __global__ void __launch_bounds__((QcLayout<Code, CW>::THREADS)) decode_qc_h2_ke
     constexpr int Z = Code::Z, NB = Code::NB, MB = Code::MB, N = L::N;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __half2 *msg_s = reinterpret_cast<__half2 *>(smem_raw);
-    uint8_t *hard_s = reinterpret_cast<uint8_t *>(msg_s + CW * L::MSG_STRIDE);           // [2*CW][HARD_STRIDE]
+    uint8_t *hard_s = smem_raw + L::MSG_BYTES;                                           // [2*CW][HARD_STRIDE]
     int *scratch = reinterpret_cast<int *>(hard_s + 2 * CW * L::HARD_STRIDE);              // [4 + 2*CW]
 
     const int tid = threadIdx.x, T = blockDim.x;
@@ -183,6 +183,12 @@ __global__ void __launch_bounds__((QcLayout<Code, CW>::THREADS)) decode_qc_h2_ke
         });
     };
 
+    if (a.iters <= 0) {                                                   // no iteration: all messages are zero
+        for (int i = tid; i < CW * L::MSG_STRIDE; i += T) msg_s[i] = __float2half2_rn(0.0f);
+#pragma unroll
+        for (int i = 0; i < (L::NLOC > 0 ? L::NLOC : 1); ++i) loc[i] = __float2half2_rn(0.0f);
+        __syncthreads();
+    }
     if (a.iters > 0) {
         if (active) var_phase(std::true_type{});
         __syncthreads();
@@ -197,13 +203,13 @@ __global__ void __launch_bounds__((QcLayout<Code, CW>::THREADS)) decode_qc_h2_ke
         __syncthreads();
     }
 
-    // ---- marginal, P(bit=1), hard decision ------------------------------------------------------------
+    // ---- marginal, P(bit=1), hard decision (output pointers tested once, see decode_qc.cu) ---------------
     if (active) {
         const __half2 half_h = __float2half2_rn(0.5f);
+        __half2 th[NB];
         static_for<NB>([&](auto cc) {
             constexpr int c = decltype(cc)::value;
             constexpr int D = kQc<Code>.col_deg[c];
-            constexpr int rho = kQc<Code>.rho[c];
             __half2 acc = __float2half2_rn(0.0f);
             static_for<D>([&](auto kk) {
                 constexpr int k = decltype(kk)::value;
@@ -216,28 +222,67 @@ __global__ void __launch_bounds__((QcLayout<Code, CW>::THREADS)) decode_qc_h2_ke
                     constexpr int off = (slot * Z - sh) * CW;
                     v = ((t < sh ? hi : lo) + off)[0];
                 }
-                if (a.iters == 0) v = __float2half2_rn(0.0f);
                 acc = (k == 0) ? v : h2_add(acc, v);
             });
-            const __half2 th = __hmul2_rn(half_h, h2_add(__hneg2(llr[c]), acc));
-            const float2 tf = __half22float2(th);
-            const float2 lf = __half22float2(llr[c]);
+            th[c] = __hmul2_rn(half_h, h2_add(__hneg2(llr[c]), acc));
+        });
+        unsigned hb0 = 0, hb1 = 0;
+        float tmin = CUDART_INF_F;
+        static_for<NB>([&](auto cc) {
+            constexpr int c = decltype(cc)::value;
+            const float2 tf = __half22float2(th[c]);
+            hb0 |= (tf.x < 0.0f ? 1u : 0u) << c;
+            hb1 |= (tf.y < 0.0f ? 1u : 0u) << c;
+            tmin = fminf(tmin, fminf(fabsf(tf.x), fabsf(tf.y)));
+        });
+        if (!(tmin > 1e-5f)) {                                             // tie band (rare)
+            hb0 = hb1 = 0;
+            static_for<NB>([&](auto cc) {
+                constexpr int c = decltype(cc)::value;
+                const float2 tf = __half22float2(th[c]);
+                hb0 |= (unsigned)hard_bit(tf.x) << c;
+                hb1 |= (unsigned)hard_bit(tf.y) << c;
+            });
+        }
+        uint8_t *const hrow = hard_s + (2 * pr) * L::HARD_STRIDE;
+        static_for<NB>([&](auto cc) {
+            constexpr int c = decltype(cc)::value;
+            constexpr int rho = kQc<Code>.rho[c];
             int zv = t + rho;
             if (zv >= Z) zv -= Z;
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                if (h == 1 && !second) break;
-                const float tm = h ? tf.y : tf.x;
-                const float lv = h ? lf.y : lf.x;
-                uint8_t hb = tm < 0.0f;
-                if (!(fabsf(tm) > 1e-5f)) hb = hard_bit(tm);              // tie band (rare)
-                hard_s[(2 * pr + h) * L::HARD_STRIDE + c * Z + zv] = hb | ((lv > 0.0f) ? 2 : 0);
-                const long long o = gbase + (long long)h * N + c * Z + zv;
-                if (a.prob) a.prob[o] = prob_one(tm);
-                if (a.llr_post) a.llr_post[o] = __fmul_rn(-2.0f, tm);
-                if (a.hard) a.hard[o] = hb;
-            }
+            const float2 lf = __half22float2(llr[c]);
+            hrow[c * Z + zv] = (uint8_t)(((hb0 >> c) & 1u) | ((lf.x > 0.0f) ? 2u : 0u));
+            if (second) hrow[L::HARD_STRIDE + c * Z + zv] = (uint8_t)(((hb1 >> c) & 1u) | ((lf.y > 0.0f) ? 2u : 0u));
         });
+        if (a.llr_post) {
+            float *const post = a.llr_post + gbase;
+            static_for<NB>([&](auto cc) {
+                constexpr int c = decltype(cc)::value;
+                constexpr int rho = kQc<Code>.rho[c];
+                int zv = t + rho;
+                if (zv >= Z) zv -= Z;
+                const float2 tf = __half22float2(th[c]);
+                post[c * Z + zv] = __fmul_rn(-2.0f, tf.x);
+                if (second) post[N + c * Z + zv] = __fmul_rn(-2.0f, tf.y);
+            });
+        }
+        if (a.prob || a.hard) {                                            // byte / probability outputs: cold path
+#pragma unroll 1
+            for (int c = 0; c < NB; ++c) {
+                float2 tf = make_float2(0.0f, 0.0f);
+                int rho = 0;
+                static_for<NB>([&](auto cc) {
+                    constexpr int c2 = decltype(cc)::value;
+                    constexpr int rho2 = kQc<Code>.rho[c2];
+                    if (c == c2) { tf = __half22float2(th[c2]); rho = rho2; }
+                });
+                int zv = t + rho;
+                if (zv >= Z) zv -= Z;
+                const long long o = gbase + c * Z + zv;
+                if (a.prob) { a.prob[o] = prob_one(tf.x); if (second) a.prob[o + N] = prob_one(tf.y); }
+                if (a.hard) { a.hard[o] = (uint8_t)((hb0 >> c) & 1u); if (second) a.hard[o + N] = (uint8_t)((hb1 >> c) & 1u); }
+            }
+        }
     }
     __syncthreads();
 
@@ -285,7 +330,7 @@ __global__ void __launch_bounds__((QcLayout<Code, CW>::THREADS)) decode_qc_h2_ke
 template <class Code, int CW, int UPD>
 static int launch_h2_one(const DecodeArgs &a, cudaStream_t s) {
     using L = QcLayout<Code, CW>;
-    const size_t smem = sizeof(__half2) * CW * L::MSG_STRIDE + (size_t)2 * CW * L::HARD_STRIDE + sizeof(int) * (8 + 2 * CW);
+    const size_t smem = L::MSG_BYTES + (size_t)2 * CW * L::HARD_STRIDE + sizeof(int) * (8 + 2 * CW);
     const long long grid = (a.B + 2 * CW - 1) / (2 * CW);
     if (grid > 0x7fffffffLL) { set_error("batch too large"); return LDPC_EINVAL; }
     auto k = decode_qc_h2_kernel<Code, CW, UPD>;

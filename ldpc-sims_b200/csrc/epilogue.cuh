@@ -10,14 +10,23 @@ namespace ldpc {
 __device__ __forceinline__ void pack_hard(const uint8_t *hard_s, int hs_stride, int ncw, int n,
                                           uint8_t *packed_g /* [ncw][ceil(n/8)] */) {
     const int nbytes = (n + 7) >> 3;
+    // fast path (8-byte aligned rows): one 64-bit load per output byte, bits 0 of the eight bytes gathered
+    // MSB-first by one multiplication (bit 8b of y lands on bit 63 - b, no two terms share a position)
+    const bool wide = ((reinterpret_cast<uintptr_t>(hard_s) | (uintptr_t)hs_stride) & 7u) == 0;
+    const int nfull = wide ? (n >> 3) : 0;
     for (int i = threadIdx.x; i < ncw * nbytes; i += blockDim.x) {
         const int cw = i / nbytes, by = i - cw * nbytes;
         const uint8_t *h = hard_s + cw * hs_stride + by * 8;
         unsigned v = 0;
+        if (by < nfull) {
+            const unsigned long long y = *reinterpret_cast<const unsigned long long *>(h) & 0x0101010101010101ull;
+            v = (unsigned)((y * 0x8040201008040201ull) >> 56);
+        } else {
 #pragma unroll
-        for (int b = 0; b < 8; ++b) {
-            const int idx = by * 8 + b;
-            v |= (idx < n ? (unsigned)(h[b] & 1) : 0u) << (7 - b);
+            for (int b = 0; b < 8; ++b) {
+                const int idx = by * 8 + b;
+                v |= (idx < n ? (unsigned)(h[b] & 1) : 0u) << (7 - b);
+            }
         }
         packed_g[(long long)cw * nbytes + by] = (uint8_t)v;
     }

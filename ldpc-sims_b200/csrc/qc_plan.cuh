@@ -127,7 +127,8 @@ struct QcLayout {
     static constexpr int HARD_STRIDE = (N + 15) & ~15;
     static constexpr int THREADS = ((CW * Z + 31) / 32) * 32;
     static constexpr int MIN_CTAS = THREADS <= 96 ? 5 : (THREADS <= 256 ? 2 : 1);   // register budget: 64K / (THREADS * MIN_CTAS)
-    static constexpr size_t SMEM = sizeof(float) * CW * MSG_STRIDE + (size_t)CW * HARD_STRIDE + sizeof(int) * (8 + 2 * CW);
+    static constexpr size_t MSG_BYTES = (sizeof(float) * CW * MSG_STRIDE + 15) & ~size_t(15);   // 4-byte message words; keeps hard_s 16-byte aligned
+    static constexpr size_t SMEM = MSG_BYTES + (size_t)CW * HARD_STRIDE + sizeof(int) * (8 + 2 * CW);
 };
 
 }  // namespace ldpc
