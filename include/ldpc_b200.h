@@ -245,6 +245,24 @@ int ldpc_sim_run(const ldpc_code_t *code, const ldpc_sim_params_t *params, void 
 int ldpc_sim_generate(const ldpc_code_t *code, const ldpc_sim_params_t *params, uint8_t *cw_packed,
                       float *llr, ldpc_stream_t stream);
 
+/* ---- MLP demapper (next row of the scope table: pytorch/nn/llr.py:7-73) ---------------------------
+ * The reference's LLR estimators are chains of nn.Linear (+ tanh) evaluated in fp32
+ * (LLRestimator_withSNR: [2N+1] -> 16N -> 16N -> 16N -> 2N, nn/llr.py:54-73; called from
+ * evaluate_quantized_snr.py:150-160).  ldpc_mlp_create uploads the weights (HOST pointers,
+ * weights[l] = nn.Linear.weight [dims[l+1], dims[l]] row-major, biases[l] = [dims[l+1]] or NULL,
+ * activations[l] != 0 -> tanh after layer l; NULL = tanh after every layer but the last) and
+ * splits them exactly into `splits` bf16 planes for the tensor cores (3 = fp32-equivalent,
+ * 2 = ~2^-16 relative, 1 = plain bf16).  Every dims[l+1] must be a multiple of 64.
+ * ldpc_mlp_forward: x [B, dims[0]] f32 row-major DEVICE -> y [B, dims[n_layers]] f32 DEVICE,
+ * asynchronous on `stream`, chunked internally (chunk_rows, 0 = default).  A handle owns scratch
+ * buffers: use it from one stream at a time. */
+typedef struct ldpc_mlp ldpc_mlp_t;
+int ldpc_mlp_create(int n_layers, const int32_t *dims, const float *const *weights,
+                    const float *const *biases, const int32_t *activations, int splits,
+                    int64_t chunk_rows, ldpc_mlp_t **out);
+int ldpc_mlp_forward(ldpc_mlp_t *mlp, const float *x, int64_t B, float *y, ldpc_stream_t stream);
+void ldpc_mlp_destroy(ldpc_mlp_t *mlp);
+
 #ifdef __cplusplus
 }
 #endif

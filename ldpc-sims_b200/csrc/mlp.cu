@@ -1,0 +1,437 @@
+// mlp.cu - the reference's MLP demappers (nn/llr.py:7-73: Linear + tanh chains, fp32) on the
+// 5th-generation tensor cores with fp32-equivalent accuracy.
+//
+// The reference evaluates  y = tanh(x W^T + b)  layer by layer in fp32 (ATen addmm).  fp32 is not a
+// tensor-core input format, so every fp32 operand is split EXACTLY into NS bf16 planes
+//     v = p0 + p1 + p2,   p0 = bf16(v), p1 = bf16(v - p0), p2 = bf16(v - p0 - p1)      (8 + 8 + 8 bits)
+// and the product is accumulated in fp32 (TMEM) from the plane pairs (i, j) with i + j < NS:
+// NS = 3 -> 6 tcgen05.mma per k-step, relative error ~2^-24 per product (fp32-equivalent, the default);
+// NS = 2 -> 3 MMAs, ~2^-16; NS = 1 -> plain bf16.
+//
+// One kernel per layer:  C[M,N] = act(A[M,K] W[N,K]^T + bias)
+//   warp 0  TMA producer: 3-D tensor maps (k, row, plane), 128-byte swizzle, [128 x 64] A boxes and
+//           [BN x 64] W boxes per plane into a 2-stage shared-memory ring (mbarrier full/empty)
+//   warp 1  allocates TMEM, one elected lane issues tcgen05.mma (cta_group::1, kind::f16, M=128, N=BN,
+//           K=16) for every plane pair and k-slice, tcgen05.commit releases the stage / signals the tile
+//   warps 2-5  epilogue: tcgen05.ld (32 lanes x 32 columns) -> + bias -> tanhf -> split into the bf16
+//           planes of the next layer's A operand (or the fp32 result of the last layer)
+// Activations of a chunk of rows ping-pong between two plane buffers that stay L2-resident.
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include <cstring>
+#include <vector>
+
+#include "common.cuh"
+
+namespace ldpc {
+namespace mlp {
+
+constexpr int BM = 128, BK = 64, STAGES = 2, UMMA_K = 16;
+constexpr int THREADS = 192;                       // warp 0 TMA, warp 1 MMA, warps 2..5 epilogue
+
+// ---- PTX wrappers --------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// Bounded spin: a protocol error traps instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok = 0;
+    for (unsigned spin = 0; !ok; ++spin) {
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+        if (!ok && spin > (1u << 26)) __trap();
+    }
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                 ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]^T, bf16 inputs, fp32 accumulate
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}"
+                 ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// K-major operand tile, 128-byte swizzle: rows of 64 bf16 (128 B), 8-row groups 1024 B apart
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);      // start address            bits [0,14)
+    d |= (uint64_t)1 << 16;                            // leading byte offset (ignored for swizzled K-major)
+    d |= (uint64_t)(1024 >> 4) << 32;                  // stride byte offset       bits [32,46)
+    d |= (uint64_t)1 << 46;                            // descriptor version (sm_100)
+    d |= (uint64_t)2 << 61;                            // SWIZZLE_128B
+    return d;
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+        "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// exact split of an fp32 value into bf16 planes
+template <int NS>
+__device__ __forceinline__ void split_bf16(float v, __nv_bfloat16 (&p)[NS]) {
+    float r = v;
+#pragma unroll
+    for (int i = 0; i < NS; ++i) {
+        p[i] = __float2bfloat16_rn(r);
+        r = __fsub_rn(r, __bfloat162float(p[i]));      // exact: p[i] is r rounded to 8 significant bits
+    }
+}
+
+// ---- fp32 rows -> bf16 planes [NS][M][Kp] (zero padding beyond K) ---------------------------------------
+template <int NS>
+__global__ void __launch_bounds__(256) split_rows_kernel(const float *x, long long ld, int K, long long M, int Kp,
+                                                         __nv_bfloat16 *planes, long long plane_stride) {
+    const long long total = M * Kp;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long m = i / Kp;
+        const int k = (int)(i - m * Kp);
+        const float v = (k < K) ? __ldg(x + m * ld + k) : 0.0f;
+        __nv_bfloat16 p[NS];
+        split_bf16<NS>(v, p);
+#pragma unroll
+        for (int s = 0; s < NS; ++s) planes[s * plane_stride + i] = p[s];
+    }
+}
+
+// ---- one layer ---------------------------------------------------------------------------------------------
+struct LayerArgs {
+    int k_blocks;                 // Kp / 64
+    int m_valid;                  // rows of this chunk that exist
+    int n_total;                  // N of the layer
+    int act;                      // 1 = tanh
+    const float *bias;            // [N] or null
+    __nv_bfloat16 *out_planes;    // [NS][chunk_rows][N] (next layer's A operand) or null
+    long long out_plane_stride;
+    float *out_f32;               // [m_valid][N] row-major (last layer) or null
+};
+
+template <int NS, int BN>
+struct Smem {
+    static constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2;
+    static constexpr int STAGE_BYTES = NS * (A_BYTES + B_BYTES);
+    static constexpr int TOTAL = STAGES * STAGE_BYTES + 1024 /* alignment slack */ + 64 /* barriers */;
+};
+
+template <int NS, int BN>
+__global__ void __launch_bounds__(THREADS, 1) layer_kernel(const __grid_constant__ CUtensorMap map_a,
+                                                            const __grid_constant__ CUtensorMap map_w, const LayerArgs args) {
+    using S = Smem<NS, BN>;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;         // swizzle-128B tiles need 1024-byte alignment
+    const uint32_t bars = base + STAGES * S::STAGE_BYTES;                  // full[STAGES], empty[STAGES], accum, tmem slot
+    auto full_bar = [&](int s) { return bars + 8u * s; };
+    auto empty_bar = [&](int s) { return bars + 8u * (STAGES + s); };
+    const uint32_t accum_bar = bars + 8u * (2 * STAGES);
+    const uint32_t tmem_slot = bars + 8u * (2 * STAGES + 1);
+    volatile uint32_t *tmem_slot_ptr = reinterpret_cast<volatile uint32_t *>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n0 = blockIdx.x * BN, m0 = blockIdx.y * BM;
+    // two fp32 accumulators: columns [0, BN) collect the leading plane pair (0, 0), columns [BN, 2 BN) the
+    // correction pairs, whose sum is ~2^-8 of the result - the tensor core's truncating fp32 accumulation
+    // then costs ~2^-8 less on five of the six product streams; the epilogue adds the two in fp32 (RN)
+    constexpr uint32_t ACC2 = NS > 1 ? BN : 0;
+    constexpr uint32_t TMEM_COLS = (BN + ACC2) < 32 ? 32 : (BN + ACC2);
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+        mbar_init(accum_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+
+    if (warp == 0) {
+        if (lane == 0) {                                                   // ===== TMA producer =====
+            for (int kb = 0; kb < args.k_blocks; ++kb) {
+                const int s = kb % STAGES;
+                const uint32_t ph = (kb / STAGES) & 1;
+                mbar_wait(empty_bar(s), ph ^ 1);
+                mbar_expect_tx(full_bar(s), S::STAGE_BYTES);
+                const uint32_t st = base + s * S::STAGE_BYTES;
+#pragma unroll
+                for (int p = 0; p < NS; ++p) {
+                    tma_load_3d(st + p * S::A_BYTES, &map_a, full_bar(s), kb * BK, m0, p);
+                    tma_load_3d(st + NS * S::A_BYTES + p * S::B_BYTES, &map_w, full_bar(s), kb * BK, n0, p);
+                }
+            }
+        }
+    } else if (warp == 1) {                                                // ===== MMA issuer =====
+        constexpr uint32_t idesc = (1u << 4) /* D = f32 */ | (1u << 7) /* A = bf16 */ | (1u << 10) /* B = bf16 */ |
+                                   ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+        for (int kb = 0; kb < args.k_blocks; ++kb) {
+            const int s = kb % STAGES;
+            const uint32_t ph = (kb / STAGES) & 1;
+            mbar_wait(full_bar(s), ph);
+            tc_fence_after();
+            if (lane == 0) {
+                const uint32_t st = base + s * S::STAGE_BYTES;
+#pragma unroll
+                for (int k = 0; k < BK / UMMA_K; ++k) {
+#pragma unroll
+                    for (int i = 0; i < NS; ++i) {
+#pragma unroll
+                        for (int j = 0; j + i < NS; ++j) {
+                            const uint64_t ad = umma_desc_sw128(st + i * S::A_BYTES + k * UMMA_K * 2);
+                            const uint64_t bd = umma_desc_sw128(st + NS * S::A_BYTES + j * S::B_BYTES + k * UMMA_K * 2);
+                            if (i + j == 0) umma_bf16(tmem_base, ad, bd, idesc, (kb | k) ? 1u : 0u);
+                            else umma_bf16(tmem_base + ACC2, ad, bd, idesc, (kb | k | (i + j - 1) | i) ? 1u : 0u);   // first correction pair: (0, 1)
+                        }
+                    }
+                }
+                tc_commit(empty_bar(s));                                   // stage free once these MMAs have read it
+                if (kb == args.k_blocks - 1) tc_commit(accum_bar);         // accumulator complete
+            }
+            __syncwarp();
+        }
+    } else {                                                               // ===== epilogue (warps 2..5) =====
+        const int quad = warp & 3;                                         // TMEM lane quadrant this warp may read
+        const int row = quad * 32 + lane;
+        const long long m = (long long)m0 + row;
+        mbar_wait(accum_bar, 0);
+        tc_fence_after();
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+            uint32_t v[32], w[32];
+            tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)c0, v);
+            if (NS > 1) tmem_ld32(tmem_base + ACC2 + ((uint32_t)(quad * 32) << 16) + (uint32_t)c0, w);
+            float o[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                float f = __uint_as_float(v[j]);
+                if (NS > 1) f = __fadd_rn(f, __uint_as_float(w[j]));
+                if (args.bias) f = __fadd_rn(f, __ldg(args.bias + n0 + c0 + j));
+                o[j] = args.act ? tanhf(f) : f;
+            }
+            if (m < args.m_valid || args.out_planes) {
+                if (args.out_f32) {
+                    if (m < args.m_valid) {
+                        float4 *dst = reinterpret_cast<float4 *>(args.out_f32 + m * args.n_total + n0 + c0);
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) dst[q] = make_float4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
+                    }
+                } else {
+                    __nv_bfloat16 pl[NS][32];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        __nv_bfloat16 p[NS];
+                        split_bf16<NS>(o[j], p);
+#pragma unroll
+                        for (int s = 0; s < NS; ++s) pl[s][j] = p[s];
+                    }
+#pragma unroll
+                    for (int s = 0; s < NS; ++s) {
+                        uint4 *dst = reinterpret_cast<uint4 *>(args.out_planes + s * args.out_plane_stride + m * args.n_total + n0 + c0);
+                        const uint4 *src = reinterpret_cast<const uint4 *>(pl[s]);
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) dst[q] = src[q];
+                    }
+                }
+            }
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    }
+}
+
+// ---- host side -----------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = [] {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) p = nullptr;
+        return reinterpret_cast<EncodeTiledFn>(p);
+    }();
+    return fn;
+}
+
+// planes [NS][rows][Kp] bf16 -> 3-D map (k, row, plane), box [64 x box_rows x 1], 128-byte swizzle
+static int make_map(CUtensorMap *map, void *ptr, int Kp, long long rows, int ns, int box_rows) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) { set_error("cuTensorMapEncodeTiled is not available from the driver"); return LDPC_ECUDA; }
+    const cuuint64_t gdim[3] = {(cuuint64_t)Kp, (cuuint64_t)rows, (cuuint64_t)ns};
+    const cuuint64_t gstr[2] = {(cuuint64_t)Kp * 2, (cuuint64_t)rows * Kp * 2};
+    const cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)box_rows, 1};
+    const cuuint32_t est[3] = {1, 1, 1};
+    const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, ptr, gdim, gstr, box, est, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d)", (int)r); return LDPC_ECUDA; }
+    return LDPC_OK;
+}
+
+struct Layer {
+    int K, Kp, N, BN, act;
+    float *d_bias = nullptr;
+    __nv_bfloat16 *d_w = nullptr;          // [NS][N][Kp]
+    CUtensorMap map_w, map_a;              // map_a: this layer's INPUT planes
+};
+
+}  // namespace mlp
+}  // namespace ldpc
+
+struct ldpc_mlp {
+    int ns, device;
+    long long chunk;
+    std::vector<ldpc::mlp::Layer> layers;
+    __nv_bfloat16 *d_act[2] = {nullptr, nullptr};   // ping-pong activation planes [NS][chunk][maxKp]
+    long long act_elems = 0;
+};
+
+using namespace ldpc;
+using namespace ldpc::mlp;
+
+template <int NS>
+static int launch_split(const float *x, long long ld, int K, long long M, int Kp, __nv_bfloat16 *planes, long long plane_stride, cudaStream_t s) {
+    const long long total = M * Kp;
+    const int grid = (int)std::min<long long>((total + 255) / 256, 148LL * 16);
+    split_rows_kernel<NS><<<grid, 256, 0, s>>>(x, ld, K, M, Kp, planes, plane_stride);
+    LDPC_CUDA_TRY(cudaGetLastError());
+    return LDPC_OK;
+}
+
+template <int NS, int BN>
+static int launch_layer(const Layer &L, const LayerArgs &a, long long rows, cudaStream_t s) {
+    auto k = layer_kernel<NS, BN>;
+    LDPC_CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<NS, BN>::TOTAL));
+    dim3 grid(L.N / BN, (unsigned)((rows + BM - 1) / BM));
+    k<<<grid, THREADS, Smem<NS, BN>::TOTAL, s>>>(L.map_a, L.map_w, a);
+    LDPC_CUDA_TRY(cudaGetLastError());
+    return LDPC_OK;
+}
+
+template <int NS>
+static int launch_layer_ns(const Layer &L, const LayerArgs &a, long long rows, cudaStream_t s) {
+    if (L.BN == 128) return launch_layer<NS, 128>(L, a, rows, s);
+    return launch_layer<NS, 64>(L, a, rows, s);
+}
+
+extern "C" {
+
+void ldpc_mlp_destroy(ldpc_mlp_t *h) {
+    if (!h) return;
+    for (auto &L : h->layers) { cudaFree(L.d_bias); cudaFree(L.d_w); }
+    cudaFree(h->d_act[0]); cudaFree(h->d_act[1]);
+    delete h;
+}
+
+int ldpc_mlp_create(int n_layers, const int32_t *dims, const float *const *weights, const float *const *biases,
+                    const int32_t *activations, int splits, int64_t chunk_rows, ldpc_mlp_t **out) {
+    if (!out || n_layers <= 0 || !dims || !weights) { set_error("ldpc_mlp_create: bad arguments"); return LDPC_EINVAL; }
+    *out = nullptr;
+    if (splits < 1 || splits > 3) { set_error("ldpc_mlp_create: splits must be 1, 2 or 3"); return LDPC_EINVAL; }
+    int dev_count = 0;
+    if (cudaGetDeviceCount(&dev_count) != cudaSuccess || dev_count == 0) { set_error("no CUDA device (there is no CPU fallback)"); return LDPC_ECUDA; }
+    for (int l = 0; l < n_layers; ++l)
+        if (dims[l] <= 0 || dims[l + 1] <= 0 || dims[l + 1] % 64 != 0 || !weights[l]) {
+            set_error("ldpc_mlp_create: layer %d: output width must be a positive multiple of 64", l);
+            return LDPC_EUNSUPPORTED;
+        }
+    ldpc_mlp *h = new ldpc_mlp();
+    h->ns = splits;
+    cudaGetDevice(&h->device);
+    if (chunk_rows <= 0) chunk_rows = 128 * 74;                           // 74 row tiles x 4 column tiles = two waves of 148 CTAs at N = 512
+    h->chunk = ((chunk_rows + BM - 1) / BM) * BM;
+    int maxw = 0;
+    h->layers.resize(n_layers);
+    for (int l = 0; l < n_layers; ++l) {
+        Layer &L = h->layers[l];
+        L.K = dims[l]; L.Kp = ((dims[l] + BK - 1) / BK) * BK; L.N = dims[l + 1];
+        L.BN = (L.N % 128 == 0) ? 128 : 64;
+        L.act = activations ? activations[l] : (l + 1 < n_layers);
+        maxw = std::max(maxw, std::max(L.Kp, L.N));
+    }
+    h->act_elems = (long long)h->chunk * maxw;
+    int rc = LDPC_OK;
+    auto fail = [&](int code) { ldpc_mlp_destroy(h); return code; };
+    for (int b = 0; b < 2; ++b)
+        if (cudaMalloc(&h->d_act[b], (size_t)h->ns * h->act_elems * sizeof(__nv_bfloat16)) != cudaSuccess) { set_error("ldpc_mlp_create: out of device memory"); return fail(LDPC_ENOMEM); }
+    for (int l = 0; l < n_layers; ++l) {
+        Layer &L = h->layers[l];
+        const size_t wel = (size_t)L.N * L.Kp;
+        float *tmp = nullptr;
+        if (cudaMalloc(&L.d_w, h->ns * wel * sizeof(__nv_bfloat16)) != cudaSuccess || cudaMalloc(&tmp, (size_t)L.N * L.K * sizeof(float)) != cudaSuccess) { cudaFree(tmp); set_error("ldpc_mlp_create: out of device memory"); return fail(LDPC_ENOMEM); }
+        cudaMemcpy(tmp, weights[l], (size_t)L.N * L.K * sizeof(float), cudaMemcpyHostToDevice);
+        if (h->ns == 1) rc = launch_split<1>(tmp, L.K, L.K, L.N, L.Kp, L.d_w, (long long)wel, 0);
+        else if (h->ns == 2) rc = launch_split<2>(tmp, L.K, L.K, L.N, L.Kp, L.d_w, (long long)wel, 0);
+        else rc = launch_split<3>(tmp, L.K, L.K, L.N, L.Kp, L.d_w, (long long)wel, 0);
+        cudaDeviceSynchronize();
+        cudaFree(tmp);
+        if (rc) return fail(rc);
+        if (biases && biases[l]) {
+            if (cudaMalloc(&L.d_bias, L.N * sizeof(float)) != cudaSuccess) { set_error("ldpc_mlp_create: out of device memory"); return fail(LDPC_ENOMEM); }
+            cudaMemcpy(L.d_bias, biases[l], L.N * sizeof(float), cudaMemcpyHostToDevice);
+        }
+        if ((rc = make_map(&L.map_w, L.d_w, L.Kp, L.N, h->ns, L.BN))) return fail(rc);
+        // input planes of layer l live in d_act[l & 1] with row length Kp
+        if ((rc = make_map(&L.map_a, h->d_act[l & 1], L.Kp, h->chunk, h->ns, BM))) return fail(rc);
+    }
+    if (cudaGetLastError() != cudaSuccess) { set_error("ldpc_mlp_create: CUDA error while uploading the weights"); return fail(LDPC_ECUDA); }
+    *out = h;
+    return LDPC_OK;
+}
+
+int ldpc_mlp_forward(ldpc_mlp_t *h, const float *x, int64_t B, float *y, ldpc_stream_t stream) {
+    if (!h || (B > 0 && (!x || !y)) || B < 0) { set_error("ldpc_mlp_forward: bad arguments"); return LDPC_EINVAL; }
+    cudaStream_t s = (cudaStream_t)stream;
+    const int nl = (int)h->layers.size();
+    const int K0 = h->layers[0].K, NL = h->layers[nl - 1].N;
+    for (long long done = 0; done < B; done += h->chunk) {
+        const long long rows = std::min<long long>(h->chunk, B - done);
+        const Layer &L0 = h->layers[0];
+        // the map of layer 0 describes [chunk][Kp0] planes with plane stride chunk * Kp0
+        const long long ps0 = h->chunk * L0.Kp;
+        int rc;
+        if (h->ns == 1) rc = launch_split<1>(x + done * K0, K0, K0, rows, L0.Kp, h->d_act[0], ps0, s);
+        else if (h->ns == 2) rc = launch_split<2>(x + done * K0, K0, K0, rows, L0.Kp, h->d_act[0], ps0, s);
+        else rc = launch_split<3>(x + done * K0, K0, K0, rows, L0.Kp, h->d_act[0], ps0, s);
+        if (rc) return rc;
+        for (int l = 0; l < nl; ++l) {
+            const Layer &L = h->layers[l];
+            LayerArgs a;
+            memset(&a, 0, sizeof(a));
+            a.k_blocks = L.Kp / BK; a.m_valid = (int)rows; a.n_total = L.N; a.act = L.act; a.bias = L.d_bias;
+            if (l + 1 < nl) { a.out_planes = h->d_act[(l + 1) & 1]; a.out_plane_stride = h->chunk * (long long)L.N; }
+            else a.out_f32 = y + done * NL;
+            if (h->ns == 1) rc = launch_layer_ns<1>(L, a, rows, s);
+            else if (h->ns == 2) rc = launch_layer_ns<2>(L, a, rows, s);
+            else rc = launch_layer_ns<3>(L, a, rows, s);
+            if (rc) return rc;
+        }
+    }
+    return LDPC_OK;
+}
+
+}  // extern "C"

@@ -98,6 +98,12 @@ def lib():
     L.ldpc_sim_run.argtypes = [vp, vp, vp, sz, vp, vp]
     L.ldpc_sim_generate.restype = ctypes.c_int
     L.ldpc_sim_generate.argtypes = [vp, vp, vp, vp, vp]
+    L.ldpc_mlp_create.restype = ctypes.c_int
+    L.ldpc_mlp_create.argtypes = [i32, vp, vp, vp, vp, i32, i64, ctypes.POINTER(vp)]
+    L.ldpc_mlp_forward.restype = ctypes.c_int
+    L.ldpc_mlp_forward.argtypes = [vp, vp, i64, vp, vp]
+    L.ldpc_mlp_destroy.restype = None
+    L.ldpc_mlp_destroy.argtypes = [vp]
     if L.ldpc_abi_version() != ABI_VERSION:
         raise ImportError(f"libldpc_b200.so ABI {L.ldpc_abi_version()} != binding {ABI_VERSION}; rebuild")
     _lib = L

@@ -1,0 +1,97 @@
+"""Drop-in LLR estimators (reference nn/llr.py:7-73), inference only.
+
+Same class names, constructor arguments and parameter names as the reference, so the
+reference's checkpoints load unchanged (``nn.DataParallel(LLRestimator_withSNR(32))`` +
+``load_state_dict(checkpoint['model_state_dict'])``, evaluate_quantized_snr.py:57-69).
+``forward`` runs the whole Linear/tanh chain in one native call (ldpc_b200.mlp.NativeMLP:
+tcgen05 tensor cores, exact bf16 plane splitting, fp32-equivalent results); CPU tensors are
+moved to the current CUDA device and the result is returned on the input's device.  There is
+no CPU path and no autograd: training the demapper (quantized_snr.py, ofdm_nn.py) is outside
+the hot path.
+
+``splits`` (keyword-only extra): 3 = fp32-equivalent (default), 2 = ~2^-16 relative, 1 = bf16.
+"""
+import numpy as np
+import torch
+import torch.nn as nn
+
+from ldpc_b200.mlp import NativeMLP
+from ofdm.ofdm_functions import DFTreal
+
+__all__ = ["LLRestimator", "LLRestimator_withSNR"]
+
+
+class _NativeChain(nn.Module):
+    """Keeps nn.Linear parameters (for state_dict compatibility) and a per-device native handle that is
+    rebuilt whenever the parameters change (load_state_dict, .to())."""
+
+    _chain = ()            # names of the Linear layers, in forward order
+    _acts = ()             # tanh after layer?
+
+    def _init_native(self, splits):
+        self._splits = int(splits)
+        self._native = {}                          # device index -> (parameter versions, NativeMLP)
+
+    def _handle(self, device):
+        layers = [getattr(self, n) for n in self._chain]
+        params = [p for l in layers for p in l.parameters()]
+        versions = tuple(p._version for p in params) + tuple(p.data_ptr() for p in params)
+        key = device.index if device.index is not None else torch.cuda.current_device()
+        hit = self._native.get(key)
+        if hit is None or hit[0] != versions:
+            hit = (versions, NativeMLP([l.weight for l in layers], [l.bias for l in layers], list(self._acts),
+                                       splits=self._splits, device=torch.device("cuda", key)))
+            self._native[key] = hit
+        return hit[1]
+
+    def forward(self, x):
+        src = x.device
+        dev = src if src.type == "cuda" else torch.device("cuda", torch.cuda.current_device())
+        y = self._handle(dev)(x.detach().to(device=dev, dtype=torch.float32))
+        return y.to(src)
+
+    def __getstate__(self):                        # DataParallel.replicate / deepcopy: never copy native handles
+        d = self.__dict__.copy()
+        d["_native"] = {}
+        return d
+
+
+class LLRestimator(_NativeChain):                  # nn/llr.py:7-52
+    _chain = ("fft_layer", "hidden3", "hidden4", "hidden5", "final")
+    _acts = (False, True, True, True, False)       # forward: fft_layer, tanh(hidden3..5), final (nn/llr.py:46-52)
+
+    def __init__(self, ofdm_size, snr_est, *, splits=3):
+        super().__init__()
+        self.ofdm_size, self.snr_est = ofdm_size, snr_est
+        self.activation = nn.Tanh()
+        n = self.ofdm_size
+        self.fft_layer = nn.Linear(2 * n, 2 * n, bias=False)
+        self.scalar = nn.Parameter(torch.ones(1, 2 * n, dtype=torch.float))
+        self.hidden1 = nn.Linear(2 * n, 8 * n, bias=True)
+        self.hidden2 = nn.Linear(8 * n, 2 * n, bias=True)
+        self.hidden3 = nn.Linear(2 * n, 16 * n, bias=True)
+        self.hidden4 = nn.Linear(16 * n, 16 * n, bias=True)
+        self.hidden5 = nn.Linear(16 * n, 16 * n, bias=True)
+        self.final = nn.Linear(16 * n, 2 * n, bias=True)
+        self.init_parameters()
+        self._init_native(splits)
+
+    def init_parameters(self):                     # nn/llr.py:30-37
+        self.fft_layer.weight.data = torch.tensor(DFTreal(self.ofdm_size), dtype=torch.float)
+        self.scalar.data = torch.tensor(2 * self.snr_est * (-2 / np.sqrt(2)), dtype=torch.float).expand_as(self.scalar.data).clone()
+
+
+class LLRestimator_withSNR(_NativeChain):          # nn/llr.py:54-73
+    _chain = ("hidden1", "hidden2", "hidden3", "final")
+    _acts = (True, True, True, False)
+
+    def __init__(self, ofdm_size, *, splits=3):
+        super().__init__()
+        self.ofdm_size = ofdm_size
+        self.activation = nn.Tanh()
+        n = self.ofdm_size
+        self.hidden1 = nn.Linear(2 * n + 1, 16 * n, bias=True)
+        self.hidden2 = nn.Linear(16 * n, 16 * n, bias=True)
+        self.hidden3 = nn.Linear(16 * n, 16 * n, bias=True)
+        self.final = nn.Linear(16 * n, 2 * n, bias=True)
+        self._init_native(splits)
