@@ -245,6 +245,21 @@ int ldpc_sim_run(const ldpc_code_t *code, const ldpc_sim_params_t *params, void 
 int ldpc_sim_generate(const ldpc_code_t *code, const ldpc_sim_params_t *params, uint8_t *cw_packed,
                       float *llr, ldpc_stream_t stream);
 
+/* ldpc_sim_generate plus the received time-domain samples (nullable) that the MLP demappers take as
+ * input (evaluate_quantized_snr.py:135-140): f32 [n_codewords * ceil((n/2)/ofdm_size), 2 ofdm_size + 1],
+ * one row per OFDM symbol = Re[0..N), Im[0..N) of the (noisy, quantized, rescaled) time signal and the
+ * linear SNR. */
+int ldpc_sim_generate_ex(const ldpc_code_t *code, const ldpc_sim_params_t *params, uint8_t *cw_packed,
+                         float *llr, float *samples, ldpc_stream_t stream);
+
+/* ldpc_decode_count - ldpc_decode with the exact link metrics fused at its tail
+ * (evaluate_quantized_snr.py:169-188): decodes llr [B,n] and ADDS {uncoded bit errors, info-bit errors,
+ * frame errors, bits, frames} into counters[5] (i64, device) against ref_packed (transmitted
+ * codewords, MSB-first [B, ceil(n/8)], device); k = number of information bits. */
+int ldpc_decode_count(const ldpc_code_t *code, const void *llr, int llr_dtype, int64_t B, int iters,
+                      int update, float clamp_value, float param, const uint8_t *ref_packed, int k,
+                      int64_t *counters, ldpc_stream_t stream);
+
 /* ---- MLP demapper (next row of the scope table: pytorch/nn/llr.py:7-73) ---------------------------
  * The reference's LLR estimators are chains of nn.Linear (+ tanh) evaluated in fp32
  * (LLRestimator_withSNR: [2N+1] -> 16N -> 16N -> 16N -> 2N, nn/llr.py:54-73; called from

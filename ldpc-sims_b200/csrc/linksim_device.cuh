@@ -50,11 +50,15 @@ __device__ __forceinline__ void fill_twiddles_f(cplx<T> *tw, int N) {
 // hide each other's latency).  Symbol slot s: OFDM symbol os[s] of global codeword gcw[s];
 // valid[s] = false skips its output.  bit(s, i) -> 0/1 code bit i of that codeword;
 // out(s, sidx, llr_b0, llr_b1) receives the LLR pair of QPSK symbol sidx < nsym.
+// samp(s, t, re, im) receives the received (noisy, quantized and rescaled) TIME sample t of the symbol -
+// the input of the MLP demappers (evaluate_quantized_snr.py:135-137); pass NoSamples to skip.
 // Per-symbol arithmetic does not depend on S.
-template <int N, int S, class BitFn, class OutFn>
+struct NoSamples { __device__ __forceinline__ void operator()(int, int, float, float) const {} };
+
+template <int N, int S, class BitFn, class OutFn, class SampFn = NoSamples>
 __device__ __forceinline__ void ofdm_symbols_llr(int lane, const int (&os)[S], const unsigned long long (&gcw)[S],
                                                  const bool (&valid)[S], int nsym, const LinkParams &p, const LinkConsts &k,
-                                                 const cplx<float> *tw, BitFn bit, OutFn out) {
+                                                 const cplx<float> *tw, BitFn bit, OutFn out, SampFn samp = SampFn()) {
     constexpr int P = N / 32, LOGN = ilog2(N);
     const Quantizer<float> quant(k.levels, k.clip);
     const Philox rng(p.seed);
@@ -89,6 +93,7 @@ __device__ __forceinline__ void ofdm_symbols_llr(int lane, const int (&os)[S], c
                     float re = x[s][rr].re + k.nstd * z[2 * h], im = x[s][rr].im + k.nstd * z[2 * h + 1];
                     if (p.qbits > 0) { re = quant(k.factor * re) / k.factor; im = quant(k.factor * im) / k.factor; }
                     x[s][rr] = {re, im};
+                    if (valid[s]) samp(s, t0 + h, re, im);
                 }
             }
         } else {
@@ -100,6 +105,7 @@ __device__ __forceinline__ void ofdm_symbols_llr(int lane, const int (&os)[S], c
             float re = x[s][0].re + k.nstd * z0, im = x[s][0].im + k.nstd * z1;
             if (p.qbits > 0) { re = quant(k.factor * re) / k.factor; im = quant(k.factor * im) / k.factor; }
             x[s][0] = {re, im};
+            if (valid[s]) samp(s, t, re, im);
         }
     }
 #pragma unroll

@@ -53,8 +53,11 @@ __global__ void __launch_bounds__(256) gen_codewords_kernel(const uint32_t *Pp /
 // ---- K2b ----------------------------------------------------------------------------------------------
 __device__ __forceinline__ int cw_bit(const uint8_t *row, int i) { return (row[i >> 3] >> (7 - (i & 7))) & 1; }
 
+// samples (nullable): [ncw * n_ofdm_per_cw][2N + 1] f32 rows (Re t = 0..N-1, Im t = 0..N-1, linear SNR): the
+// input_samples of the MLP demappers (evaluate_quantized_snr.py:135-140)
 template <int N>
-__global__ void __launch_bounds__(256) linksim_llr_kernel(const uint8_t *cw_packed, long long ncw, LinkParams p, float *llr) {
+__global__ void __launch_bounds__(256) linksim_llr_kernel(const uint8_t *cw_packed, long long ncw, LinkParams p, float *llr,
+                                                          float *samples) {
     __shared__ cplx<float> tw[N / 2];
     fill_twiddles_f<float>(tw, N);
     __syncthreads();
@@ -81,9 +84,20 @@ __global__ void __launch_bounds__(256) linksim_llr_kernel(const uint8_t *cw_pack
             row[s] = cw_packed + c * nby;
             orow[s] = llr + c * p.n;
         }
-        ofdm_symbols_llr<N, S>(lane, os, gcw, valid, nsym, p, k, tw,
-                               [&](int s, int i) { return cw_bit(row[s], i); },
-                               [&](int s, int sidx, float l0, float l1) { *reinterpret_cast<float2 *>(orow[s] + 2 * sidx) = make_float2(l0, l1); });
+        auto bitf = [&](int s, int i) { return cw_bit(row[s], i); };
+        auto outf = [&](int s, int sidx, float l0, float l1) { *reinterpret_cast<float2 *>(orow[s] + 2 * sidx) = make_float2(l0, l1); };
+        if (samples) {
+            float *srow[S];
+#pragma unroll
+            for (int s = 0; s < S; ++s) {
+                srow[s] = samples + (o0 + s) * (2 * N + 1);
+                if (valid[s] && lane == 0) srow[s][2 * N] = p.snr;
+            }
+            ofdm_symbols_llr<N, S>(lane, os, gcw, valid, nsym, p, k, tw, bitf, outf,
+                                   [&](int s, int t, float re, float im) { srow[s][t] = re; srow[s][N + t] = im; });
+        } else {
+            ofdm_symbols_llr<N, S>(lane, os, gcw, valid, nsym, p, k, tw, bitf, outf);
+        }
     }
 }
 
@@ -122,7 +136,7 @@ static int check_sim(const ldpc_code_t *code, const ldpc_sim_params_t *sp) {
 }
 
 static int launch_frontend(const ldpc_code_t *code, const ldpc_sim_params_t *sp, long long first, long long cnt,
-                           uint8_t *cw_packed, float *llr, cudaStream_t s) {
+                           uint8_t *cw_packed, float *llr, cudaStream_t s, float *samples = nullptr) {
     const int n = code->n, k = code->k_info, kw = (k + 31) / 32;
     const size_t sm = (size_t)kw * 4 + ((n + 3) & ~3);
     const int g1 = (int)std::min<long long>(cnt, 148LL * 8);
@@ -136,10 +150,10 @@ static int launch_frontend(const ldpc_code_t *code, const ldpc_sim_params_t *sp,
     const long long warps = cnt * lp.n_ofdm_per_cw;
     const int g2 = (int)std::min<long long>((warps + 7) / 8, 148LL * 16);
     switch (sp->ofdm_size) {
-        case 32: linksim_llr_kernel<32><<<g2, 256, 0, s>>>(cw_packed, cnt, lp, llr); break;
-        case 64: linksim_llr_kernel<64><<<g2, 256, 0, s>>>(cw_packed, cnt, lp, llr); break;
-        case 128: linksim_llr_kernel<128><<<g2, 256, 0, s>>>(cw_packed, cnt, lp, llr); break;
-        default: linksim_llr_kernel<256><<<g2, 256, 0, s>>>(cw_packed, cnt, lp, llr); break;
+        case 32: linksim_llr_kernel<32><<<g2, 256, 0, s>>>(cw_packed, cnt, lp, llr, samples); break;
+        case 64: linksim_llr_kernel<64><<<g2, 256, 0, s>>>(cw_packed, cnt, lp, llr, samples); break;
+        case 128: linksim_llr_kernel<128><<<g2, 256, 0, s>>>(cw_packed, cnt, lp, llr, samples); break;
+        default: linksim_llr_kernel<256><<<g2, 256, 0, s>>>(cw_packed, cnt, lp, llr, samples); break;
     }
     LDPC_CUDA_TRY(cudaGetLastError());
     return LDPC_OK;
@@ -152,6 +166,32 @@ int ldpc_sim_generate(const ldpc_code_t *code, const ldpc_sim_params_t *sp, uint
     if (!cw_packed || !llr) { set_error("ldpc_sim_generate: null output"); return LDPC_EINVAL; }
     if (sp->n_codewords == 0) return LDPC_OK;
     return launch_frontend(code, sp, sp->first_codeword, sp->n_codewords, cw_packed, llr, (cudaStream_t)stream);
+}
+
+int ldpc_sim_generate_ex(const ldpc_code_t *code, const ldpc_sim_params_t *sp, uint8_t *cw_packed, float *llr,
+                         float *samples, ldpc_stream_t stream) {
+    int rc = check_sim(code, sp);
+    if (rc) return rc;
+    if (!cw_packed || !llr) { set_error("ldpc_sim_generate_ex: null output"); return LDPC_EINVAL; }
+    if (sp->n_codewords == 0) return LDPC_OK;
+    return launch_frontend(code, sp, sp->first_codeword, sp->n_codewords, cw_packed, llr, (cudaStream_t)stream, samples);
+}
+
+int ldpc_decode_count(const ldpc_code_t *code, const void *llr, int llr_dtype, int64_t B, int iters, int update,
+                      float clamp_value, float param, const uint8_t *ref_packed, int k_info, int64_t *counters,
+                      ldpc_stream_t stream) {
+    if (!code || !llr || !ref_packed || !counters || B < 0) { set_error("ldpc_decode_count: null argument"); return LDPC_EINVAL; }
+    if (iters < 0 || update < LDPC_UPDATE_SP || update > LDPC_UPDATE_OMS || !(clamp_value > 0.0f)) { set_error("ldpc_decode_count: bad decoder parameters"); return LDPC_EINVAL; }
+    if (llr_dtype != LDPC_F32 && llr_dtype != LDPC_F64 && llr_dtype != LDPC_F16) { set_error("ldpc_decode_count: bad llr dtype"); return LDPC_EINVAL; }
+    if (k_info <= 0 || k_info > code->n) { set_error("ldpc_decode_count: bad k"); return LDPC_EINVAL; }
+    if (B == 0) return LDPC_OK;
+    DecodeArgs a;
+    memset(&a, 0, sizeof(a));
+    a.llr = llr; a.llr_dtype = llr_dtype; a.B = B; a.iters = iters; a.update = update;
+    a.clampv = clamp_value; a.param = param;
+    a.ref_packed = ref_packed; a.counters = reinterpret_cast<unsigned long long *>(counters); a.k_info = k_info;
+    a.precision = code->precision;
+    return decode_dispatch(code, a, (cudaStream_t)stream);
 }
 
 int ldpc_sim_run(const ldpc_code_t *code, const ldpc_sim_params_t *sp, void *workspace, size_t workspace_bytes,

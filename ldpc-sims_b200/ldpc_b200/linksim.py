@@ -185,15 +185,59 @@ def attach_generator(code, G=None, k=None):
     return code
 
 
-def sim_generate(code, cfg: LinkConfig, first, count):
-    """K2 alone: (codewords packed MSB-first [count, ceil(n/8)] u8, llr f32 [count, n]) CUDA tensors."""
+def sim_generate(code, cfg: LinkConfig, first, count, want_samples=False):
+    """K2 alone: (codewords packed MSB-first [count, ceil(n/8)] u8, llr f32 [count, n]) CUDA tensors;
+    with want_samples also the MLP demappers' input rows f32 [count * symbols_per_codeword, 2N+1]
+    (Re, Im of the received time samples and the linear SNR, evaluate_quantized_snr.py:135-140)."""
     dev = code.device
     cwp = torch.empty(count, code.packed_bytes, dtype=torch.uint8, device=dev)
     llr = torch.empty(count, code.n, dtype=torch.float32, device=dev)
     sp = cfg.to_struct(first, count)
+    smp = None
+    if want_samples:
+        per_cw = (code.n // 2 + cfg.ofdm_size - 1) // cfg.ofdm_size
+        smp = torch.zeros(count * per_cw, 2 * cfg.ofdm_size + 1, dtype=torch.float32, device=dev)
     with torch.cuda.device(dev):
-        N.check(N.lib().ldpc_sim_generate(code._h, ctypes.byref(sp), cwp.data_ptr(), llr.data_ptr(), _stream()))
-    return cwp, llr
+        N.check(N.lib().ldpc_sim_generate_ex(code._h, ctypes.byref(sp), cwp.data_ptr(), llr.data_ptr(),
+                                             None if smp is None else smp.data_ptr(), _stream()))
+    return (cwp, llr, smp) if want_samples else (cwp, llr)
+
+
+def decode_count(code, llr, ref_packed, cfg: LinkConfig, counters=None):
+    """Decode llr [B,n] and add the exact link metrics against the transmitted codewords (packed) into
+    `counters` (int64[5] CUDA tensor): one launch, ldpc_decode_count."""
+    from .decoder import _update_id, _DTYPES
+    dev = llr.device
+    if counters is None:
+        counters = torch.zeros(5, dtype=torch.int64, device=dev)
+    if llr.dtype not in _DTYPES:
+        llr = llr.float()
+    llr = llr.contiguous()
+    with torch.cuda.device(dev):
+        N.check(N.lib().ldpc_decode_count(code._h, llr.data_ptr(), _DTYPES[llr.dtype], llr.shape[0], int(cfg.iters),
+                                          _update_id(cfg.update), float(cfg.clamp_value), float(cfg.param),
+                                          ref_packed.data_ptr(), int(code.k), counters.data_ptr(), _stream()))
+    return counters
+
+
+def sim_run_nn(code, cfg: LinkConfig, demapper, first, count, counters=None, chunk=1 << 16):
+    """The NN-demapper link (evaluate_quantized_snr.py:91-188, the *_nn results): front end -> received
+    time samples -> MLP LLR estimates -> BP decoder -> exact counters, all on the GPU.  `demapper`
+    maps CUDA f32 [S, 2N+1] -> [S, 2N] (ldpc_b200.mlp.NativeMLP or the drop-in nn.llr modules).
+    Needs n to be a multiple of 2 * ofdm_size (the reference uses n = 2 * ofdm_size)."""
+    if code.n % (2 * cfg.ofdm_size):
+        raise ValueError("the NN demapper path needs n to be a multiple of 2 * ofdm_size")
+    dev = code.device
+    if counters is None:
+        counters = torch.zeros(5, dtype=torch.int64, device=dev)
+    done = 0
+    while done < count:
+        cnt = min(chunk, count - done)
+        cwp, _, smp = sim_generate(code, cfg, first + done, cnt, want_samples=True)
+        llr_est = demapper(smp).reshape(cnt, code.n)
+        decode_count(code, llr_est, cwp, cfg, counters)
+        done += cnt
+    return counters
 
 
 def sim_run(code, cfg: LinkConfig, first, count, counters=None, workspace=None):

@@ -22,7 +22,7 @@ sys.path.insert(0, os.path.join(ROOT, "oracle"))
 
 from bp.parity import H, G                                # noqa: E402  (the reference)
 import ofdm.ofdm_functions as F                           # noqa: E402
-from nn.llr import LLRestimator_withSNR                   # noqa: E402
+from nn.llr import LLRestimator, LLRestimator_withSNR     # noqa: E402
 import nn_oracle as NO                                    # noqa: E402
 
 CKPT = "outputs/model/20191214-172134_qbits=3_clipdb=0_snrlow=5_snrhigh=15_lr=0.1.pth"   # evaluate_quantized_snr.py:25,67
@@ -65,6 +65,17 @@ def main():
         out[tag + "_meta"] = np.array([snrdb, iters, clamp], np.float64)
         ber = np.mean(np.abs(dec[:, :32] - enc.reshape(-1, 64)[:, :32]))
         print(f"  {tag}: {nsym} OFDM symbols, oracle-vs-reference max err {err:.2e} of scale, coded BER (NN LLRs) {ber:.4f}")
+    # the plain LLRestimator chain (fft_layer without bias / tanh, nn/llr.py:46-52): pinned here at mint time
+    # on a seeded random initialisation (no fixture: the weights would be another 2.4 MB)
+    torch.manual_seed(0)
+    plain = LLRestimator(ofdm_size, 10.0).eval()
+    xp = torch.randn(300, 2 * ofdm_size)
+    with torch.no_grad():
+        yp = plain(xp).numpy()
+    yo = NO.mlp_forward({k: v.detach().numpy() for k, v in plain.state_dict().items()}, xp.numpy(), layers=NO.PLAIN_LAYERS, acts=NO.PLAIN_ACTS)
+    err = np.max(np.abs(yo - yp)) / np.max(np.abs(yp))
+    assert err < 1e-5, err
+    print(f"  plain LLRestimator chain: oracle-vs-reference max err {err:.2e} of scale")
     out["names"] = np.array(names)
     p = os.path.join(ROOT, "tests", "golden", "nn_demapper.npz")
     np.savez_compressed(p, **out)

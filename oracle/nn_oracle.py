@@ -18,6 +18,7 @@ import numpy as np
 
 WITHSNR_LAYERS = ("hidden1", "hidden2", "hidden3", "final")          # nn/llr.py:62-66
 PLAIN_LAYERS = ("fft_layer", "hidden3", "hidden4", "hidden5", "final")   # nn/llr.py:46-52 (forward)
+PLAIN_ACTS = (False, True, True, True, False)                             # no tanh after fft_layer (nn/llr.py:46-47)
 
 
 def strip_module_prefix(state):
@@ -25,8 +26,10 @@ def strip_module_prefix(state):
     return {(k[7:] if k.startswith("module.") else k): np.asarray(v, dtype=np.float32) for k, v in state.items()}
 
 
-def mlp_forward(state, x, layers=WITHSNR_LAYERS):
-    """fp32 forward; tanh after every layer except the last (nn/llr.py:68-73)."""
+def mlp_forward(state, x, layers=WITHSNR_LAYERS, acts=None):
+    """fp32 forward; acts[i] -> tanh after layer i (default: every layer except the last, nn/llr.py:68-73)."""
+    if acts is None:
+        acts = tuple(i + 1 < len(layers) for i in range(len(layers)))
     s = strip_module_prefix(state)
     h = np.asarray(x, dtype=np.float32)
     for i, name in enumerate(layers):
@@ -35,7 +38,7 @@ def mlp_forward(state, x, layers=WITHSNR_LAYERS):
         if name + ".bias" in s:
             h = h + s[name + ".bias"]
         h = h.astype(np.float32)
-        if i + 1 < len(layers):
+        if acts[i]:
             h = np.tanh(h).astype(np.float32)
     return h
 

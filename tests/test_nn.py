@@ -90,7 +90,8 @@ def test_native_mlp_matches_oracle_ragged_and_chunked():
         assert _scale_err(y, ref) < 1e-5, B
     m = _model(3)
     x = torch.tensor(GOLD["snr15_x"][:100])
-    assert _scale_err(m(x).numpy(), GOLD["snr15_llr"][:100]) < 1e-5 and not m(x).is_cuda
+    y = m.module(x)                                      # CPU tensor in -> CPU tensor out (DataParallel itself returns CUDA)
+    assert not y.is_cuda and _scale_err(y.numpy(), GOLD["snr15_llr"][:100]) < 1e-5
 
 
 @pytest.mark.gpu
@@ -121,5 +122,70 @@ def test_llrestimator_plain_chain_matches_oracle():
     x = torch.randn(300, 64)
     y = m(x.cuda()).cpu().numpy()
     state = {k: v.detach().numpy() for k, v in m.state_dict().items()}
-    ref = NO.mlp_forward(state, x.numpy(), layers=NO.PLAIN_LAYERS)
+    ref = NO.mlp_forward(state, x.numpy(), layers=NO.PLAIN_LAYERS, acts=NO.PLAIN_ACTS)
     assert _scale_err(y, ref) < 1e-5
+
+
+def _default_code():
+    from ldpc_b200.codes import peg_64_32
+    from ldpc_b200.decoder import LdpcCode
+    from ldpc_b200.linksim import attach_generator
+    H, G = peg_64_32()
+    return attach_generator(LdpcCode(H), G), H
+
+
+@pytest.mark.gpu
+def test_frontend_samples_are_the_time_signal_behind_the_llrs():
+    """The sample rows the MLP sees (evaluate_quantized_snr.py:135-140) and the conventional LLRs of the
+    same launch describe the same received signal: DFT(samples) -> QPSK LLR reproduces the kernel's LLRs,
+    the scaled samples sit on the quantizer grid, the last column is the linear SNR."""
+    import torch
+    from ldpc_b200.linksim import LinkConfig, sim_generate
+    code, _ = _default_code()
+    for N, qbits in ((32, 3), (32, 0)):
+        cfg = LinkConfig(snr_db=15.0, ofdm_size=N, qbits=qbits, agc_mode=1, seed=77)
+        cwp, llr, smp = sim_generate(code, cfg, 5, 300, want_samples=True)
+        cwp2, llr2 = sim_generate(code, cfg, 5, 300)
+        assert torch.equal(cwp, cwp2) and torch.equal(llr, llr2)          # asking for samples changes nothing else
+        s = smp.cpu().numpy().astype(np.float64)
+        snr = 10 ** 1.5
+        assert np.allclose(s[:, 2 * N], snr, rtol=1e-6)
+        t = s[:, :N] + 1j * s[:, N:2 * N]
+        k = np.arange(N)
+        W = np.exp(-2j * np.pi * np.outer(k, k) / N) / np.sqrt(N)          # ofdm_functions.py:86-93
+        R = t @ W.T
+        ref = np.stack([-2 * np.sqrt(2) * snr * R.real, -2 * np.sqrt(2) * snr * R.imag], axis=2).reshape(300, 2 * N)
+        got = llr.cpu().numpy()
+        assert np.max(np.abs(got - ref)) <= 2e-4 * np.max(np.abs(ref))
+        if qbits:
+            factor = 10.0 / (0.5 * (1 + 1 / snr))
+            step = 2 * 10.0 / (2 ** qbits - 1)
+            lev = s[:, :2 * N] * factor / step
+            edge = 2 ** qbits / 2 - 1 / step          # the reference clips at (L/2) * step - 1 in VALUE units (ofdm_functions.py:45)
+            off = np.minimum(np.abs(lev - np.round(lev)), np.abs(np.abs(lev) - edge))
+            assert np.max(off) < 1e-3
+
+
+@pytest.mark.gpu
+def test_nn_link_counters_are_exact():
+    """sim_run_nn (front end -> MLP -> decoder -> fused counters) against the same chain evaluated step by
+    step with separate calls and numpy integer arithmetic (evaluate_quantized_snr.py:169-188)."""
+    import torch
+    from ldpc_b200.linksim import LinkConfig, sim_generate, sim_run_nn
+    code, H = _default_code()
+    m = _model(3).module
+    cfg = LinkConfig(snr_db=10.0, ofdm_size=32, qbits=3, agc_mode=1, iters=10, update="sp", clamp_value=100.0, seed=5)
+    cnt = 3000
+    c = sim_run_nn(code, cfg, m, 0, cnt, chunk=1024).cpu().numpy()
+    cwp, _, smp = sim_generate(code, cfg, 0, cnt, want_samples=True)
+    llr_est = m(smp)
+    out = code.decode(llr_est, 10, 100.0, update="sp", want=("hard",))
+    hard = out["hard"].cpu().numpy()
+    enc = np.unpackbits(cwp.cpu().numpy(), axis=1)[:, :64]
+    L = llr_est.cpu().numpy()
+    unc = int(np.sum(((np.sign(L) + 1) // 2).astype(np.uint8) != enc))
+    inf = int(np.sum(hard[:, :32] != enc[:, :32]))
+    fe = int(np.sum(np.any(hard != enc, axis=1)))
+    assert c.tolist() == [unc, inf, fe, cnt * 64, cnt]
+    # the learned demapper is a sane LLR estimator at this operating point (reference: coded BER 4e-4 at 10 dB)
+    assert inf / (cnt * 32) < 5e-3
