@@ -41,6 +41,8 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-f16", action="store_true")
+    ap.add_argument("--no-nn", action="store_true", help="skip the NN-demapper link (BASELINE.json configs[4])")
+    ap.add_argument("--nn-symbols", type=int, default=1 << 20, help="OFDM symbols per GPU of the NN-demapper measurement")
     return ap.parse_args()
 
 
@@ -155,6 +157,55 @@ class Clocks:
         return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
 
 
+def bench_nn(a, dev, world, barrier, peaks):
+    """evaluate_quantized_snr.py:91-188 with the reference's checkpoint (weights from tests/golden/nn_demapper.npz):
+    front end -> received time samples -> MLP (tcgen05, fp32-equivalent) -> sum-product decoder -> counters."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from ldpc_b200.codes import peg_64_32
+    from ldpc_b200.decoder import LdpcCode
+    from ldpc_b200.linksim import LinkConfig, attach_generator, sim_run_nn
+    from ldpc_b200.mlp import NativeMLP
+    g = np.load(os.path.join(ROOT, "tests", "golden", "nn_demapper.npz"))
+    names = ("hidden1", "hidden2", "hidden3", "final")
+    W = [g[f"w_module.{n}.weight"] for n in names]
+    net = NativeMLP(W, [g[f"w_module.{n}.bias"] for n in names], splits=3, device=dev)
+    H, G = peg_64_32()
+    code = attach_generator(LdpcCode(H, device=dev), G)
+    cfg = LinkConfig(snr_db=15.0, ofdm_size=32, qbits=3, agc_mode=1, iters=10, update="sp", clamp_value=100.0, seed=99)
+    S = a.nn_symbols
+    x = torch.randn(S, 65, device=dev) * 0.7
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    def timed(fn, reps):
+        fn()
+        barrier()
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1) / reps], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+    ms_mlp = timed(lambda: net(x), 3)
+    counters = torch.zeros(5, dtype=torch.int64, device=dev)
+    ms_link = timed(lambda: sim_run_nn(code, cfg, net, 0, S, counters), 2)
+    flops = 2.0 * sum(w.shape[0] * w.shape[1] for w in W) * S
+    tf_peak = float(peaks.get("bf16_tflops", 2250.0))
+    c = counters.cpu().numpy().astype(np.float64)
+    return {"workload": "LLRestimator_withSNR(32) 65-512-512-512-64 tanh (reference checkpoint) + (64,32) code, sum-product x10, 15 dB, 3-bit ADC",
+            "ofdm_symbols_per_gpu": S, "link_ms": ms_link, "link_symbols_per_s": S * world / (ms_link * 1e-3),
+            "link_info_gbps": S * world * 32 / (ms_link * 1e-3) / 1e9, "mlp_ms": ms_mlp,
+            "mlp_fp32_equivalent_tflops": flops / (ms_mlp * 1e-3) / 1e12,
+            "roofline": {"bound": "tensor", "achieved": 6 * flops / (ms_mlp * 1e-3) / 1e12, "peak": tf_peak, "unit": "TFLOP/s",
+                         "frac": 6 * flops / (ms_mlp * 1e-3) / 1e12 / tf_peak, "traffic": None,
+                         "note": "bf16 tcgen05.mma flops issued: 6 plane pairs per fp32 product (3 exact bf16 planes per operand)"},
+            "coded_ber_nn": c[1] / max(c[4] * 32, 1), "uncoded_ber_nn": c[0] / max(c[3], 1), "gpu_launches_per_chunk": 8}
+
+
 def main():
     a = parse()
     if a.impl == "reference":
@@ -252,10 +303,13 @@ def main():
     # n_sm blocks exchanged through shared memory (the other n_loc blocks and the LLRs are registers)
     smem_bytes_per_update = 4 * n_sm * 81 * 4 / (2 * E_CODE) if n_sm else (4 * E_CODE + N_CODE) * 4 / (2 * E_CODE)
     smem_peak = 148 * 128 * sm_mhz * 1e6 / smem_bytes_per_update
-    # issue ceiling of the instruction stream: 739 SASS instructions per thread-iteration
-    # (profiles/r01_sass_loop.txt), thr_cta/cw_cta thread slots per codeword, 2*E updates per iteration
-    lane_instr_per_update = 739 * (thr_cta / max(cw_cta, 1)) / (2 * E_CODE) if n_sm else None
+    # issue ceiling of the instruction stream: 734 SASS instructions per thread-iteration (378 variable
+    # phase + 356 check phase, profiles/r01_sass_loop.txt), thr_cta/cw_cta thread slots per codeword,
+    # 2*E updates per iteration; ALU-pipe ceiling: 248 FMNMX.XORSIGN + 66 ISETP/SEL per thread-iteration on
+    # the half-rate ALU pipe (measured 0.5 warp-instr/clk/SMSP, profiles/r01_pipe_rates.txt)
+    lane_instr_per_update = 734 * (thr_cta / max(cw_cta, 1)) / (2 * E_CODE) if n_sm else None
     issue_peak = 148 * 4 * 32 * sm_mhz * 1e6 / lane_instr_per_update if lane_instr_per_update else None
+    alu_peak = 148 * 4 * 16 * sm_mhz * 1e6 / (314 * (thr_cta / max(cw_cta, 1)) / (2 * E_CODE)) if n_sm else None
     out = {
         "metric": METRIC, "value": value, "unit": "Gbit/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -269,14 +323,14 @@ def main():
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                      "frac": achieved / hbm_peak,
                      # dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture of this launch
-                     # shape (profiles/r01_decode_qc_ncu_summary.txt): 15 756 B per codeword
-                     "traffic": (15756.0 * B / 1e9) if (code.kernel and a.update != "sp") else None, "traffic_unit": "GB per launch",
+                     # shape (profiles/r01_decode_qc_ncu_summary.txt): 15 618 B per codeword
+                     "traffic": (15618.0 * B / 1e9) if (code.kernel and a.update != "sp") else None, "traffic_unit": "GB per launch",
                      "algorithmic_bytes_per_launch_gb": alg_bytes / 1e9, "peak_source": peak_src,
                      "note": "decoder is shared-memory/issue bound, not HBM bound: see roofline_decoder"},
         "roofline_decoder": {"bound": "issue" if (issue_peak and issue_peak < smem_peak) else "smem",
                              "achieved": upd_s, "peak": min(smem_peak, issue_peak or smem_peak),
                              "unit": "edge-updates/s", "frac": upd_s / min(smem_peak, issue_peak or smem_peak),
-                             "smem_peak": smem_peak, "issue_peak": issue_peak,
+                             "smem_peak": smem_peak, "issue_peak": issue_peak, "alu_pipe_peak": alu_peak,
                              "plan": {"register_blocks": n_loc, "smem_blocks": n_sm, "threads_per_cta": thr_cta, "codewords_per_cta": cw_cta},
                              "peak_source": f"smem: 148 SMs x 128 B/clk x {sm_mhz:.0f} MHz / {smem_bytes_per_update:.2f} B per directed edge-update; "
                                             f"issue: 148 SMs x 4 SMSP x 32 lanes x {sm_mhz:.0f} MHz / {lane_instr_per_update or 0:.2f} lane-instr per update"},
@@ -304,6 +358,10 @@ def main():
         code.set_precision("f32")
         step()
         barrier()
+
+    # ---- BASELINE.json configs[4]: NN demapper + quantized OFDM + BP decoder on the default (64,32) code ------
+    if not a.no_nn:
+        out["nn_demapper"] = bench_nn(a, dev, world, barrier, peaks)
 
     # ---- e2e: the C-ABI host call (decode_bits path): pinned host LLRs in, packed bits out ---------
     if not a.no_e2e:
