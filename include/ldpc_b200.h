@@ -266,8 +266,9 @@ int ldpc_decode_count(const ldpc_code_t *code, const void *llr, int llr_dtype, i
  * evaluate_quantized_snr.py:150-160).  ldpc_mlp_create uploads the weights (HOST pointers,
  * weights[l] = nn.Linear.weight [dims[l+1], dims[l]] row-major, biases[l] = [dims[l+1]] or NULL,
  * activations[l] != 0 -> tanh after layer l; NULL = tanh after every layer but the last) and
- * splits them exactly into `splits` bf16 planes for the tensor cores (3 = fp32-equivalent,
- * 2 = ~2^-16 relative, 1 = plain bf16).  Every dims[l+1] must be a multiple of 64.
+ * splits them exactly into `splits` binary16 planes for the tensor cores (2 = fp32-equivalent:
+ * 22+ significant bits, 3 MMAs per product; 3 = 33 bits, 6 MMAs; 1 = plain fp16).  Operands must stay
+ * below 65504 in magnitude.  Every dims[l+1] must be a multiple of 64.
  * ldpc_mlp_forward: x [B, dims[0]] f32 row-major DEVICE -> y [B, dims[n_layers]] f32 DEVICE,
  * asynchronous on `stream`, chunked internally (chunk_rows, 0 = default).  A handle owns scratch
  * buffers: use it from one stream at a time. */

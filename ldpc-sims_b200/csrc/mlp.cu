@@ -2,24 +2,26 @@
 // 5th-generation tensor cores with fp32-equivalent accuracy.
 //
 // The reference evaluates  y = tanh(x W^T + b)  layer by layer in fp32 (ATen addmm).  fp32 is not a
-// tensor-core input format, so every fp32 operand is split EXACTLY into NS bf16 planes
-//     v = p0 + p1 + p2,   p0 = bf16(v), p1 = bf16(v - p0), p2 = bf16(v - p0 - p1)      (8 + 8 + 8 bits)
+// tensor-core input format, so every fp32 operand is split EXACTLY into NS binary16 planes
+//     v = p0 + p1 (+ p2),   p0 = f16(v), p1 = f16(v - p0), ...            (11 + 11 (+ 11) significant bits)
 // and the product is accumulated in fp32 (TMEM) from the plane pairs (i, j) with i + j < NS:
-// NS = 3 -> 6 tcgen05.mma per k-step, relative error ~2^-24 per product (fp32-equivalent, the default);
-// NS = 2 -> 3 MMAs, ~2^-16; NS = 1 -> plain bf16.
+// NS = 2 -> 3 tcgen05.mma per k-step, |v - p0 - p1| <= 2^-23 |v|: fp32-equivalent (the default);
+// NS = 3 -> 6 MMAs (beyond fp32); NS = 1 -> plain fp16.  Operands must stay below 65504 in magnitude
+// (LLR-scale inputs, trained weights and tanh outputs do).
 //
 // One kernel per layer:  C[M,N] = act(A[M,K] W[N,K]^T + bias)
 //   warp 0  TMA producer: 3-D tensor maps (k, row, plane), 128-byte swizzle, [128 x 64] A boxes and
-//           [BN x 64] W boxes per plane into a 2-stage shared-memory ring (mbarrier full/empty)
+//           [BN x 64] W boxes per plane into a shared-memory ring (mbarrier full/empty)
 //   warp 1  allocates TMEM, one elected lane issues tcgen05.mma (cta_group::1, kind::f16, M=128, N=BN,
 //           K=16) for every plane pair and k-slice, tcgen05.commit releases the stage / signals the tile
-//   warps 2-5  epilogue: tcgen05.ld (32 lanes x 32 columns) -> + bias -> tanhf -> split into the bf16
+//   warps 2-5  epilogue: tcgen05.ld (32 lanes x 32 columns) -> + bias -> tanhf -> split into the f16
 //           planes of the next layer's A operand (or the fp32 result of the last layer)
 // Activations of a chunk of rows ping-pong between two plane buffers that stay L2-resident.
 #include <cuda.h>
-#include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -28,7 +30,9 @@
 namespace ldpc {
 namespace mlp {
 
-constexpr int BM = 128, BK = 64, STAGES = 2, UMMA_K = 16;
+// TWO co-resident CTAs per SM (2 x 256 TMEM columns): while one CTA runs its epilogue the other one's
+// MMAs keep the tensor pipe busy.
+constexpr int BM = 128, BK = 64, UMMA_K = 16;
 constexpr int THREADS = 192;                       // warp 0 TMA, warp 1 MMA, warps 2..5 epilogue
 
 // ---- PTX wrappers --------------------------------------------------------------------------------------
@@ -58,12 +62,12 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
-// D[tmem] (+)= A[smem] * B[smem]^T, bf16 inputs, fp32 accumulate
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+// D[tmem] (+)= A[smem] * B[smem]^T, binary16 inputs, fp32 accumulate
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
     asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}"
                  ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
-// K-major operand tile, 128-byte swizzle: rows of 64 bf16 (128 B), 8-row groups 1024 B apart
+// K-major operand tile, 128-byte swizzle: rows of 64 halves (128 B), 8-row groups 1024 B apart
 __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
     uint64_t d = 0;
     d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);      // start address            bits [0,14)
@@ -85,28 +89,32 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-// exact split of an fp32 value into bf16 planes
+// libm tanhf (~1 ulp): measured FASTER in this epilogue than an ex2/rcp formulation (10.2 vs 12.1 ms per 2^20
+// rows) and it keeps the activations within an ulp of the reference's ATen tanh.
+__device__ __forceinline__ float tanh_act(float x) { return tanhf(x); }
+
+// exact split of an fp32 value into binary16 planes
 template <int NS>
-__device__ __forceinline__ void split_bf16(float v, __nv_bfloat16 (&p)[NS]) {
+__device__ __forceinline__ void split_f16(float v, __half (&p)[NS]) {
     float r = v;
 #pragma unroll
     for (int i = 0; i < NS; ++i) {
-        p[i] = __float2bfloat16_rn(r);
-        r = __fsub_rn(r, __bfloat162float(p[i]));      // exact: p[i] is r rounded to 8 significant bits
+        p[i] = __float2half_rn(r);
+        r = __fsub_rn(r, __half2float(p[i]));      // exact: p[i] is r rounded to 11 significant bits
     }
 }
 
-// ---- fp32 rows -> bf16 planes [NS][M][Kp] (zero padding beyond K) ---------------------------------------
+// ---- fp32 rows -> f16 planes [NS][M][Kp] (zero padding beyond K) ---------------------------------------
 template <int NS>
 __global__ void __launch_bounds__(256) split_rows_kernel(const float *x, long long ld, int K, long long M, int Kp,
-                                                         __nv_bfloat16 *planes, long long plane_stride) {
+                                                         __half *planes, long long plane_stride) {
     const long long total = M * Kp;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         const long long m = i / Kp;
         const int k = (int)(i - m * Kp);
         const float v = (k < K) ? __ldg(x + m * ld + k) : 0.0f;
-        __nv_bfloat16 p[NS];
-        split_bf16<NS>(v, p);
+        __half p[NS];
+        split_f16<NS>(v, p);
 #pragma unroll
         for (int s = 0; s < NS; ++s) planes[s * plane_stride + i] = p[s];
     }
@@ -119,22 +127,23 @@ struct LayerArgs {
     int n_total;                  // N of the layer
     int act;                      // 1 = tanh
     const float *bias;            // [N] or null
-    __nv_bfloat16 *out_planes;    // [NS][chunk_rows][N] (next layer's A operand) or null
+    __half *out_planes;    // [NS][chunk_rows][N] (next layer's A operand) or null
     long long out_plane_stride;
     float *out_f32;               // [m_valid][N] row-major (last layer) or null
 };
 
-template <int NS, int BN>
+template <int NS, int BN, int STAGES>
 struct Smem {
     static constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2;
     static constexpr int STAGE_BYTES = NS * (A_BYTES + B_BYTES);
-    static constexpr int TOTAL = STAGES * STAGE_BYTES + 1024 /* alignment slack */ + 64 /* barriers */;
+    static constexpr int NEEDED = STAGES * STAGE_BYTES + 1024 /* alignment slack */ + 64 /* barriers */;
+    static constexpr int TOTAL = NEEDED > 100 * 1024 ? NEEDED : 100 * 1024;   // never more than two CTAs per SM (TMEM columns)
 };
 
-template <int NS, int BN>
-__global__ void __launch_bounds__(THREADS, 1) layer_kernel(const __grid_constant__ CUtensorMap map_a,
+template <int NS, int BN, int STAGES>
+__global__ void __launch_bounds__(THREADS, 2) layer_kernel(const __grid_constant__ CUtensorMap map_a,
                                                             const __grid_constant__ CUtensorMap map_w, const LayerArgs args) {
-    using S = Smem<NS, BN>;
+    using S = Smem<NS, BN, STAGES>;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;         // swizzle-128B tiles need 1024-byte alignment
     const uint32_t bars = base + STAGES * S::STAGE_BYTES;                  // full[STAGES], empty[STAGES], accum, tmem slot
@@ -147,8 +156,8 @@ __global__ void __launch_bounds__(THREADS, 1) layer_kernel(const __grid_constant
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n0 = blockIdx.x * BN, m0 = blockIdx.y * BM;
     // two fp32 accumulators: columns [0, BN) collect the leading plane pair (0, 0), columns [BN, 2 BN) the
-    // correction pairs, whose sum is ~2^-8 of the result - the tensor core's truncating fp32 accumulation
-    // then costs ~2^-8 less on five of the six product streams; the epilogue adds the two in fp32 (RN)
+    // correction pairs, whose sum is ~2^-11 of the result - the tensor core's truncating fp32 accumulation
+    // then costs ~2^-11 less on the correction streams; the epilogue adds the two in fp32 (RN)
     constexpr uint32_t ACC2 = NS > 1 ? BN : 0;
     constexpr uint32_t TMEM_COLS = (BN + ACC2) < 32 ? 32 : (BN + ACC2);
 
@@ -182,7 +191,7 @@ __global__ void __launch_bounds__(THREADS, 1) layer_kernel(const __grid_constant
             }
         }
     } else if (warp == 1) {                                                // ===== MMA issuer =====
-        constexpr uint32_t idesc = (1u << 4) /* D = f32 */ | (1u << 7) /* A = bf16 */ | (1u << 10) /* B = bf16 */ |
+        constexpr uint32_t idesc = (1u << 4) /* D = f32; A = B = f16 (format 0), both K-major */ |
                                    ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
         for (int kb = 0; kb < args.k_blocks; ++kb) {
             const int s = kb % STAGES;
@@ -199,8 +208,8 @@ __global__ void __launch_bounds__(THREADS, 1) layer_kernel(const __grid_constant
                         for (int j = 0; j + i < NS; ++j) {
                             const uint64_t ad = umma_desc_sw128(st + i * S::A_BYTES + k * UMMA_K * 2);
                             const uint64_t bd = umma_desc_sw128(st + NS * S::A_BYTES + j * S::B_BYTES + k * UMMA_K * 2);
-                            if (i + j == 0) umma_bf16(tmem_base, ad, bd, idesc, (kb | k) ? 1u : 0u);
-                            else umma_bf16(tmem_base + ACC2, ad, bd, idesc, (kb | k | (i + j - 1) | i) ? 1u : 0u);   // first correction pair: (0, 1)
+                            if (i + j == 0) umma_f16(tmem_base, ad, bd, idesc, (kb | k) ? 1u : 0u);
+                            else umma_f16(tmem_base + ACC2, ad, bd, idesc, (kb | k | (i + j - 1) | i) ? 1u : 0u);   // first correction pair: (0, 1)
                         }
                     }
                 }
@@ -226,7 +235,7 @@ __global__ void __launch_bounds__(THREADS, 1) layer_kernel(const __grid_constant
                 float f = __uint_as_float(v[j]);
                 if (NS > 1) f = __fadd_rn(f, __uint_as_float(w[j]));
                 if (args.bias) f = __fadd_rn(f, __ldg(args.bias + n0 + c0 + j));
-                o[j] = args.act ? tanhf(f) : f;
+                o[j] = args.act ? tanh_act(f) : f;
             }
             if (m < args.m_valid || args.out_planes) {
                 if (args.out_f32) {
@@ -236,20 +245,23 @@ __global__ void __launch_bounds__(THREADS, 1) layer_kernel(const __grid_constant
                         for (int q = 0; q < 8; ++q) dst[q] = make_float4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
                     }
                 } else {
-                    __nv_bfloat16 pl[NS][32];
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        __nv_bfloat16 p[NS];
-                        split_bf16<NS>(o[j], p);
-#pragma unroll
-                        for (int s = 0; s < NS; ++s) pl[s][j] = p[s];
-                    }
+                    // exact plane split, two values per conversion (cvt.rn.f16x2.f32), 64 contiguous bytes per plane
 #pragma unroll
                     for (int s = 0; s < NS; ++s) {
-                        uint4 *dst = reinterpret_cast<uint4 *>(args.out_planes + s * args.out_plane_stride + m * args.n_total + n0 + c0);
-                        const uint4 *src = reinterpret_cast<const uint4 *>(pl[s]);
+                        uint32_t pk[16];
 #pragma unroll
-                        for (int q = 0; q < 4; ++q) dst[q] = src[q];
+                        for (int q = 0; q < 16; ++q) {
+                            const __half2 h = __floats2half2_rn(o[2 * q], o[2 * q + 1]);
+                            pk[q] = *reinterpret_cast<const uint32_t *>(&h);
+                            if (s + 1 < NS) {
+                                const float2 hf = __half22float2(h);
+                                o[2 * q] = __fsub_rn(o[2 * q], hf.x);          // exact residuals
+                                o[2 * q + 1] = __fsub_rn(o[2 * q + 1], hf.y);
+                            }
+                        }
+                        uint4 *dst = reinterpret_cast<uint4 *>(args.out_planes + s * args.out_plane_stride + m * args.n_total + n0 + c0);
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) dst[q] = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
                     }
                 }
             }
@@ -278,7 +290,7 @@ static EncodeTiledFn encode_fn() {
     return fn;
 }
 
-// planes [NS][rows][Kp] bf16 -> 3-D map (k, row, plane), box [64 x box_rows x 1], 128-byte swizzle
+// planes [NS][rows][Kp] f16 -> 3-D map (k, row, plane), box [64 x box_rows x 1], 128-byte swizzle
 static int make_map(CUtensorMap *map, void *ptr, int Kp, long long rows, int ns, int box_rows) {
     EncodeTiledFn fn = encode_fn();
     if (!fn) { set_error("cuTensorMapEncodeTiled is not available from the driver"); return LDPC_ECUDA; }
@@ -286,7 +298,7 @@ static int make_map(CUtensorMap *map, void *ptr, int Kp, long long rows, int ns,
     const cuuint64_t gstr[2] = {(cuuint64_t)Kp * 2, (cuuint64_t)rows * Kp * 2};
     const cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)box_rows, 1};
     const cuuint32_t est[3] = {1, 1, 1};
-    const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, ptr, gdim, gstr, box, est, CU_TENSOR_MAP_INTERLEAVE_NONE,
+    const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, ptr, gdim, gstr, box, est, CU_TENSOR_MAP_INTERLEAVE_NONE,
                           CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d)", (int)r); return LDPC_ECUDA; }
     return LDPC_OK;
@@ -295,7 +307,7 @@ static int make_map(CUtensorMap *map, void *ptr, int Kp, long long rows, int ns,
 struct Layer {
     int K, Kp, N, BN, act;
     float *d_bias = nullptr;
-    __nv_bfloat16 *d_w = nullptr;          // [NS][N][Kp]
+    __half *d_w = nullptr;          // [NS][N][Kp]
     CUtensorMap map_w, map_a;              // map_a: this layer's INPUT planes
 };
 
@@ -306,7 +318,7 @@ struct ldpc_mlp {
     int ns, device;
     long long chunk;
     std::vector<ldpc::mlp::Layer> layers;
-    __nv_bfloat16 *d_act[2] = {nullptr, nullptr};   // ping-pong activation planes [NS][chunk][maxKp]
+    __half *d_act[2] = {nullptr, nullptr};   // ping-pong activation planes [NS][chunk][maxKp]
     long long act_elems = 0;
 };
 
@@ -314,7 +326,7 @@ using namespace ldpc;
 using namespace ldpc::mlp;
 
 template <int NS>
-static int launch_split(const float *x, long long ld, int K, long long M, int Kp, __nv_bfloat16 *planes, long long plane_stride, cudaStream_t s) {
+static int launch_split(const float *x, long long ld, int K, long long M, int Kp, __half *planes, long long plane_stride, cudaStream_t s) {
     const long long total = M * Kp;
     const int grid = (int)std::min<long long>((total + 255) / 256, 148LL * 16);
     split_rows_kernel<NS><<<grid, 256, 0, s>>>(x, ld, K, M, Kp, planes, plane_stride);
@@ -324,10 +336,19 @@ static int launch_split(const float *x, long long ld, int K, long long M, int Kp
 
 template <int NS, int BN>
 static int launch_layer(const Layer &L, const LayerArgs &a, long long rows, cudaStream_t s) {
-    auto k = layer_kernel<NS, BN>;
-    LDPC_CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<NS, BN>::TOTAL));
+    constexpr int STAGES = (NS == 1) ? 3 : 1;                            // <= ~110 KB per CTA: two CTAs per SM
+    static const bool deep = [] { const char *e = getenv("LDPC_MLP_DEEP"); return e && atoi(e) != 0; }();   // A/B: 3 stages, one CTA per SM
     dim3 grid(L.N / BN, (unsigned)((rows + BM - 1) / BM));
-    k<<<grid, THREADS, Smem<NS, BN>::TOTAL, s>>>(L.map_a, L.map_w, a);
+    if (NS == 2 && deep) {
+        auto k3 = layer_kernel<NS, BN, (NS == 2 ? 3 : STAGES)>;
+        LDPC_CUDA_TRY(cudaFuncSetAttribute(k3, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<NS, BN, (NS == 2 ? 3 : STAGES)>::TOTAL));
+        k3<<<grid, THREADS, Smem<NS, BN, (NS == 2 ? 3 : STAGES)>::TOTAL, s>>>(L.map_a, L.map_w, a);
+        LDPC_CUDA_TRY(cudaGetLastError());
+        return LDPC_OK;
+    }
+    auto k = layer_kernel<NS, BN, STAGES>;
+    LDPC_CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<NS, BN, STAGES>::TOTAL));
+    k<<<grid, THREADS, Smem<NS, BN, STAGES>::TOTAL, s>>>(L.map_a, L.map_w, a);
     LDPC_CUDA_TRY(cudaGetLastError());
     return LDPC_OK;
 }
@@ -377,12 +398,12 @@ int ldpc_mlp_create(int n_layers, const int32_t *dims, const float *const *weigh
     int rc = LDPC_OK;
     auto fail = [&](int code) { ldpc_mlp_destroy(h); return code; };
     for (int b = 0; b < 2; ++b)
-        if (cudaMalloc(&h->d_act[b], (size_t)h->ns * h->act_elems * sizeof(__nv_bfloat16)) != cudaSuccess) { set_error("ldpc_mlp_create: out of device memory"); return fail(LDPC_ENOMEM); }
+        if (cudaMalloc(&h->d_act[b], (size_t)h->ns * h->act_elems * sizeof(__half)) != cudaSuccess) { set_error("ldpc_mlp_create: out of device memory"); return fail(LDPC_ENOMEM); }
     for (int l = 0; l < n_layers; ++l) {
         Layer &L = h->layers[l];
         const size_t wel = (size_t)L.N * L.Kp;
         float *tmp = nullptr;
-        if (cudaMalloc(&L.d_w, h->ns * wel * sizeof(__nv_bfloat16)) != cudaSuccess || cudaMalloc(&tmp, (size_t)L.N * L.K * sizeof(float)) != cudaSuccess) { cudaFree(tmp); set_error("ldpc_mlp_create: out of device memory"); return fail(LDPC_ENOMEM); }
+        if (cudaMalloc(&L.d_w, h->ns * wel * sizeof(__half)) != cudaSuccess || cudaMalloc(&tmp, (size_t)L.N * L.K * sizeof(float)) != cudaSuccess) { cudaFree(tmp); set_error("ldpc_mlp_create: out of device memory"); return fail(LDPC_ENOMEM); }
         cudaMemcpy(tmp, weights[l], (size_t)L.N * L.K * sizeof(float), cudaMemcpyHostToDevice);
         if (h->ns == 1) rc = launch_split<1>(tmp, L.K, L.K, L.N, L.Kp, L.d_w, (long long)wel, 0);
         else if (h->ns == 2) rc = launch_split<2>(tmp, L.K, L.K, L.N, L.Kp, L.d_w, (long long)wel, 0);

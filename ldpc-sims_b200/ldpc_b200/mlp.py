@@ -1,5 +1,5 @@
 """Native MLP forward (ldpc_mlp_* of include/ldpc_b200.h): Linear + tanh chains on the tensor
-cores with fp32-equivalent accuracy (exact bf16 plane splitting, csrc/mlp.cu).  Replaces the
+cores with fp32-equivalent accuracy (exact binary16 plane splitting, csrc/mlp.cu).  Replaces the
 ATen addmm/tanh calls under the reference's LLR estimators (pytorch/nn/llr.py:46-73)."""
 from __future__ import annotations
 
@@ -15,7 +15,7 @@ class NativeMLP:
     """weights[l]: [out_l, in_l] float32 (nn.Linear.weight), biases[l]: [out_l] or None,
     activations[l]: True -> tanh after layer l (default: every layer but the last)."""
 
-    def __init__(self, weights, biases=None, activations=None, splits=3, chunk_rows=0, device=None):
+    def __init__(self, weights, biases=None, activations=None, splits=2, chunk_rows=0, device=None):
         N.require_cuda()
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         ws = [np.ascontiguousarray(_np(w), dtype=np.float32) for w in weights]

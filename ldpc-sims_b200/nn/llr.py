@@ -4,12 +4,12 @@ Same class names, constructor arguments and parameter names as the reference, so
 reference's checkpoints load unchanged (``nn.DataParallel(LLRestimator_withSNR(32))`` +
 ``load_state_dict(checkpoint['model_state_dict'])``, evaluate_quantized_snr.py:57-69).
 ``forward`` runs the whole Linear/tanh chain in one native call (ldpc_b200.mlp.NativeMLP:
-tcgen05 tensor cores, exact bf16 plane splitting, fp32-equivalent results); CPU tensors are
+tcgen05 tensor cores, exact binary16 plane splitting, fp32-equivalent results); CPU tensors are
 moved to the current CUDA device and the result is returned on the input's device.  There is
 no CPU path and no autograd: training the demapper (quantized_snr.py, ofdm_nn.py) is outside
 the hot path.
 
-``splits`` (keyword-only extra): 3 = fp32-equivalent (default), 2 = ~2^-16 relative, 1 = bf16.
+``splits`` (keyword-only extra): 2 = fp32-equivalent (default), 3 = beyond fp32, 1 = plain fp16.
 """
 import numpy as np
 import torch
@@ -60,7 +60,7 @@ class LLRestimator(_NativeChain):                  # nn/llr.py:7-52
     _chain = ("fft_layer", "hidden3", "hidden4", "hidden5", "final")
     _acts = (False, True, True, True, False)       # forward: fft_layer, tanh(hidden3..5), final (nn/llr.py:46-52)
 
-    def __init__(self, ofdm_size, snr_est, *, splits=3):
+    def __init__(self, ofdm_size, snr_est, *, splits=2):
         super().__init__()
         self.ofdm_size, self.snr_est = ofdm_size, snr_est
         self.activation = nn.Tanh()
@@ -85,7 +85,7 @@ class LLRestimator_withSNR(_NativeChain):          # nn/llr.py:54-73
     _chain = ("hidden1", "hidden2", "hidden3", "final")
     _acts = (True, True, True, False)
 
-    def __init__(self, ofdm_size, *, splits=3):
+    def __init__(self, ofdm_size, *, splits=2):
         super().__init__()
         self.ofdm_size = ofdm_size
         self.activation = nn.Tanh()

@@ -4,7 +4,7 @@ CPU: the numpy oracle against the golden vectors minted from the reference's own
 (tests/golden/nn_demapper.npz, oracle/make_golden_nn.py).  GPU: the native tensor-core kernel
 through the drop-in nn.llr module against the same vectors, then through the decoder.
 Tolerance (fp32 GEMM chains do not pin a summation order): 1e-5 of the output scale for the
-fp32-equivalent mode (3 bf16 planes), 2e-4 for 2 planes.
+fp32-equivalent mode (2 binary16 planes, the default) and for 3 planes.
 """
 import ctypes
 import os
@@ -63,7 +63,7 @@ def _model(splits):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("splits,tol", [(3, 1e-5), (2, 1e-4)])
+@pytest.mark.parametrize("splits,tol", [(2, 1e-5), (3, 1e-5), (1, 5e-3)])
 def test_native_mlp_matches_reference_golden(splits, tol):
     import torch
     m = _model(splits)
@@ -88,7 +88,7 @@ def test_native_mlp_matches_oracle_ragged_and_chunked():
         ref = NO.mlp_forward(STATE, x)
         assert y.shape == ref.shape
         assert _scale_err(y, ref) < 1e-5, B
-    m = _model(3)
+    m = _model(2)
     x = torch.tensor(GOLD["snr15_x"][:100])
     y = m.module(x)                                      # CPU tensor in -> CPU tensor out (DataParallel itself returns CUDA)
     assert not y.is_cuda and _scale_err(y.numpy(), GOLD["snr15_llr"][:100]) < 1e-5
@@ -100,7 +100,7 @@ def test_nn_demapper_then_decoder_matches_reference_bits():
     import torch
     from ofdm.ofdm_functions import decode_bits
     from bp.parity import H
-    m = _model(3)
+    m = _model(2)
     for tag in GOLD["names"]:
         snrdb, iters, clamp = GOLD[f"{tag}_meta"]
         x = torch.tensor(GOLD[f"{tag}_x"], dtype=torch.float, device="cuda")
@@ -173,7 +173,7 @@ def test_nn_link_counters_are_exact():
     import torch
     from ldpc_b200.linksim import LinkConfig, sim_generate, sim_run_nn
     code, H = _default_code()
-    m = _model(3).module
+    m = _model(2).module
     cfg = LinkConfig(snr_db=10.0, ofdm_size=32, qbits=3, agc_mode=1, iters=10, update="sp", clamp_value=100.0, seed=5)
     cnt = 3000
     c = sim_run_nn(code, cfg, m, 0, cnt, chunk=1024).cpu().numpy()
