@@ -10,12 +10,14 @@
 // (LLR-scale inputs, trained weights and tanh outputs do).
 //
 // One kernel per layer:  C[M,N] = act(A[M,K] W[N,K]^T + bias)
+// (persistent CTAs, one per SM, walking the [128 x BN] output tiles)
 //   warp 0  TMA producer: 3-D tensor maps (k, row, plane), 128-byte swizzle, [128 x 64] A boxes and
-//           [BN x 64] W boxes per plane into a shared-memory ring (mbarrier full/empty)
+//           [BN x 64] W boxes per plane into a shared-memory ring (mbarrier full/empty, ~200 KB deep)
 //   warp 1  allocates TMEM, one elected lane issues tcgen05.mma (cta_group::1, kind::f16, M=128, N=BN,
 //           K=16) for every plane pair and k-slice, tcgen05.commit releases the stage / signals the tile
-//   warps 2-5  epilogue: tcgen05.ld (32 lanes x 32 columns) -> + bias -> tanhf -> split into the f16
-//           planes of the next layer's A operand (or the fp32 result of the last layer)
+//   warps 2-9  epilogue: tcgen05.ld (32 lanes x 32 columns) -> + bias -> tanhf -> split into the f16
+//           planes of the next layer's A operand (or the fp32 result of the last layer); TMEM holds two
+//           accumulator sets, so the epilogue of a tile overlaps the loads and MMAs of the next one
 // Activations of a chunk of rows ping-pong between two plane buffers that stay L2-resident.
 #include <cuda.h>
 #include <cuda_fp16.h>
@@ -30,10 +32,9 @@
 namespace ldpc {
 namespace mlp {
 
-// TWO co-resident CTAs per SM (2 x 256 TMEM columns): while one CTA runs its epilogue the other one's
-// MMAs keep the tensor pipe busy.
 constexpr int BM = 128, BK = 64, UMMA_K = 16;
-constexpr int THREADS = 192;                       // warp 0 TMA, warp 1 MMA, warps 2..5 epilogue
+constexpr int EPI_WARPS = 8;
+constexpr int THREADS = 32 * (2 + EPI_WARPS);      // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (two per TMEM lane quadrant)
 
 // ---- PTX wrappers --------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -124,6 +125,7 @@ __global__ void __launch_bounds__(256) split_rows_kernel(const float *x, long lo
 struct LayerArgs {
     int k_blocks;                 // Kp / 64
     int m_valid;                  // rows of this chunk that exist
+    int m_rows;                   // rows to compute (m_valid rounded up to the tile)
     int n_total;                  // N of the layer
     int act;                      // 1 = tanh
     const float *bias;            // [N] or null
@@ -132,38 +134,50 @@ struct LayerArgs {
     float *out_f32;               // [m_valid][N] row-major (last layer) or null
 };
 
-template <int NS, int BN, int STAGES>
+template <int NS, int BN>
 struct Smem {
     static constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2;
     static constexpr int STAGE_BYTES = NS * (A_BYTES + B_BYTES);
-    static constexpr int NEEDED = STAGES * STAGE_BYTES + 1024 /* alignment slack */ + 64 /* barriers */;
-    static constexpr int TOTAL = NEEDED > 100 * 1024 ? NEEDED : 100 * 1024;   // never more than two CTAs per SM (TMEM columns)
+    static constexpr int STAGES = (200 * 1024 / STAGE_BYTES) > 6 ? 6 : (200 * 1024 / STAGE_BYTES);
+    static constexpr int TOTAL = STAGES * STAGE_BYTES + 1024 /* alignment slack */ + 128 /* barriers */;
 };
 
-template <int NS, int BN, int STAGES>
-__global__ void __launch_bounds__(THREADS, 2) layer_kernel(const __grid_constant__ CUtensorMap map_a,
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+// Persistent: gridDim.x CTAs (one per SM) walk the output tiles t = blockIdx.x, + gridDim.x, ... (column
+// tile fastest, so the CTAs running side by side share their A tile in L2).  TMEM holds TWO accumulator
+// sets, so the epilogue of tile i overlaps the TMA loads and MMAs of tile i + 1.
+template <int NS, int BN>
+__global__ void __launch_bounds__(THREADS, 1) layer_kernel(const __grid_constant__ CUtensorMap map_a,
                                                             const __grid_constant__ CUtensorMap map_w, const LayerArgs args) {
-    using S = Smem<NS, BN, STAGES>;
+    using S = Smem<NS, BN>;
+    constexpr int STAGES = S::STAGES;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;         // swizzle-128B tiles need 1024-byte alignment
-    const uint32_t bars = base + STAGES * S::STAGE_BYTES;                  // full[STAGES], empty[STAGES], accum, tmem slot
+    const uint32_t bars = base + STAGES * S::STAGE_BYTES;                  // full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2], slot
     auto full_bar = [&](int s) { return bars + 8u * s; };
     auto empty_bar = [&](int s) { return bars + 8u * (STAGES + s); };
-    const uint32_t accum_bar = bars + 8u * (2 * STAGES);
-    const uint32_t tmem_slot = bars + 8u * (2 * STAGES + 1);
+    auto tfull_bar = [&](int a) { return bars + 8u * (2 * STAGES + a); };
+    auto tempty_bar = [&](int a) { return bars + 8u * (2 * STAGES + 2 + a); };
+    const uint32_t tmem_slot = bars + 8u * (2 * STAGES + 4);
     volatile uint32_t *tmem_slot_ptr = reinterpret_cast<volatile uint32_t *>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int n0 = blockIdx.x * BN, m0 = blockIdx.y * BM;
-    // two fp32 accumulators: columns [0, BN) collect the leading plane pair (0, 0), columns [BN, 2 BN) the
-    // correction pairs, whose sum is ~2^-11 of the result - the tensor core's truncating fp32 accumulation
+    const int tiles_n = args.n_total / BN;
+    const int n_tiles = tiles_n * ((args.m_rows + BM - 1) / BM);
+    // two fp32 accumulators per set: columns [0, BN) collect the leading plane pair (0, 0), columns [BN, 2 BN)
+    // the correction pairs, whose sum is ~2^-11 of the result - the tensor core's truncating fp32 accumulation
     // then costs ~2^-11 less on the correction streams; the epilogue adds the two in fp32 (RN)
     constexpr uint32_t ACC2 = NS > 1 ? BN : 0;
-    constexpr uint32_t TMEM_COLS = (BN + ACC2) < 32 ? 32 : (BN + ACC2);
+    constexpr uint32_t ACC_COLS = BN + ACC2;
+    constexpr uint32_t TMEM_COLS = 2 * ACC_COLS <= 32 ? 32 : (2 * ACC_COLS <= 64 ? 64 : (2 * ACC_COLS <= 128 ? 128 : (2 * ACC_COLS <= 256 ? 256 : 512)));
+    static_assert(2 * ACC_COLS <= 512, "accumulator sets do not fit the tensor memory");
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-        mbar_init(accum_bar, 1);
+        for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), EPI_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -177,67 +191,83 @@ __global__ void __launch_bounds__(THREADS, 2) layer_kernel(const __grid_constant
 
     if (warp == 0) {
         if (lane == 0) {                                                   // ===== TMA producer =====
-            for (int kb = 0; kb < args.k_blocks; ++kb) {
-                const int s = kb % STAGES;
-                const uint32_t ph = (kb / STAGES) & 1;
-                mbar_wait(empty_bar(s), ph ^ 1);
-                mbar_expect_tx(full_bar(s), S::STAGE_BYTES);
-                const uint32_t st = base + s * S::STAGE_BYTES;
+            uint32_t it = 0;
+            for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+                const int m0 = (t / tiles_n) * BM, n0 = (t % tiles_n) * BN;
+                for (int kb = 0; kb < args.k_blocks; ++kb, ++it) {
+                    const int s = it % STAGES;
+                    const uint32_t ph = (it / STAGES) & 1;
+                    mbar_wait(empty_bar(s), ph ^ 1);
+                    mbar_expect_tx(full_bar(s), S::STAGE_BYTES);
+                    const uint32_t st = base + s * S::STAGE_BYTES;
 #pragma unroll
-                for (int p = 0; p < NS; ++p) {
-                    tma_load_3d(st + p * S::A_BYTES, &map_a, full_bar(s), kb * BK, m0, p);
-                    tma_load_3d(st + NS * S::A_BYTES + p * S::B_BYTES, &map_w, full_bar(s), kb * BK, n0, p);
+                    for (int p = 0; p < NS; ++p) {
+                        tma_load_3d(st + p * S::A_BYTES, &map_a, full_bar(s), kb * BK, m0, p);
+                        tma_load_3d(st + NS * S::A_BYTES + p * S::B_BYTES, &map_w, full_bar(s), kb * BK, n0, p);
+                    }
                 }
             }
         }
     } else if (warp == 1) {                                                // ===== MMA issuer =====
         constexpr uint32_t idesc = (1u << 4) /* D = f32; A = B = f16 (format 0), both K-major */ |
                                    ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-        for (int kb = 0; kb < args.k_blocks; ++kb) {
-            const int s = kb % STAGES;
-            const uint32_t ph = (kb / STAGES) & 1;
-            mbar_wait(full_bar(s), ph);
+        uint32_t it = 0, ti = 0;
+        for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++ti) {
+            const uint32_t acc = ti & 1, acc_ph = (ti >> 1) & 1;
+            mbar_wait(tempty_bar(acc), acc_ph ^ 1);                        // the epilogue has drained this accumulator set
             tc_fence_after();
-            if (lane == 0) {
-                const uint32_t st = base + s * S::STAGE_BYTES;
+            const uint32_t d_main = tmem_base + acc * ACC_COLS;
+            for (int kb = 0; kb < args.k_blocks; ++kb, ++it) {
+                const int s = it % STAGES;
+                const uint32_t ph = (it / STAGES) & 1;
+                mbar_wait(full_bar(s), ph);
+                tc_fence_after();
+                if (lane == 0) {
+                    const uint32_t st = base + s * S::STAGE_BYTES;
 #pragma unroll
-                for (int k = 0; k < BK / UMMA_K; ++k) {
+                    for (int k = 0; k < BK / UMMA_K; ++k) {
 #pragma unroll
-                    for (int i = 0; i < NS; ++i) {
+                        for (int i = 0; i < NS; ++i) {
 #pragma unroll
-                        for (int j = 0; j + i < NS; ++j) {
-                            const uint64_t ad = umma_desc_sw128(st + i * S::A_BYTES + k * UMMA_K * 2);
-                            const uint64_t bd = umma_desc_sw128(st + NS * S::A_BYTES + j * S::B_BYTES + k * UMMA_K * 2);
-                            if (i + j == 0) umma_f16(tmem_base, ad, bd, idesc, (kb | k) ? 1u : 0u);
-                            else umma_f16(tmem_base + ACC2, ad, bd, idesc, (kb | k | (i + j - 1) | i) ? 1u : 0u);   // first correction pair: (0, 1)
+                            for (int j = 0; j + i < NS; ++j) {
+                                const uint64_t ad = umma_desc_sw128(st + i * S::A_BYTES + k * UMMA_K * 2);
+                                const uint64_t bd = umma_desc_sw128(st + NS * S::A_BYTES + j * S::B_BYTES + k * UMMA_K * 2);
+                                if (i + j == 0) umma_f16(d_main, ad, bd, idesc, (kb | k) ? 1u : 0u);
+                                else umma_f16(d_main + ACC2, ad, bd, idesc, (kb | k | (i + j - 1) | i) ? 1u : 0u);   // first correction pair: (0, 1)
+                            }
                         }
                     }
+                    tc_commit(empty_bar(s));                               // stage free once these MMAs have read it
+                    if (kb == args.k_blocks - 1) tc_commit(tfull_bar(acc)); // accumulator set complete
                 }
-                tc_commit(empty_bar(s));                                   // stage free once these MMAs have read it
-                if (kb == args.k_blocks - 1) tc_commit(accum_bar);         // accumulator complete
+                __syncwarp();
             }
-            __syncwarp();
         }
-    } else {                                                               // ===== epilogue (warps 2..5) =====
+    } else {                                                               // ===== epilogue (warps 2..9) =====
         const int quad = warp & 3;                                         // TMEM lane quadrant this warp may read
+        const int half = (warp - 2) >> 2;                                  // which half of the tile's columns
         const int row = quad * 32 + lane;
-        const long long m = (long long)m0 + row;
-        mbar_wait(accum_bar, 0);
-        tc_fence_after();
+        uint32_t ti = 0;
+        for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++ti) {
+            const int m0 = (t / tiles_n) * BM, n0 = (t % tiles_n) * BN;
+            const uint32_t acc = ti & 1, acc_ph = (ti >> 1) & 1;
+            const long long m = (long long)m0 + row;
+            mbar_wait(tfull_bar(acc), acc_ph);
+            tc_fence_after();
+            const uint32_t d_main = tmem_base + acc * ACC_COLS + ((uint32_t)(quad * 32) << 16);
 #pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 32) {
-            uint32_t v[32], w[32];
-            tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)c0, v);
-            if (NS > 1) tmem_ld32(tmem_base + ACC2 + ((uint32_t)(quad * 32) << 16) + (uint32_t)c0, w);
-            float o[32];
+            for (int c0 = half * (BN / 2); c0 < (half + 1) * (BN / 2); c0 += 32) {
+                uint32_t v[32], w[32];
+                tmem_ld32(d_main + (uint32_t)c0, v);
+                if (NS > 1) tmem_ld32(d_main + ACC2 + (uint32_t)c0, w);
+                float o[32];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                float f = __uint_as_float(v[j]);
-                if (NS > 1) f = __fadd_rn(f, __uint_as_float(w[j]));
-                if (args.bias) f = __fadd_rn(f, __ldg(args.bias + n0 + c0 + j));
-                o[j] = args.act ? tanh_act(f) : f;
-            }
-            if (m < args.m_valid || args.out_planes) {
+                for (int j = 0; j < 32; ++j) {
+                    float f = __uint_as_float(v[j]);
+                    if (NS > 1) f = __fadd_rn(f, __uint_as_float(w[j]));
+                    if (args.bias) f = __fadd_rn(f, __ldg(args.bias + n0 + c0 + j));
+                    o[j] = args.act ? tanh_act(f) : f;
+                }
                 if (args.out_f32) {
                     if (m < args.m_valid) {
                         float4 *dst = reinterpret_cast<float4 *>(args.out_f32 + m * args.n_total + n0 + c0);
@@ -265,9 +295,12 @@ __global__ void __launch_bounds__(THREADS, 2) layer_kernel(const __grid_constant
                     }
                 }
             }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty_bar(acc));                   // this warp is done with the accumulator set
         }
-        tc_fence_before();
     }
+    tc_fence_before();
     __syncthreads();
     if (warp == 1) {
         tc_fence_after();
@@ -336,19 +369,13 @@ static int launch_split(const float *x, long long ld, int K, long long M, int Kp
 
 template <int NS, int BN>
 static int launch_layer(const Layer &L, const LayerArgs &a, long long rows, cudaStream_t s) {
-    constexpr int STAGES = (NS == 1) ? 3 : 1;                            // <= ~110 KB per CTA: two CTAs per SM
-    static const bool deep = [] { const char *e = getenv("LDPC_MLP_DEEP"); return e && atoi(e) != 0; }();   // A/B: 3 stages, one CTA per SM
-    dim3 grid(L.N / BN, (unsigned)((rows + BM - 1) / BM));
-    if (NS == 2 && deep) {
-        auto k3 = layer_kernel<NS, BN, (NS == 2 ? 3 : STAGES)>;
-        LDPC_CUDA_TRY(cudaFuncSetAttribute(k3, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<NS, BN, (NS == 2 ? 3 : STAGES)>::TOTAL));
-        k3<<<grid, THREADS, Smem<NS, BN, (NS == 2 ? 3 : STAGES)>::TOTAL, s>>>(L.map_a, L.map_w, a);
-        LDPC_CUDA_TRY(cudaGetLastError());
-        return LDPC_OK;
-    }
-    auto k = layer_kernel<NS, BN, STAGES>;
-    LDPC_CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<NS, BN, STAGES>::TOTAL));
-    k<<<grid, THREADS, Smem<NS, BN, STAGES>::TOTAL, s>>>(L.map_a, L.map_w, a);
+    auto k = layer_kernel<NS, BN>;
+    LDPC_CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<NS, BN>::TOTAL));
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const long long tiles = (long long)(L.N / BN) * ((rows + BM - 1) / BM);
+    k<<<(unsigned)std::min<long long>(tiles, sms), THREADS, Smem<NS, BN>::TOTAL, s>>>(L.map_a, L.map_w, a);
     LDPC_CUDA_TRY(cudaGetLastError());
     return LDPC_OK;
 }
@@ -383,7 +410,7 @@ int ldpc_mlp_create(int n_layers, const int32_t *dims, const float *const *weigh
     ldpc_mlp *h = new ldpc_mlp();
     h->ns = splits;
     cudaGetDevice(&h->device);
-    if (chunk_rows <= 0) chunk_rows = 128 * 74;                           // 74 row tiles x 4 column tiles = two waves of 148 CTAs at N = 512
+    if (chunk_rows <= 0) chunk_rows = 128 * 148;                          // 148 row tiles x 4 column tiles at N = 512: four tiles per persistent CTA
     h->chunk = ((chunk_rows + BM - 1) / BM) * BM;
     int maxw = 0;
     h->layers.resize(n_layers);
@@ -443,7 +470,7 @@ int ldpc_mlp_forward(ldpc_mlp_t *h, const float *x, int64_t B, float *y, ldpc_st
             const Layer &L = h->layers[l];
             LayerArgs a;
             memset(&a, 0, sizeof(a));
-            a.k_blocks = L.Kp / BK; a.m_valid = (int)rows; a.n_total = L.N; a.act = L.act; a.bias = L.d_bias;
+            a.k_blocks = L.Kp / BK; a.m_valid = (int)rows; a.m_rows = (int)rows; a.n_total = L.N; a.act = L.act; a.bias = L.d_bias;
             if (l + 1 < nl) { a.out_planes = h->d_act[(l + 1) & 1]; a.out_plane_stride = h->chunk * (long long)L.N; }
             else a.out_f32 = y + done * NL;
             if (h->ns == 1) rc = launch_layer_ns<1>(L, a, rows, s);
