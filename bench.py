@@ -323,8 +323,8 @@ def main():
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                      "frac": achieved / hbm_peak,
                      # dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture of this launch
-                     # shape (profiles/r01_decode_qc_ncu_summary.txt): 15 618 B per codeword
-                     "traffic": (15618.0 * B / 1e9) if (code.kernel and a.update != "sp") else None, "traffic_unit": "GB per launch",
+                     # shape (profiles/r01_decode_qc_ncu_summary.txt): 15 756 B per codeword
+                     "traffic": (15756.0 * B / 1e9) if (code.kernel and a.update != "sp") else None, "traffic_unit": "GB per launch",
                      "algorithmic_bytes_per_launch_gb": alg_bytes / 1e9, "peak_source": peak_src,
                      "note": "decoder is shared-memory/issue bound, not HBM bound: see roofline_decoder"},
         "roofline_decoder": {"bound": "issue" if (issue_peak and issue_peak < smem_peak) else "smem",
