@@ -315,7 +315,7 @@ def main():
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload_name(a), "codewords_per_gpu_per_step": B,
-                   "outputs": "posterior LLR f32 + packed hard bits", "kernel": "qc" if code.kernel else "generic",
+                   "outputs": "posterior LLR f32 + packed hard bits", "kernel": ("generic", "qc", "tiny")[code.kernel],
                    "l2_policy": f"inputs larger than L2 ({B * N_CODE * 4 / 1e9:.2f} GB of LLRs per step)"},
         "codewords_per_s": cw_per_s, "edge_updates_per_s": upd_s * world,
         "gpu_launches": a.steps,
@@ -324,7 +324,7 @@ def main():
                      "frac": achieved / hbm_peak,
                      # dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture of this launch
                      # shape (profiles/r01_decode_qc_ncu_summary.txt): 15 756 B per codeword
-                     "traffic": (15756.0 * B / 1e9) if (code.kernel and a.update != "sp") else None, "traffic_unit": "GB per launch",
+                     "traffic": (15756.0 * B / 1e9) if (code.kernel == 1 and a.update != "sp") else None, "traffic_unit": "GB per launch",
                      "algorithmic_bytes_per_launch_gb": alg_bytes / 1e9, "peak_source": peak_src,
                      "note": "decoder is shared-memory/issue bound, not HBM bound: see roofline_decoder"},
         "roofline_decoder": {"bound": "issue" if (issue_peak and issue_peak < smem_peak) else "smem",

@@ -54,6 +54,7 @@ struct ldpc_code {
     int m, n, E, max_dc, max_dv;
     int kernel;         // LDPC_KERNEL_*
     int qc_id;          // index of the compiled specialisation or -1
+    int tiny_id;        // index of the compiled register-resident specialisation (decode_tiny.cu) or -1
     int qc_Z;
     int device;
     int32_t *d_tables;  // one allocation: chk_ptr | chk_var | var_ptr | cm_of_vm
@@ -84,6 +85,8 @@ int launch_decode_qc_h2(int qc_id, const DecodeArgs &a, cudaStream_t s);
 struct LinkParams;
 int launch_sim_fused_qc(int qc_id, const DecodeArgs &a, const LinkParams &lp, cudaStream_t s);   // LDPC_EUNSUPPORTED -> use the 3-launch chain
 int qc_lookup(int Z, int mb, int nb, const int16_t *proto);   // -1 if no compiled specialisation
+int tiny_lookup(int m, int n, const int32_t *row_ptr, const int32_t *col_idx);   // -1 if no compiled register-resident specialisation
+int launch_decode_tiny(int tiny_id, const DecodeArgs &a, cudaStream_t s);
 void qc_plan_info(int qc_id, int out[4]);                     // {register-resident blocks, shared-memory blocks, threads/CTA, codewords/CTA}
 
 }  // namespace ldpc

@@ -79,6 +79,8 @@ int ldpc_code_create(const int32_t *row_ptr, const int32_t *col_idx, int m, int 
     if (!h) { set_error("out of host memory"); return LDPC_ENOMEM; }
     h->m = m; h->n = n; h->E = E; h->max_dc = max_dc; h->max_dv = max_dv; h->device = dev;
     h->qc_Z = 0; h->qc_id = -1; h->kernel = LDPC_KERNEL_GENERIC; h->d_tables = nullptr;
+    h->tiny_id = tiny_lookup(m, n, row_ptr, col_idx);
+    if (h->tiny_id >= 0) h->kernel = LDPC_KERNEL_TINY;
     h->d_gen = nullptr; h->k_info = 0; h->host_pipe = nullptr; h->precision = LDPC_PREC_F32;
     const size_t words = (size_t)(m + 1) + E + (n + 1) + E;
     cudaError_t e = cudaMalloc(&h->d_tables, words * sizeof(int32_t));
@@ -153,6 +155,7 @@ int ldpc_code_set_kernel(ldpc_code_t *code, int kernel) {
     if (!code) { set_error("null code"); return LDPC_EINVAL; }
     if (kernel == LDPC_KERNEL_GENERIC) { code->kernel = kernel; return LDPC_OK; }
     if (kernel == LDPC_KERNEL_QC && code->qc_id >= 0) { code->kernel = kernel; return LDPC_OK; }
+    if (kernel == LDPC_KERNEL_TINY && code->tiny_id >= 0) { code->kernel = kernel; return LDPC_OK; }
     set_error("kernel %d not available for this code", kernel);
     return LDPC_EUNSUPPORTED;
 }
@@ -178,6 +181,8 @@ int decode_dispatch(const ldpc_code *code, const DecodeArgs &a, cudaStream_t s) 
             return launch_decode_qc_h2(code->qc_id, a, s);
         return launch_decode_qc(code->qc_id, a, s);
     }
+    if (code->kernel == LDPC_KERNEL_TINY && a.x0 == nullptr && a.x_out == nullptr && !a.early_exit)
+        return launch_decode_tiny(code->tiny_id, a, s);
     return launch_decode_generic(code->g, code->max_dv, code->max_dc, a, s);
 }
 }  // namespace ldpc

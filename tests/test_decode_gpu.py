@@ -16,6 +16,7 @@ import bp_oracle as O
 import c_oracle as C
 import linksim_oracle as LO
 from ldpc_b200.codes import ieee80211n_1944_r12, peg_64_32
+from ldpc_b200.decoder import LdpcCode
 
 pytestmark = pytest.mark.gpu
 
@@ -61,10 +62,10 @@ def dec(code, llr, iters, clamp, update="sp", param=1.0, x0=None,
 
 def test_default_code_against_reference_golden(dcode, golden_dir):
     g = np.load(os.path.join(golden_dir, "bp_default_code.npz"))
-    assert dcode.kernel == 0 and dcode.E == 96
+    assert dcode.kernel == 2 and dcode.E == 96            # register-resident specialisation selected ...
     for name in g["names"]:
         llr, iters, clamp = g[f"{name}_llr"], int(g[f"{name}_iters"]), float(g[f"{name}_clamp"])
-        o = dec(dcode, llr, iters, clamp)
+        o = dec(dcode, llr, iters, clamp)                   # ... but asking for the messages ("x") runs the generic kernel
         assert np.array_equal(o["hard_packed"], g[f"{name}_hard"]), f"{name}: hard bits differ from the reference"
         assert np.array_equal(np.packbits(o["hard"], axis=1), g[f"{name}_hard"])
         assert np.array_equal(o["syndrome"], g[f"{name}_syndrome"]), name
@@ -74,6 +75,58 @@ def test_default_code_against_reference_golden(dcode, golden_dir):
         assert np.mean(dp <= 1e-5) >= FRAC_OK and dp.max() <= 5e-3, (name, dp.max())
         fx, wx, _ = sp_close(o["x"][:64], g[f"{name}_x"])
         assert fx >= FRAC_OK and wx, name
+
+
+def test_default_code_tiny_kernel_against_reference_golden(dcode, golden_dir):
+    """The register-resident kernel (decode_tiny.cu, one thread per codeword) on the reference's golden vectors."""
+    g = np.load(os.path.join(golden_dir, "bp_default_code.npz"))
+    assert dcode.kernel == 2
+    for name in g["names"]:
+        llr, iters, clamp = g[f"{name}_llr"], int(g[f"{name}_iters"]), float(g[f"{name}_clamp"])
+        o = dec(dcode, llr, iters, clamp, want=("prob", "llr_post", "hard", "hard_packed", "syndrome"))
+        assert np.array_equal(o["hard_packed"], g[f"{name}_hard"]), f"{name}: hard bits differ from the reference"
+        assert np.array_equal(np.packbits(o["hard"], axis=1), g[f"{name}_hard"])
+        assert np.array_equal(o["syndrome"], g[f"{name}_syndrome"]), name
+        frac, worst_ok, mx = sp_close(o["llr_post"] / -2.0, g[f"{name}_t"])
+        assert frac >= FRAC_OK and worst_ok, (name, frac, mx)
+        dp = np.abs(o["prob"][:64] - g[f"{name}_prob"])
+        assert np.mean(dp <= 1e-5) >= FRAC_OK and dp.max() <= 5e-3, (name, dp.max())
+
+
+@pytest.mark.parametrize("update,param", [("sp", 1.0), ("minsum", 1.0), ("nms", 0.8125), ("oms", 0.35)])
+def test_tiny_equals_generic_kernel(update, param):
+    """Same node arithmetic in the same order => bit-identical outputs, sum-product included; ragged batch,
+    zero iterations, f64 / f16 inputs."""
+    H = peg_64_32()[0]
+    tiny, gen = LdpcCode(H), LdpcCode(H)
+    gen.set_kernel("generic")
+    assert tiny.kernel == 2 and gen.kernel == 0
+    rng = np.random.RandomState(123)
+    llr = (rng.randn(1001, 64) * 4).astype(np.float32)
+    llr[3] = 0.0
+    llr[4] = 1e4 * np.sign(llr[4] + 1e-9)
+    want = ("prob", "llr_post", "hard", "hard_packed", "syndrome")
+    for iters in (0, 1, 10):
+        a = dec(tiny, llr, iters, 20, update, param, want=want)
+        b = dec(gen, llr, iters, 20, update, param, want=want)
+        for k in want:
+            assert np.array_equal(a[k], b[k]), (update, iters, k)
+    for dt in (np.float64, np.float16):
+        a = dec(tiny, llr[:257].astype(dt), 5, 10, update, param, want=("llr_post", "hard_packed"))
+        b = dec(gen, llr[:257].astype(dt), 5, 10, update, param, want=("llr_post", "hard_packed"))
+        assert np.array_equal(a["llr_post"], b["llr_post"]) and np.array_equal(a["hard_packed"], b["hard_packed"])
+
+
+def test_tiny_fused_counters_equal_generic():
+    from ldpc_b200.linksim import LinkConfig, attach_generator, sim_generate, decode_count
+    H, G = peg_64_32()
+    tiny, gen = attach_generator(LdpcCode(H), G), attach_generator(LdpcCode(H), G)
+    gen.set_kernel("generic")
+    cfg = LinkConfig(snr_db=3.0, ofdm_size=32, qbits=0, iters=5, update="sp", clamp_value=20.0, seed=11)
+    cwp, llr = sim_generate(tiny, cfg, 0, 5000)
+    ct = decode_count(tiny, llr, cwp, cfg).cpu().numpy()
+    cg = decode_count(gen, llr, cwp, cfg).cpu().numpy()
+    assert ct.tolist() == cg.tolist() and ct[4] == 5000 and ct[2] > 0
 
 
 @pytest.mark.parametrize("update,param", [("minsum", 1.0), ("nms", 0.8125), ("oms", 0.35)])
