@@ -7,6 +7,7 @@ hand-written kernels of csrc/frontend.cu and csrc/sim.cu.
 from __future__ import annotations
 
 import ctypes
+import os
 import dataclasses
 
 import numpy as np
@@ -283,6 +284,87 @@ def sweep(code, cfg_per_snr, codewords_per_point, rank=0, world=1, group=None):
         import torch.distributed as dist
         dist.all_reduce(counters, op=dist.ReduceOp.SUM, group=group)
     return counters.cpu().numpy()
+
+
+def weighted_mse_sums(est, ref, epsilon=10e-4):
+    """Sum and count of (est - ref)^2 / (|ref| + eps) (ofdm_functions.py:80-81 / evaluate_quantized_snr.py:163-165)."""
+    d = (est.double() - ref.double()) ** 2 / (ref.double().abs() + epsilon)
+    return torch.stack([d.sum(), torch.tensor(float(d.numel()), dtype=torch.float64, device=d.device)])
+
+
+def evaluate_point(code, cfg_q: LinkConfig, demapper, first, count, chunk=1 << 16):
+    """One SNR point of evaluate_quantized_snr.py:91-188 on the SAME noise realisation (the simulator's draws
+    depend on (seed, codeword index) only): unquantized link, quantized link with the conventional LLRs and -
+    if `demapper` is given - quantized link with the MLP's LLR estimates.  Returns (int64 [3,5] counters in the
+    order traditional / nn / quantized, float64 [2,2] weighted-MSE (sum, count) of nn / quantized LLRs)."""
+    dev = code.device
+    counters = torch.zeros(3, 5, dtype=torch.int64, device=dev)
+    wm = torch.zeros(2, 2, dtype=torch.float64, device=dev)
+    cfg_u = dataclasses.replace(cfg_q, qbits=0)
+    done = 0
+    while done < count:
+        cnt = min(chunk, count - done)
+        cwp, llr_u = sim_generate(code, cfg_u, first + done, cnt)
+        decode_count(code, llr_u, cwp, cfg_u, counters[0])
+        if cfg_q.qbits > 0:
+            cwq, llr_q, smp = sim_generate(code, cfg_q, first + done, cnt, want_samples=demapper is not None)
+            decode_count(code, llr_q, cwq, cfg_q, counters[2])
+            wm[1] += weighted_mse_sums(llr_q, llr_u)
+            if demapper is not None:
+                llr_n = demapper(smp).reshape(cnt, code.n)
+                decode_count(code, llr_n, cwq, cfg_q, counters[1])
+                wm[0] += weighted_mse_sums(llr_n, llr_u)
+        done += cnt
+    return counters, wm
+
+
+def evaluate_full(code, cfgs_q, demapper, codewords_per_point, rank=0, world=1, group=None, state_path=None, chunk=1 << 16):
+    """The whole evaluate_quantized_snr.py result set (every key plots.py:11-27 reads) for a list of SNR points,
+    sharded by batch over the ranks, reduced with ONE all-reduce per dtype at the end.  With `state_path` every
+    finished point of this rank is checkpointed (npz) and skipped on restart: multi-hour sweeps resume."""
+    dev = code.device
+    S = len(cfgs_q)
+    counters = torch.zeros(S, 3, 5, dtype=torch.int64, device=dev)
+    wm = torch.zeros(S, 2, 2, dtype=torch.float64, device=dev)
+    done = np.zeros(S, dtype=bool)
+    path = None if state_path is None else f"{state_path}.rank{rank}of{world}.npz"
+    import zlib
+    sig = np.array([codewords_per_point] + [zlib.crc32(repr(dataclasses.astuple(c)).encode()) for c in cfgs_q], dtype=np.int64)
+    if path and os.path.exists(path):
+        st = np.load(path)
+        if np.array_equal(st["sig"], sig):
+            done = st["done"].copy()
+            counters.copy_(torch.as_tensor(st["counters"]))
+            wm.copy_(torch.as_tensor(st["wm"]))
+    first, count = shard_range(codewords_per_point, rank, world)
+    for i, cfg in enumerate(cfgs_q):
+        if done[i] or count == 0:
+            continue
+        c, w = evaluate_point(code, cfg, demapper, first, count, chunk)
+        counters[i], wm[i] = c, w
+        done[i] = True
+        if path:
+            torch.cuda.synchronize()
+            tmp = path + ".tmp.npz"
+            np.savez(tmp, sig=sig, done=done, counters=counters.cpu().numpy(), wm=wm.cpu().numpy())
+            os.replace(tmp, path)
+    if world > 1:
+        import torch.distributed as dist
+        dist.all_reduce(counters, op=dist.ReduceOp.SUM, group=group)
+        dist.all_reduce(wm, op=dist.ReduceOp.SUM, group=group)
+    return counters.cpu().numpy(), wm.cpu().numpy()
+
+
+def results_dict(snrdb, counters, wm, n, k):
+    """Counters of evaluate_full -> the reference's result pickle (evaluate_quantized_snr.py:192-212)."""
+    out = {"snrdb": np.asarray(snrdb)}
+    for j, suffix in enumerate(("", "_nn", "_quantized")):
+        r = rates(counters[:, j], n, k)
+        for key, val in r.items():
+            out[key + suffix] = val
+    out["wmse_nn"] = wm[:, 0, 0] / np.maximum(wm[:, 0, 1], 1)
+    out["wmse_quantized"] = wm[:, 1, 0] / np.maximum(wm[:, 1, 1], 1)
+    return out
 
 
 def rates(counters, n, k):

@@ -189,3 +189,33 @@ def test_nn_link_counters_are_exact():
     assert c.tolist() == [unc, inf, fe, cnt * 64, cnt]
     # the learned demapper is a sane LLR estimator at this operating point (reference: coded BER 4e-4 at 10 dB)
     assert inf / (cnt * 32) < 5e-3
+
+
+@pytest.mark.gpu
+def test_evaluate_full_writes_every_key_plots_py_reads_and_resumes(tmp_path):
+    """evaluate_quantized_snr.py:192-212 / plots.py:11-27: the full result set on one noise realisation,
+    checkpointed per SNR point; a restart reuses the finished points and gives identical counters."""
+    import torch
+    from ldpc_b200.linksim import LinkConfig, evaluate_full, evaluate_point, results_dict, sim_run
+    code, _ = _default_code()
+    m = _model(2).module
+    cfgs = [LinkConfig(snr_db=s, ofdm_size=32, qbits=3, agc_mode=1, iters=10, update="sp", clamp_value=100.0, seed=21) for s in (5.0, 10.0, 15.0)]
+    state = str(tmp_path / "state")
+    c1, w1 = evaluate_full(code, cfgs, m, 4096, state_path=state, chunk=1500)
+    assert os.path.exists(state + ".rank0of1.npz")
+    res = results_dict([5.0, 10.0, 15.0], c1, w1, 64, 32)
+    for key in ("snrdb", "uncoded_ber", "coded_ber", "coded_bler", "uncoded_ber_nn", "coded_ber_nn", "coded_bler_nn",
+                "uncoded_ber_quantized", "coded_ber_quantized", "coded_bler_quantized", "wmse_nn", "wmse_quantized"):
+        assert key in res and len(res[key]) == 3, key
+    # resume: nothing is recomputed (poison the demapper), same numbers
+    c2, w2 = evaluate_full(code, cfgs, lambda x: 1 / 0, 4096, state_path=state, chunk=1500)
+    assert np.array_equal(c1, c2) and np.array_equal(w1, w2)
+    # the traditional and quantized rows are the fused simulator's counters for the same seed
+    for i, cfg in enumerate(cfgs):
+        assert c1[i, 2].tolist() == sim_run(code, cfg, 0, 4096).cpu().numpy().tolist()
+    # sanity of the physics: quantization hurts, the learned demapper recovers most of it at 15 dB
+    assert res["coded_ber"][2] <= res["coded_ber_nn"][2] <= 5e-3 and res["wmse_nn"][2] < res["wmse_quantized"][2]
+    # sharding invariance: two half-ranges add up to the whole
+    a, _ = evaluate_point(code, cfgs[1], m, 0, 2048)
+    b, _ = evaluate_point(code, cfgs[1], m, 2048, 2048)
+    assert np.array_equal((a + b).cpu().numpy(), c1[1])
