@@ -41,6 +41,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-f16", action="store_true")
+    ap.add_argument("--no-sp", action="store_true", help="skip the sum-product measurement")
     ap.add_argument("--no-nn", action="store_true", help="skip the NN-demapper link (BASELINE.json configs[4])")
     ap.add_argument("--nn-symbols", type=int, default=1 << 20, help="OFDM symbols per GPU of the NN-demapper measurement")
     return ap.parse_args()
@@ -356,6 +357,32 @@ def main():
                         "note": "same workload and outputs, messages and LLRs in binary16, two codewords per thread (LDPC_PREC_F16X2); "
                                 "bit-exact against oracle/bp_oracle.py::bp_decode_f16; not the headline value"}
         code.set_precision("f32")
+        step()
+        barrier()
+
+    # ---- BASELINE.json configs[2] names both update rules: the reference's own rule (tanh sum-product), same kernel family ----
+    if a.update == "minsum" and not a.no_sp:
+        Bs = min(B, 262144)
+
+        def sp_step():
+            N.check(lib.ldpc_decode(code._h, llr.data_ptr(), N.F32, Bs, a.iters, N.UPDATE_IDS["sp"], a.clamp, 1.0, None, None,
+                                    post.data_ptr(), None, packed.data_ptr(), None, None, ctypes.c_void_p(stream.cuda_stream)))
+        sp_step()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(2):
+            sp_step()
+        e1.record(stream)
+        barrier()
+        tt = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms_sp = float(tt.item()) / 2
+        out["sum_product"] = {"value": Bs * world / (ms_sp * 1e-3) * K_CODE / 1e9, "unit": "Gbit/s", "ms_per_step": ms_sp,
+                              "codewords_per_gpu_per_step": Bs, "dtype": "f32",
+                              "note": "the reference's update rule (tanh product, clamp, log((1+p)/(1-p)), bp/bp_cv.py:38-50) on the same kernel; "
+                                      "libm tanhf/logf and a correctly rounded division per edge (~5 150 SASS instructions per thread-iteration vs 734)"}
         step()
         barrier()
 

@@ -15,9 +15,11 @@
 //           [BN x 64] W boxes per plane into a shared-memory ring (mbarrier full/empty, ~200 KB deep)
 //   warp 1  allocates TMEM, one elected lane issues tcgen05.mma (cta_group::1, kind::f16, M=128, N=BN,
 //           K=16) for every plane pair and k-slice, tcgen05.commit releases the stage / signals the tile
-//   warps 2-9  epilogue: tcgen05.ld (32 lanes x 32 columns) -> + bias -> tanhf -> split into the f16
-//           planes of the next layer's A operand (or the fp32 result of the last layer); TMEM holds two
-//           accumulator sets, so the epilogue of a tile overlaps the loads and MMAs of the next one
+//   warps 2-17 epilogue: tcgen05.ld (32 lanes x 32 columns) -> + bias -> tanhf -> split into the f16
+//           planes of the next layer's A operand, transposed through a swizzled shared-memory patch so that
+//           every store instruction writes 8 rows x 64 contiguous bytes (or the fp32 result of the last
+//           layer); TMEM holds two accumulator sets, so the epilogue of a tile overlaps the loads and MMAs
+//           of the next one
 // Activations of a chunk of rows ping-pong between two plane buffers that stay L2-resident.
 #include <cuda.h>
 #include <cuda_fp16.h>
@@ -33,8 +35,11 @@ namespace ldpc {
 namespace mlp {
 
 constexpr int BM = 128, BK = 64, UMMA_K = 16;
-constexpr int EPI_WARPS = 8;
-constexpr int THREADS = 32 * (2 + EPI_WARPS);      // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (two per TMEM lane quadrant)
+#ifndef MLP_EPI_WARPS
+#define MLP_EPI_WARPS 16
+#endif
+constexpr int EPI_WARPS = MLP_EPI_WARPS;
+constexpr int THREADS = 32 * (2 + EPI_WARPS);      // warp 0 TMA, warp 1 MMA, then the epilogue warps (EPI_WARPS / 4 per TMEM lane quadrant)
 
 // ---- PTX wrappers --------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -90,8 +95,8 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-// libm tanhf (~1 ulp): measured FASTER in this epilogue than an ex2/rcp formulation (10.2 vs 12.1 ms per 2^20
-// rows) and it keeps the activations within an ulp of the reference's ATen tanh.
+// libm tanhf (~1 ulp): measured FASTER in this epilogue than an ex2.approx/rcp.approx formulation (twice, on two
+// kernel generations) and it keeps the activations within an ulp of the reference's ATen tanh.
 __device__ __forceinline__ float tanh_act(float x) { return tanhf(x); }
 
 // exact split of an fp32 value into binary16 planes
@@ -139,8 +144,19 @@ struct Smem {
     static constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2;
     static constexpr int STAGE_BYTES = NS * (A_BYTES + B_BYTES);
     static constexpr int STAGES = (200 * 1024 / STAGE_BYTES) > 6 ? 6 : (200 * 1024 / STAGE_BYTES);
-    static constexpr int TOTAL = STAGES * STAGE_BYTES + 1024 /* alignment slack */ + 128 /* barriers */;
+    static constexpr int STORE_STAGING = EPI_WARPS * 2048;   // per epilogue warp: 32 rows x 64 B of one output plane
+    static constexpr int TOTAL = STAGES * STAGE_BYTES + 1024 /* alignment slack */ + 128 /* barriers */ + STORE_STAGING;
 };
+
+// -DMLP_TRACE: CTA 0 records clock64() at its pipeline events (stage refilled / stage full / epilogue start, end);
+// ldpc_mlp_debug_trace() reads them back.  This is how the store transpose above was found.
+#ifdef MLP_TRACE
+__device__ long long g_trace[3][256];
+__device__ int g_trace_n[3];
+#define TRACE(role) do { if (blockIdx.x == 0) { int i_ = g_trace_n[role]; if (i_ < 256) { g_trace[role][i_] = clock64(); g_trace_n[role] = i_ + 1; } } } while (0)
+#else
+#define TRACE(role) do { } while (0)
+#endif
 
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
@@ -162,6 +178,7 @@ __global__ void __launch_bounds__(THREADS, 1) layer_kernel(const __grid_constant
     auto tfull_bar = [&](int a) { return bars + 8u * (2 * STAGES + a); };
     auto tempty_bar = [&](int a) { return bars + 8u * (2 * STAGES + 2 + a); };
     const uint32_t tmem_slot = bars + 8u * (2 * STAGES + 4);
+    const uint32_t store_staging = bars + 128u;                           // [EPI_WARPS][2048]
     volatile uint32_t *tmem_slot_ptr = reinterpret_cast<volatile uint32_t *>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -198,6 +215,7 @@ __global__ void __launch_bounds__(THREADS, 1) layer_kernel(const __grid_constant
                     const int s = it % STAGES;
                     const uint32_t ph = (it / STAGES) & 1;
                     mbar_wait(empty_bar(s), ph ^ 1);
+                    TRACE(0);
                     mbar_expect_tx(full_bar(s), S::STAGE_BYTES);
                     const uint32_t st = base + s * S::STAGE_BYTES;
 #pragma unroll
@@ -223,6 +241,7 @@ __global__ void __launch_bounds__(THREADS, 1) layer_kernel(const __grid_constant
                 mbar_wait(full_bar(s), ph);
                 tc_fence_after();
                 if (lane == 0) {
+                    TRACE(1);
                     const uint32_t st = base + s * S::STAGE_BYTES;
 #pragma unroll
                     for (int k = 0; k < BK / UMMA_K; ++k) {
@@ -245,7 +264,9 @@ __global__ void __launch_bounds__(THREADS, 1) layer_kernel(const __grid_constant
         }
     } else {                                                               // ===== epilogue (warps 2..9) =====
         const int quad = warp & 3;                                         // TMEM lane quadrant this warp may read
-        const int half = (warp - 2) >> 2;                                  // which half of the tile's columns
+        constexpr int PARTS = EPI_WARPS / 4;                               // column slices per tile (warps past BN / 32 idle)
+        constexpr int PART_COLS = (BN / PARTS) < 32 ? 32 : (BN / PARTS);
+        const int part = (warp - 2) >> 2;
         const int row = quad * 32 + lane;
         uint32_t ti = 0;
         for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++ti) {
@@ -254,9 +275,10 @@ __global__ void __launch_bounds__(THREADS, 1) layer_kernel(const __grid_constant
             const long long m = (long long)m0 + row;
             mbar_wait(tfull_bar(acc), acc_ph);
             tc_fence_after();
+            if (warp == 2 && lane == 0) TRACE(2);
             const uint32_t d_main = tmem_base + acc * ACC_COLS + ((uint32_t)(quad * 32) << 16);
 #pragma unroll 1
-            for (int c0 = half * (BN / 2); c0 < (half + 1) * (BN / 2); c0 += 32) {
+            for (int c0 = part * PART_COLS; c0 < (part + 1) * PART_COLS && c0 < BN; c0 += 32) {
                 uint32_t v[32], w[32];
                 tmem_ld32(d_main + (uint32_t)c0, v);
                 if (NS > 1) tmem_ld32(d_main + ACC2 + (uint32_t)c0, w);
@@ -275,7 +297,11 @@ __global__ void __launch_bounds__(THREADS, 1) layer_kernel(const __grid_constant
                         for (int q = 0; q < 8; ++q) dst[q] = make_float4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
                     }
                 } else {
-                    // exact plane split, two values per conversion (cvt.rn.f16x2.f32), 64 contiguous bytes per plane
+                    // exact plane split, two values per conversion (cvt.rn.f16x2.f32).  A thread owns one ROW (TMEM lane):
+                    // storing its 64 bytes directly would make every warp store touch 32 lines with 16 bytes each
+                    // (measured: 60 % of the epilogue and a 40 % longer tile).  The warp transposes through a swizzled
+                    // 2 KB shared-memory patch instead, so each store instruction writes 8 rows x 64 contiguous bytes.
+                    const uint32_t stg = store_staging + (uint32_t)(warp - 2) * 2048u;
 #pragma unroll
                     for (int s = 0; s < NS; ++s) {
                         uint32_t pk[16];
@@ -289,14 +315,27 @@ __global__ void __launch_bounds__(THREADS, 1) layer_kernel(const __grid_constant
                                 o[2 * q + 1] = __fsub_rn(o[2 * q + 1], hf.y);
                             }
                         }
-                        uint4 *dst = reinterpret_cast<uint4 *>(args.out_planes + s * args.out_plane_stride + m * args.n_total + n0 + c0);
 #pragma unroll
-                        for (int q = 0; q < 4; ++q) dst[q] = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+                        for (int q = 0; q < 4; ++q)                            // chunk q of row `lane`, XOR-swizzled: conflict-free both ways
+                            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg + (uint32_t)lane * 64u + (uint32_t)((q ^ ((lane >> 1) & 3)) << 4)),
+                                         "r"(pk[4 * q]), "r"(pk[4 * q + 1]), "r"(pk[4 * q + 2]), "r"(pk[4 * q + 3]) : "memory");
+                        __syncwarp();
+                        __half *const plane = args.out_planes + s * args.out_plane_stride + ((long long)m0 + quad * 32) * args.n_total + n0 + c0;
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const int R = 8 * i + (lane >> 2), C = lane & 3;
+                            uint4 v;
+                            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                                         : "r"(stg + (uint32_t)R * 64u + (uint32_t)((C ^ ((R >> 1) & 3)) << 4)) : "memory");
+                            *reinterpret_cast<uint4 *>(plane + (long long)R * args.n_total + C * 8) = v;
+                        }
+                        __syncwarp();
                     }
                 }
             }
             tc_fence_before();
             __syncwarp();
+            if (warp == 2 && lane == 0) TRACE(2);
             if (lane == 0) mbar_arrive(tempty_bar(acc));                   // this warp is done with the accumulator set
         }
     }
@@ -388,6 +427,16 @@ static int launch_layer_ns(const Layer &L, const LayerArgs &a, long long rows, c
 
 extern "C" {
 
+#ifdef MLP_TRACE
+int ldpc_mlp_debug_trace(long long *out, int *counts, int reset) {
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(out, g_trace, sizeof(long long) * 3 * 256);
+    cudaMemcpyFromSymbol(counts, g_trace_n, sizeof(int) * 3);
+    if (reset) { int z[3] = {0, 0, 0}; cudaMemcpyToSymbol(g_trace_n, z, sizeof(z)); }
+    return 0;
+}
+#endif
+
 void ldpc_mlp_destroy(ldpc_mlp_t *h) {
     if (!h) return;
     for (auto &L : h->layers) { cudaFree(L.d_bias); cudaFree(L.d_w); }
@@ -410,7 +459,7 @@ int ldpc_mlp_create(int n_layers, const int32_t *dims, const float *const *weigh
     ldpc_mlp *h = new ldpc_mlp();
     h->ns = splits;
     cudaGetDevice(&h->device);
-    if (chunk_rows <= 0) chunk_rows = 128 * 148;                          // 148 row tiles x 4 column tiles at N = 512: four tiles per persistent CTA
+    if (chunk_rows <= 0) chunk_rows = 128 * 148 * 4;                      // 592 row tiles x 4 column tiles at N = 512: 16 tiles per persistent CTA (fill/drain amortised)
     h->chunk = ((chunk_rows + BM - 1) / BM) * BM;
     int maxw = 0;
     h->layers.resize(n_layers);
