@@ -245,14 +245,26 @@ __global__ void __launch_bounds__(THREADS, 1) layer_kernel(const __grid_constant
                     const uint32_t st = base + s * S::STAGE_BYTES;
 #pragma unroll
                     for (int k = 0; k < BK / UMMA_K; ++k) {
+                        if constexpr (NS == 2) {
+                            // The W planes of a stage are adjacent [BN x 64] tiles = ONE [2 BN x 64] K-major operand, and the two
+                            // accumulators are adjacent column ranges: A0 [W0;W1]^T is a single N = 2 BN instruction that yields the
+                            // leading pair (0,0) and the correction pair (0,1) together (one read of A0 from shared memory instead
+                            // of two: the operand reads of three N = 128 instructions saturate the 128 B/clk shared-memory port).
+                            constexpr uint32_t idesc2 = (1u << 4) | ((uint32_t)((2 * BN) >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+                            const uint64_t a0 = umma_desc_sw128(st + k * UMMA_K * 2), a1 = umma_desc_sw128(st + S::A_BYTES + k * UMMA_K * 2);
+                            const uint64_t b0 = umma_desc_sw128(st + NS * S::A_BYTES + k * UMMA_K * 2);
+                            umma_f16(d_main, a0, b0, idesc2, (kb | k) ? 1u : 0u);
+                            umma_f16(d_main + ACC2, a1, b0, idesc, 1u);                     // correction pair (1,0)
+                        } else {
 #pragma unroll
-                        for (int i = 0; i < NS; ++i) {
+                            for (int i = 0; i < NS; ++i) {
 #pragma unroll
-                            for (int j = 0; j + i < NS; ++j) {
-                                const uint64_t ad = umma_desc_sw128(st + i * S::A_BYTES + k * UMMA_K * 2);
-                                const uint64_t bd = umma_desc_sw128(st + NS * S::A_BYTES + j * S::B_BYTES + k * UMMA_K * 2);
-                                if (i + j == 0) umma_f16(d_main, ad, bd, idesc, (kb | k) ? 1u : 0u);
-                                else umma_f16(d_main + ACC2, ad, bd, idesc, (kb | k | (i + j - 1) | i) ? 1u : 0u);   // first correction pair: (0, 1)
+                                for (int j = 0; j + i < NS; ++j) {
+                                    const uint64_t ad = umma_desc_sw128(st + i * S::A_BYTES + k * UMMA_K * 2);
+                                    const uint64_t bd = umma_desc_sw128(st + NS * S::A_BYTES + j * S::B_BYTES + k * UMMA_K * 2);
+                                    if (i + j == 0) umma_f16(d_main, ad, bd, idesc, (kb | k) ? 1u : 0u);
+                                    else umma_f16(d_main + ACC2, ad, bd, idesc, (kb | k | (i + j - 1) | i) ? 1u : 0u);   // first correction pair: (0, 1)
+                                }
                             }
                         }
                     }
