@@ -292,3 +292,62 @@ def systematic_generator(H: np.ndarray) -> np.ndarray:
         sel = sel[sel != c]
         aug[sel] ^= aug[c]
     return np.concatenate([np.eye(k, dtype=np.uint8), aug[:, m:]], axis=0)
+
+
+# --------------------------------------------------------------------------------------
+# parity-check matrix import / export (bp/masking.py:151-153 hints at .mat files)
+# --------------------------------------------------------------------------------------
+def load_alist(path_or_text) -> np.ndarray:
+    """MacKay alist -> dense H (uint8 [m,n]).  Accepts a path or the text itself; zero entries pad short rows."""
+    text = path_or_text
+    if "\n" not in str(path_or_text):
+        with open(path_or_text) as f:
+            text = f.read()
+    tok = [int(t) for t in str(text).split()]
+    n, m = tok[0], tok[1]
+    pos = 4 + n + m                                    # n m | max_dv max_dc | dv[n] | dc[m]
+    max_dv, max_dc = tok[2], tok[3]
+    dv = tok[4:4 + n]
+    padded = len(tok) >= 4 + n + m + n * max_dv + m * max_dc          # rows padded with zeros to the maximum degree
+    H = np.zeros((m, n), dtype=np.uint8)
+    for v in range(n):
+        for k in range(max_dv if padded else dv[v]):
+            c = tok[pos]; pos += 1
+            if c > 0:
+                H[c - 1, v] = 1
+    if any(int(H[:, v].sum()) != dv[v] for v in range(n)):
+        raise ValueError("alist column degrees do not match the listed entries")
+    return H
+
+
+def save_alist(H: np.ndarray) -> str:
+    Hb = (np.asarray(H) != 0)
+    m, n = Hb.shape
+    dv, dc = Hb.sum(0), Hb.sum(1)
+    out = [f"{n} {m}", f"{int(dv.max())} {int(dc.max())}", " ".join(str(int(d)) for d in dv), " ".join(str(int(d)) for d in dc)]
+    for v in range(n):
+        rows = (np.nonzero(Hb[:, v])[0] + 1).tolist()
+        out.append(" ".join(str(r) for r in rows + [0] * (int(dv.max()) - len(rows))))
+    for c in range(m):
+        cols = (np.nonzero(Hb[c])[0] + 1).tolist()
+        out.append(" ".join(str(r) for r in cols + [0] * (int(dc.max()) - len(cols))))
+    return "\n".join(out) + "\n"
+
+
+def load_mat(path, key=None) -> np.ndarray:
+    """H from a MATLAB .mat file (scipy.io.loadmat; first 2-D array or `key`)."""
+    import scipy.io
+    d = scipy.io.loadmat(path)
+    if key is None:
+        key = next(k for k, v in d.items() if not k.startswith("__") and getattr(v, "ndim", 0) == 2)
+    M = d[key]
+    M = M.toarray() if hasattr(M, "toarray") else np.asarray(M)
+    return (M != 0).astype(np.uint8)
+
+
+def qc_block_size(H: np.ndarray, candidates=(81, 54, 27, 96, 64, 48, 32, 24, 16, 8)):
+    """Largest candidate Z for which H is block-circulant (so LdpcCode(H, qc_Z=Z) can pick a compiled kernel), else 0."""
+    for Z in candidates:
+        if detect_qc(H, Z) is not None:
+            return Z
+    return 0

@@ -70,3 +70,19 @@ def test_edge_tables_random(seed):
 def _dedup(H):
     # masks_to_H cannot tell identical rows apart; the random H above has distinct rows w.h.p.
     return H
+
+
+def test_alist_and_mat_round_trip(tmp_path):
+    import scipy.io
+    from ldpc_b200.codes import load_alist, save_alist, load_mat, qc_block_size, peg_64_32, ieee80211n_1944_r12
+    H = peg_64_32()[0]
+    txt = save_alist(H)
+    assert np.array_equal(load_alist(txt), H != 0)
+    p = tmp_path / "h.alist"
+    p.write_text(txt)
+    assert np.array_equal(load_alist(str(p)), H != 0)
+    scipy.io.savemat(str(tmp_path / "h.mat"), {"H": H})
+    assert np.array_equal(load_mat(str(tmp_path / "h.mat")), H != 0)
+    Hw = ieee80211n_1944_r12().H
+    assert np.array_equal(load_alist(save_alist(Hw)), Hw != 0)
+    assert qc_block_size(Hw) == 81 and qc_block_size(H) in (0, 8, 16, 32)
