@@ -111,18 +111,31 @@ __device__ __forceinline__ void split_f16(float v, __half (&p)[NS]) {
 }
 
 // ---- fp32 rows -> f16 planes [NS][M][Kp] (zero padding beyond K) ---------------------------------------
+// One thread converts 8 consecutive columns of a row: one 16-byte store per plane.
 template <int NS>
 __global__ void __launch_bounds__(256) split_rows_kernel(const float *x, long long ld, int K, long long M, int Kp,
                                                          __half *planes, long long plane_stride) {
-    const long long total = M * Kp;
+    const int groups = Kp >> 3;                                           // Kp is a multiple of 64
+    const long long total = M * groups;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const long long m = i / Kp;
-        const int k = (int)(i - m * Kp);
-        const float v = (k < K) ? __ldg(x + m * ld + k) : 0.0f;
-        __half p[NS];
-        split_f16<NS>(v, p);
+        const long long m = i / groups;
+        const int k0 = (int)(i - m * groups) << 3;
+        float v[8];
 #pragma unroll
-        for (int s = 0; s < NS; ++s) planes[s * plane_stride + i] = p[s];
+        for (int j = 0; j < 8; ++j) v[j] = (k0 + j < K) ? __ldg(x + m * ld + k0 + j) : 0.0f;
+#pragma unroll
+        for (int s = 0; s < NS; ++s) {
+            uint32_t pk[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const __half2 h = __floats2half2_rn(v[2 * q], v[2 * q + 1]);
+                pk[q] = *reinterpret_cast<const uint32_t *>(&h);
+                const float2 hf = __half22float2(h);
+                v[2 * q] = __fsub_rn(v[2 * q], hf.x);                     // exact residuals
+                v[2 * q + 1] = __fsub_rn(v[2 * q + 1], hf.y);
+            }
+            *reinterpret_cast<uint4 *>(planes + s * plane_stride + m * Kp + k0) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        }
     }
 }
 
@@ -411,7 +424,7 @@ using namespace ldpc::mlp;
 
 template <int NS>
 static int launch_split(const float *x, long long ld, int K, long long M, int Kp, __half *planes, long long plane_stride, cudaStream_t s) {
-    const long long total = M * Kp;
+    const long long total = M * (Kp >> 3);
     const int grid = (int)std::min<long long>((total + 255) / 256, 148LL * 16);
     split_rows_kernel<NS><<<grid, 256, 0, s>>>(x, ld, K, M, Kp, planes, plane_stride);
     LDPC_CUDA_TRY(cudaGetLastError());
