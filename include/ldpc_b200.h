@@ -111,6 +111,18 @@ int ldpc_decode(const ldpc_code_t *code, const void *llr, int llr_dtype, int64_t
                 float *prob, float *llr_post, uint8_t *hard, uint8_t *hard_packed,
                 int32_t *syndrome, float *x_out, ldpc_stream_t stream);
 
+/* ldpc_decode_weighted - ldpc_decode with the reference's TRAINABLE weights (bp/bp_vc.py:16-32, 60-122: input_weight
+ * per (output edge, input edge) pair of a variable and llr_weight per variable, one set per iteration layer plus the
+ * final layer, bp/bp.py:26-39): V->C = 0.5 (w_llr[v] llr' + sum_{j != k} w_edge[e_k][j] x_j), marginal likewise.
+ * DEVICE tables: w_edge [iters][E][w_stride] (row = variable-major output edge, column j = weight of the variable's
+ * j-th edge as input, w_stride >= max_dv), w_llr [iters][n], wf_edge [E] (variable-major), wf_llr [n].
+ * Runs on the generic kernel. */
+int ldpc_decode_weighted(const ldpc_code_t *code, const void *llr, int llr_dtype, int64_t B, int iters, int update,
+                         float clamp_value, float param, const float *w_edge, const float *w_llr,
+                         const float *wf_edge, const float *wf_llr, int w_stride, float *prob, float *llr_post,
+                         uint8_t *hard, uint8_t *hard_packed, int32_t *syndrome, float *x_out,
+                         ldpc_stream_t stream);
+
 /* ldpc_decode_ex - ldpc_decode with the extensible parameter block; adds syndrome-based early
  * termination (north star; NOT in the reference, whose iteration count is fixed, bp/bp.py:46-47,
  * so it is off in every parity run).  With early_exit != 0 a codeword is frozen after the first

@@ -39,6 +39,8 @@ class BeliefPropagation(nn.Module):
         self.update, self.param, self.warm_start, self._qc_Z = update, float(param), bool(warm_start), int(qc_Z)
         self.layer_size_val = int(self._H.sum())
         self._codes = {}                           # device index -> LdpcCode (one native handle per GPU)
+        self._ref_state = None                     # a reference state_dict with trained weights (load_state_dict)
+        self._weights = {}                         # device index -> sparse weight tables
 
     def _code(self, device):
         key = device.index if device.index is not None else torch.cuda.current_device()
@@ -58,17 +60,48 @@ class BeliefPropagation(nn.Module):
         if return_llr: want.append("llr_post")
         if return_hard: want.append("hard")
         if return_syndrome: want.append("syndrome")
-        out = code.decode(llr.detach().to(dev), self.iterations, clamp_value, update=self.update, param=self.param,
-                          x0=(x.detach().to(dev) if (self.warm_start and x is not None) else None), want=tuple(want))
+        if self._ref_state is not None:            # trained weights (bp_vc.py:101-107): weighted generic kernel
+            key = dev.index if dev.index is not None else torch.cuda.current_device()
+            if key not in self._weights:
+                self._weights[key] = code.sparse_weights(self._ref_state, self.iterations)
+            if self._weights[key] is None:
+                self._ref_state = None             # every weight is 1: nothing to apply
+        if self._ref_state is not None:
+            out = code.decode_weighted(llr.detach().to(dev), self._weights[key], clamp_value, update=self.update,
+                                       param=self.param, want=tuple(want))
+        else:
+            out = code.decode(llr.detach().to(dev), self.iterations, clamp_value, update=self.update, param=self.param,
+                              x0=(x.detach().to(dev) if (self.warm_start and x is not None) else None), want=tuple(want))
         res = [out[k].to(src) for k in want]
         return res[0] if len(res) == 1 else tuple(res)
 
     def layer_size(self):
         return self.layer_size_val
 
+    def load_state_dict(self, state_dict, strict=True):
+        """Accepts the state_dict of a REFERENCE BeliefPropagation (bp/bp.py:26-39, optionally with the 'module.' /
+        'BP.' prefixes of DataParallel / nn/joint.py): its trainable input_weight / llr_weight tensors are converted to
+        sparse tables and applied by the weighted kernel; the dense masks are not kept."""
+        st = {}
+        for k, v in state_dict.items():
+            for pre in ("module.", "BP."):
+                if k.startswith(pre):
+                    k = k[len(pre):]
+            st[k] = v
+        need = [f"layers.{i}.0.{w}" for i in range(self.iterations) for w in ("input_weight", "llr_weight")]
+        need += ["final_layer.0.input_weight", "final_layer.0.llr_weight"]
+        missing = [k for k in need if k not in st]
+        if missing and strict:
+            raise KeyError(f"not a reference BeliefPropagation state_dict for {self.iterations} iterations: missing {missing[:3]}...")
+        if not missing:
+            self._ref_state = {k: st[k] for k in need}
+            self._weights = {}
+        return self
+
     def __getstate__(self):                        # DataParallel.replicate / deepcopy: never copy native handles
         d = self.__dict__.copy()
         d["_codes"] = {}
+        d["_weights"] = {}
         return d
 
 

@@ -31,6 +31,11 @@ struct DecodeArgs {
     int32_t *iters_used;
     void *host_pipe;    // lazily created staging state of ldpc_decode_host
     int precision;      // LDPC_PREC_*
+    // the reference's trainable weights (bp_vc.py:16-32), nullable (generic kernel only):
+    // w_edge [iters][E][w_stride]: row = variable-major OUT edge, column j = weight of the variable's j-th edge as input;
+    // w_llr [iters][n]; wf_edge [E] (variable-major) and wf_llr [n] for the final marginal
+    const float *w_edge, *w_llr, *wf_edge, *wf_llr;
+    int w_stride;
 };
 
 struct GraphTables {        // device pointers

@@ -72,7 +72,11 @@ __global__ void __launch_bounds__(256) decode_generic_kernel(const GenericParams
 #pragma unroll
                 for (int k = 0; k < MAXDV; ++k)
                     if (k < d) { slot[k] = __ldg(g.cm_of_vm + b + k); in[k] = mrow[slot[k]]; }
-                var_node<MAXDV, IS_SP>(in, d, llr_s[cw * p.llr_stride + v], out);
+                if (a.w_edge)
+                    var_node_weighted<MAXDV, IS_SP>(in, d, llr_s[cw * p.llr_stride + v], __ldg(a.w_llr + (long long)it * n + v),
+                                                    a.w_edge + ((long long)it * E + b) * a.w_stride, a.w_stride, out);
+                else
+                    var_node<MAXDV, IS_SP>(in, d, llr_s[cw * p.llr_stride + v], out);
 #pragma unroll
                 for (int k = 0; k < MAXDV; ++k)
                     if (k < d) mrow[slot[k]] = out[k];
@@ -111,7 +115,8 @@ __global__ void __launch_bounds__(256) decode_generic_kernel(const GenericParams
 #pragma unroll
             for (int k = 0; k < MAXDV; ++k)
                 if (k < d) in[k] = mrow[__ldg(g.cm_of_vm + b + k)];
-            const float t = marginal_t<MAXDV>(in, d, llr_s[cw * p.llr_stride + v]);
+            const float t = a.wf_edge ? marginal_t_weighted<MAXDV>(in, d, llr_s[cw * p.llr_stride + v], __ldg(a.wf_llr + v), a.wf_edge + b)
+                                      : marginal_t<MAXDV>(in, d, llr_s[cw * p.llr_stride + v]);
             const uint8_t hb = hard_bit(t);                  // np.round(prob): tie 0.5 -> 0
             hard_s[cw * p.hard_stride + v] = hb | ((llr_s[cw * p.llr_stride + v] > 0.0f) ? 2 : 0);
             if (last) {

@@ -175,6 +175,7 @@ static int check_decode_args(const ldpc_code_t *code, const void *llr, int llr_d
 
 namespace ldpc {
 int decode_dispatch(const ldpc_code *code, const DecodeArgs &a, cudaStream_t s) {
+    if (a.w_edge || a.wf_edge) return launch_decode_generic(code->g, code->max_dv, code->max_dc, a, s);   // trainable weights: generic kernel
     if (code->kernel == LDPC_KERNEL_QC && a.x0 == nullptr && a.x_out == nullptr) {
         if (code->precision == LDPC_PREC_F16X2 && (a.update == LDPC_UPDATE_MINSUM || a.update == LDPC_UPDATE_NMS) &&
             !a.early_exit && !a.iters_used)
@@ -200,6 +201,23 @@ int ldpc_decode(const ldpc_code_t *code, const void *llr, int llr_dtype, int64_t
     a.clampv = clamp_value; a.param = param; a.x0 = x0;
     a.prob = prob; a.llr_post = llr_post; a.hard = hard; a.hard_packed = hard_packed;
     a.syndrome = syndrome; a.x_out = x_out;
+    return decode_dispatch(code, a, (cudaStream_t)stream);
+}
+
+int ldpc_decode_weighted(const ldpc_code_t *code, const void *llr, int llr_dtype, int64_t B, int iters, int update,
+                         float clamp_value, float param, const float *w_edge, const float *w_llr, const float *wf_edge,
+                         const float *wf_llr, int w_stride, float *prob, float *llr_post, uint8_t *hard, uint8_t *hard_packed,
+                         int32_t *syndrome, float *x_out, ldpc_stream_t stream) {
+    int rc = check_decode_args(code, llr, llr_dtype, B, iters, update, clamp_value);
+    if (rc) return rc;
+    if (!w_edge || !w_llr || !wf_edge || !wf_llr || w_stride < code->max_dv) { set_error("ldpc_decode_weighted: weight tables missing or w_stride < max_dv (%d)", code->max_dv); return LDPC_EINVAL; }
+    DecodeArgs a;
+    memset(&a, 0, sizeof(a));
+    a.llr = llr; a.llr_dtype = llr_dtype; a.B = B; a.iters = iters; a.update = update;
+    a.clampv = clamp_value; a.param = param;
+    a.prob = prob; a.llr_post = llr_post; a.hard = hard; a.hard_packed = hard_packed;
+    a.syndrome = syndrome; a.x_out = x_out;
+    a.w_edge = w_edge; a.w_llr = w_llr; a.wf_edge = wf_edge; a.wf_llr = wf_llr; a.w_stride = w_stride;
     return decode_dispatch(code, a, (cudaStream_t)stream);
 }
 

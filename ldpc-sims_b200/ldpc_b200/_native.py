@@ -74,6 +74,8 @@ def lib():
     L.ldpc_code_set_kernel.argtypes = [vp, i32]
     L.ldpc_decode.restype = ctypes.c_int
     L.ldpc_decode.argtypes = [vp, vp, i32, i64, i32, i32, f32, f32, vp, vp, vp, vp, vp, vp, vp, vp]
+    L.ldpc_decode_weighted.restype = ctypes.c_int
+    L.ldpc_decode_weighted.argtypes = [vp, vp, i32, i64, i32, i32, f32, f32, vp, vp, vp, vp, i32, vp, vp, vp, vp, vp, vp, vp]
     L.ldpc_decode_ex.restype = ctypes.c_int
     L.ldpc_decode_ex.argtypes = [vp, ctypes.POINTER(DecodeParams), vp]
     L.ldpc_decode_host.restype = ctypes.c_int

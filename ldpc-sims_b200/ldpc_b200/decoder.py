@@ -127,6 +127,63 @@ class LdpcCode:
                 out[k] = v
         return out
 
+    def sparse_weights(self, state, iterations):
+        """Dense parameters of a reference BeliefPropagation state_dict (bp/bp.py:26-39: layers.{i}.0.input_weight
+        [E,E], layers.{i}.0.llr_weight [1,n], final_layer.0.input_weight [n,E], final_layer.0.llr_weight [1,n]) ->
+        the device tables of ldpc_decode_weighted.  Returns None when every weight is 1 (the unweighted kernels apply)."""
+        T = self.tables
+        A = lambda k: (state[k].detach().cpu().numpy() if isinstance(state[k], torch.Tensor) else np.asarray(state[k])).astype(np.float32)
+        E, n, mdv = self.E, self.n, int(self.max_dv)
+        dv = np.diff(T.var_ptr)
+        vm_var = np.repeat(np.arange(n), dv)                       # variable of a variable-major edge
+        pos = np.arange(E) - T.var_ptr[vm_var]                     # its position k inside the variable
+        w_edge = np.ones((iterations, E, mdv), np.float32)
+        w_llr = np.ones((iterations, n), np.float32)
+        for i in range(iterations):
+            W = A(f"layers.{i}.0.input_weight")
+            w_llr[i] = A(f"layers.{i}.0.llr_weight").reshape(-1)
+            for j in range(mdv):
+                sel = np.nonzero((dv[vm_var] > j) & (pos != j))[0]        # out edges whose variable has a j-th edge
+                w_edge[i, sel, j] = W[sel, T.cm_of_vm[T.var_ptr[vm_var[sel]] + j]]
+        wf_edge = A("final_layer.0.input_weight")[vm_var, T.cm_of_vm]
+        wf_llr = A("final_layer.0.llr_weight").reshape(-1)
+        mask = np.ones((E, mdv), bool)
+        for j in range(mdv):
+            mask[:, j] = (dv[vm_var] > j) & (pos != j)
+        if np.all(w_edge[:, mask] == 1) and np.all(w_llr == 1) and np.all(wf_edge == 1) and np.all(wf_llr == 1):
+            return None
+        dev = self.device
+        return dict(w_edge=torch.as_tensor(w_edge).to(dev), w_llr=torch.as_tensor(w_llr).to(dev),
+                    wf_edge=torch.as_tensor(np.ascontiguousarray(wf_edge)).to(dev), wf_llr=torch.as_tensor(wf_llr).to(dev),
+                    iterations=int(iterations), stride=mdv)
+
+    def decode_weighted(self, llr, weights, clamp_value, update="sp", param=1.0, want=("prob", "hard"), stream=None):
+        """decode() with the reference's trainable weights (sparse_weights); runs on the generic kernel."""
+        if not llr.is_cuda:
+            raise ValueError("llr must be a CUDA tensor (no CPU fallback)")
+        if llr.dim() != 2 or llr.shape[1] != self.n:
+            raise ValueError(f"llr must be [B,{self.n}], got {tuple(llr.shape)}")
+        if llr.dtype not in _DTYPES:
+            llr = llr.float()
+        llr = llr.contiguous()
+        B, dev = llr.shape[0], llr.device
+        mk = lambda shape, dt: torch.empty(shape, dtype=dt, device=dev)
+        prob = mk((B, self.n), torch.float32) if "prob" in want else None
+        post = mk((B, self.n), torch.float32) if "llr_post" in want else None
+        hard = mk((B, self.n), torch.uint8) if "hard" in want else None
+        packed = mk((B, self.packed_bytes), torch.uint8) if "hard_packed" in want else None
+        synd = mk((B,), torch.int32) if "syndrome" in want else None
+        xo = mk((B, self.E), torch.float32) if "x" in want else None
+        w = {k: (v.to(dev) if isinstance(v, torch.Tensor) else v) for k, v in weights.items()}
+        with torch.cuda.device(dev):
+            s = torch.cuda.current_stream(dev).cuda_stream if stream is None else stream
+            N.check(N.lib().ldpc_decode_weighted(
+                self._h, _ptr(llr), _DTYPES[llr.dtype], B, int(w["iterations"]), _update_id(update), float(clamp_value), float(param),
+                _ptr(w["w_edge"]), _ptr(w["w_llr"]), _ptr(w["wf_edge"]), _ptr(w["wf_llr"]), int(w["stride"]),
+                _ptr(prob), _ptr(post), _ptr(hard), _ptr(packed), _ptr(synd), _ptr(xo), ctypes.c_void_p(s)))
+        return {k: v for k, v in (("prob", prob), ("llr_post", post), ("hard", hard), ("hard_packed", packed),
+                                  ("syndrome", synd), ("x", xo)) if v is not None}
+
     def count_errors(self, hard, ref_bits, k, llr=None, counters=None):
         """Exact link metrics (evaluate_quantized_snr.py:169-188) accumulated into an int64[5]
         CUDA tensor: uncoded errs, info errs, frame errs, bits, frames."""

@@ -111,8 +111,37 @@ def _two_atanh(p):
     return torch.div(1 + tp, 1 - tp).log_().numpy()        # bp_cv.py:50
 
 
+def weights_from_reference_state(g, state, iterations):
+    """Dense parameters of a reference BeliefPropagation (bp/bp.py:26-39; keys layers.{i}.0.input_weight [E,E],
+    layers.{i}.0.llr_weight [1,n], final_layer.0.input_weight [n,E], final_layer.0.llr_weight [1,n]) -> the sparse
+    tables of the weighted decoder: w_edge [iters][E, max_dv] (row = variable-major OUT edge, column j = weight
+    of the variable's j-th edge as INPUT, bp_vc.py:19: output_vm = input_cm @ (mask * weight)^T),
+    w_llr [iters][n], wf_edge [E] (variable-major), wf_llr [n]."""
+    mdv = int(g.dv.max())
+    E, n = g.E, g.n
+    w_edge = np.ones((iterations, E, mdv), F32)
+    w_llr = np.ones((iterations, n), F32)
+    A = lambda k: np.asarray(state[k].detach().cpu().numpy() if hasattr(state[k], "detach") else state[k], dtype=F32)
+    for i in range(iterations):
+        W = A(f"layers.{i}.0.input_weight")
+        w_llr[i] = A(f"layers.{i}.0.llr_weight").reshape(-1)
+        for v in range(n):
+            b, d = int(g.var_ptr[v]), int(g.dv[v])
+            for k in range(d):
+                for j in range(d):
+                    if j != k:
+                        w_edge[i, b + k, j] = W[b + k, g.cm_of_vm[b + j]]
+    Wf = A("final_layer.0.input_weight")
+    wf_edge = np.ones(E, F32)
+    for v in range(n):
+        b, d = int(g.var_ptr[v]), int(g.dv[v])
+        for k in range(d):
+            wf_edge[b + k] = Wf[v, g.cm_of_vm[b + k]]
+    return dict(w_edge=w_edge, w_llr=w_llr, wf_edge=wf_edge, wf_llr=A("final_layer.0.llr_weight").reshape(-1).astype(F32))
+
+
 def bp_decode(H, llr, iterations, clamp_value, update="sp", x0=None, alpha=1.0, beta=0.0,
-              graph=None, trace=False, early_exit=False):
+              graph=None, trace=False, early_exit=False, weights=None):
     """Decode a batch.  llr: [B,n] (log P1/P0, the callers' convention, ofdm_functions.py:72).
 
     Returns dict with
@@ -121,6 +150,10 @@ def bp_decode(H, llr, iterations, clamp_value, update="sp", x0=None, alpha=1.0, 
       prob   [B,n] f32  P(bit=1) = 1 - sigmoid(t)           (bp.py:51)
       hard   [B,n] u8   np.round(prob)  (ties -> 0)         (ofdm_functions.py:161)
       syndrome [B] i32  number of unsatisfied checks of `hard`
+    weights (weights_from_reference_state): the reference's trainable weights (bp_vc.py:16-32):
+      V->C  0.5 * ( fl(w_llr[v] * llr') + ((w_0 x_0) + (w_1 x_1)) + ... over the OTHER edges, ascending ),
+      marginal 0.5 * ( fl(wf_llr[v] * llr') + ((wf_0 x_0) + (wf_1 x_1)) + ... ); every product and sum rounded
+      to fp32 separately.  With all-ones weights this equals the unweighted definition for dv <= 3.
     early_exit (NOT in the reference, bp.py:46-47 runs a fixed count): after every iteration but
     the last, rows whose hard decision satisfies every check are frozen (their messages stop
     changing); out["iters_used"] [B] i32 is the number of iterations each row ran.
@@ -137,12 +170,26 @@ def bp_decode(H, llr, iterations, clamp_value, update="sp", x0=None, alpha=1.0, 
     cl = F32(clamp_value)
     half = F32(0.5)
     traces = []
-    for _ in range(int(iterations)):
+    for it in range(int(iterations)):
         # ---- V -> C (variable-major output) ----
         for d, vs, vm, cm in g.var_groups:
             if d == 0:
                 continue
             xin = [x[:, cm[:, k]] for k in range(d)]
+            if weights is not None:
+                wl = (weights["w_llr"][it][vs][None, :] * Lp[:, vs]).astype(F32)
+                for k in range(d):
+                    acc = None
+                    for j in range(d):
+                        if j == k:
+                            continue
+                        term = (weights["w_edge"][it][vm[:, k], j][None, :] * xin[j]).astype(F32)
+                        acc = term if acc is None else (acc + term).astype(F32)
+                    if acc is None:
+                        acc = np.zeros((B, vs.size), F32)
+                    s = (wl + acc).astype(F32)
+                    y[:, vm[:, k]] = _tanh(half * s) if upd == UPDATE_SP else s
+                continue
             if d == 1:
                 S = [np.zeros((B, vs.size), F32)]
             else:
@@ -187,10 +234,14 @@ def bp_decode(H, llr, iterations, clamp_value, update="sp", x0=None, alpha=1.0, 
     for d, vs, vm, cm in g.var_groups:
         acc = None
         for k in range(d):
-            acc = x[:, cm[:, k]] if acc is None else (acc + x[:, cm[:, k]]).astype(F32)
+            term = x[:, cm[:, k]]
+            if weights is not None:
+                term = (weights["wf_edge"][vm[:, k]][None, :] * term).astype(F32)
+            acc = term if acc is None else (acc + term).astype(F32)
         if acc is None:
             acc = np.zeros((B, vs.size), F32)
-        t[:, vs] = half * (Lp[:, vs] + acc)
+        lp = Lp[:, vs] if weights is None else (weights["wf_llr"][vs][None, :] * Lp[:, vs]).astype(F32)
+        t[:, vs] = half * (lp + acc)
     prob = (-1 * torch.sigmoid(_t(t)) + 1).numpy()          # bp.py:51
     hard = np.round(prob).astype(np.uint8)                  # ofdm_functions.py:161
     synd = syndrome_weight(g, hard)
