@@ -413,10 +413,11 @@ struct Layer {
 
 struct ldpc_mlp {
     int ns, device;
-    long long chunk;
+    long long chunk = 0;       // rows the activation buffers currently hold (grown on demand up to chunk_max)
+    long long chunk_max = 0;
+    int maxw = 0;              // widest layer (elements per row)
     std::vector<ldpc::mlp::Layer> layers;
-    __half *d_act[2] = {nullptr, nullptr};   // ping-pong activation planes [NS][chunk][maxKp]
-    long long act_elems = 0;
+    __half *d_act[2] = {nullptr, nullptr};   // ping-pong activation planes [NS][chunk][maxw]
 };
 
 using namespace ldpc;
@@ -485,7 +486,7 @@ int ldpc_mlp_create(int n_layers, const int32_t *dims, const float *const *weigh
     h->ns = splits;
     cudaGetDevice(&h->device);
     if (chunk_rows <= 0) chunk_rows = 128 * 148 * 4;                      // 592 row tiles x 4 column tiles at N = 512: 16 tiles per persistent CTA (fill/drain amortised)
-    h->chunk = ((chunk_rows + BM - 1) / BM) * BM;
+    h->chunk_max = ((chunk_rows + BM - 1) / BM) * BM;
     int maxw = 0;
     h->layers.resize(n_layers);
     for (int l = 0; l < n_layers; ++l) {
@@ -495,11 +496,9 @@ int ldpc_mlp_create(int n_layers, const int32_t *dims, const float *const *weigh
         L.act = activations ? activations[l] : (l + 1 < n_layers);
         maxw = std::max(maxw, std::max(L.Kp, L.N));
     }
-    h->act_elems = (long long)h->chunk * maxw;
+    h->maxw = maxw;
     int rc = LDPC_OK;
     auto fail = [&](int code) { ldpc_mlp_destroy(h); return code; };
-    for (int b = 0; b < 2; ++b)
-        if (cudaMalloc(&h->d_act[b], (size_t)h->ns * h->act_elems * sizeof(__half)) != cudaSuccess) { set_error("ldpc_mlp_create: out of device memory"); return fail(LDPC_ENOMEM); }
     for (int l = 0; l < n_layers; ++l) {
         Layer &L = h->layers[l];
         const size_t wel = (size_t)L.N * L.Kp;
@@ -517,17 +516,43 @@ int ldpc_mlp_create(int n_layers, const int32_t *dims, const float *const *weigh
             cudaMemcpy(L.d_bias, biases[l], L.N * sizeof(float), cudaMemcpyHostToDevice);
         }
         if ((rc = make_map(&L.map_w, L.d_w, L.Kp, L.N, h->ns, L.BN))) return fail(rc);
-        // input planes of layer l live in d_act[l & 1] with row length Kp
-        if ((rc = make_map(&L.map_a, h->d_act[l & 1], L.Kp, h->chunk, h->ns, BM))) return fail(rc);
     }
     if (cudaGetLastError() != cudaSuccess) { set_error("ldpc_mlp_create: CUDA error while uploading the weights"); return fail(LDPC_ECUDA); }
     *out = h;
     return LDPC_OK;
 }
 
+// Activation buffers are sized for the batches actually seen (up to chunk_max rows): 4 KB per row at width 512.
+static int ensure_activation_buffers(ldpc_mlp *h, long long rows, cudaStream_t s) {
+    const long long want = std::min<long long>(h->chunk_max, ((rows + BM - 1) / BM) * BM);
+    if (want <= h->chunk) return LDPC_OK;
+    if (h->chunk) LDPC_CUDA_TRY(cudaStreamSynchronize(s));                // earlier launches may still read the old buffers
+    for (int b = 0; b < 2; ++b) {
+        cudaFree(h->d_act[b]);
+        h->d_act[b] = nullptr;
+        if (cudaMalloc(&h->d_act[b], (size_t)h->ns * want * h->maxw * sizeof(__half)) != cudaSuccess) {
+            h->chunk = 0;
+            set_error("ldpc_mlp_forward: out of device memory (%lld activation rows)", want);
+            return LDPC_ENOMEM;
+        }
+    }
+    h->chunk = want;
+    for (size_t l = 0; l < h->layers.size(); ++l) {                       // input planes of layer l live in d_act[l & 1] with row length Kp
+        Layer &L = h->layers[l];
+        const int rc = make_map(&L.map_a, h->d_act[l & 1], L.Kp, h->chunk, h->ns, BM);
+        if (rc) return rc;
+    }
+    return LDPC_OK;
+}
+
 int ldpc_mlp_forward(ldpc_mlp_t *h, const float *x, int64_t B, float *y, ldpc_stream_t stream) {
     if (!h || (B > 0 && (!x || !y)) || B < 0) { set_error("ldpc_mlp_forward: bad arguments"); return LDPC_EINVAL; }
     cudaStream_t s = (cudaStream_t)stream;
+    if (B == 0) return LDPC_OK;
+    {
+        const int rc0 = ensure_activation_buffers(h, B, s);
+        if (rc0) return rc0;
+    }
     const int nl = (int)h->layers.size();
     const int K0 = h->layers[0].K, NL = h->layers[nl - 1].N;
     for (long long done = 0; done < B; done += h->chunk) {
