@@ -43,8 +43,60 @@ struct TinyPlan {
 template <class Code>
 inline constexpr TinyPlan<Code> kTiny{};
 
+// marginal t_v of one variable (recomputed where needed: keeping all N of them live next to the messages spills)
+template <class Code, int v>
+__device__ __forceinline__ float tiny_marginal(const float (&x)[Code::M * Code::DC], const float (&llr)[Code::N]) {
+    constexpr int D = kTiny<Code>.dv[v];
+    float in[D > 0 ? D : 1];
+    static_for<D>([&](auto kk) {
+        constexpr int k = decltype(kk)::value;
+        constexpr int e = kTiny<Code>.var_edge[v][k];
+        in[k] = x[e];
+    });
+    return marginal_t<(D > 0 ? D : 1)>(in, D, llr[v]);
+}
+
+// hard decision (bit v of hb) - also the convergence test of the early-termination mode
+template <class Code>
+__device__ __forceinline__ void tiny_hard(const float (&x)[Code::M * Code::DC], const float (&llr)[Code::N], unsigned long long &hb) {
+    constexpr int N = Code::N;
+    float tmin = CUDART_INF_F;
+    hb = 0;
+    static_for<N>([&](auto vv) {
+        constexpr int v = decltype(vv)::value;
+        const float t = tiny_marginal<Code, v>(x, llr);
+        tmin = fminf(tmin, fabsf(t));
+        hb |= (unsigned long long)(t < 0.0f ? 1u : 0u) << v;
+    });
+    if (!(tmin > 1e-5f)) {                               // tie band (rare): round the way the reference does
+        hb = 0;
+        static_for<N>([&](auto vv) {
+            constexpr int v = decltype(vv)::value;
+            hb |= (unsigned long long)hard_bit(tiny_marginal<Code, v>(x, llr)) << v;
+        });
+    }
+}
+
+template <class Code>
+__device__ __forceinline__ int tiny_syndrome(unsigned long long hb) {
+    int w = 0;
+    static_for<Code::M>([&](auto rr) {
+        constexpr int r = decltype(rr)::value;
+        unsigned par = 0;
+        static_for<Code::DC>([&](auto jj) {
+            constexpr int j = decltype(jj)::value;
+            constexpr int v = kTiny<Code>.chk_var[r][j];
+            par ^= (unsigned)(hb >> v) & 1u;
+        });
+        w += (int)par;
+    });
+    return w;
+}
+
 // ---- kernel ---------------------------------------------------------------------------------------------------
-template <class Code, int UPD>
+// EE: syndrome-based early termination compiled in (a separate instantiation: the convergence test inside the loop costs
+// the fixed-iteration path 25 % through register pressure)
+template <class Code, int UPD, bool EE>
 __global__ void __launch_bounds__(128) decode_tiny_kernel(const DecodeArgs a) {
     constexpr bool IS_SP = (UPD == UPD_SP);
     constexpr int N = Code::N, M = Code::M, DC = Code::DC, E = M * DC, NBY = (N + 7) / 8;
@@ -68,8 +120,11 @@ __global__ void __launch_bounds__(128) decode_tiny_kernel(const DecodeArgs a) {
     }
     static_for<E>([&](auto ee) { x[decltype(ee)::value] = 0.0f; });      // the zeros every reference caller passes (ofdm_functions.py:157)
 
-#pragma unroll 1
-    for (int it = 0; it < a.iters; ++it) {
+    unsigned long long hb = 0;
+    auto marginal_and_hard = [&]() { tiny_hard<Code>(x, llr, hb); };
+    auto syndrome_weight = [&]() { return tiny_syndrome<Code>(hb); };
+
+    auto iterate = [&]() {
         // V -> C, in place
         static_for<N>([&](auto vv) {
             constexpr int v = decltype(vv)::value;
@@ -98,36 +153,34 @@ __global__ void __launch_bounds__(128) decode_tiny_kernel(const DecodeArgs a) {
             else check_node_ms_ct<DC, UPD>(in, a.clampv, a.param, out);
             static_for<DC>([&](auto jj) { constexpr int j = decltype(jj)::value; x[r * DC + j] = out[j]; });
         });
+    };
+    int used = a.iters;
+    if constexpr (!EE) {
+        // fixed iteration count (the reference's schedule, bp/bp.py:46-47)
+#pragma unroll 1
+        for (int it = 0; it < a.iters; ++it) iterate();
+        marginal_and_hard();
+    } else {
+        // syndrome-based early termination (not in the reference, off in parity runs): marginal + hard decision after EVERY
+        // iteration; a codeword whose hard decision satisfies every check stops there.  Every phase appears once in the
+        // loop (a second copy of the marginal block pushes some instantiations over the inliner's budget and their
+        // register arrays into local memory).
+        int it = 0;
+#pragma unroll 1
+        for (;;) {
+            if (it < a.iters) { iterate(); ++it; }
+            marginal_and_hard();
+            if (it >= a.iters) break;
+            if (syndrome_weight() == 0) { used = it; break; }
+        }
     }
 
-    // ---- marginal, hard decision, outputs -------------------------------------------------------------------
-    float tm[N];
-    float tmin = CUDART_INF_F;
+    // ---- outputs --------------------------------------------------------------------------------------------
+    unsigned long long ub = 0;                           // bit v = uncoded channel decision (llr > 0)
     static_for<N>([&](auto vv) {
         constexpr int v = decltype(vv)::value;
-        constexpr int D = kTiny<Code>.dv[v];
-        float in[D > 0 ? D : 1];
-        static_for<D>([&](auto kk) {
-            constexpr int k = decltype(kk)::value;
-            constexpr int e = kTiny<Code>.var_edge[v][k];
-            in[k] = x[e];
-        });
-        tm[v] = marginal_t<(D > 0 ? D : 1)>(in, D, llr[v]);
-        tmin = fminf(tmin, fabsf(tm[v]));
-    });
-    unsigned long long hb = 0, ub = 0;                   // bit v = decoded bit / uncoded channel decision (llr > 0)
-    static_for<N>([&](auto vv) {
-        constexpr int v = decltype(vv)::value;
-        hb |= (unsigned long long)(tm[v] < 0.0f ? 1u : 0u) << v;
         ub |= (unsigned long long)(llr[v] > 0.0f ? 1u : 0u) << v;
     });
-    if (!(tmin > 1e-5f)) {                               // tie band (rare): round the way the reference does
-        hb = 0;
-        static_for<N>([&](auto vv) {
-            constexpr int v = decltype(vv)::value;
-            hb |= (unsigned long long)hard_bit(tm[v]) << v;
-        });
-    }
     // MSB-first bytes (numpy.packbits): byte b bit 7-j = bit 8b+j
     auto pack = [&](unsigned long long bits) {
         unsigned long long w = 0;                        // little-endian word whose byte b is the packed byte b
@@ -145,8 +198,8 @@ __global__ void __launch_bounds__(128) decode_tiny_kernel(const DecodeArgs a) {
             float4 *dst = reinterpret_cast<float4 *>(a.llr_post + row * N);
             static_for<N / 4>([&](auto qq) {
                 constexpr int q = decltype(qq)::value;
-                dst[q] = make_float4(__fmul_rn(-2.0f, tm[4 * q]), __fmul_rn(-2.0f, tm[4 * q + 1]), __fmul_rn(-2.0f, tm[4 * q + 2]),
-                                     __fmul_rn(-2.0f, tm[4 * q + 3]));
+                dst[q] = make_float4(__fmul_rn(-2.0f, tiny_marginal<Code, 4 * q>(x, llr)), __fmul_rn(-2.0f, tiny_marginal<Code, 4 * q + 1>(x, llr)),
+                                     __fmul_rn(-2.0f, tiny_marginal<Code, 4 * q + 2>(x, llr)), __fmul_rn(-2.0f, tiny_marginal<Code, 4 * q + 3>(x, llr)));
             });
         }
         if (a.prob) {
@@ -156,7 +209,10 @@ __global__ void __launch_bounds__(128) decode_tiny_kernel(const DecodeArgs a) {
                 float t4[4] = {0.0f, 0.0f, 0.0f, 0.0f};
                 static_for<N / 4>([&](auto qq) {
                     constexpr int q2 = decltype(qq)::value;
-                    if (q == q2) { t4[0] = tm[4 * q2]; t4[1] = tm[4 * q2 + 1]; t4[2] = tm[4 * q2 + 2]; t4[3] = tm[4 * q2 + 3]; }
+                    if (q == q2) {
+                        t4[0] = tiny_marginal<Code, 4 * q2>(x, llr); t4[1] = tiny_marginal<Code, 4 * q2 + 1>(x, llr);
+                        t4[2] = tiny_marginal<Code, 4 * q2 + 2>(x, llr); t4[3] = tiny_marginal<Code, 4 * q2 + 3>(x, llr);
+                    }
                 });
                 dst[q] = make_float4(prob_one(t4[0]), prob_one(t4[1]), prob_one(t4[2]), prob_one(t4[3]));
             }
@@ -173,21 +229,8 @@ __global__ void __launch_bounds__(128) decode_tiny_kernel(const DecodeArgs a) {
             if constexpr (NBY == 8) *reinterpret_cast<unsigned long long *>(a.hard_packed + row * NBY) = hpk;
             else static_for<NBY>([&](auto bb) { constexpr int b = decltype(bb)::value; a.hard_packed[row * NBY + b] = (uint8_t)(hpk >> (8 * b)); });
         }
-        if (a.syndrome) {
-            int w = 0;
-            static_for<M>([&](auto rr) {
-                constexpr int r = decltype(rr)::value;
-                unsigned par = 0;
-                static_for<DC>([&](auto jj) {
-                    constexpr int j = decltype(jj)::value;
-                    constexpr int v = kTiny<Code>.chk_var[r][j];
-                    par ^= (unsigned)(hb >> v) & 1u;
-                });
-                w += (int)par;
-            });
-            a.syndrome[row] = w;
-        }
-        if (a.iters_used) a.iters_used[row] = a.iters;
+        if (a.syndrome) a.syndrome[row] = syndrome_weight();
+        if (a.iters_used) a.iters_used[row] = used;
     }
     // ---- fused exact link metrics (evaluate_quantized_snr.py:169-188) ----------------------------------------
     if (a.counters) {
@@ -249,12 +292,14 @@ template <class Code>
 static int launch_tiny_t(const DecodeArgs &a, cudaStream_t s) {
     const long long grid = (a.B + 127) / 128;
     if (grid > 0x7fffffffLL) { set_error("batch too large"); return LDPC_EINVAL; }
+    void (*k)(const DecodeArgs) = nullptr;
     switch (a.update) {
-        case UPD_SP: decode_tiny_kernel<Code, UPD_SP><<<(int)grid, 128, 0, s>>>(a); break;
-        case UPD_MINSUM: decode_tiny_kernel<Code, UPD_MINSUM><<<(int)grid, 128, 0, s>>>(a); break;
-        case UPD_NMS: decode_tiny_kernel<Code, UPD_NMS><<<(int)grid, 128, 0, s>>>(a); break;
-        default: decode_tiny_kernel<Code, UPD_OMS><<<(int)grid, 128, 0, s>>>(a); break;
+        case UPD_SP: k = a.early_exit ? decode_tiny_kernel<Code, UPD_SP, true> : decode_tiny_kernel<Code, UPD_SP, false>; break;
+        case UPD_MINSUM: k = a.early_exit ? decode_tiny_kernel<Code, UPD_MINSUM, true> : decode_tiny_kernel<Code, UPD_MINSUM, false>; break;
+        case UPD_NMS: k = a.early_exit ? decode_tiny_kernel<Code, UPD_NMS, true> : decode_tiny_kernel<Code, UPD_NMS, false>; break;
+        default: k = a.early_exit ? decode_tiny_kernel<Code, UPD_OMS, true> : decode_tiny_kernel<Code, UPD_OMS, false>; break;
     }
+    k<<<(int)grid, 128, 0, s>>>(a);
     LDPC_CUDA_TRY(cudaGetLastError());
     return LDPC_OK;
 }

@@ -182,7 +182,7 @@ int decode_dispatch(const ldpc_code *code, const DecodeArgs &a, cudaStream_t s) 
             return launch_decode_qc_h2(code->qc_id, a, s);
         return launch_decode_qc(code->qc_id, a, s);
     }
-    if (code->kernel == LDPC_KERNEL_TINY && a.x0 == nullptr && a.x_out == nullptr && !a.early_exit)
+    if (code->kernel == LDPC_KERNEL_TINY && a.x0 == nullptr && a.x_out == nullptr)
         return launch_decode_tiny(code->tiny_id, a, s);
     return launch_decode_generic(code->g, code->max_dv, code->max_dc, a, s);
 }
