@@ -194,6 +194,13 @@ def bench_nn(a, dev, world, barrier, peaks):
     ms_mlp = timed(lambda: net(x), 3)
     counters = torch.zeros(5, dtype=torch.int64, device=dev)
     ms_link = timed(lambda: sim_run_nn(code, cfg, net, 0, S, counters), 2)
+    # the reference's default code alone (BASELINE.json configs[0]/[1]): register-resident kernel, LLRs resident in HBM
+    from ldpc_b200.linksim import sim_generate, decode_count
+    cwp, llr_d = sim_generate(code, cfg, 0, S)
+    cfg_ms = LinkConfig(snr_db=15.0, ofdm_size=32, qbits=3, agc_mode=1, iters=10, update="minsum", clamp_value=100.0, seed=99)
+    c2 = torch.zeros(5, dtype=torch.int64, device=dev)
+    ms_sp = timed(lambda: decode_count(code, llr_d, cwp, cfg, c2), 3)
+    ms_ms = timed(lambda: decode_count(code, llr_d, cwp, cfg_ms, c2), 3)
     flops = 2.0 * sum(w.shape[0] * w.shape[1] for w in W) * S
     tf_peak = float(peaks.get("bf16_tflops", 2250.0))
     c = counters.cpu().numpy().astype(np.float64)
@@ -204,7 +211,11 @@ def bench_nn(a, dev, world, barrier, peaks):
             "roofline": {"bound": "tensor", "achieved": 3 * flops / (ms_mlp * 1e-3) / 1e12, "peak": tf_peak, "unit": "TFLOP/s",
                          "frac": 3 * flops / (ms_mlp * 1e-3) / 1e12 / tf_peak, "traffic": None,
                          "note": "16-bit tcgen05.mma flops issued: 3 plane pairs per fp32 product (2 exact binary16 planes per operand)"},
-            "coded_ber_nn": c[1] / max(c[4] * 32, 1), "uncoded_ber_nn": c[0] / max(c[3], 1), "gpu_launches_per_chunk": 8}
+            "coded_ber_nn": c[1] / max(c[4] * 32, 1), "uncoded_ber_nn": c[0] / max(c[3], 1), "gpu_launches_per_chunk": 8,
+            "default_code_decode": {"codewords_per_gpu": S, "kernel": ("generic", "qc", "tiny")[code.kernel],
+                                    "sum_product_x10_info_gbps": S * world * 32 / (ms_sp * 1e-3) / 1e9, "sum_product_ms": ms_sp,
+                                    "min_sum_x10_info_gbps": S * world * 32 / (ms_ms * 1e-3) / 1e9, "min_sum_ms": ms_ms,
+                                    "note": "(64,32) code of bp/parity.py, one thread per codeword, decode + fused counters, LLRs resident in HBM"}}
 
 
 def main():

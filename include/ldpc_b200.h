@@ -116,7 +116,7 @@ int ldpc_decode(const ldpc_code_t *code, const void *llr, int llr_dtype, int64_t
  * final layer, bp/bp.py:26-39): V->C = 0.5 (w_llr[v] llr' + sum_{j != k} w_edge[e_k][j] x_j), marginal likewise.
  * DEVICE tables: w_edge [iters][E][w_stride] (row = variable-major output edge, column j = weight of the variable's
  * j-th edge as input, w_stride >= max_dv), w_llr [iters][n], wf_edge [E] (variable-major), wf_llr [n].
- * Runs on the generic kernel. */
+ * Runs on the register-resident kernel for the default (64,32) code (sum-product / min-sum), else on the generic kernel. */
 int ldpc_decode_weighted(const ldpc_code_t *code, const void *llr, int llr_dtype, int64_t B, int iters, int update,
                          float clamp_value, float param, const float *w_edge, const float *w_llr,
                          const float *wf_edge, const float *wf_llr, int w_stride, float *prob, float *llr_post,

@@ -31,6 +31,7 @@ struct TinyPlan {
     int chk_var[M][DC] = {};
     int dv[N] = {};
     int var_edge[N][Code::MAXDV] = {};                   // check-major edge ids of a variable, ascending check
+    int var_base[N] = {};                                // variable-major id of a variable's first edge
     constexpr TinyPlan() {
         for (int r = 0; r < M; ++r)
             for (int j = 0; j < DC; ++j) {
@@ -38,14 +39,15 @@ struct TinyPlan {
                 chk_var[r][j] = v;
                 var_edge[v][dv[v]++] = r * DC + j;       // rows visited ascending => checks ascending
             }
+        for (int v = 1; v < N; ++v) var_base[v] = var_base[v - 1] + dv[v - 1];
     }
 };
 template <class Code>
 inline constexpr TinyPlan<Code> kTiny{};
 
 // marginal t_v of one variable (recomputed where needed: keeping all N of them live next to the messages spills)
-template <class Code, int v>
-__device__ __forceinline__ float tiny_marginal(const float (&x)[Code::M * Code::DC], const float (&llr)[Code::N]) {
+template <class Code, int v, bool WT = false>
+__device__ __forceinline__ float tiny_marginal(const float (&x)[Code::M * Code::DC], const float (&llr)[Code::N], const DecodeArgs &a) {
     constexpr int D = kTiny<Code>.dv[v];
     float in[D > 0 ? D : 1];
     static_for<D>([&](auto kk) {
@@ -53,18 +55,24 @@ __device__ __forceinline__ float tiny_marginal(const float (&x)[Code::M * Code::
         constexpr int e = kTiny<Code>.var_edge[v][k];
         in[k] = x[e];
     });
-    return marginal_t<(D > 0 ? D : 1)>(in, D, llr[v]);
+    if constexpr (WT) {
+        constexpr int vb = kTiny<Code>.var_base[v];
+        return marginal_t_weighted<(D > 0 ? D : 1)>(in, D, llr[v], __ldg(a.wf_llr + v), a.wf_edge + vb);
+    } else {
+        return marginal_t<(D > 0 ? D : 1)>(in, D, llr[v]);
+    }
 }
 
 // hard decision (bit v of hb) - also the convergence test of the early-termination mode
-template <class Code>
-__device__ __forceinline__ void tiny_hard(const float (&x)[Code::M * Code::DC], const float (&llr)[Code::N], unsigned long long &hb) {
+template <class Code, bool WT>
+__device__ __forceinline__ void tiny_hard(const float (&x)[Code::M * Code::DC], const float (&llr)[Code::N], const DecodeArgs &a,
+                                          unsigned long long &hb) {
     constexpr int N = Code::N;
     float tmin = CUDART_INF_F;
     hb = 0;
     static_for<N>([&](auto vv) {
         constexpr int v = decltype(vv)::value;
-        const float t = tiny_marginal<Code, v>(x, llr);
+        const float t = tiny_marginal<Code, v, WT>(x, llr, a);
         tmin = fminf(tmin, fabsf(t));
         hb |= (unsigned long long)(t < 0.0f ? 1u : 0u) << v;
     });
@@ -72,7 +80,7 @@ __device__ __forceinline__ void tiny_hard(const float (&x)[Code::M * Code::DC], 
         hb = 0;
         static_for<N>([&](auto vv) {
             constexpr int v = decltype(vv)::value;
-            hb |= (unsigned long long)hard_bit(tiny_marginal<Code, v>(x, llr)) << v;
+            hb |= (unsigned long long)hard_bit(tiny_marginal<Code, v, WT>(x, llr, a)) << v;
         });
     }
 }
@@ -96,7 +104,9 @@ __device__ __forceinline__ int tiny_syndrome(unsigned long long hb) {
 // ---- kernel ---------------------------------------------------------------------------------------------------
 // EE: syndrome-based early termination compiled in (a separate instantiation: the convergence test inside the loop costs
 // the fixed-iteration path 25 % through register pressure)
-template <class Code, int UPD, bool EE>
+// WT: the reference's trainable weights (bp_vc.py:16-32) read from the tables of ldpc_decode_weighted (broadcast loads:
+// every thread of a warp reads the same word)
+template <class Code, int UPD, bool EE, bool WT = false>
 __global__ void __launch_bounds__(128) decode_tiny_kernel(const DecodeArgs a) {
     constexpr bool IS_SP = (UPD == UPD_SP);
     constexpr int N = Code::N, M = Code::M, DC = Code::DC, E = M * DC, NBY = (N + 7) / 8;
@@ -121,9 +131,10 @@ __global__ void __launch_bounds__(128) decode_tiny_kernel(const DecodeArgs a) {
     static_for<E>([&](auto ee) { x[decltype(ee)::value] = 0.0f; });      // the zeros every reference caller passes (ofdm_functions.py:157)
 
     unsigned long long hb = 0;
-    auto marginal_and_hard = [&]() { tiny_hard<Code>(x, llr, hb); };
+    auto marginal_and_hard = [&]() { tiny_hard<Code, WT>(x, llr, a, hb); };
     auto syndrome_weight = [&]() { return tiny_syndrome<Code>(hb); };
 
+    int wit = 0;                                         // iteration index of the weight tables
     auto iterate = [&]() {
         // V -> C, in place
         static_for<N>([&](auto vv) {
@@ -136,7 +147,13 @@ __global__ void __launch_bounds__(128) decode_tiny_kernel(const DecodeArgs a) {
                     constexpr int e = kTiny<Code>.var_edge[v][k];
                     in[k] = x[e];
                 });
-                var_node<D, IS_SP>(in, D, llr[v], out);
+                if constexpr (WT) {
+                    constexpr int vb = kTiny<Code>.var_base[v];
+                    var_node_weighted<D, IS_SP>(in, D, llr[v], __ldg(a.w_llr + (long long)wit * N + v),
+                                                a.w_edge + ((long long)wit * E + vb) * a.w_stride, a.w_stride, out);
+                }
+                else
+                    var_node<D, IS_SP>(in, D, llr[v], out);
                 static_for<D>([&](auto kk) {
                     constexpr int k = decltype(kk)::value;
                     constexpr int e = kTiny<Code>.var_edge[v][k];
@@ -158,7 +175,7 @@ __global__ void __launch_bounds__(128) decode_tiny_kernel(const DecodeArgs a) {
     if constexpr (!EE) {
         // fixed iteration count (the reference's schedule, bp/bp.py:46-47)
 #pragma unroll 1
-        for (int it = 0; it < a.iters; ++it) iterate();
+        for (int it = 0; it < a.iters; ++it) { wit = it; iterate(); }
         marginal_and_hard();
     } else {
         // syndrome-based early termination (not in the reference, off in parity runs): marginal + hard decision after EVERY
@@ -168,7 +185,7 @@ __global__ void __launch_bounds__(128) decode_tiny_kernel(const DecodeArgs a) {
         int it = 0;
 #pragma unroll 1
         for (;;) {
-            if (it < a.iters) { iterate(); ++it; }
+            if (it < a.iters) { wit = it; iterate(); ++it; }
             marginal_and_hard();
             if (it >= a.iters) break;
             if (syndrome_weight() == 0) { used = it; break; }
@@ -198,8 +215,8 @@ __global__ void __launch_bounds__(128) decode_tiny_kernel(const DecodeArgs a) {
             float4 *dst = reinterpret_cast<float4 *>(a.llr_post + row * N);
             static_for<N / 4>([&](auto qq) {
                 constexpr int q = decltype(qq)::value;
-                dst[q] = make_float4(__fmul_rn(-2.0f, tiny_marginal<Code, 4 * q>(x, llr)), __fmul_rn(-2.0f, tiny_marginal<Code, 4 * q + 1>(x, llr)),
-                                     __fmul_rn(-2.0f, tiny_marginal<Code, 4 * q + 2>(x, llr)), __fmul_rn(-2.0f, tiny_marginal<Code, 4 * q + 3>(x, llr)));
+                dst[q] = make_float4(__fmul_rn(-2.0f, tiny_marginal<Code, 4 * q, WT>(x, llr, a)), __fmul_rn(-2.0f, tiny_marginal<Code, 4 * q + 1, WT>(x, llr, a)),
+                                     __fmul_rn(-2.0f, tiny_marginal<Code, 4 * q + 2, WT>(x, llr, a)), __fmul_rn(-2.0f, tiny_marginal<Code, 4 * q + 3, WT>(x, llr, a)));
             });
         }
         if (a.prob) {
@@ -210,8 +227,8 @@ __global__ void __launch_bounds__(128) decode_tiny_kernel(const DecodeArgs a) {
                 static_for<N / 4>([&](auto qq) {
                     constexpr int q2 = decltype(qq)::value;
                     if (q == q2) {
-                        t4[0] = tiny_marginal<Code, 4 * q2>(x, llr); t4[1] = tiny_marginal<Code, 4 * q2 + 1>(x, llr);
-                        t4[2] = tiny_marginal<Code, 4 * q2 + 2>(x, llr); t4[3] = tiny_marginal<Code, 4 * q2 + 3>(x, llr);
+                        t4[0] = tiny_marginal<Code, 4 * q2, WT>(x, llr, a); t4[1] = tiny_marginal<Code, 4 * q2 + 1, WT>(x, llr, a);
+                        t4[2] = tiny_marginal<Code, 4 * q2 + 2, WT>(x, llr, a); t4[3] = tiny_marginal<Code, 4 * q2 + 3, WT>(x, llr, a);
                     }
                 });
                 dst[q] = make_float4(prob_one(t4[0]), prob_one(t4[1]), prob_one(t4[2]), prob_one(t4[3]));
@@ -293,6 +310,14 @@ static int launch_tiny_t(const DecodeArgs &a, cudaStream_t s) {
     const long long grid = (a.B + 127) / 128;
     if (grid > 0x7fffffffLL) { set_error("batch too large"); return LDPC_EINVAL; }
     void (*k)(const DecodeArgs) = nullptr;
+    if (a.w_edge) {                                      // trainable weights: sum-product and min-sum, fixed iteration count
+        if (a.update == UPD_SP) k = decode_tiny_kernel<Code, UPD_SP, false, true>;
+        else if (a.update == UPD_MINSUM) k = decode_tiny_kernel<Code, UPD_MINSUM, false, true>;
+        else return LDPC_EUNSUPPORTED;
+        k<<<(int)grid, 128, 0, s>>>(a);
+        LDPC_CUDA_TRY(cudaGetLastError());
+        return LDPC_OK;
+    }
     switch (a.update) {
         case UPD_SP: k = a.early_exit ? decode_tiny_kernel<Code, UPD_SP, true> : decode_tiny_kernel<Code, UPD_SP, false>; break;
         case UPD_MINSUM: k = a.early_exit ? decode_tiny_kernel<Code, UPD_MINSUM, true> : decode_tiny_kernel<Code, UPD_MINSUM, false>; break;

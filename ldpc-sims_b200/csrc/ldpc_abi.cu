@@ -175,7 +175,12 @@ static int check_decode_args(const ldpc_code_t *code, const void *llr, int llr_d
 
 namespace ldpc {
 int decode_dispatch(const ldpc_code *code, const DecodeArgs &a, cudaStream_t s) {
-    if (a.w_edge || a.wf_edge) return launch_decode_generic(code->g, code->max_dv, code->max_dc, a, s);   // trainable weights: generic kernel
+    if (a.w_edge || a.wf_edge) {                       // trainable weights: register-resident kernel where compiled, else generic
+        if (code->kernel == LDPC_KERNEL_TINY && a.x0 == nullptr && a.x_out == nullptr && !a.early_exit &&
+            (a.update == LDPC_UPDATE_SP || a.update == LDPC_UPDATE_MINSUM))
+            return launch_decode_tiny(code->tiny_id, a, s);
+        return launch_decode_generic(code->g, code->max_dv, code->max_dc, a, s);
+    }
     if (code->kernel == LDPC_KERNEL_QC && a.x0 == nullptr && a.x_out == nullptr) {
         if (code->precision == LDPC_PREC_F16X2 && (a.update == LDPC_UPDATE_MINSUM || a.update == LDPC_UPDATE_NMS) &&
             !a.early_exit && !a.iters_used)
