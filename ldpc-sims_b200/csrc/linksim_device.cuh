@@ -91,7 +91,7 @@ __device__ __forceinline__ void ofdm_symbols_llr(int lane, const int (&os)[S], c
                 for (int h = 0; h < 2; ++h) {
                     const int rr = r + h * (P / 2);
                     float re = x[s][rr].re + k.nstd * z[2 * h], im = x[s][rr].im + k.nstd * z[2 * h + 1];
-                    if (p.qbits > 0) { re = quant(k.factor * re) / k.factor; im = quant(k.factor * im) / k.factor; }
+                    if (p.qbits > 0) { re = div_rn_nochk(quant(k.factor * re), k.factor); im = div_rn_nochk(quant(k.factor * im), k.factor); }
                     x[s][rr] = {re, im};
                     if (valid[s]) samp(s, t0 + h, re, im);
                 }
@@ -103,7 +103,7 @@ __device__ __forceinline__ void ofdm_symbols_llr(int lane, const int (&os)[S], c
             float z0, z1;
             box_muller<float>(rnd[2 * (t & 1)], rnd[2 * (t & 1) + 1], z0, z1);
             float re = x[s][0].re + k.nstd * z0, im = x[s][0].im + k.nstd * z1;
-            if (p.qbits > 0) { re = quant(k.factor * re) / k.factor; im = quant(k.factor * im) / k.factor; }
+            if (p.qbits > 0) { re = div_rn_nochk(quant(k.factor * re), k.factor); im = div_rn_nochk(quant(k.factor * im), k.factor); }
             x[s][0] = {re, im};
             if (valid[s]) samp(s, t, re, im);
         }
