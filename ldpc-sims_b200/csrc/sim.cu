@@ -50,6 +50,25 @@ __global__ void __launch_bounds__(256) gen_codewords_kernel(const uint32_t *Pp /
     }
 }
 
+// Small codes (n <= 64, k <= 32: the reference's default (64,32) code): one THREAD per codeword - the information word
+// is one Philox output, every parity bit one popc, the packed bytes one 64-bit store.  Same bits as the kernel above.
+__global__ void __launch_bounds__(256) gen_codewords_small_kernel(const uint32_t *Pp /*[m][1]*/, int n, int k, long long cw_first,
+                                                                  long long ncw, unsigned long long seed, uint8_t *cw_packed) {
+    const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= ncw) return;
+    const Philox rng(seed);
+    uint32_t u = 0;
+    info_words_block(rng, (unsigned long long)(cw_first + c), 0, k, &u);
+    unsigned long long bits = u;                                        // bit i = code bit i (information bits first)
+    const int m = n - k;
+    for (int r = 0; r < m; ++r) bits |= (unsigned long long)(__popc(__ldg(Pp + r) & u) & 1) << (k + r);
+    const int nby = (n + 7) / 8;
+    unsigned long long w = 0;                                           // byte b = MSB-first packed byte b
+    for (int b = 0; b < nby; ++b) w |= (unsigned long long)(__brev((unsigned)((bits >> (8 * b)) & 0xffu)) >> 24) << (8 * b);
+    if (nby == 8) *reinterpret_cast<unsigned long long *>(cw_packed + c * 8) = w;
+    else for (int b = 0; b < nby; ++b) cw_packed[c * nby + b] = (uint8_t)(w >> (8 * b));
+}
+
 // ---- K2b ----------------------------------------------------------------------------------------------
 __device__ __forceinline__ int cw_bit(const uint8_t *row, int i) { return (row[i >> 3] >> (7 - (i & 7))) & 1; }
 
@@ -139,8 +158,12 @@ static int launch_frontend(const ldpc_code_t *code, const ldpc_sim_params_t *sp,
                            uint8_t *cw_packed, float *llr, cudaStream_t s, float *samples = nullptr) {
     const int n = code->n, k = code->k_info, kw = (k + 31) / 32;
     const size_t sm = (size_t)kw * 4 + ((n + 3) & ~3);
-    const int g1 = (int)std::min<long long>(cnt, 148LL * 8);
-    gen_codewords_kernel<<<g1, 256, sm, s>>>(code->d_gen, n, k, first, cnt, sp->seed, cw_packed);
+    if (n <= 64 && k <= 32) {
+        gen_codewords_small_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, s>>>(code->d_gen, n, k, first, cnt, sp->seed, cw_packed);
+    } else {
+        const int g1 = (int)std::min<long long>(cnt, 148LL * 8);
+        gen_codewords_kernel<<<g1, 256, sm, s>>>(code->d_gen, n, k, first, cnt, sp->seed, cw_packed);
+    }
     LDPC_CUDA_TRY(cudaGetLastError());
     LinkParams lp;
     lp.n = n; lp.n_ofdm_per_cw = (n / 2 + sp->ofdm_size - 1) / sp->ofdm_size; lp.ofdm_size = sp->ofdm_size;

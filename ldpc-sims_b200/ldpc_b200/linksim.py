@@ -221,7 +221,7 @@ def decode_count(code, llr, ref_packed, cfg: LinkConfig, counters=None):
     return counters
 
 
-def sim_run_nn(code, cfg: LinkConfig, demapper, first, count, counters=None, chunk=1 << 16):
+def sim_run_nn(code, cfg: LinkConfig, demapper, first, count, counters=None, chunk=1 << 20):
     """The NN-demapper link (evaluate_quantized_snr.py:91-188, the *_nn results): front end -> received
     time samples -> MLP LLR estimates -> BP decoder -> exact counters, all on the GPU.  `demapper`
     maps CUDA f32 [S, 2N+1] -> [S, 2N] (ldpc_b200.mlp.NativeMLP or the drop-in nn.llr modules).
@@ -249,7 +249,7 @@ def sim_run(code, cfg: LinkConfig, first, count, counters=None, workspace=None):
         counters = torch.zeros(5, dtype=torch.int64, device=dev)
     if workspace is None:
         per_cw = 4 * code.n + ((code.packed_bytes + 15) & ~15)
-        chunk = int(min(max(count, 1024), 16384))
+        chunk = int(min(max(count, 1024), max(16384, (256 << 20) // per_cw)))     # up to 256 MB of LLR tile per chunk
         chunk = (chunk + 1023) & ~1023
         workspace = torch.empty(chunk * per_cw, dtype=torch.uint8, device=dev)
     sp = cfg.to_struct(first, count)
@@ -278,7 +278,7 @@ def sweep(code, cfg_per_snr, codewords_per_point, rank=0, world=1, group=None):
         if count:
             if ws is None:
                 per_cw = 4 * code.n + ((code.packed_bytes + 15) & ~15)
-                ws = torch.empty(((min(max(count, 1024), 16384) + 1023) & ~1023) * per_cw, dtype=torch.uint8, device=dev)
+                ws = torch.empty(((min(max(count, 1024), max(16384, (256 << 20) // per_cw)) + 1023) & ~1023) * per_cw, dtype=torch.uint8, device=dev)
             sim_run(code, cfg, first, count, counters[i], ws)
     if world > 1:
         import torch.distributed as dist
