@@ -38,11 +38,23 @@ class _NativeChain(nn.Module):
         versions = tuple(p._version for p in params) + tuple(p.data_ptr() for p in params)
         key = device.index if device.index is not None else torch.cuda.current_device()
         hit = self._native.get(key)
-        if hit is None or hit[0] != versions:
+        if hit is not None and hit[0] != versions:
+            # nn.DataParallel re-broadcasts the parameters on every forward (new tensors, same values): compare a cheap
+            # checksum of the values before rebuilding the native handle (weight upload + plane split)
+            chk = self._checksum(params)
+            hit = (versions, hit[1], chk) if (len(hit) > 2 and hit[2] == chk) else None
+            if hit is not None:
+                self._native[key] = hit
+        if hit is None:
             hit = (versions, NativeMLP([l.weight for l in layers], [l.bias for l in layers], list(self._acts),
-                                       splits=self._splits, device=torch.device("cuda", key)))
+                                       splits=self._splits, device=torch.device("cuda", key)), self._checksum(params))
             self._native[key] = hit
         return hit[1]
+
+    @staticmethod
+    def _checksum(params):
+        with torch.no_grad():
+            return tuple(float(v) for p in params for v in (p.double().sum(), (p.double() ** 2).sum()))
 
     def forward(self, x):
         src = x.device

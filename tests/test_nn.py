@@ -219,3 +219,22 @@ def test_evaluate_full_writes_every_key_plots_py_reads_and_resumes(tmp_path):
     a, _ = evaluate_point(code, cfgs[1], m, 0, 2048)
     b, _ = evaluate_point(code, cfgs[1], m, 2048, 2048)
     assert np.array_equal((a + b).cpu().numpy(), c1[1])
+
+
+@pytest.mark.gpu
+def test_data_parallel_replicas_reuse_native_handles():
+    """evaluate_quantized_snr.py:53-57 wraps the demapper in nn.DataParallel: on one GPU it forwards to the module, on
+    several it re-broadcasts the parameters every call - the native handle must be reused (value checksum), not rebuilt."""
+    import torch
+    m = _model(2)
+    x = torch.tensor(GOLD["snr15_x"], dtype=torch.float, device="cuda")
+    y1 = m(x)
+    handles = {k: v[1] for k, v in m.module._native.items()}
+    y2 = m(x)
+    assert torch.equal(y1, y2)
+    assert all(m.module._native[k][1] is h for k, h in handles.items())
+    # a weight update invalidates the handle
+    with torch.no_grad():
+        m.module.final.bias.add_(1.0)
+    y3 = m(x)
+    assert torch.allclose(y3, y1 + 1.0, atol=1e-4)
