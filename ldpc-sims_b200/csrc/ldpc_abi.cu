@@ -174,9 +174,15 @@ static int check_decode_args(const ldpc_code_t *code, const void *llr, int llr_d
 }  // extern "C"
 
 namespace ldpc {
+// the register-resident kernel moves whole rows with 16-byte accesses: raw C-ABI callers may pass any pointer
+static bool tiny_alignment_ok(const DecodeArgs &a) {
+    auto al = [](const void *p, uintptr_t m) { return (reinterpret_cast<uintptr_t>(p) & (m - 1)) == 0; };
+    return (a.llr_dtype != LDPC_F32 || al(a.llr, 16)) && al(a.llr_post, 16) && al(a.prob, 16) && al(a.hard, 4) && al(a.hard_packed, 8);
+}
+
 int decode_dispatch(const ldpc_code *code, const DecodeArgs &a, cudaStream_t s) {
     if (a.w_edge || a.wf_edge) {                       // trainable weights: register-resident kernel where compiled, else generic
-        if (code->kernel == LDPC_KERNEL_TINY && a.x0 == nullptr && a.x_out == nullptr && !a.early_exit &&
+        if (code->kernel == LDPC_KERNEL_TINY && a.x0 == nullptr && a.x_out == nullptr && !a.early_exit && tiny_alignment_ok(a) &&
             (a.update == LDPC_UPDATE_SP || a.update == LDPC_UPDATE_MINSUM))
             return launch_decode_tiny(code->tiny_id, a, s);
         return launch_decode_generic(code->g, code->max_dv, code->max_dc, a, s);
@@ -187,7 +193,7 @@ int decode_dispatch(const ldpc_code *code, const DecodeArgs &a, cudaStream_t s) 
             return launch_decode_qc_h2(code->qc_id, a, s);
         return launch_decode_qc(code->qc_id, a, s);
     }
-    if (code->kernel == LDPC_KERNEL_TINY && a.x0 == nullptr && a.x_out == nullptr)
+    if (code->kernel == LDPC_KERNEL_TINY && a.x0 == nullptr && a.x_out == nullptr && tiny_alignment_ok(a))
         return launch_decode_tiny(code->tiny_id, a, s);
     return launch_decode_generic(code->g, code->max_dv, code->max_dc, a, s);
 }

@@ -549,6 +549,7 @@ int ldpc_mlp_forward(ldpc_mlp_t *h, const float *x, int64_t B, float *y, ldpc_st
     if (!h || (B > 0 && (!x || !y)) || B < 0) { set_error("ldpc_mlp_forward: bad arguments"); return LDPC_EINVAL; }
     cudaStream_t s = (cudaStream_t)stream;
     if (B == 0) return LDPC_OK;
+    if (reinterpret_cast<uintptr_t>(y) & 15) { set_error("ldpc_mlp_forward: y must be 16-byte aligned"); return LDPC_EINVAL; }
     {
         const int rc0 = ensure_activation_buffers(h, B, s);
         if (rc0) return rc0;

@@ -349,3 +349,17 @@ def test_early_termination_matches_oracle(wcode, wcode_generic, dcode):
     o2 = dcode.decode(torch.as_tensor(l2).cuda(), 8, 20, early_exit=True, want=("hard", "iters_used", "syndrome"))
     assert np.array_equal(o2["iters_used"].cpu().numpy(), a2["iters_used"])
     assert np.array_equal(o2["hard"].cpu().numpy(), a2["hard"])
+
+
+def test_unaligned_pointers_take_the_generic_kernel(dcode):
+    """Raw C-ABI callers may pass rows that are not 16-byte aligned: the register-resident kernel (vector loads) is
+    bypassed and the result is unchanged."""
+    rng = np.random.RandomState(8)
+    llr = torch.as_tensor((rng.randn(257, 64) * 3).astype(np.float32)).cuda()
+    ref = dcode.decode(llr, 5, 20, update="minsum", want=("llr_post", "hard_packed"))
+    buf = torch.empty(257 * 64 + 1, dtype=torch.float32, device="cuda")
+    view = buf[1:].view(257, 64)                      # 4-byte offset
+    view.copy_(llr)
+    assert view.data_ptr() % 16 == 4
+    out = dcode.decode(view, 5, 20, update="minsum", want=("llr_post", "hard_packed"))
+    assert torch.equal(out["llr_post"], ref["llr_post"]) and torch.equal(out["hard_packed"], ref["hard_packed"])
