@@ -41,6 +41,8 @@ class LdpcCode:
         self.tables = EdgeTables.from_H(H)
         self.m, self.n, self.E = self.tables.m, self.tables.n, self.tables.E
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
         if qc_Z and qc_proto is None:
             qc_proto = detect_qc(H, qc_Z)
             if qc_proto is None:
@@ -88,6 +90,8 @@ class LdpcCode:
         early_exit=True freezes a codeword once its hard decision satisfies every check."""
         if not llr.is_cuda:
             raise ValueError("llr must be a CUDA tensor (no CPU fallback); use decode_host for numpy input")
+        if llr.device != self.device:
+            raise ValueError(f"llr is on {llr.device}, this code's edge tables are on {self.device}")
         if llr.dim() != 2 or llr.shape[1] != self.n:
             raise ValueError(f"llr must be [B,{self.n}], got {tuple(llr.shape)}")
         if llr.dtype not in _DTYPES:
@@ -161,6 +165,8 @@ class LdpcCode:
         """decode() with the reference's trainable weights (sparse_weights); runs on the generic kernel."""
         if not llr.is_cuda:
             raise ValueError("llr must be a CUDA tensor (no CPU fallback)")
+        if llr.device != self.device:
+            raise ValueError(f"llr is on {llr.device}, this code's edge tables are on {self.device}")
         if llr.dim() != 2 or llr.shape[1] != self.n:
             raise ValueError(f"llr must be [B,{self.n}], got {tuple(llr.shape)}")
         if llr.dtype not in _DTYPES:

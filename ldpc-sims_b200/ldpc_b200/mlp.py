@@ -18,6 +18,8 @@ class NativeMLP:
     def __init__(self, weights, biases=None, activations=None, splits=2, chunk_rows=0, device=None):
         N.require_cuda()
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
         ws = [np.ascontiguousarray(_np(w), dtype=np.float32) for w in weights]
         nl = len(ws)
         bs = [None] * nl if biases is None else [None if b is None else np.ascontiguousarray(_np(b), dtype=np.float32) for b in biases]
@@ -43,6 +45,8 @@ class NativeMLP:
         """x: CUDA float32 [B, dims[0]] -> CUDA float32 [B, dims[-1]]."""
         if not x.is_cuda:
             raise ValueError("x must be a CUDA tensor (there is no CPU fallback)")
+        if x.device != self.device:
+            raise ValueError(f"x is on {x.device}, this handle's weights are on {self.device}")
         if x.dim() != 2 or x.shape[1] != self.dims[0]:
             raise ValueError(f"x must be [B,{self.dims[0]}], got {tuple(x.shape)}")
         x = x.to(dtype=torch.float32).contiguous()
