@@ -212,7 +212,7 @@ def bench_nn(a, dev, world, barrier, peaks):
                          "frac": 3 * flops / (ms_mlp * 1e-3) / 1e12 / tf_peak, "traffic": None,
                          "note": "16-bit tcgen05.mma flops issued: 3 plane pairs per fp32 product (2 exact binary16 planes per operand)"},
             "coded_ber_nn": c[1] / max(c[4] * 32, 1), "uncoded_ber_nn": c[0] / max(c[3], 1), "gpu_launches_per_chunk": 8,
-            "default_code_decode": {"codewords_per_gpu": S, "kernel": ("generic", "qc", "tiny")[code.kernel],
+            "default_code_decode": {"codewords_per_gpu": S, "kernel": ("generic", "qc", "tiny", "qc_rt")[code.kernel],
                                     "sum_product_x10_info_gbps": S * world * 32 / (ms_sp * 1e-3) / 1e9, "sum_product_ms": ms_sp,
                                     "min_sum_x10_info_gbps": S * world * 32 / (ms_ms * 1e-3) / 1e9, "min_sum_ms": ms_ms,
                                     "note": "(64,32) code of bp/parity.py, one thread per codeword, decode + fused counters, LLRs resident in HBM"}}
@@ -327,7 +327,7 @@ def main():
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload_name(a), "codewords_per_gpu_per_step": B,
-                   "outputs": "posterior LLR f32 + packed hard bits", "kernel": ("generic", "qc", "tiny")[code.kernel],
+                   "outputs": "posterior LLR f32 + packed hard bits", "kernel": ("generic", "qc", "tiny", "qc_rt")[code.kernel],
                    "l2_policy": f"inputs larger than L2 ({B * N_CODE * 4 / 1e9:.2f} GB of LLRs per step)"},
         "codewords_per_s": cw_per_s, "edge_updates_per_s": upd_s * world,
         "gpu_launches": a.steps,

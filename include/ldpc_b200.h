@@ -44,7 +44,8 @@ enum {
 enum { LDPC_F32 = 0, LDPC_F64 = 1, LDPC_F16 = 2 };
 
 /* ---- which kernel a code handle dispatches to ---------------------------------------- */
-enum { LDPC_KERNEL_GENERIC = 0, LDPC_KERNEL_QC = 1, LDPC_KERNEL_TINY = 2 /* register-resident, one thread per codeword: the reference's default (64,32) code */ };
+enum { LDPC_KERNEL_GENERIC = 0, LDPC_KERNEL_QC = 1, LDPC_KERNEL_TINY = 2 /* register-resident, one thread per codeword: the reference's default (64,32) code */,
+       LDPC_KERNEL_QC_RT = 3 /* any quasi-cyclic code, prototype matrix at run time (qc_Z / qc_proto without a compiled specialisation) */ };
 
 typedef struct ldpc_code ldpc_code_t;
 typedef void *ldpc_stream_t;             /* a cudaStream_t (CUstream); NULL = default stream */

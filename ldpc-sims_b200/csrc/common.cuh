@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <cuda_fp16.h>
 #include <stdint.h>
+#include <vector>
 #include "../../include/ldpc_b200.h"
 
 namespace ldpc {
@@ -60,6 +61,8 @@ struct ldpc_code {
     int kernel;         // LDPC_KERNEL_*
     int qc_id;          // index of the compiled specialisation or -1
     int tiny_id;        // index of the compiled register-resident specialisation (decode_tiny.cu) or -1
+    int32_t *d_qc_rt;   // device tables of the run-time QC kernel (decode_qc_rt.cu) or null
+    int qc_mb, qc_nb, qc_nblk;
     int qc_Z;
     int device;
     int32_t *d_tables;  // one allocation: chk_ptr | chk_var | var_ptr | cm_of_vm
@@ -92,6 +95,9 @@ int launch_sim_fused_qc(int qc_id, const DecodeArgs &a, const LinkParams &lp, cu
 int qc_lookup(int Z, int mb, int nb, const int16_t *proto);   // -1 if no compiled specialisation
 int tiny_lookup(int m, int n, const int32_t *row_ptr, const int32_t *col_idx);   // -1 if no compiled register-resident specialisation
 int launch_decode_tiny(int tiny_id, const DecodeArgs &a, cudaStream_t s);
+int launch_decode_qc_rt(const int32_t *d_tab, int Z, int mb, int nb, int nblk, int max_dv, int max_dc, const DecodeArgs &a, cudaStream_t s);
+bool qc_rt_supported(int Z, int mb, int nb, int nblk, int max_dv, int max_dc);
+int qc_rt_build_tables(int Z, int mb, int nb, const int16_t *proto, std::vector<int32_t> &out, int *max_dv, int *max_dc);
 void qc_plan_info(int qc_id, int out[4]);                     // {register-resident blocks, shared-memory blocks, threads/CTA, codewords/CTA}
 
 }  // namespace ldpc

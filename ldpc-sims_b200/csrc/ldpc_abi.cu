@@ -79,6 +79,7 @@ int ldpc_code_create(const int32_t *row_ptr, const int32_t *col_idx, int m, int 
     if (!h) { set_error("out of host memory"); return LDPC_ENOMEM; }
     h->m = m; h->n = n; h->E = E; h->max_dc = max_dc; h->max_dv = max_dv; h->device = dev;
     h->qc_Z = 0; h->qc_id = -1; h->kernel = LDPC_KERNEL_GENERIC; h->d_tables = nullptr;
+    h->d_qc_rt = nullptr; h->qc_mb = h->qc_nb = h->qc_nblk = 0;
     h->tiny_id = tiny_lookup(m, n, row_ptr, col_idx);
     if (h->tiny_id >= 0) h->kernel = LDPC_KERNEL_TINY;
     h->d_gen = nullptr; h->k_info = 0; h->host_pipe = nullptr; h->precision = LDPC_PREC_F32;
@@ -114,6 +115,21 @@ int ldpc_code_create(const int32_t *row_ptr, const int32_t *col_idx, int m, int 
         h->qc_Z = qc_Z;
         h->qc_id = qc_lookup(qc_Z, mb, nb, qc_proto);
         if (h->qc_id >= 0) h->kernel = LDPC_KERNEL_QC;
+        {   // run-time QC tables: the fast path of every QC code without a compiled specialisation
+            std::vector<int32_t> tab;
+            int mdv = 0, mdc = 0;
+            const int words = qc_rt_build_tables(qc_Z, mb, nb, qc_proto, tab, &mdv, &mdc);
+            const int nblk = (int)(cnt / qc_Z);
+            if (words > 0 && qc_rt_supported(qc_Z, mb, nb, nblk, mdv, mdc) &&
+                cudaMalloc(&h->d_qc_rt, (size_t)words * sizeof(int32_t)) == cudaSuccess) {
+                cudaMemcpy(h->d_qc_rt, tab.data(), (size_t)words * sizeof(int32_t), cudaMemcpyHostToDevice);
+                h->qc_mb = mb; h->qc_nb = nb; h->qc_nblk = nblk;
+                if (h->qc_id < 0 && h->tiny_id < 0) h->kernel = LDPC_KERNEL_QC_RT;
+            } else {
+                h->d_qc_rt = nullptr;
+                cudaGetLastError();
+            }
+        }
     }
     *out = h;
     return LDPC_OK;
@@ -123,6 +139,7 @@ void ldpc_code_destroy(ldpc_code_t *code) {
     if (!code) return;
     if (code->d_tables) cudaFree(code->d_tables);
     if (code->d_gen) cudaFree(code->d_gen);
+    if (code->d_qc_rt) cudaFree(code->d_qc_rt);
     if (code->host_pipe) ldpc_host_pipe_free(code->host_pipe);
     delete code;
 }
@@ -156,6 +173,7 @@ int ldpc_code_set_kernel(ldpc_code_t *code, int kernel) {
     if (kernel == LDPC_KERNEL_GENERIC) { code->kernel = kernel; return LDPC_OK; }
     if (kernel == LDPC_KERNEL_QC && code->qc_id >= 0) { code->kernel = kernel; return LDPC_OK; }
     if (kernel == LDPC_KERNEL_TINY && code->tiny_id >= 0) { code->kernel = kernel; return LDPC_OK; }
+    if (kernel == LDPC_KERNEL_QC_RT && code->d_qc_rt) { code->kernel = kernel; return LDPC_OK; }
     set_error("kernel %d not available for this code", kernel);
     return LDPC_EUNSUPPORTED;
 }
@@ -193,6 +211,8 @@ int decode_dispatch(const ldpc_code *code, const DecodeArgs &a, cudaStream_t s) 
             return launch_decode_qc_h2(code->qc_id, a, s);
         return launch_decode_qc(code->qc_id, a, s);
     }
+    if (code->kernel == LDPC_KERNEL_QC_RT && a.x0 == nullptr && a.x_out == nullptr && !a.early_exit)
+        return launch_decode_qc_rt(code->d_qc_rt, code->qc_Z, code->qc_mb, code->qc_nb, code->qc_nblk, code->max_dv, code->max_dc, a, s);
     if (code->kernel == LDPC_KERNEL_TINY && a.x0 == nullptr && a.x_out == nullptr && tiny_alignment_ok(a))
         return launch_decode_tiny(code->tiny_id, a, s);
     return launch_decode_generic(code->g, code->max_dv, code->max_dc, a, s);

@@ -363,3 +363,37 @@ def test_unaligned_pointers_take_the_generic_kernel(dcode):
     assert view.data_ptr() % 16 == 4
     out = dcode.decode(view, 5, 20, update="minsum", want=("llr_post", "hard_packed"))
     assert torch.equal(out["llr_post"], ref["llr_post"]) and torch.equal(out["hard_packed"], ref["hard_packed"])
+
+
+@pytest.mark.parametrize("update,param", [("sp", 1.0), ("minsum", 1.0), ("nms", 0.75), ("oms", 0.5)])
+def test_runtime_qc_kernel_equals_generic(update, param):
+    """decode_qc_rt.cu (prototype matrix at run time) against the generic kernel: same node arithmetic in the same edge
+    order => bit-identical, on the 802.11n code (forced) and on a random QC code without a compiled specialisation."""
+    from ldpc_b200.codes import expand_qc
+    rng = np.random.RandomState(77)
+    qc = ieee80211n_1944_r12()
+    cases = [("wifi", qc.H, 81, np.asarray(qc.proto, dtype=np.int16), 70)]
+    Z, mb, nb = 27, 4, 8
+    proto = -np.ones((mb, nb), np.int16)
+    for r in range(mb):
+        for c in rng.choice(nb, size=5, replace=False):
+            proto[r, c] = rng.randint(Z)
+    for c in range(nb):
+        if (proto[:, c] < 0).all():
+            proto[rng.randint(mb), c] = rng.randint(Z)
+    cases.append(("random-qc", expand_qc(proto, Z), Z, proto, 301))
+    for name, H, Zc, pr, B in cases:
+        rt = LdpcCode(H, qc_Z=Zc, qc_proto=pr)
+        rt.set_kernel("qc_rt")
+        gen = LdpcCode(H)
+        gen.set_kernel("generic")
+        assert rt.kernel == 3 and gen.kernel == 0, name
+        if name == "random-qc":
+            assert LdpcCode(H, qc_Z=Zc, qc_proto=pr).kernel == 3          # selected automatically: no compiled specialisation
+        llr = (rng.randn(B, H.shape[1]) * 3 + 1.0).astype(np.float32)
+        want = ("prob", "llr_post", "hard", "hard_packed", "syndrome")
+        for iters in (0, 1, 6):
+            a = dec(rt, llr, iters, 20, update, param, want=want)
+            b = dec(gen, llr, iters, 20, update, param, want=want)
+            for k in want:
+                assert np.array_equal(a[k], b[k]), (name, update, iters, k)
