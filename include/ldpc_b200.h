@@ -124,6 +124,25 @@ int ldpc_decode_weighted(const ldpc_code_t *code, const void *llr, int llr_dtype
                          uint8_t *hard, uint8_t *hard_packed, int32_t *syndrome, float *x_out,
                          ldpc_stream_t stream);
 
+/* ldpc_bp_train_forward / ldpc_bp_train_backward - the TRAINING path of the weighted decoder (sum-product): what
+ * autograd does in the reference through BeliefPropagationVC_Function / BeliefPropagationCV_Function (bp/bp_vc.py:16-58,
+ * bp/bp_cv.py:22-96, unrolled by bp/bp.py:43-51; joint training loop ofdm/ofdm_nn.py:257-396) with dense [E,E] masks
+ * and a [B,E,E,E] intermediate.  forward: prob [B,n] = P(bit=1), identical to ldpc_decode_weighted, and the tape
+ * [(iters+1)][E][B] of C->V messages entering every iteration (x0 [B,E] check-major or null = zeros).
+ * backward: given grad_prob [B,n] writes grad_llr [B,n] and the batch-summed weight gradients g_w_edge
+ * [iters][E][w_stride], g_w_llr [iters][n], g_wf_edge [E], g_wf_llr [n] (overwritten; unused (k,k) / padding entries
+ * stay 0).  workspace: 2*E*B floats.  All DEVICE pointers, f32, asynchronous on `stream`.  The gradient is the exact
+ * derivative of the forward (clamps pass it inside or on the bound, like torch.clamp); the weight sums use float
+ * atomics, so their last bits depend on the order of arrival. */
+int ldpc_bp_train_forward(const ldpc_code_t *code, const float *llr, int64_t B, int iters, float clamp_value,
+                          const float *w_edge, const float *w_llr, const float *wf_edge, const float *wf_llr,
+                          int w_stride, const float *x0, float *prob, float *tape, ldpc_stream_t stream);
+int ldpc_bp_train_backward(const ldpc_code_t *code, const float *llr, int64_t B, int iters, float clamp_value,
+                           const float *w_edge, const float *w_llr, const float *wf_edge, const float *wf_llr,
+                           int w_stride, const float *tape, const float *grad_prob, float *grad_llr,
+                           float *g_w_edge, float *g_w_llr, float *g_wf_edge, float *g_wf_llr, float *workspace,
+                           ldpc_stream_t stream);
+
 /* ldpc_decode_ex - ldpc_decode with the extensible parameter block; adds syndrome-based early
  * termination (north star; NOT in the reference, whose iteration count is fixed, bp/bp.py:46-47,
  * so it is off in every parity run).  With early_exit != 0 a codeword is frozen after the first

@@ -16,6 +16,8 @@ import numpy as np
 import torch
 import torch.nn as nn
 
+from ldpc_b200.codes import (EdgeTables, _weight_slots, reference_state_from_sparse_weights,
+                              sparse_weights_from_reference_state)
 from ldpc_b200.decoder import LdpcCode
 from .masking import generate_masks, masks_to_H  # noqa: F401
 
@@ -26,7 +28,37 @@ def pyd(tensor):                                   # bp/bp.py:16-17
     return tensor.detach().cpu().numpy()
 
 
+class _WeightedBP(torch.autograd.Function):
+    """prob = BP(llr; weights) with the native forward-with-tape / sparse backward pair (ldpc_bp_train_forward /
+    ldpc_bp_train_backward) in place of the reference's dense autograd Functions (bp/bp_vc.py:6-58, bp/bp_cv.py:6-96)."""
+
+    @staticmethod
+    def forward(ctx, llr, w_edge, w_llr, wf_edge, wf_llr, code, clamp_value, x0):
+        w = dict(w_edge=w_edge, w_llr=w_llr, wf_edge=wf_edge, wf_llr=wf_llr, iterations=w_edge.shape[0], stride=w_edge.shape[2])
+        prob, tape = code.train_forward(llr, w, clamp_value, x0)
+        ctx.code, ctx.clamp_value = code, clamp_value
+        ctx.save_for_backward(llr, w_edge, w_llr, wf_edge, wf_llr, tape)
+        return prob
+
+    @staticmethod
+    def backward(ctx, grad_prob):
+        llr, w_edge, w_llr, wf_edge, wf_llr, tape = ctx.saved_tensors
+        w = dict(w_edge=w_edge, w_llr=w_llr, wf_edge=wf_edge, wf_llr=wf_llr, iterations=w_edge.shape[0], stride=w_edge.shape[2])
+        g = ctx.code.train_backward(llr, w, ctx.clamp_value, tape, grad_prob)
+        return g["grad_llr"], g["w_edge"], g["w_llr"], g["wf_edge"], g["wf_llr"], None, None, None
+
+
+_PARAMS = ("w_edge", "w_llr", "wf_edge", "wf_llr")
+
+
 class BeliefPropagation(nn.Module):
+    """The reference's trainable weights (bp/bp_vc.py:101-107, one set per iteration layer and one for the final layer,
+    bp/bp.py:26-39) are nn.Parameters here too, initialised to ones and requiring gradients, but SPARSE:
+    w_edge [iterations, E, max_dv], w_llr [iterations, n], wf_edge [E], wf_llr [n] (layout: ldpc_decode_weighted).
+    In training mode with autograd enabled the forward keeps a tape and .backward() runs the native sparse backward;
+    otherwise (model.eval() / torch.no_grad(), as ofdm_functions.py:147 does) the inference kernels run - the
+    unweighted fast paths while every weight is still 1."""
+
     def __init__(self, H, iterations, *legacy, update="sp", param=1.0, warm_start=False, qc_Z=0):
         super().__init__()
         if len(legacy) == 3:                       # (mask_vc, mask_cv, mask_v_final, llr_expander, iterations)
@@ -37,16 +69,30 @@ class BeliefPropagation(nn.Module):
         self._H = (np.asarray(_np(H)) != 0).astype(np.uint8)
         self.iterations = int(iterations)
         self.update, self.param, self.warm_start, self._qc_Z = update, float(param), bool(warm_start), int(qc_Z)
-        self.layer_size_val = int(self._H.sum())
+        self._tables = EdgeTables.from_H(self._H)
+        self.layer_size_val = int(self._tables.E)
+        E, n, mdv = self._tables.E, self._tables.n, self._tables.max_dv
+        self.w_edge = nn.Parameter(torch.ones(self.iterations, E, mdv))
+        self.w_llr = nn.Parameter(torch.ones(self.iterations, n))
+        self.wf_edge = nn.Parameter(torch.ones(E))
+        self.wf_llr = nn.Parameter(torch.ones(n))
         self._codes = {}                           # device index -> LdpcCode (one native handle per GPU)
-        self._ref_state = None                     # a reference state_dict with trained weights (load_state_dict)
-        self._weights = {}                         # device index -> sparse weight tables
+        self._trivial = (None, True)               # (parameter versions, every weight == 1)
 
     def _code(self, device):
         key = device.index if device.index is not None else torch.cuda.current_device()
         if key not in self._codes:
             self._codes[key] = LdpcCode(self._H, qc_Z=self._qc_Z, device=torch.device("cuda", key))
         return self._codes[key]
+
+    def _all_ones(self):
+        ps = [getattr(self, k) for k in _PARAMS]
+        ver = tuple((p.data_ptr(), p._version) for p in ps)
+        if self._trivial[0] != ver:
+            used = torch.as_tensor(_weight_slots(self._tables)[2], device=self.w_edge.device)
+            ones = bool((self.w_edge.detach()[:, used] == 1).all()) and all(bool((p.detach() == 1).all()) for p in ps[1:])
+            self._trivial = (ver, ones)
+        return self._trivial[1]
 
     def forward(self, x, llr, clamp_value, *, return_llr=False, return_hard=False, return_syndrome=False):
         src = llr.device
@@ -56,19 +102,23 @@ class BeliefPropagation(nn.Module):
         if x is not None and tuple(x.shape) != (llr.shape[0], self.layer_size_val):
             raise ValueError(f"x must be [B,{self.layer_size_val}] (check-major C->V messages)")
         code = self._code(dev)
+        ps = [getattr(self, k) for k in _PARAMS]
+        if self.training and torch.is_grad_enabled() and (llr.requires_grad or any(p.requires_grad for p in ps)):
+            if self.update not in ("sp", "tanh", "sum-product"):
+                raise ValueError("the training path is sum-product (the reference's rule); call .eval() for min-sum decoding")
+            if return_llr or return_hard or return_syndrome:
+                raise ValueError("return_llr / return_hard / return_syndrome are inference outputs: call under torch.no_grad() or .eval()")
+            x0 = x.detach().to(dev) if (self.warm_start and x is not None) else None
+            prob = _WeightedBP.apply(llr.to(dev).float(), *[p.to(dev) for p in ps], code, float(clamp_value), x0)
+            return prob.to(src)
         want = ["prob"]
         if return_llr: want.append("llr_post")
         if return_hard: want.append("hard")
         if return_syndrome: want.append("syndrome")
-        if self._ref_state is not None:            # trained weights (bp_vc.py:101-107): weighted generic kernel
-            key = dev.index if dev.index is not None else torch.cuda.current_device()
-            if key not in self._weights:
-                self._weights[key] = code.sparse_weights(self._ref_state, self.iterations)
-            if self._weights[key] is None:
-                self._ref_state = None             # every weight is 1: nothing to apply
-        if self._ref_state is not None:
-            out = code.decode_weighted(llr.detach().to(dev), self._weights[key], clamp_value, update=self.update,
-                                       param=self.param, want=tuple(want))
+        if not self._all_ones():                   # trained weights: weighted kernels
+            w = {k: p.detach().to(dev) for k, p in zip(_PARAMS, ps)}
+            w.update(iterations=self.iterations, stride=int(self.w_edge.shape[2]))
+            out = code.decode_weighted(llr.detach().to(dev), w, clamp_value, update=self.update, param=self.param, want=tuple(want))
         else:
             out = code.decode(llr.detach().to(dev), self.iterations, clamp_value, update=self.update, param=self.param,
                               x0=(x.detach().to(dev) if (self.warm_start and x is not None) else None), want=tuple(want))
@@ -79,29 +129,39 @@ class BeliefPropagation(nn.Module):
         return self.layer_size_val
 
     def load_state_dict(self, state_dict, strict=True):
-        """Accepts the state_dict of a REFERENCE BeliefPropagation (bp/bp.py:26-39, optionally with the 'module.' /
-        'BP.' prefixes of DataParallel / nn/joint.py): its trainable input_weight / llr_weight tensors are converted to
-        sparse tables and applied by the weighted kernel; the dense masks are not kept."""
+        """Accepts this module's own state_dict (the four sparse tables) or the state_dict of a REFERENCE
+        BeliefPropagation (bp/bp.py:26-39, optionally with the 'module.' / 'BP.' prefixes of DataParallel /
+        nn/joint.py): its dense input_weight / llr_weight tensors are converted to the sparse tables; the masks are
+        not kept."""
         st = {}
         for k, v in state_dict.items():
             for pre in ("module.", "BP."):
                 if k.startswith(pre):
                     k = k[len(pre):]
             st[k] = v
+        if all(k in st for k in _PARAMS):
+            return super().load_state_dict({k: st[k] for k in _PARAMS}, strict=True)
         need = [f"layers.{i}.0.{w}" for i in range(self.iterations) for w in ("input_weight", "llr_weight")]
         need += ["final_layer.0.input_weight", "final_layer.0.llr_weight"]
         missing = [k for k in need if k not in st]
         if missing and strict:
             raise KeyError(f"not a reference BeliefPropagation state_dict for {self.iterations} iterations: missing {missing[:3]}...")
         if not missing:
-            self._ref_state = {k: st[k] for k in need}
-            self._weights = {}
+            w = sparse_weights_from_reference_state(self._tables, st, self.iterations)
+            with torch.no_grad():
+                for k in _PARAMS:
+                    getattr(self, k).copy_(torch.as_tensor(w[k]))
         return self
+
+    def reference_state_dict(self):
+        """The trainable tensors in the REFERENCE's dense layout and key names (layers.{i}.0.input_weight [E,E], ...),
+        for checkpoints the reference's scripts can load (masks omitted: load with strict=False there)."""
+        w = {k: getattr(self, k).detach().cpu().numpy() for k in _PARAMS}
+        return {k: torch.as_tensor(v) for k, v in reference_state_from_sparse_weights(self._tables, w).items()}
 
     def __getstate__(self):                        # DataParallel.replicate / deepcopy: never copy native handles
         d = self.__dict__.copy()
         d["_codes"] = {}
-        d["_weights"] = {}
         return d
 
 

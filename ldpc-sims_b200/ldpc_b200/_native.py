@@ -76,6 +76,10 @@ def lib():
     L.ldpc_decode.argtypes = [vp, vp, i32, i64, i32, i32, f32, f32, vp, vp, vp, vp, vp, vp, vp, vp]
     L.ldpc_decode_weighted.restype = ctypes.c_int
     L.ldpc_decode_weighted.argtypes = [vp, vp, i32, i64, i32, i32, f32, f32, vp, vp, vp, vp, i32, vp, vp, vp, vp, vp, vp, vp]
+    L.ldpc_bp_train_forward.restype = ctypes.c_int
+    L.ldpc_bp_train_forward.argtypes = [vp, vp, i64, i32, f32, vp, vp, vp, vp, i32, vp, vp, vp, vp]
+    L.ldpc_bp_train_backward.restype = ctypes.c_int
+    L.ldpc_bp_train_backward.argtypes = [vp, vp, i64, i32, f32, vp, vp, vp, vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp]
     L.ldpc_decode_ex.restype = ctypes.c_int
     L.ldpc_decode_ex.argtypes = [vp, ctypes.POINTER(DecodeParams), vp]
     L.ldpc_decode_host.restype = ctypes.c_int

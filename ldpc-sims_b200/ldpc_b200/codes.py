@@ -227,6 +227,63 @@ class EdgeTables:
 
 
 # --------------------------------------------------------------------------------------
+# The reference's trainable weights (bp/bp_vc.py:101-107) <-> sparse tables
+# --------------------------------------------------------------------------------------
+def _weight_slots(T: "EdgeTables"):
+    """vm_var [E] (variable of a variable-major edge), pos [E] (its position inside the variable), used [E,max_dv]
+    (entry (e, j) is a real weight: the variable has a j-th edge and it is not e itself)."""
+    dv = np.diff(T.var_ptr)
+    vm_var = np.repeat(np.arange(T.n), dv)
+    pos = np.arange(T.E) - T.var_ptr[vm_var]
+    used = np.zeros((T.E, T.max_dv), bool)
+    for j in range(T.max_dv):
+        used[:, j] = (dv[vm_var] > j) & (pos != j)
+    return vm_var, pos, used
+
+
+def sparse_weights_from_reference_state(T: "EdgeTables", state, iterations):
+    """Dense parameters of a reference BeliefPropagation state_dict (bp/bp.py:26-39: layers.{i}.0.input_weight [E,E],
+    layers.{i}.0.llr_weight [1,n], final_layer.0.input_weight [n,E], final_layer.0.llr_weight [1,n]) -> numpy tables
+    w_edge [iters,E,max_dv] (row = variable-major OUT edge, column j = weight of the variable's j-th edge as INPUT;
+    unused entries 1), w_llr [iters,n], wf_edge [E] (variable-major), wf_llr [n]."""
+    A = lambda k: np.asarray(state[k].detach().cpu().numpy() if hasattr(state[k], "detach") else state[k], dtype=np.float32)
+    vm_var, pos, used = _weight_slots(T)
+    E, n, mdv = T.E, T.n, T.max_dv
+    w_edge = np.ones((iterations, E, mdv), np.float32)
+    w_llr = np.ones((iterations, n), np.float32)
+    for i in range(iterations):
+        W = A(f"layers.{i}.0.input_weight")
+        w_llr[i] = A(f"layers.{i}.0.llr_weight").reshape(-1)
+        for j in range(mdv):
+            sel = np.nonzero(used[:, j])[0]
+            w_edge[i, sel, j] = W[sel, T.cm_of_vm[T.var_ptr[vm_var[sel]] + j]]
+    wf_edge = np.ascontiguousarray(A("final_layer.0.input_weight")[vm_var, T.cm_of_vm])
+    return dict(w_edge=w_edge, w_llr=w_llr, wf_edge=wf_edge, wf_llr=A("final_layer.0.llr_weight").reshape(-1).copy())
+
+
+def reference_state_from_sparse_weights(T: "EdgeTables", w):
+    """Inverse of sparse_weights_from_reference_state: the dense trainable tensors of the reference's state_dict
+    (masks are not included; load with strict=False there).  Dense [E,E] per layer: small codes only."""
+    if T.E > 4096:
+        raise ValueError(f"E = {T.E}: the reference's dense [E,E] layout is impractical for this code")
+    vm_var, pos, used = _weight_slots(T)
+    w_edge, w_llr = np.asarray(w["w_edge"], np.float32), np.asarray(w["w_llr"], np.float32)
+    out = {}
+    for i in range(w_edge.shape[0]):
+        W = np.zeros((T.E, T.E), np.float32)
+        for j in range(T.max_dv):
+            sel = np.nonzero(used[:, j])[0]
+            W[sel, T.cm_of_vm[T.var_ptr[vm_var[sel]] + j]] = w_edge[i, sel, j]
+        out[f"layers.{i}.0.input_weight"] = W
+        out[f"layers.{i}.0.llr_weight"] = w_llr[i].reshape(1, -1).copy()
+    Wf = np.zeros((T.n, T.E), np.float32)
+    Wf[vm_var, T.cm_of_vm] = np.asarray(w["wf_edge"], np.float32)
+    out["final_layer.0.input_weight"] = Wf
+    out["final_layer.0.llr_weight"] = np.asarray(w["wf_llr"], np.float32).reshape(1, -1).copy()
+    return out
+
+
+# --------------------------------------------------------------------------------------
 # QC detection and dense GF(2) helpers
 # --------------------------------------------------------------------------------------
 def detect_qc(H: np.ndarray, Z: int):

@@ -132,34 +132,65 @@ class LdpcCode:
         return out
 
     def sparse_weights(self, state, iterations):
-        """Dense parameters of a reference BeliefPropagation state_dict (bp/bp.py:26-39: layers.{i}.0.input_weight
-        [E,E], layers.{i}.0.llr_weight [1,n], final_layer.0.input_weight [n,E], final_layer.0.llr_weight [1,n]) ->
-        the device tables of ldpc_decode_weighted.  Returns None when every weight is 1 (the unweighted kernels apply)."""
-        T = self.tables
-        A = lambda k: (state[k].detach().cpu().numpy() if isinstance(state[k], torch.Tensor) else np.asarray(state[k])).astype(np.float32)
-        E, n, mdv = self.E, self.n, int(self.max_dv)
-        dv = np.diff(T.var_ptr)
-        vm_var = np.repeat(np.arange(n), dv)                       # variable of a variable-major edge
-        pos = np.arange(E) - T.var_ptr[vm_var]                     # its position k inside the variable
-        w_edge = np.ones((iterations, E, mdv), np.float32)
-        w_llr = np.ones((iterations, n), np.float32)
-        for i in range(iterations):
-            W = A(f"layers.{i}.0.input_weight")
-            w_llr[i] = A(f"layers.{i}.0.llr_weight").reshape(-1)
-            for j in range(mdv):
-                sel = np.nonzero((dv[vm_var] > j) & (pos != j))[0]        # out edges whose variable has a j-th edge
-                w_edge[i, sel, j] = W[sel, T.cm_of_vm[T.var_ptr[vm_var[sel]] + j]]
-        wf_edge = A("final_layer.0.input_weight")[vm_var, T.cm_of_vm]
-        wf_llr = A("final_layer.0.llr_weight").reshape(-1)
-        mask = np.ones((E, mdv), bool)
-        for j in range(mdv):
-            mask[:, j] = (dv[vm_var] > j) & (pos != j)
-        if np.all(w_edge[:, mask] == 1) and np.all(w_llr == 1) and np.all(wf_edge == 1) and np.all(wf_llr == 1):
+        """Dense parameters of a reference BeliefPropagation state_dict -> the device tables of ldpc_decode_weighted
+        (codes.sparse_weights_from_reference_state).  Returns None when every weight is 1 (the unweighted kernels apply)."""
+        from .codes import sparse_weights_from_reference_state, _weight_slots
+        w = sparse_weights_from_reference_state(self.tables, state, iterations)
+        used = _weight_slots(self.tables)[2]
+        if np.all(w["w_edge"][:, used] == 1) and np.all(w["w_llr"] == 1) and np.all(w["wf_edge"] == 1) and np.all(w["wf_llr"] == 1):
             return None
         dev = self.device
-        return dict(w_edge=torch.as_tensor(w_edge).to(dev), w_llr=torch.as_tensor(w_llr).to(dev),
-                    wf_edge=torch.as_tensor(np.ascontiguousarray(wf_edge)).to(dev), wf_llr=torch.as_tensor(wf_llr).to(dev),
-                    iterations=int(iterations), stride=mdv)
+        return dict(w_edge=torch.as_tensor(w["w_edge"]).to(dev), w_llr=torch.as_tensor(w["w_llr"]).to(dev),
+                    wf_edge=torch.as_tensor(w["wf_edge"]).to(dev), wf_llr=torch.as_tensor(w["wf_llr"]).to(dev),
+                    iterations=int(iterations), stride=int(self.max_dv))
+
+    def _train_args(self, llr, weights):
+        if not llr.is_cuda or llr.device != self.device:
+            raise ValueError(f"llr must be a CUDA tensor on {self.device} (no CPU fallback)")
+        if llr.dim() != 2 or llr.shape[1] != self.n:
+            raise ValueError(f"llr must be [B,{self.n}], got {tuple(llr.shape)}")
+        iters, stride = int(weights["iterations"]), int(weights["stride"])
+        shapes = dict(w_edge=(iters, self.E, stride), w_llr=(iters, self.n), wf_edge=(self.E,), wf_llr=(self.n,))
+        w = {}
+        for k, shp in shapes.items():
+            t = weights[k]
+            if tuple(t.shape) != shp or t.device != self.device:
+                raise ValueError(f"{k} must be {shp} on {self.device}, got {tuple(t.shape)} on {t.device}")
+            w[k] = t.detach().float().contiguous()
+        return llr.detach().float().contiguous(), w, iters, stride
+
+    def train_forward(self, llr, weights, clamp_value, x0=None):
+        """Weighted sum-product forward that keeps the tape for train_backward: -> (prob [B,n], tape).  prob is
+        bit-identical to decode_weighted(update='sp')."""
+        llr, w, iters, stride = self._train_args(llr, weights)
+        B = llr.shape[0]
+        prob = torch.empty((B, self.n), dtype=torch.float32, device=self.device)
+        tape = torch.empty(((iters + 1), self.E, B), dtype=torch.float32, device=self.device)
+        if x0 is not None:
+            x0 = x0.detach().float().contiguous()
+        with torch.cuda.device(self.device):
+            N.check(N.lib().ldpc_bp_train_forward(
+                self._h, _ptr(llr), B, iters, float(clamp_value), _ptr(w["w_edge"]), _ptr(w["w_llr"]), _ptr(w["wf_edge"]), _ptr(w["wf_llr"]),
+                stride, _ptr(x0), _ptr(prob), _ptr(tape), ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)))
+        return prob, tape
+
+    def train_backward(self, llr, weights, clamp_value, tape, grad_prob):
+        """-> dict(grad_llr [B,n], w_edge, w_llr, wf_edge, wf_llr): the gradient of sum(prob * grad_prob), weight
+        gradients summed over the batch (ldpc_bp_train_backward)."""
+        llr, w, iters, stride = self._train_args(llr, weights)
+        B = llr.shape[0]
+        grad_prob = grad_prob.detach().float().contiguous()
+        if tuple(grad_prob.shape) != (B, self.n) or tuple(tape.shape) != (iters + 1, self.E, B):
+            raise ValueError("grad_prob must be [B,n] and tape the one train_forward returned for this batch")
+        mk = lambda *shape: torch.empty(shape, dtype=torch.float32, device=self.device)
+        g = dict(grad_llr=mk(B, self.n), w_edge=mk(iters, self.E, stride), w_llr=mk(iters, self.n), wf_edge=mk(self.E), wf_llr=mk(self.n))
+        ws = mk(2 * self.E * max(B, 1))
+        with torch.cuda.device(self.device):
+            N.check(N.lib().ldpc_bp_train_backward(
+                self._h, _ptr(llr), B, iters, float(clamp_value), _ptr(w["w_edge"]), _ptr(w["w_llr"]), _ptr(w["wf_edge"]), _ptr(w["wf_llr"]),
+                stride, _ptr(tape), _ptr(grad_prob), _ptr(g["grad_llr"]), _ptr(g["w_edge"]), _ptr(g["w_llr"]), _ptr(g["wf_edge"]),
+                _ptr(g["wf_llr"]), _ptr(ws), ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)))
+        return g
 
     def decode_weighted(self, llr, weights, clamp_value, update="sp", param=1.0, want=("prob", "hard"), stream=None):
         """decode() with the reference's trainable weights (sparse_weights); runs on the generic kernel."""

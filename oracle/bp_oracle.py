@@ -353,3 +353,54 @@ def bp_decode_f16(H, llr, iterations, clamp_value, update="minsum", alpha=1.0, g
     prob = (-1 * torch.sigmoid(_t(t32)) + 1).numpy()
     hard = np.round(prob).astype(np.uint8)
     return dict(t=t32, prob=prob, hard=hard, syndrome=syndrome_weight(g, hard))
+
+
+def bp_weighted_grad(H, llr, iterations, clamp_value, weights, grad_prob, graph=None, dtype=torch.float64):
+    """Gradient oracle of the weighted decoder: the forward of bp_decode(weights=...) restated with differentiable torch
+    ops (bp/bp_vc.py:16-32, nn.Tanh bp/bp.py:29, bp/bp_cv.py:22-55, clamp bp/bp.py:47, final layer bp/bp.py:36-39,51)
+    in float64, differentiated by autograd.  Every clamp is torch.clamp (gradient passes inside and on the bound), so
+    a saturated product has zero gradient; the reference's hand-written CV backward (bp_cv.py:57-91) keeps
+    2/(1-q^2) there - the two agree wherever nothing saturates, which is where make_golden_grad.py pins this function
+    against the reference's own .backward().
+    Returns dict(prob, grad_llr [B,n], g_w_edge [iters,E,max_dv], g_w_llr [iters,n], g_wf_edge [E], g_wf_llr [n])."""
+    g = graph or Graph(H)
+    E, n = g.E, g.n
+    mdv, mdc = int(g.dv.max()), int(g.dc.max())
+    vm_var = np.repeat(np.arange(n), g.dv)
+    pos = np.arange(E) - g.var_ptr[vm_var]
+    vidx = np.zeros((E, mdv), np.int64); vmask = np.zeros((E, mdv), bool)
+    for j in range(mdv):
+        has = g.dv[vm_var] > j
+        vidx[has, j] = g.cm_of_vm[g.var_ptr[vm_var[has]] + j]
+        vmask[:, j] = has & (pos != j)
+    cm_chk = np.repeat(np.arange(g.m), g.dc)
+    cpos = np.arange(E) - g.chk_ptr[cm_chk]
+    cidx = np.zeros((E, mdc), np.int64); cmask = np.zeros((E, mdc), bool)
+    for j in range(mdc):
+        has = g.dc[cm_chk] > j
+        cidx[has, j] = g.chk_ptr[cm_chk[has]] + j
+        cmask[:, j] = has & (cpos != j)
+    T = lambda a: torch.as_tensor(np.asarray(a))
+    P = lambda a: torch.tensor(np.asarray(a), dtype=dtype, requires_grad=True)
+    L = P(llr)
+    w_edge, w_llr, wf_edge, wf_llr = P(weights["w_edge"]), P(weights["w_llr"]), P(weights["wf_edge"]), P(weights["wf_llr"])
+    vidx_t, vmask_t, cidx_t, cmask_t = T(vidx), T(vmask).to(dtype), T(cidx), T(cmask)
+    vm_var_t, cm_of_vm_t, vm_of_cm_t = T(vm_var), T(g.cm_of_vm), T(g.vm_of_cm)
+    lim = float(P_CLAMP)
+    x = torch.zeros(L.shape[0], E, dtype=dtype)
+    Lp = -L
+    for it in range(iterations):
+        acc = (w_edge[it, :, :mdv] * vmask_t * x[:, vidx_t]).sum(-1)                     # [B, E] variable-major
+        u_vm = torch.tanh(0.5 * (w_llr[it][vm_var_t] * Lp[:, vm_var_t] + acc))
+        u_cm = u_vm[:, vm_of_cm_t]
+        p = torch.where(cmask_t, u_cm[:, cidx_t], torch.ones((), dtype=dtype)).prod(-1)
+        p = torch.clamp(p, -lim, lim)
+        x = torch.clamp(torch.log((1 + p) / (1 - p)), -float(clamp_value), float(clamp_value))
+    t_edges = wf_edge * x[:, cm_of_vm_t]                                                  # [B, E] variable-major
+    t = 0.5 * (wf_llr * Lp + torch.zeros(L.shape[0], n, dtype=dtype).index_add(1, vm_var_t, t_edges))
+    prob = 1 - torch.sigmoid(t)
+    prob.backward(torch.as_tensor(np.asarray(grad_prob), dtype=dtype))
+    gw = w_edge.grad.numpy().copy()
+    gw[:, ~vmask] = 0                                                                     # unused (k,k) / padding entries
+    return dict(prob=prob.detach().numpy(), grad_llr=L.grad.numpy(), g_w_edge=gw, g_w_llr=w_llr.grad.numpy(),
+                g_wf_edge=wf_edge.grad.numpy(), g_wf_llr=wf_llr.grad.numpy())

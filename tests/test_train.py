@@ -1,0 +1,163 @@
+"""Training path of the weighted decoder, SURVEY.md section 8f rank 2 (reference autograd Functions bp/bp_vc.py:34-58,
+bp/bp_cv.py:57-91; training loop ofdm/ofdm_nn.py:257-396).  Golden gradients: the reference model's own .backward()
+on CPU (oracle/make_golden_grad.py); oracle: float64 autograd of the restated forward (bp_oracle.bp_weighted_grad)."""
+import os
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+G = np.load(os.path.join(ROOT, "tests", "golden", "bp_grad.npz"))
+STATE = {k[2:]: G[k] for k in G.files if k.startswith("s_")}
+KEYS = ("g_w_edge", "g_w_llr", "g_wf_edge", "g_wf_llr")
+
+
+def _rel(a, b):
+    return float(np.abs(np.asarray(a, np.float64) - b).max() / max(np.abs(b).max(), 1e-30))
+
+
+def test_gradient_oracle_matches_reference_backward():
+    """Unsaturated regime: the reference's hand-written backward is the derivative of its forward there."""
+    import bp_oracle as O
+    from ldpc_b200.codes import peg_64_32
+    H = peg_64_32()[0]
+    g = O.Graph(H)
+    w = O.weights_from_reference_state(g, STATE, int(G["iters"]))
+    o = O.bp_weighted_grad(H, G["llr"], int(G["iters"]), float(G["clamp"]), w, G["grad_prob"], graph=g)
+    assert np.abs(o["prob"] - G["prob"]).max() < 1e-6
+    assert _rel(G["grad_llr"], o["grad_llr"]) < 2e-4
+    for k in KEYS:
+        assert _rel(G[k], o[k]) < 2e-4, k
+
+
+def test_sparse_dense_weight_round_trip():
+    from ldpc_b200.codes import EdgeTables, peg_64_32, sparse_weights_from_reference_state, reference_state_from_sparse_weights
+    import bp_oracle as O
+    H = peg_64_32()[0]
+    T = EdgeTables.from_H(H)
+    w = sparse_weights_from_reference_state(T, STATE, int(G["iters"]))
+    ow = O.weights_from_reference_state(O.Graph(H), STATE, int(G["iters"]))
+    for k in ("w_edge", "w_llr", "wf_edge", "wf_llr"):
+        assert np.array_equal(w[k], ow[k]), k
+    back = reference_state_from_sparse_weights(T, w)
+    for k, v in STATE.items():
+        assert np.array_equal(back[k], v), k                  # the reference keeps weights masked: zeros elsewhere
+
+
+def _module(iters):
+    import torch
+    from bp.bp import BeliefPropagation
+    from bp.parity import H
+    m = BeliefPropagation(H, iters)
+    m.load_state_dict({k: torch.tensor(v) for k, v in STATE.items()})
+    return m.cuda()
+
+
+@pytest.mark.gpu
+def test_backward_matches_reference_golden():
+    """loss.backward() through the drop-in module = the gradients the reference left on its dense parameters."""
+    import torch
+    m = _module(int(G["iters"]))
+    llr = torch.tensor(G["llr"]).cuda().requires_grad_(True)
+    prob = m(torch.zeros(llr.shape[0], m.layer_size(), device="cuda"), llr, float(G["clamp"]))
+    assert np.abs(prob.detach().cpu().numpy() - G["prob"]).max() < 1e-5
+    loss = torch.nn.functional.binary_cross_entropy(prob, torch.tensor(G["target"]).float().cuda())
+    loss.backward()
+    assert _rel(llr.grad.cpu().numpy(), G["grad_llr"].astype(np.float64)) < 1e-4
+    for k, p in (("g_w_edge", m.w_edge), ("g_w_llr", m.w_llr), ("g_wf_edge", m.wf_edge), ("g_wf_llr", m.wf_llr)):
+        assert _rel(p.grad.cpu().numpy(), G[k].astype(np.float64)) < 1e-4, k
+    # forward of the tape kernel == the inference kernel, bit for bit
+    with torch.no_grad():
+        assert torch.equal(m(None, llr.detach(), float(G["clamp"])), prob.detach())
+
+
+@pytest.mark.gpu
+def test_backward_with_saturated_clamp():
+    """clamp_value = 3 (joint_evaluate.py:23 uses it): many messages sit ON the clamp, far from the boundary in the
+    well-conditioned part of 2 atanh, and must pass no gradient (torch.clamp semantics = the derivative of the
+    forward).  Rows in which fp32 and the float64 oracle fall on different sides of a clamp boundary may differ as a
+    whole; the bulk must agree."""
+    import torch
+    import bp_oracle as O
+    from ldpc_b200.codes import peg_64_32, EdgeTables, sparse_weights_from_reference_state
+    from ldpc_b200.decoder import LdpcCode
+    H = peg_64_32()[0]
+    iters, clamp = int(G["iters"]), 3.0
+    code = LdpcCode(H)
+    w = sparse_weights_from_reference_state(EdgeTables.from_H(H), STATE, iters)
+    dw = {k: torch.as_tensor(v).cuda() for k, v in w.items()}
+    dw.update(iterations=iters, stride=w["w_edge"].shape[2])
+    llr_np, gp_np = (2.5 * G["llr"]).astype(np.float32), G["grad_prob"]
+    o = O.bp_weighted_grad(H, llr_np, iters, clamp, w, gp_np)
+    llr, gp = torch.tensor(llr_np).cuda(), torch.tensor(gp_np).cuda()
+    prob, tape = code.train_forward(llr, dw, clamp)
+    assert float((tape[1:].abs() == clamp).float().mean()) > 0.05          # the case is about saturation
+    g = code.train_backward(llr, dw, clamp, tape, gp)
+    d = np.abs(g["grad_llr"].cpu().numpy() - o["grad_llr"])
+    rows_ok = d.max(axis=1) <= 1e-3 * np.abs(o["grad_llr"]).max()
+    assert rows_ok.mean() >= 0.95, rows_ok.mean()
+    assert _rel(g["w_llr"].cpu().numpy(), o["g_w_llr"]) < 0.05
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["default", "wifi"])
+def test_backward_random_weights_against_oracle(name):
+    """Random weights and ragged batch sizes, default code and the 802.11n code (dv up to 11, dc 8)."""
+    import torch
+    import bp_oracle as O
+    from ldpc_b200.codes import peg_64_32, ieee80211n_1944_r12
+    from ldpc_b200.decoder import LdpcCode
+    rng = np.random.RandomState(23)
+    H, B, iters, scale = (peg_64_32()[0], 77, 4, 1.0) if name == "default" else (ieee80211n_1944_r12().H, 9, 2, 0.5)
+    g = O.Graph(H)
+    code = LdpcCode(H)
+    mdv = int(g.dv.max())
+    w = dict(w_edge=(0.5 + rng.rand(iters, g.E, mdv)).astype(np.float32), w_llr=(0.5 + rng.rand(iters, g.n)).astype(np.float32),
+             wf_edge=(0.5 + rng.rand(g.E)).astype(np.float32), wf_llr=(0.5 + rng.rand(g.n)).astype(np.float32))
+    llr = (rng.randn(B, g.n) * scale).astype(np.float32)
+    gp = rng.randn(B, g.n).astype(np.float32)
+    o = O.bp_weighted_grad(H, llr, iters, 20.0, w, gp, graph=g)
+    dw = {k: torch.as_tensor(v).cuda() for k, v in w.items()}
+    dw.update(iterations=iters, stride=mdv)
+    prob, tape = code.train_forward(torch.as_tensor(llr).cuda(), dw, 20.0)
+    assert np.abs(prob.cpu().numpy() - o["prob"]).max() < 2e-5
+    ref = code.decode_weighted(torch.as_tensor(llr).cuda(), dw, 20.0, update="sp", want=("prob",))["prob"]
+    assert torch.equal(prob, ref)
+    out = code.train_backward(torch.as_tensor(llr).cuda(), dw, 20.0, tape, torch.as_tensor(gp).cuda())
+    assert _rel(out["grad_llr"].cpu().numpy(), o["grad_llr"]) < 2e-4
+    for k in ("w_edge", "w_llr", "wf_edge", "wf_llr"):
+        assert _rel(out[k].cpu().numpy(), o["g_" + k]) < 2e-4, k
+
+
+@pytest.mark.gpu
+def test_joint_training_step_reduces_loss():
+    """The reference's joint loop in miniature (ofdm/ofdm_nn.py:281-337): BCE through the decoder, SGD on its weights
+    AND on a layer in front of it (the gradient reaches the demapper through grad_llr)."""
+    import torch
+    from bp.bp import BeliefPropagation
+    from bp.parity import H, G as GEN
+    torch.manual_seed(0)
+    rng = np.random.RandomState(1)
+    bits = rng.randint(0, 2, (512, 32))
+    cw = (bits @ np.asarray(GEN).T % 2).astype(np.float32) if np.asarray(GEN).shape[0] == 64 else (bits @ np.asarray(GEN) % 2).astype(np.float32)
+    y = torch.tensor(cw).cuda()
+    obs = ((2 * y - 1) * 1.2 + torch.randn_like(y) * 1.5)          # log(P1/P0)-like observations, deliberately mis-scaled
+    bp = BeliefPropagation(H, 3).cuda()
+    scale = torch.nn.Parameter(torch.tensor(0.3, device="cuda"))
+    opt = torch.optim.SGD([{"params": bp.parameters()}, {"params": [scale]}], lr=0.5)
+    losses = []
+    for _ in range(25):
+        opt.zero_grad()
+        prob = bp(None, obs * scale, 20.0)
+        loss = torch.nn.functional.binary_cross_entropy(prob.clamp(1e-6, 1 - 1e-6), y)
+        loss.backward()
+        opt.step()
+        losses.append(float(loss.detach()))
+    assert losses[-1] < 0.9 * losses[0], losses
+    assert float(scale) != 0.3 and not bp.eval()._all_ones()
+    # the trained module exports a checkpoint in the reference's layout and reads it back
+    st = bp.reference_state_dict()
+    bp2 = BeliefPropagation(H, 3)
+    bp2.load_state_dict(st)
+    for k in ("w_edge", "w_llr", "wf_edge", "wf_llr"):
+        assert torch.equal(getattr(bp, k).detach().cpu(), getattr(bp2, k).detach()), k

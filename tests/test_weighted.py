@@ -35,17 +35,19 @@ def test_drop_in_module_loads_reference_weights():
     m = BeliefPropagation(H, int(G["iters"]))
     m.load_state_dict({("module." + k): torch.tensor(v) for k, v in STATE.items()})
     llr = torch.tensor(G["llr"]).cuda()
-    prob = m(torch.zeros(llr.shape[0], m.layer_size(), device="cuda"), llr, float(G["clamp"])).cpu().numpy()
+    prob = m(torch.zeros(llr.shape[0], m.layer_size(), device="cuda"), llr, float(G["clamp"])).cpu().detach().numpy()   # as ofdm_functions.py:161
     dp = np.abs(prob - G["prob"])                       # CUDA libm vs ATen tanh/log: same bar as the unweighted SP tests
     assert np.mean(dp <= 1e-5) >= 0.999 and dp.max() <= 5e-3
     assert np.array_equal(np.packbits(np.round(prob).astype(np.uint8), axis=1), G["hard"])
     # a state_dict whose weights are all ones keeps the fast unweighted kernels
     ones = {k: torch.ones(v.shape) for k, v in STATE.items()}
-    m1 = BeliefPropagation(H, int(G["iters"]))
+    m1 = BeliefPropagation(H, int(G["iters"])).eval()
     m1.load_state_dict(ones)
     p1 = m1(None, llr, 20.0).cpu().numpy()
-    p0 = BeliefPropagation(H, int(G["iters"]))(None, llr, 20.0).cpu().numpy()
-    assert m1._ref_state is None and np.array_equal(p1, p0)
+    p0 = BeliefPropagation(H, int(G["iters"])).eval()(None, llr, 20.0).cpu().numpy()
+    assert m1._all_ones() and not m.eval()._all_ones() and np.array_equal(p1, p0)
+    # training mode (tape kernel) and inference mode (weighted decoder) give the same bits
+    assert np.array_equal(m.eval()(None, llr, float(G["clamp"])).cpu().numpy(), prob)
     with pytest.raises(KeyError):
         BeliefPropagation(H, 5).load_state_dict({k: torch.tensor(v) for k, v in STATE.items()})
 
