@@ -43,6 +43,7 @@ def parse():
     ap.add_argument("--no-f16", action="store_true")
     ap.add_argument("--no-sp", action="store_true", help="skip the sum-product measurement")
     ap.add_argument("--no-nn", action="store_true", help="skip the NN-demapper link (BASELINE.json configs[4])")
+    ap.add_argument("--no-train", action="store_true", help="skip the weighted-BP training step (SURVEY 8f rank 2)")
     ap.add_argument("--nn-symbols", type=int, default=1 << 20, help="OFDM symbols per GPU of the NN-demapper measurement")
     return ap.parse_args()
 
@@ -216,6 +217,43 @@ def bench_nn(a, dev, world, barrier, peaks):
                                     "sum_product_x10_info_gbps": S * world * 32 / (ms_sp * 1e-3) / 1e9, "sum_product_ms": ms_sp,
                                     "min_sum_x10_info_gbps": S * world * 32 / (ms_ms * 1e-3) / 1e9, "min_sum_ms": ms_ms,
                                     "note": "(64,32) code of bp/parity.py, one thread per codeword, decode + fused counters, LLRs resident in HBM"}}
+
+
+def bench_train(dev, world, barrier):
+    """ofdm/ofdm_nn.py:281-343 in miniature: BCE through the weighted decoder on the default code, loss.backward() on
+    the native sparse backward, at the reference's minibatch (512) and at a GPU-sized batch."""
+    import torch
+    import torch.distributed as dist
+    from bp.bp import BeliefPropagation
+    from bp.parity import H
+    res = {}
+    for tag, B, iters in (("minibatch_512_iters_3", 512, 3), ("batch_65536_iters_5", 65536, 5)):
+        m = BeliefPropagation(H, iters).to(dev)
+        llr = (torch.randn(B, 64, device=dev) * 2).requires_grad_(True)
+        y = (torch.rand(B, 64, device=dev) > 0.5).float()
+
+        def step():
+            m.zero_grad()
+            llr.grad = None
+            loss = torch.nn.functional.binary_cross_entropy(m(None, llr, 20.0).clamp(1e-6, 1 - 1e-6), y)
+            loss.backward()
+        for _ in range(3):
+            step()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(10):
+            step()
+        e1.record()
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1) / 10], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        res[tag] = {"step_ms": ms, "codewords_per_s": B * world / (ms * 1e-3)}
+    res["note"] = ("default (64,32) code, sum-product, forward with tape + BCE + backward (ldpc_bp_train_forward/backward, 2 kernel launches "
+                   "per step + torch loss ops); the reference's check-node backward alone materialises [B,E,E,E] = 1.8 GB at B = 512")
+    return res
 
 
 def main():
@@ -400,6 +438,9 @@ def main():
     # ---- BASELINE.json configs[4]: NN demapper + quantized OFDM + BP decoder on the default (64,32) code ------
     if not a.no_nn:
         out["nn_demapper"] = bench_nn(a, dev, world, barrier, peaks)
+
+    if not a.no_train:
+        out["bp_training"] = bench_train(dev, world, barrier)
 
     # ---- e2e: the C-ABI host call (decode_bits path): pinned host LLRs in, packed bits out ---------
     if not a.no_e2e:

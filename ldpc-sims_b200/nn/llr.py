@@ -1,4 +1,4 @@
-"""Drop-in LLR estimators (reference nn/llr.py:7-73), inference only.
+"""Drop-in LLR estimators (reference nn/llr.py:7-73).
 
 Same class names, constructor arguments and parameter names as the reference, so the
 reference's checkpoints load unchanged (``nn.DataParallel(LLRestimator_withSNR(32))`` +
@@ -6,8 +6,9 @@ reference's checkpoints load unchanged (``nn.DataParallel(LLRestimator_withSNR(3
 ``forward`` runs the whole Linear/tanh chain in one native call (ldpc_b200.mlp.NativeMLP:
 tcgen05 tensor cores, exact binary16 plane splitting, fp32-equivalent results); CPU tensors are
 moved to the current CUDA device and the result is returned on the input's device.  There is
-no CPU path and no autograd: training the demapper (quantized_snr.py, ofdm_nn.py) is outside
-the hot path.
+no CPU path.  In training mode with autograd enabled (joint training through the decoder,
+ofdm/ofdm_nn.py:257-396) the same chain runs as torch Linear/tanh ops on the GPU so gradients reach
+the parameters; the native tensor-core chain is the inference path.
 
 ``splits`` (keyword-only extra): 2 = fp32-equivalent (default), 3 = beyond fp32, 1 = plain fp16.
 """
@@ -59,6 +60,13 @@ class _NativeChain(nn.Module):
     def forward(self, x):
         src = x.device
         dev = src if src.type == "cuda" else torch.device("cuda", torch.cuda.current_device())
+        if self.training and torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters())):
+            y = x.to(device=dev, dtype=torch.float32)        # training: library GEMMs under autograd (parameters must be on dev)
+            for name, act in zip(self._chain, self._acts):
+                y = getattr(self, name)(y)
+                if act:
+                    y = torch.tanh(y)
+            return y.to(src)
         y = self._handle(dev)(x.detach().to(device=dev, dtype=torch.float32))
         return y.to(src)
 

@@ -154,10 +154,42 @@ def test_joint_training_step_reduces_loss():
         opt.step()
         losses.append(float(loss.detach()))
     assert losses[-1] < 0.9 * losses[0], losses
-    assert float(scale) != 0.3 and not bp.eval()._all_ones()
+    assert float(scale.detach()) != 0.3 and not bp.eval()._all_ones()
     # the trained module exports a checkpoint in the reference's layout and reads it back
     st = bp.reference_state_dict()
     bp2 = BeliefPropagation(H, 3)
     bp2.load_state_dict(st)
     for k in ("w_edge", "w_llr", "wf_edge", "wf_llr"):
         assert torch.equal(getattr(bp, k).detach().cpu(), getattr(bp2, k).detach()), k
+
+
+@pytest.mark.gpu
+def test_train_joint_drop_in(tmp_path):
+    """train_joint with the reference's argument list on a small quantized-link data set: the loss falls, the test BER
+    does not get worse than the untrained model's, the checkpoint has the reference's keys."""
+    import torch
+    from bp.parity import H, G as GEN
+    from ofdm.ofdm_functions import create_bits, encode_bits, modulate_bits, gen_data, gen_qdata
+    from ofdm.ofdm_nn import train_joint
+    np.random.seed(0)
+    torch.manual_seed(0)
+    ofdm_size, snrdb = 32, 5.0
+
+    def make(n_cw):
+        bits = create_bits(n_cw * 32)
+        enc = encode_bits(bits, GEN)
+        tx = modulate_bits(enc)
+        rx_signal = gen_data(tx, snrdb, ofdm_size)[0]
+        q = gen_qdata(rx_signal, snrdb, 3, 1.0, ofdm_size)[0]
+        x = np.concatenate((q.real.T, q.imag.T), axis=1).reshape(-1, 2 * ofdm_size)
+        return x, enc.reshape(-1, 2 * ofdm_size)
+
+    x, y = make(2048)
+    xt, yt = make(512)
+    name, model = train_joint(x, y, xt, yt, H, 3, 20, "test", snrdb, 0.01, 3, 0, ofdm_size, 3, 1024, model_dir=str(tmp_path),
+                              minibatch_size=256, verbose=False, return_model=True)
+    ck = torch.load(os.path.join(str(tmp_path), name), weights_only=False)
+    assert ck["loss"].shape == (3,) and ck["loss"][-1] < ck["loss"][0]
+    keys = set(ck["model_state_dict"].keys())
+    assert {"module.LLRest.final.weight", "module.BP.w_edge", "module.BP.wf_llr"} <= keys
+    assert not model.module.BP.eval()._all_ones()
