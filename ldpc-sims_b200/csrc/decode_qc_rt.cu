@@ -11,7 +11,6 @@
 // Arithmetic = node_math.cuh with the generic kernel's edge order (a variable's edges ascending in the check index,
 // a check's edges ascending in the variable index), so the results are bit-identical to decode_generic.cu.
 #include <algorithm>
-#include <utility>
 #include <vector>
 
 #include "common.cuh"
@@ -19,17 +18,6 @@
 #include "node_math.cuh"
 
 namespace ldpc {
-
-// Calls f(std::integral_constant<int, d>) for the run-time degree d in [1, MAXD]: all threads of a CTA work on the same
-// block row / column, so the branch is uniform and the node code behind it has a COMPILE-TIME degree (register arrays;
-// with a run-time degree the per-node arrays end up in local memory and the kernel is no faster than the generic one).
-template <int D, int MAXD, class F>
-__device__ __forceinline__ void degree_switch(int d, F &&f) {
-    if constexpr (D <= MAXD) {
-        if (d == D) f(std::integral_constant<int, D>{});
-        else degree_switch<D + 1, MAXD>(d, static_cast<F &&>(f));
-    }
-}
 
 struct QcRtParams {
     DecodeArgs a;

@@ -34,51 +34,75 @@ struct TrainArgs {
     float *ws_u, *ws_g;        // [E][B] each
 };
 
-template <int MAXDV, int MAXDC>
+// Node code with a COMPILE-TIME degree: all lanes of a warp are on the same node, so a uniform branch on the degree
+// (degree_switch) selects a body whose arrays are registers.  With a run-time degree below a cap the compiler turns the
+// "last / first element" cases of the leave-one-out sweeps into indexed local-memory accesses - the kernels are chains of
+// dependent operations and every such access is on the critical path.  SW = false (degree caps above 12): one body with
+// the cap as array size and the run-time degree as bound.
+template <int MAXD, bool SW, class F>
+__device__ __forceinline__ void with_degree(int d, F &&f) {
+    if constexpr (SW) degree_switch<1, MAXD>(d, [&](auto dd) { f(dd, decltype(dd)::value); });
+    else f(std::integral_constant<int, MAXD>{}, d);
+}
+
+// (Keeping the working arrays in per-thread columns of shared memory was measured too: no faster at a batch of 512 -
+// the chains are instruction-, not load-bound once the degrees are compile-time - and 2x slower at 262 144.)
+template <int MAXDV, int MAXDC, bool SW>
 __global__ void __launch_bounds__(128) bp_train_forward_kernel(const TrainArgs a) {
     const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= a.B) return;
     const GraphTables &g = a.g;
     const int n = g.n, m = g.m, E = g.E;
     const long long B = a.B;
+    const long long S = B;                                         // stride of the [edge][B] arrays
     const float *L = a.llr + b * n;
     for (int e = 0; e < E; ++e) a.tape[(long long)e * B + b] = a.x0 ? __ldg(a.x0 + b * E + e) : 0.0f;
     for (int it = 0; it < a.iters; ++it) {
-        const float *xin = a.tape + (long long)it * E * B + b;
         float *xout = a.tape + (long long)(it + 1) * E * B + b;
+        const float *xin = a.tape + (long long)it * E * B + b;
+        float *xw = xout;                                         // the check phase works in place: a node's edges are its own
         for (int v = 0; v < n; ++v) {
-            const int b0 = __ldg(g.var_ptr + v), d = __ldg(g.var_ptr + v + 1) - b0;
-            int slot[MAXDV];
-            float in[MAXDV], out[MAXDV];
+            const int b0 = __ldg(g.var_ptr + v);
+            with_degree<MAXDV, SW>(__ldg(g.var_ptr + v + 1) - b0, [&](auto cap, int d) {
+                constexpr int D = decltype(cap)::value;
+                int slot[D];
+                float in[D], out[D];
 #pragma unroll
-            for (int k = 0; k < MAXDV; ++k)
-                if (k < d) { slot[k] = __ldg(g.cm_of_vm + b0 + k); in[k] = xin[(long long)slot[k] * B]; }
-            var_node_weighted<MAXDV, true>(in, d, __ldg(L + v), __ldg(a.w_llr + (long long)it * n + v),
+                for (int k = 0; k < D; ++k)
+                    if (k < d) { slot[k] = __ldg(g.cm_of_vm + b0 + k); in[k] = xin[slot[k] * S]; }
+                var_node_weighted<D, true>(in, d, __ldg(L + v), __ldg(a.w_llr + (long long)it * n + v),
                                            a.w_edge + ((long long)it * E + b0) * a.w_stride, a.w_stride, out);
 #pragma unroll
-            for (int k = 0; k < MAXDV; ++k)
-                if (k < d) xout[(long long)slot[k] * B] = out[k];
+                for (int k = 0; k < D; ++k)
+                    if (k < d) xw[slot[k] * S] = out[k];
+            });
         }
-        for (int c = 0; c < m; ++c) {                       // in place: a check's edges are its own
-            const int b0 = __ldg(g.chk_ptr + c), d = __ldg(g.chk_ptr + c + 1) - b0;
-            float in[MAXDC], out[MAXDC];
+        for (int c = 0; c < m; ++c) {
+            const int b0 = __ldg(g.chk_ptr + c);
+            with_degree<MAXDC, SW>(__ldg(g.chk_ptr + c + 1) - b0, [&](auto cap, int d) {
+                constexpr int D = decltype(cap)::value;
+                float in[D], out[D];
 #pragma unroll
-            for (int j = 0; j < MAXDC; ++j)
-                if (j < d) in[j] = xout[(long long)(b0 + j) * B];
-            check_node_sp<MAXDC>(in, d, a.clampv, out);
+                for (int j = 0; j < D; ++j)
+                    if (j < d) in[j] = xw[(b0 + j) * S];
+                check_node_sp<D>(in, d, a.clampv, out);
 #pragma unroll
-            for (int j = 0; j < MAXDC; ++j)
-                if (j < d) xout[(long long)(b0 + j) * B] = out[j];
+                for (int j = 0; j < D; ++j)
+                    if (j < d) xw[(b0 + j) * S] = out[j];
+            });
         }
     }
     const float *xl = a.tape + (long long)a.iters * E * B + b;
     for (int v = 0; v < n; ++v) {
-        const int b0 = __ldg(g.var_ptr + v), d = __ldg(g.var_ptr + v + 1) - b0;
-        float in[MAXDV];
+        const int b0 = __ldg(g.var_ptr + v);
+        with_degree<MAXDV, SW>(__ldg(g.var_ptr + v + 1) - b0, [&](auto cap, int d) {
+            constexpr int D = decltype(cap)::value;
+            float in[D];
 #pragma unroll
-        for (int k = 0; k < MAXDV; ++k)
-            if (k < d) in[k] = xl[(long long)__ldg(g.cm_of_vm + b0 + k) * B];
-        a.prob[b * n + v] = prob_one(marginal_t_weighted<MAXDV>(in, d, __ldg(L + v), __ldg(a.wf_llr + v), a.wf_edge + b0));
+            for (int k = 0; k < D; ++k)
+                if (k < d) in[k] = xl[__ldg(g.cm_of_vm + b0 + k) * S];
+            a.prob[b * n + v] = prob_one(marginal_t_weighted<D>(in, d, __ldg(L + v), __ldg(a.wf_llr + v), a.wf_edge + b0));
+        });
     }
 }
 
@@ -89,7 +113,7 @@ __device__ __forceinline__ void batch_add(float *dst, float v) {
     if ((threadIdx.x & 31) == 0 && v != 0.0f) atomicAdd(dst, v);
 }
 
-template <int MAXDV, int MAXDC>
+template <int MAXDV, int MAXDC, bool SW>
 __global__ void __launch_bounds__(128) bp_train_backward_kernel(const TrainArgs a) {
     const long long bb = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const bool valid = bb < a.B;
@@ -98,30 +122,34 @@ __global__ void __launch_bounds__(128) bp_train_backward_kernel(const TrainArgs 
     const GraphTables &g = a.g;
     const int n = g.n, m = g.m, E = g.E;
     const long long B = a.B;
+    const long long S = B;
     const float *L = a.llr + b * n;
-    float *GX = a.ws_g + bb, *U = a.ws_u + bb;            // idle lanes never store (guarded below)
+    float *U = a.ws_u + bb, *GX = a.ws_g + bb;            // tanh(V->C), message gradients; idle lanes never store (guarded below)
 
     // ---- marginal + sigmoid (bp/bp.py:36-39,51): prob = 1 - sigmoid(t), dprob/dt = -prob (1 - prob) -------------
     {
         const float *xl = a.tape + (long long)a.iters * E * B + b;
         for (int v = 0; v < n; ++v) {
-            const int b0 = __ldg(g.var_ptr + v), d = __ldg(g.var_ptr + v + 1) - b0;
-            int slot[MAXDV];
-            float in[MAXDV];
+            const int b0 = __ldg(g.var_ptr + v);
+            with_degree<MAXDV, SW>(__ldg(g.var_ptr + v + 1) - b0, [&](auto cap, int d) {
+                constexpr int D = decltype(cap)::value;
+                int slot[D];
+                float in[D];
 #pragma unroll
-            for (int k = 0; k < MAXDV; ++k)
-                if (k < d) { slot[k] = __ldg(g.cm_of_vm + b0 + k); in[k] = xl[(long long)slot[k] * B]; }
-            const float l = __ldg(L + v), wl = __ldg(a.wf_llr + v);
-            const float P = prob_one(marginal_t_weighted<MAXDV>(in, d, l, wl, a.wf_edge + b0));
-            const float h = 0.5f * live * __ldg(a.grad_prob + b * n + v) * (-(P * (1.0f - P)));
-            batch_add(a.g_wf_llr + v, h * -l);
-            if (valid) a.grad_llr[b * n + v] = h * -wl;
+                for (int k = 0; k < D; ++k)
+                    if (k < d) { slot[k] = __ldg(g.cm_of_vm + b0 + k); in[k] = xl[(long long)slot[k] * B]; }
+                const float l = __ldg(L + v), wl = __ldg(a.wf_llr + v);
+                const float P = prob_one(marginal_t_weighted<D>(in, d, l, wl, a.wf_edge + b0));
+                const float h = 0.5f * live * __ldg(a.grad_prob + b * n + v) * (-(P * (1.0f - P)));
+                batch_add(a.g_wf_llr + v, h * -l);
+                if (valid) a.grad_llr[b * n + v] = h * -wl;
 #pragma unroll
-            for (int k = 0; k < MAXDV; ++k)
-                if (k < d) {
-                    batch_add(a.g_wf_edge + b0 + k, h * in[k]);
-                    if (valid) GX[(long long)slot[k] * B] = h * __ldg(a.wf_edge + b0 + k);
-                }
+                for (int k = 0; k < D; ++k)
+                    if (k < d) {
+                        batch_add(a.g_wf_edge + b0 + k, h * in[k]);
+                        if (valid) GX[slot[k] * S] = h * __ldg(a.wf_edge + b0 + k);
+                    }
+            });
         }
     }
 
@@ -130,100 +158,113 @@ __global__ void __launch_bounds__(128) bp_train_backward_kernel(const TrainArgs 
         const float *wE = a.w_edge + (long long)it * E * a.w_stride;
         // ---- recompute tanh(V->C) of this iteration --------------------------------------------------------------
         for (int v = 0; v < n; ++v) {
-            const int b0 = __ldg(g.var_ptr + v), d = __ldg(g.var_ptr + v + 1) - b0;
-            int slot[MAXDV];
-            float in[MAXDV], out[MAXDV];
+            const int b0 = __ldg(g.var_ptr + v);
+            with_degree<MAXDV, SW>(__ldg(g.var_ptr + v + 1) - b0, [&](auto cap, int d) {
+                constexpr int D = decltype(cap)::value;
+                int slot[D];
+                float in[D], out[D];
 #pragma unroll
-            for (int k = 0; k < MAXDV; ++k)
-                if (k < d) { slot[k] = __ldg(g.cm_of_vm + b0 + k); in[k] = xin[(long long)slot[k] * B]; }
-            var_node_weighted<MAXDV, true>(in, d, __ldg(L + v), __ldg(a.w_llr + (long long)it * n + v),
+                for (int k = 0; k < D; ++k)
+                    if (k < d) { slot[k] = __ldg(g.cm_of_vm + b0 + k); in[k] = xin[slot[k] * S]; }
+                var_node_weighted<D, true>(in, d, __ldg(L + v), __ldg(a.w_llr + (long long)it * n + v),
                                            wE + (long long)b0 * a.w_stride, a.w_stride, out);
-            if (valid)
+                if (valid)
 #pragma unroll
-                for (int k = 0; k < MAXDV; ++k)
-                    if (k < d) U[(long long)slot[k] * B] = out[k];
+                    for (int k = 0; k < D; ++k)
+                        if (k < d) U[slot[k] * S] = out[k];
+            });
         }
         // ---- check node backward: GX (d/d message out) -> GX (d/d pre-tanh V->C value) ------------------------------
         if (valid)
             for (int c = 0; c < m; ++c) {
-                const int b0 = __ldg(g.chk_ptr + c), d = __ldg(g.chk_ptr + c + 1) - b0;
-                float u[MAXDC], p[MAXDC], gp[MAXDC];
+                const int b0 = __ldg(g.chk_ptr + c);
+                with_degree<MAXDC, SW>(__ldg(g.chk_ptr + c + 1) - b0, [&](auto cap, int d) {
+                    constexpr int D = decltype(cap)::value;
+                    float u[D], p[D], gp[D], gu[D];
 #pragma unroll
-                for (int j = 0; j < MAXDC; ++j)
-                    if (j < d) u[j] = U[(long long)(b0 + j) * B];
-                prod_others<MAXDC>(u, d, p);
+                    for (int j = 0; j < D; ++j)
+                        if (j < d) u[j] = U[(b0 + j) * S];
+                    prod_others<D>(u, d, p);
 #pragma unroll
-                for (int j = 0; j < MAXDC; ++j)
-                    if (j < d) {
-                        const float q = clampf(p[j], LDPC_P_CLAMP);
-                        const float o = logf(div_rn_one_plus_minus(q));
-                        const bool pass = fabsf(p[j]) <= LDPC_P_CLAMP && fabsf(o) <= a.clampv;
-                        gp[j] = pass ? GX[(long long)(b0 + j) * B] * (2.0f / ((1.0f - q) * (1.0f + q))) : 0.0f;
-                    }
-#pragma unroll
-                for (int i = 0; i < MAXDC; ++i)
-                    if (i < d) {
-                        float acc = 0.0f;                   // d/du_i = sum_{j != i} gp_j prod_{k != i,j} u_k
-                        for (int j = 0; j < d; ++j) {
-                            if (j == i) continue;
-                            float pr = 1.0f;
-                            for (int k = 0; k < d; ++k)
-                                if (k != i && k != j) pr *= u[k];
-                            acc = fmaf(gp[j], pr, acc);
+                    for (int j = 0; j < D; ++j) {
+                        gu[j] = 0.0f;
+                        if (j < d) {
+                            const float q = clampf(p[j], LDPC_P_CLAMP);
+                            const float o = logf(div_rn_one_plus_minus(q));
+                            const bool pass = fabsf(p[j]) <= LDPC_P_CLAMP && fabsf(o) <= a.clampv;
+                            gp[j] = pass ? GX[(b0 + j) * S] * (2.0f / ((1.0f - q) * (1.0f + q))) : 0.0f;
                         }
-                        GX[(long long)(b0 + i) * B] = acc * (1.0f - u[i] * u[i]);
                     }
+                    // d/du_i = sum_{j != i} gp_j prod_{k != i,j} u_k: for every j, the leave-one-out products of u with u_j := 1
+#pragma unroll
+                    for (int j = 0; j < D; ++j)
+                        if (j < d) {
+                            float uj[D], pj[D];
+#pragma unroll
+                            for (int k = 0; k < D; ++k) uj[k] = (k == j) ? 1.0f : u[k];
+                            prod_others<D>(uj, d, pj);
+#pragma unroll
+                            for (int i = 0; i < D; ++i)
+                                if (i < d && i != j) gu[i] = fmaf(gp[j], pj[i], gu[i]);
+                        }
+#pragma unroll
+                    for (int i = 0; i < D; ++i)
+                        if (i < d) GX[(b0 + i) * S] = gu[i] * (1.0f - u[i] * u[i]);
+                });
             }
         // ---- variable node backward -------------------------------------------------------------------------------------
         for (int v = 0; v < n; ++v) {
-            const int b0 = __ldg(g.var_ptr + v), d = __ldg(g.var_ptr + v + 1) - b0;
-            int slot[MAXDV];
-            float x[MAXDV], hs[MAXDV];
-            float sum = 0.0f;
+            const int b0 = __ldg(g.var_ptr + v);
+            with_degree<MAXDV, SW>(__ldg(g.var_ptr + v + 1) - b0, [&](auto cap, int d) {
+                constexpr int D = decltype(cap)::value;
+                int slot[D];
+                float x[D], hs[D];
+                float sum = 0.0f;
 #pragma unroll
-            for (int k = 0; k < MAXDV; ++k)
-                if (k < d) {
-                    slot[k] = __ldg(g.cm_of_vm + b0 + k);
-                    x[k] = xin[(long long)slot[k] * B];
-                    hs[k] = valid ? 0.5f * GX[(long long)slot[k] * B] : 0.0f;
-                    sum += hs[k];
-                }
-            const float l = __ldg(L + v), wl = __ldg(a.w_llr + (long long)it * n + v);
-            batch_add(a.g_w_llr + (long long)it * n + v, sum * -l);
-            if (valid) a.grad_llr[b * n + v] += sum * -wl;
-            const float *w = wE + (long long)b0 * a.w_stride;
-            float *gw = a.g_w_edge + ((long long)it * E + b0) * a.w_stride;
+                for (int k = 0; k < D; ++k)
+                    if (k < d) {
+                        slot[k] = __ldg(g.cm_of_vm + b0 + k);
+                        x[k] = xin[slot[k] * S];
+                        hs[k] = valid ? 0.5f * GX[slot[k] * S] : 0.0f;
+                        sum += hs[k];
+                    }
+                const float l = __ldg(L + v), wl = __ldg(a.w_llr + (long long)it * n + v);
+                batch_add(a.g_w_llr + (long long)it * n + v, sum * -l);
+                if (valid) a.grad_llr[b * n + v] += sum * -wl;
+                const float *w = wE + (long long)b0 * a.w_stride;
+                float *gw = a.g_w_edge + ((long long)it * E + b0) * a.w_stride;
 #pragma unroll
-            for (int j = 0; j < MAXDV; ++j)
-                if (j < d) {
-                    float gx = 0.0f;
+                for (int j = 0; j < D; ++j)
+                    if (j < d) {
+                        float gx = 0.0f;
 #pragma unroll
-                    for (int k = 0; k < MAXDV; ++k)
-                        if (k < d && k != j) {
-                            batch_add(gw + k * a.w_stride + j, hs[k] * x[j]);
-                            gx = fmaf(hs[k], __ldg(w + k * a.w_stride + j), gx);
-                        }
-                    if (valid) GX[(long long)slot[j] * B] = gx;
-                }
+                        for (int k = 0; k < D; ++k)
+                            if (k < d && k != j) {
+                                batch_add(gw + k * a.w_stride + j, hs[k] * x[j]);
+                                gx = fmaf(hs[k], __ldg(w + k * a.w_stride + j), gx);
+                            }
+                        if (valid) GX[slot[j] * S] = gx;
+                    }
+            });
         }
     }
 }
 
-template <int MAXDV, int MAXDC>
+template <int MAXDV, int MAXDC, bool SW>
 static int launch_train_t(const TrainArgs &a, bool backward, cudaStream_t s) {
     const int threads = 128;
     const long long grid = (a.B + threads - 1) / threads;
     if (grid > 0x7fffffffLL) { set_error("batch too large"); return LDPC_EINVAL; }
-    if (backward) bp_train_backward_kernel<MAXDV, MAXDC><<<(int)grid, threads, 0, s>>>(a);
-    else bp_train_forward_kernel<MAXDV, MAXDC><<<(int)grid, threads, 0, s>>>(a);
+    if (backward) bp_train_backward_kernel<MAXDV, MAXDC, SW><<<(int)grid, threads, 0, s>>>(a);
+    else bp_train_forward_kernel<MAXDV, MAXDC, SW><<<(int)grid, threads, 0, s>>>(a);
     LDPC_CUDA_TRY(cudaGetLastError());
     return LDPC_OK;
 }
 
 static int launch_train(const ldpc_code *code, const TrainArgs &a, bool backward, cudaStream_t s) {
-    if (code->max_dv <= 4 && code->max_dc <= 8) return launch_train_t<4, 8>(a, backward, s);
-    if (code->max_dv <= 12 && code->max_dc <= 8) return launch_train_t<12, 8>(a, backward, s);
-    if (code->max_dv <= 32 && code->max_dc <= 32) return launch_train_t<32, 32>(a, backward, s);
+    if (code->max_dv <= 4 && code->max_dc <= 8) return launch_train_t<4, 8, true>(a, backward, s);     // the default (64,32) code
+    if (code->max_dv <= 12 && code->max_dc <= 8) return launch_train_t<12, 8, true>(a, backward, s);   // 802.11n
+    if (code->max_dv <= 32 && code->max_dc <= 32) return launch_train_t<32, 32, false>(a, backward, s);
     set_error("node degree above 32");
     return LDPC_EUNSUPPORTED;
 }
