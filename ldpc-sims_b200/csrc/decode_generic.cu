@@ -26,7 +26,7 @@ struct GenericParams {
     int hard_stride;   // bytes per codeword in the hard-bit tile
 };
 
-template <int MAXDV, int MAXDC, bool IS_SP>
+template <int MAXDV, int MAXDC, bool IS_SP, bool SW>
 __global__ void __launch_bounds__(256) decode_generic_kernel(const GenericParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const GraphTables &g = p.g;
@@ -67,19 +67,22 @@ __global__ void __launch_bounds__(256) decode_generic_kernel(const GenericParams
                 const int b = __ldg(g.var_ptr + v), d = __ldg(g.var_ptr + v + 1) - b;
                 if (d == 0) continue;
                 float *mrow = msg + cw * p.msg_stride;
-                int slot[MAXDV];
-                float in[MAXDV], out[MAXDV];
+                with_degree<MAXDV, SW>(d, [&](auto cap, int d) {          // compile-time degree: register arrays
+                    constexpr int D = decltype(cap)::value;
+                    int slot[D];
+                    float in[D], out[D];
 #pragma unroll
-                for (int k = 0; k < MAXDV; ++k)
-                    if (k < d) { slot[k] = __ldg(g.cm_of_vm + b + k); in[k] = mrow[slot[k]]; }
-                if (a.w_edge)
-                    var_node_weighted<MAXDV, IS_SP>(in, d, llr_s[cw * p.llr_stride + v], __ldg(a.w_llr + (long long)it * n + v),
+                    for (int k = 0; k < D; ++k)
+                        if (k < d) { slot[k] = __ldg(g.cm_of_vm + b + k); in[k] = mrow[slot[k]]; }
+                    if (a.w_edge)
+                        var_node_weighted<D, IS_SP>(in, d, llr_s[cw * p.llr_stride + v], __ldg(a.w_llr + (long long)it * n + v),
                                                     a.w_edge + ((long long)it * E + b) * a.w_stride, a.w_stride, out);
-                else
-                    var_node<MAXDV, IS_SP>(in, d, llr_s[cw * p.llr_stride + v], out);
+                    else
+                        var_node<D, IS_SP>(in, d, llr_s[cw * p.llr_stride + v], out);
 #pragma unroll
-                for (int k = 0; k < MAXDV; ++k)
-                    if (k < d) mrow[slot[k]] = out[k];
+                    for (int k = 0; k < D; ++k)
+                        if (k < d) mrow[slot[k]] = out[k];
+                });
             }
             __syncthreads();
             // ---- C -> V -----------------------------------------------------------------------
@@ -89,15 +92,18 @@ __global__ void __launch_bounds__(256) decode_generic_kernel(const GenericParams
                 const int b = __ldg(g.chk_ptr + c), d = __ldg(g.chk_ptr + c + 1) - b;
                 if (d == 0) continue;
                 float *mrow = msg + cw * p.msg_stride + b;
-                float in[MAXDC], out[MAXDC];
+                with_degree<MAXDC, SW>(d, [&](auto cap, int d) {
+                    constexpr int D = decltype(cap)::value;
+                    float in[D], out[D];
 #pragma unroll
-                for (int j = 0; j < MAXDC; ++j)
-                    if (j < d) in[j] = mrow[j];
-                if (IS_SP) check_node_sp<MAXDC>(in, d, a.clampv, out);
-                else check_node_ms<MAXDC>(in, d, a.update, a.clampv, a.param, out);
+                    for (int j = 0; j < D; ++j)
+                        if (j < d) in[j] = mrow[j];
+                    if (IS_SP) check_node_sp<D>(in, d, a.clampv, out);
+                    else check_node_ms<D>(in, d, a.update, a.clampv, a.param, out);
 #pragma unroll
-                for (int j = 0; j < MAXDC; ++j)
-                    if (j < d) mrow[j] = out[j];
+                    for (int j = 0; j < D; ++j)
+                        if (j < d) mrow[j] = out[j];
+                });
             }
             __syncthreads();
             ++it;
@@ -111,12 +117,17 @@ __global__ void __launch_bounds__(256) decode_generic_kernel(const GenericParams
             if (!last && frozen_s[cw]) continue;
             const int b = __ldg(g.var_ptr + v), d = __ldg(g.var_ptr + v + 1) - b;
             const float *mrow = msg + cw * p.msg_stride;
-            float in[MAXDV];
+            float t = __fmul_rn(0.5f, __fadd_rn(-llr_s[cw * p.llr_stride + v], 0.0f));      // a variable without edges
+            if (a.wf_edge && d == 0) t = __fmul_rn(0.5f, __fadd_rn(__fmul_rn(__ldg(a.wf_llr + v), -llr_s[cw * p.llr_stride + v]), 0.0f));
+            with_degree<MAXDV, SW>(d, [&](auto cap, int d) {
+                constexpr int D = decltype(cap)::value;
+                float in[D];
 #pragma unroll
-            for (int k = 0; k < MAXDV; ++k)
-                if (k < d) in[k] = mrow[__ldg(g.cm_of_vm + b + k)];
-            const float t = a.wf_edge ? marginal_t_weighted<MAXDV>(in, d, llr_s[cw * p.llr_stride + v], __ldg(a.wf_llr + v), a.wf_edge + b)
-                                      : marginal_t<MAXDV>(in, d, llr_s[cw * p.llr_stride + v]);
+                for (int k = 0; k < D; ++k)
+                    if (k < d) in[k] = mrow[__ldg(g.cm_of_vm + b + k)];
+                t = a.wf_edge ? marginal_t_weighted<D>(in, d, llr_s[cw * p.llr_stride + v], __ldg(a.wf_llr + v), a.wf_edge + b)
+                              : marginal_t<D>(in, d, llr_s[cw * p.llr_stride + v]);
+            });
             const uint8_t hb = hard_bit(t);                  // np.round(prob): tie 0.5 -> 0
             hard_s[cw * p.hard_stride + v] = hb | ((llr_s[cw * p.llr_stride + v] > 0.0f) ? 2 : 0);
             if (last) {
@@ -169,14 +180,14 @@ __global__ void __launch_bounds__(256) decode_generic_kernel(const GenericParams
     }
 }
 
-template <int MAXDV, int MAXDC>
+template <int MAXDV, int MAXDC, bool SW>
 static int launch_t(const GenericParams &p, size_t smem, int grid, cudaStream_t s) {
     if (p.a.update == UPD_SP) {
-        auto k = decode_generic_kernel<MAXDV, MAXDC, true>;
+        auto k = decode_generic_kernel<MAXDV, MAXDC, true, SW>;
         LDPC_CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         k<<<grid, 256, smem, s>>>(p);
     } else {
-        auto k = decode_generic_kernel<MAXDV, MAXDC, false>;
+        auto k = decode_generic_kernel<MAXDV, MAXDC, false, SW>;
         LDPC_CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         k<<<grid, 256, smem, s>>>(p);
     }
@@ -208,9 +219,9 @@ int launch_decode_generic(const GraphTables &g, int max_dv, int max_dc, const De
     const size_t smem = CW * per_cw + sizeof(int) * (8 + 2 * CW) + 16;
     const long long grid = (a.B + CW - 1) / CW;
     if (grid > 0x7fffffffLL) { set_error("batch too large"); return LDPC_EINVAL; }
-    if (max_dv <= 4 && max_dc <= 4) return launch_t<4, 4>(p, smem, (int)grid, s);
-    if (max_dv <= 12 && max_dc <= 8) return launch_t<12, 8>(p, smem, (int)grid, s);
-    if (max_dv <= 32 && max_dc <= 32) return launch_t<32, 32>(p, smem, (int)grid, s);
+    if (max_dv <= 4 && max_dc <= 4) return launch_t<4, 4, true>(p, smem, (int)grid, s);
+    if (max_dv <= 12 && max_dc <= 8) return launch_t<12, 8, true>(p, smem, (int)grid, s);
+    if (max_dv <= 32 && max_dc <= 32) return launch_t<32, 32, false>(p, smem, (int)grid, s);
     set_error("node degree above 32 is not supported (max_dv=%d, max_dc=%d)", max_dv, max_dc);
     return LDPC_EUNSUPPORTED;
 }

@@ -34,17 +34,6 @@ struct TrainArgs {
     float *ws_u, *ws_g;        // [E][B] each
 };
 
-// Node code with a COMPILE-TIME degree: all lanes of a warp are on the same node, so a uniform branch on the degree
-// (degree_switch) selects a body whose arrays are registers.  With a run-time degree below a cap the compiler turns the
-// "last / first element" cases of the leave-one-out sweeps into indexed local-memory accesses - the kernels are chains of
-// dependent operations and every such access is on the critical path.  SW = false (degree caps above 12): one body with
-// the cap as array size and the run-time degree as bound.
-template <int MAXD, bool SW, class F>
-__device__ __forceinline__ void with_degree(int d, F &&f) {
-    if constexpr (SW) degree_switch<1, MAXD>(d, [&](auto dd) { f(dd, decltype(dd)::value); });
-    else f(std::integral_constant<int, MAXD>{}, d);
-}
-
 // (Keeping the working arrays in per-thread columns of shared memory was measured too: no faster at a batch of 512 -
 // the chains are instruction-, not load-bound once the degrees are compile-time - and 2x slower at 262 144.)
 template <int MAXDV, int MAXDC, bool SW>
