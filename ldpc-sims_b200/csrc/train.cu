@@ -264,9 +264,9 @@ using namespace ldpc;
 
 static int check_train(const ldpc_code_t *code, const float *llr, int64_t B, int iters, float clamp_value, const float *w_edge,
                        const float *w_llr, const float *wf_edge, const float *wf_llr, int w_stride, const float *tape) {
-    if (!code || !llr || !tape) { set_error("ldpc_bp_train: null argument"); return LDPC_EINVAL; }
+    if (!code || ((!llr || !tape) && B > 0)) { set_error("ldpc_bp_train: null argument"); return LDPC_EINVAL; }
     if (B < 0 || iters < 0 || !(clamp_value > 0.0f)) { set_error("ldpc_bp_train: bad B / iters / clamp"); return LDPC_EINVAL; }
-    if (!w_edge || !w_llr || !wf_edge || !wf_llr || w_stride < code->max_dv) {
+    if (((!w_edge || !w_llr) && iters > 0) || !wf_edge || !wf_llr || w_stride < code->max_dv) {   // zero iterations: empty per-iteration tables
         set_error("ldpc_bp_train: weight tables missing or w_stride < max_dv (%d)", code->max_dv);
         return LDPC_EINVAL;
     }
@@ -283,7 +283,7 @@ int ldpc_bp_train_forward(const ldpc_code_t *code, const float *llr, int64_t B, 
                           const float *x0, float *prob, float *tape, ldpc_stream_t stream) {
     int rc = check_train(code, llr, B, iters, clamp_value, w_edge, w_llr, wf_edge, wf_llr, w_stride, tape);
     if (rc) return rc;
-    if (!prob) { set_error("ldpc_bp_train_forward: prob is null"); return LDPC_EINVAL; }
+    if (!prob && B > 0) { set_error("ldpc_bp_train_forward: prob is null"); return LDPC_EINVAL; }
     if (B == 0) return LDPC_OK;
     TrainArgs a = {};
     a.g = code->g; a.llr = llr; a.B = B; a.iters = iters; a.w_stride = w_stride; a.clampv = clamp_value;
@@ -297,14 +297,16 @@ int ldpc_bp_train_backward(const ldpc_code_t *code, const float *llr, int64_t B,
                            float *g_wf_edge, float *g_wf_llr, float *workspace, ldpc_stream_t stream) {
     int rc = check_train(code, llr, B, iters, clamp_value, w_edge, w_llr, wf_edge, wf_llr, w_stride, tape);
     if (rc) return rc;
-    if (!grad_prob || !grad_llr || !g_w_edge || !g_w_llr || !g_wf_edge || !g_wf_llr || !workspace) {
+    if (((!g_w_edge || !g_w_llr) && iters > 0) || ((!grad_prob || !grad_llr) && B > 0) || !g_wf_edge || !g_wf_llr || !workspace) {
         set_error("ldpc_bp_train_backward: null output or workspace");
         return LDPC_EINVAL;
     }
     cudaStream_t s = (cudaStream_t)stream;
     const size_t E = code->E, n = code->n;
-    LDPC_CUDA_TRY(cudaMemsetAsync(g_w_edge, 0, sizeof(float) * (size_t)iters * E * w_stride, s));
-    LDPC_CUDA_TRY(cudaMemsetAsync(g_w_llr, 0, sizeof(float) * (size_t)iters * n, s));
+    if (iters > 0) {
+        LDPC_CUDA_TRY(cudaMemsetAsync(g_w_edge, 0, sizeof(float) * (size_t)iters * E * w_stride, s));
+        LDPC_CUDA_TRY(cudaMemsetAsync(g_w_llr, 0, sizeof(float) * (size_t)iters * n, s));
+    }
     LDPC_CUDA_TRY(cudaMemsetAsync(g_wf_edge, 0, sizeof(float) * E, s));
     LDPC_CUDA_TRY(cudaMemsetAsync(g_wf_llr, 0, sizeof(float) * n, s));
     if (B == 0) return LDPC_OK;

@@ -400,7 +400,8 @@ def bp_weighted_grad(H, llr, iterations, clamp_value, weights, grad_prob, graph=
     t = 0.5 * (wf_llr * Lp + torch.zeros(L.shape[0], n, dtype=dtype).index_add(1, vm_var_t, t_edges))
     prob = 1 - torch.sigmoid(t)
     prob.backward(torch.as_tensor(np.asarray(grad_prob), dtype=dtype))
-    gw = w_edge.grad.numpy().copy()
+    G = lambda p: (torch.zeros_like(p) if p.grad is None else p.grad).numpy()            # zero iterations: unused tables
+    gw = G(w_edge).copy()
     gw[:, ~vmask] = 0                                                                     # unused (k,k) / padding entries
-    return dict(prob=prob.detach().numpy(), grad_llr=L.grad.numpy(), g_w_edge=gw, g_w_llr=w_llr.grad.numpy(),
+    return dict(prob=prob.detach().numpy(), grad_llr=L.grad.numpy(), g_w_edge=gw, g_w_llr=G(w_llr),
                 g_wf_edge=wf_edge.grad.numpy(), g_wf_llr=wf_llr.grad.numpy())

@@ -193,3 +193,49 @@ def test_train_joint_drop_in(tmp_path):
     keys = set(ck["model_state_dict"].keys())
     assert {"module.LLRest.final.weight", "module.BP.w_edge", "module.BP.wf_llr"} <= keys
     assert not model.module.BP.eval()._all_ones()
+
+
+@pytest.mark.gpu
+def test_training_edge_cases():
+    """Zero iterations (marginal of the channel LLR only), an empty batch, a ragged batch that leaves idle lanes in the
+    last warp, and the argument checks of the training entry points."""
+    import torch
+    import bp_oracle as O
+    from bp.bp import BeliefPropagation
+    from ldpc_b200.codes import peg_64_32
+    from ldpc_b200.decoder import LdpcCode
+    H = peg_64_32()[0]
+    g = O.Graph(H)
+    code = LdpcCode(H)
+    rng = np.random.RandomState(5)
+    mdv = int(g.dv.max())
+    for iters, B in ((0, 5), (2, 1), (1, 33)):
+        w = dict(w_edge=(0.5 + rng.rand(iters, g.E, mdv)).astype(np.float32), w_llr=(0.5 + rng.rand(iters, g.n)).astype(np.float32),
+                 wf_edge=(0.5 + rng.rand(g.E)).astype(np.float32), wf_llr=(0.5 + rng.rand(g.n)).astype(np.float32))
+        llr, gp = rng.randn(B, g.n).astype(np.float32), rng.randn(B, g.n).astype(np.float32)
+        o = O.bp_weighted_grad(H, llr, iters, 20.0, w, gp, graph=g)
+        dw = {k: torch.as_tensor(v).cuda() for k, v in w.items()}
+        dw.update(iterations=iters, stride=mdv)
+        prob, tape = code.train_forward(torch.as_tensor(llr).cuda(), dw, 20.0)
+        out = code.train_backward(torch.as_tensor(llr).cuda(), dw, 20.0, tape, torch.as_tensor(gp).cuda())
+        assert np.abs(prob.cpu().numpy() - o["prob"]).max() < 2e-5
+        assert _rel(out["grad_llr"].cpu().numpy(), o["grad_llr"]) < 2e-4
+        assert _rel(out["wf_edge"].cpu().numpy(), o["g_wf_edge"]) < 2e-4
+        if iters:
+            assert _rel(out["w_edge"].cpu().numpy(), o["g_w_edge"]) < 2e-4
+    # empty batch: outputs exist, weight gradients are zero
+    dw0 = {k: torch.ones(s, device="cuda") for k, s in (("w_edge", (1, g.E, mdv)), ("w_llr", (1, g.n)), ("wf_edge", (g.E,)), ("wf_llr", (g.n,)))}
+    dw0.update(iterations=1, stride=mdv)
+    prob, tape = code.train_forward(torch.zeros(0, g.n, device="cuda"), dw0, 20.0)
+    out = code.train_backward(torch.zeros(0, g.n, device="cuda"), dw0, 20.0, tape, torch.zeros(0, g.n, device="cuda"))
+    assert prob.shape == (0, g.n) and float(out["w_edge"].abs().sum()) == 0.0
+    with pytest.raises(ValueError):
+        code.train_forward(torch.zeros(4, g.n + 1, device="cuda"), dw0, 20.0)
+    with pytest.raises(ValueError):
+        code.train_forward(torch.zeros(4, g.n), dw0, 20.0)                       # CPU tensor: no CPU fallback
+    with pytest.raises(ValueError):
+        code.train_backward(torch.zeros(4, g.n, device="cuda"), dw0, 20.0, torch.zeros(2, g.E, 3, device="cuda"), torch.zeros(4, g.n, device="cuda"))
+    m = BeliefPropagation(H, 2, update="minsum").cuda()
+    with pytest.raises(ValueError):
+        m(None, torch.zeros(4, 64, device="cuda"), 20.0)                         # training mode is sum-product only
+    assert m.eval()(None, torch.zeros(4, 64, device="cuda"), 20.0).shape == (4, 64)
