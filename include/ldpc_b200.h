@@ -128,7 +128,7 @@ int ldpc_decode_weighted(const ldpc_code_t *code, const void *llr, int llr_dtype
  * autograd does in the reference through BeliefPropagationVC_Function / BeliefPropagationCV_Function (bp/bp_vc.py:16-58,
  * bp/bp_cv.py:22-96, unrolled by bp/bp.py:43-51; joint training loop ofdm/ofdm_nn.py:257-396) with dense [E,E] masks
  * and a [B,E,E,E] intermediate.  forward: prob [B,n] = P(bit=1), identical to ldpc_decode_weighted, and the tape
- * [(iters+1)][E][B] of C->V messages entering every iteration (x0 [B,E] check-major or null = zeros).
+ * ((iters+1)*E*B floats, layout private to the pair) of C->V messages entering every iteration (x0 [B,E] check-major or null = zeros).
  * backward: given grad_prob [B,n] writes grad_llr [B,n] and the batch-summed weight gradients g_w_edge
  * [iters][E][w_stride], g_w_llr [iters][n], g_wf_edge [E], g_wf_llr [n] (overwritten; unused (k,k) / padding entries
  * stay 0).  workspace: 2*E*B floats.  All DEVICE pointers, f32, asynchronous on `stream`.  The gradient is the exact

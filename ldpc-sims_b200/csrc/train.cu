@@ -26,7 +26,8 @@ struct TrainArgs {
     const float *w_edge, *w_llr, *wf_edge, *wf_llr;
     const float *x0;           // [B][E] or null
     float *prob;               // [B][n]
-    float *tape;               // [(iters+1)][E][B]: C->V messages entering iteration it (tape[iters] feeds the marginal)
+    float *tape;               // C->V messages entering iteration it (tape[iters] feeds the marginal): [iters+1][E][B] for the
+                               // thread-per-codeword pair, [iters+1][B][E] for the warp-per-codeword pair (opaque to callers)
     // backward only
     const float *grad_prob;    // [B][n]
     float *grad_llr;           // [B][n]
@@ -92,6 +93,8 @@ __global__ void __launch_bounds__(128) bp_train_forward_kernel(const TrainArgs a
                 if (k < d) in[k] = xl[__ldg(g.cm_of_vm + b0 + k) * S];
             a.prob[b * n + v] = prob_one(marginal_t_weighted<D>(in, d, __ldg(L + v), __ldg(a.wf_llr + v), a.wf_edge + b0));
         });
+        if (SW && __ldg(g.var_ptr + v + 1) == b0)             // a variable without edges has no switch case
+            a.prob[b * n + v] = prob_one(__fmul_rn(0.5f, __fadd_rn(__fmul_rn(__ldg(a.wf_llr + v), -__ldg(L + v)), 0.0f)));
     }
 }
 
@@ -120,6 +123,13 @@ __global__ void __launch_bounds__(128) bp_train_backward_kernel(const TrainArgs 
         const float *xl = a.tape + (long long)a.iters * E * B + b;
         for (int v = 0; v < n; ++v) {
             const int b0 = __ldg(g.var_ptr + v);
+            if (SW && __ldg(g.var_ptr + v + 1) == b0) {          // a variable without edges has no switch case
+                const float l = __ldg(L + v), wl = __ldg(a.wf_llr + v);
+                const float P = prob_one(__fmul_rn(0.5f, __fadd_rn(__fmul_rn(wl, -l), 0.0f)));
+                const float h = 0.5f * live * __ldg(a.grad_prob + b * n + v) * (-(P * (1.0f - P)));
+                batch_add(a.g_wf_llr + v, h * -l);
+                if (valid) a.grad_llr[b * n + v] = h * -wl;
+            }
             with_degree<MAXDV, SW>(__ldg(g.var_ptr + v + 1) - b0, [&](auto cap, int d) {
                 constexpr int D = decltype(cap)::value;
                 int slot[D];
@@ -239,8 +249,237 @@ __global__ void __launch_bounds__(128) bp_train_backward_kernel(const TrainArgs 
     }
 }
 
+// ---- small batches: ONE WARP PER CODEWORD ---------------------------------------------------------------------------
+// With a few hundred codewords (the reference trains on minibatches of 512, ofdm/ofdm_nn.py:262) one thread per
+// codeword leaves the GPU with 16 warps, each walking the whole graph serially.  Here the 32 lanes of a warp take the
+// nodes of ONE codeword (variable v = lane, lane + 32, ...), the working arrays are a per-warp slice of shared memory,
+// phases are separated by __syncwarp, and every weight-gradient term goes straight to a float atomic (B atomics per
+// weight - cheap while B is small, which is exactly when this variant is selected).  Tape layout here: [it][B][E].
+template <int MAXDV, int MAXDC, bool SW>
+__global__ void __launch_bounds__(128) bp_train_forward_wpc_kernel(const TrainArgs a) {
+    extern __shared__ float sm[];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, W = blockDim.x >> 5;
+    const long long cw = (long long)blockIdx.x * W + w;
+    if (cw >= a.B) return;                                   // whole warps leave; only __syncwarp below
+    const GraphTables &g = a.g;
+    const int n = g.n, m = g.m, E = g.E;
+    float *X = sm + (size_t)w * E;
+    const float *L = a.llr + cw * n;
+    float *t0 = a.tape + cw * E;
+    for (int e = lane; e < E; e += 32) { const float x = a.x0 ? __ldg(a.x0 + cw * E + e) : 0.0f; X[e] = x; t0[e] = x; }
+    __syncwarp();
+    for (int it = 0; it < a.iters; ++it) {
+        float *tout = a.tape + ((long long)(it + 1) * a.B + cw) * E;
+        for (int v = lane; v < n; v += 32) {                 // in place: a variable's slots are its own
+            const int b0 = __ldg(g.var_ptr + v);
+            with_degree<MAXDV, SW>(__ldg(g.var_ptr + v + 1) - b0, [&](auto cap, int d) {
+                constexpr int D = decltype(cap)::value;
+                int slot[D];
+                float in[D], out[D];
+#pragma unroll
+                for (int k = 0; k < D; ++k)
+                    if (k < d) { slot[k] = __ldg(g.cm_of_vm + b0 + k); in[k] = X[slot[k]]; }
+                var_node_weighted<D, true>(in, d, __ldg(L + v), __ldg(a.w_llr + (long long)it * n + v),
+                                           a.w_edge + ((long long)it * E + b0) * a.w_stride, a.w_stride, out);
+#pragma unroll
+                for (int k = 0; k < D; ++k)
+                    if (k < d) X[slot[k]] = out[k];
+            });
+        }
+        __syncwarp();
+        for (int c = lane; c < m; c += 32) {
+            const int b0 = __ldg(g.chk_ptr + c);
+            with_degree<MAXDC, SW>(__ldg(g.chk_ptr + c + 1) - b0, [&](auto cap, int d) {
+                constexpr int D = decltype(cap)::value;
+                float in[D], out[D];
+#pragma unroll
+                for (int j = 0; j < D; ++j)
+                    if (j < d) in[j] = X[b0 + j];
+                check_node_sp<D>(in, d, a.clampv, out);
+#pragma unroll
+                for (int j = 0; j < D; ++j)
+                    if (j < d) { X[b0 + j] = out[j]; tout[b0 + j] = out[j]; }
+            });
+        }
+        __syncwarp();
+    }
+    for (int v = lane; v < n; v += 32) {
+        const int b0 = __ldg(g.var_ptr + v);
+        with_degree<MAXDV, SW>(__ldg(g.var_ptr + v + 1) - b0, [&](auto cap, int d) {
+            constexpr int D = decltype(cap)::value;
+            float in[D];
+#pragma unroll
+            for (int k = 0; k < D; ++k)
+                if (k < d) in[k] = X[__ldg(g.cm_of_vm + b0 + k)];
+            a.prob[cw * n + v] = prob_one(marginal_t_weighted<D>(in, d, __ldg(L + v), __ldg(a.wf_llr + v), a.wf_edge + b0));
+        });
+        if (__ldg(g.var_ptr + v + 1) == b0) a.prob[cw * n + v] = prob_one(__fmul_rn(0.5f, __fadd_rn(__fmul_rn(__ldg(a.wf_llr + v), -__ldg(L + v)), 0.0f)));
+    }
+}
+
+__device__ __forceinline__ void red_add(float *dst, float v) {
+    if (v != 0.0f) atomicAdd(dst, v);
+}
+
+template <int MAXDV, int MAXDC, bool SW>
+__global__ void __launch_bounds__(128) bp_train_backward_wpc_kernel(const TrainArgs a) {
+    extern __shared__ float sm[];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, W = blockDim.x >> 5;
+    const long long cw = (long long)blockIdx.x * W + w;
+    if (cw >= a.B) return;
+    const GraphTables &g = a.g;
+    const int n = g.n, m = g.m, E = g.E;
+    float *X = sm + (size_t)w * 3 * E, *U = X + E, *GX = U + E;
+    const float *L = a.llr + cw * n;
+    {
+        const float *xl = a.tape + ((long long)a.iters * a.B + cw) * E;
+        for (int v = lane; v < n; v += 32) {
+            const int b0 = __ldg(g.var_ptr + v), dd = __ldg(g.var_ptr + v + 1) - b0;
+            const float l = __ldg(L + v), wl = __ldg(a.wf_llr + v);
+            if (SW && dd == 0) {                             // a variable without edges: only the channel term (no switch case)
+                const float P = prob_one(__fmul_rn(0.5f, __fadd_rn(__fmul_rn(wl, -l), 0.0f)));
+                const float h = 0.5f * __ldg(a.grad_prob + cw * n + v) * (-(P * (1.0f - P)));
+                red_add(a.g_wf_llr + v, h * -l);
+                a.grad_llr[cw * n + v] = h * -wl;
+            }
+            with_degree<MAXDV, SW>(dd, [&](auto cap, int d) {
+                constexpr int D = decltype(cap)::value;
+                int slot[D];
+                float in[D];
+#pragma unroll
+                for (int k = 0; k < D; ++k)
+                    if (k < d) { slot[k] = __ldg(g.cm_of_vm + b0 + k); in[k] = xl[slot[k]]; }
+                const float P = prob_one(marginal_t_weighted<D>(in, d, l, wl, a.wf_edge + b0));
+                const float h = 0.5f * __ldg(a.grad_prob + cw * n + v) * (-(P * (1.0f - P)));
+                red_add(a.g_wf_llr + v, h * -l);
+                a.grad_llr[cw * n + v] = h * -wl;
+#pragma unroll
+                for (int k = 0; k < D; ++k)
+                    if (k < d) {
+                        red_add(a.g_wf_edge + b0 + k, h * in[k]);
+                        GX[slot[k]] = h * __ldg(a.wf_edge + b0 + k);
+                    }
+            });
+        }
+    }
+    __syncwarp();
+    for (int it = a.iters - 1; it >= 0; --it) {
+        const float *xg = a.tape + ((long long)it * a.B + cw) * E;
+        const float *wE = a.w_edge + (long long)it * E * a.w_stride;
+        for (int e = lane; e < E; e += 32) X[e] = xg[e];
+        __syncwarp();
+        for (int v = lane; v < n; v += 32) {                 // recompute tanh(V->C)
+            const int b0 = __ldg(g.var_ptr + v);
+            with_degree<MAXDV, SW>(__ldg(g.var_ptr + v + 1) - b0, [&](auto cap, int d) {
+                constexpr int D = decltype(cap)::value;
+                int slot[D];
+                float in[D], out[D];
+#pragma unroll
+                for (int k = 0; k < D; ++k)
+                    if (k < d) { slot[k] = __ldg(g.cm_of_vm + b0 + k); in[k] = X[slot[k]]; }
+                var_node_weighted<D, true>(in, d, __ldg(L + v), __ldg(a.w_llr + (long long)it * n + v),
+                                           wE + (long long)b0 * a.w_stride, a.w_stride, out);
+#pragma unroll
+                for (int k = 0; k < D; ++k)
+                    if (k < d) U[slot[k]] = out[k];
+            });
+        }
+        __syncwarp();
+        for (int c = lane; c < m; c += 32) {                 // check node backward, in place on GX
+            const int b0 = __ldg(g.chk_ptr + c);
+            with_degree<MAXDC, SW>(__ldg(g.chk_ptr + c + 1) - b0, [&](auto cap, int d) {
+                constexpr int D = decltype(cap)::value;
+                float u[D], p[D], gp[D], gu[D];
+#pragma unroll
+                for (int j = 0; j < D; ++j)
+                    if (j < d) u[j] = U[b0 + j];
+                prod_others<D>(u, d, p);
+#pragma unroll
+                for (int j = 0; j < D; ++j) {
+                    gu[j] = 0.0f;
+                    if (j < d) {
+                        const float q = clampf(p[j], LDPC_P_CLAMP);
+                        const float o = logf(div_rn_one_plus_minus(q));
+                        const bool pass = fabsf(p[j]) <= LDPC_P_CLAMP && fabsf(o) <= a.clampv;
+                        gp[j] = pass ? GX[b0 + j] * (2.0f / ((1.0f - q) * (1.0f + q))) : 0.0f;
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < D; ++j)
+                    if (j < d) {
+                        float uj[D], pj[D];
+#pragma unroll
+                        for (int k = 0; k < D; ++k) uj[k] = (k == j) ? 1.0f : u[k];
+                        prod_others<D>(uj, d, pj);
+#pragma unroll
+                        for (int i = 0; i < D; ++i)
+                            if (i < d && i != j) gu[i] = fmaf(gp[j], pj[i], gu[i]);
+                    }
+#pragma unroll
+                for (int i = 0; i < D; ++i)
+                    if (i < d) GX[b0 + i] = gu[i] * (1.0f - u[i] * u[i]);
+            });
+        }
+        __syncwarp();
+        for (int v = lane; v < n; v += 32) {                 // variable node backward
+            const int b0 = __ldg(g.var_ptr + v);
+            with_degree<MAXDV, SW>(__ldg(g.var_ptr + v + 1) - b0, [&](auto cap, int d) {
+                constexpr int D = decltype(cap)::value;
+                int slot[D];
+                float x[D], hs[D];
+                float sum = 0.0f;
+#pragma unroll
+                for (int k = 0; k < D; ++k)
+                    if (k < d) {
+                        slot[k] = __ldg(g.cm_of_vm + b0 + k);
+                        x[k] = X[slot[k]];
+                        hs[k] = 0.5f * GX[slot[k]];
+                        sum += hs[k];
+                    }
+                const float l = __ldg(L + v), wl = __ldg(a.w_llr + (long long)it * n + v);
+                red_add(a.g_w_llr + (long long)it * n + v, sum * -l);
+                a.grad_llr[cw * n + v] += sum * -wl;
+                const float *wr = wE + (long long)b0 * a.w_stride;
+                float *gw = a.g_w_edge + ((long long)it * E + b0) * a.w_stride;
+#pragma unroll
+                for (int j = 0; j < D; ++j)
+                    if (j < d) {
+                        float gx = 0.0f;
+#pragma unroll
+                        for (int k = 0; k < D; ++k)
+                            if (k < d && k != j) {
+                                red_add(gw + k * a.w_stride + j, hs[k] * x[j]);
+                                gx = fmaf(hs[k], __ldg(wr + k * a.w_stride + j), gx);
+                            }
+                        GX[slot[j]] = gx;
+                    }
+            });
+        }
+        __syncwarp();
+    }
+}
+
+// Which variant serves a batch: forward and backward MUST agree (the tape layout differs).
+static int wpc_warps(const TrainArgs &a) {
+    if (a.B > 8192) return 0;                                                  // large batches: one thread per codeword
+    const size_t per_warp = (size_t)a.g.E * 3 * sizeof(float);
+    if (per_warp * 4 <= 96 * 1024) return 4;
+    if (per_warp * 2 <= 200 * 1024) return 2;
+    if (per_warp <= 200 * 1024) return 1;
+    return 0;
+}
+
 template <int MAXDV, int MAXDC, bool SW>
 static int launch_train_t(const TrainArgs &a, bool backward, cudaStream_t s) {
+    if (const int W = wpc_warps(a)) {
+        const long long grid = (a.B + W - 1) / W;
+        const size_t bytes = (size_t)W * a.g.E * sizeof(float) * (backward ? 3 : 1);
+        void (*k)(const TrainArgs) = backward ? bp_train_backward_wpc_kernel<MAXDV, MAXDC, SW> : bp_train_forward_wpc_kernel<MAXDV, MAXDC, SW>;
+        if (bytes > 48 * 1024) LDPC_CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+        k<<<(int)grid, 32 * W, bytes, s>>>(a);
+        LDPC_CUDA_TRY(cudaGetLastError());
+        return LDPC_OK;
+    }
     const int threads = 128;
     const long long grid = (a.B + threads - 1) / threads;
     if (grid > 0x7fffffffLL) { set_error("batch too large"); return LDPC_EINVAL; }

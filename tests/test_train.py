@@ -239,3 +239,42 @@ def test_training_edge_cases():
     with pytest.raises(ValueError):
         m(None, torch.zeros(4, 64, device="cuda"), 20.0)                         # training mode is sum-product only
     assert m.eval()(None, torch.zeros(4, 64, device="cuda"), 20.0).shape == (4, 64)
+
+
+@pytest.mark.gpu
+def test_both_training_variants_and_isolated_variable():
+    """The warp-per-codeword pair (batches up to 8192) and the thread-per-codeword pair (larger) give the same result;
+    H here has a variable without any check (a degree the compile-time-degree switch has no case for)."""
+    import torch
+    import bp_oracle as O
+    from ldpc_b200.decoder import LdpcCode
+    rng = np.random.RandomState(3)
+    H = (rng.rand(12, 24) < 0.2).astype(np.uint8)
+    H[:, 5] = 0                                               # isolated variable
+    H[np.arange(12), np.arange(12)] = 1                       # no empty check
+    H[:, 7] = 0; H[3, 7] = 1                                  # a degree-1 variable
+    g = O.Graph(H)
+    code = LdpcCode(H)
+    mdv, iters = int(g.dv.max()), 2
+    w = dict(w_edge=(0.5 + rng.rand(iters, g.E, mdv)).astype(np.float32), w_llr=(0.5 + rng.rand(iters, g.n)).astype(np.float32),
+             wf_edge=(0.5 + rng.rand(g.E)).astype(np.float32), wf_llr=(0.5 + rng.rand(g.n)).astype(np.float32))
+    dw = {k: torch.as_tensor(v).cuda() for k, v in w.items()}
+    dw.update(iterations=iters, stride=mdv)
+    small = 50
+    llr = (rng.randn(small, g.n)).astype(np.float32)
+    gp = rng.randn(small, g.n).astype(np.float32)
+    o = O.bp_weighted_grad(H, llr, iters, 20.0, w, gp, graph=g)
+    big = 8192 + 64                                           # same rows tiled past the variant threshold
+    reps = -(-big // small)
+    llr_b, gp_b = np.tile(llr, (reps, 1))[:big], np.tile(gp, (reps, 1))[:big]
+    res = {}
+    for tag, L, Gp in (("warp", llr, gp), ("thread", llr_b, gp_b)):
+        prob, tape = code.train_forward(torch.as_tensor(L).cuda(), dw, 20.0)
+        out = code.train_backward(torch.as_tensor(L).cuda(), dw, 20.0, tape, torch.as_tensor(Gp).cuda())
+        res[tag] = (prob.cpu().numpy(), out["grad_llr"].cpu().numpy())
+        assert np.abs(res[tag][0][:small] - o["prob"]).max() < 2e-5, tag
+        assert _rel(res[tag][1][:small], o["grad_llr"]) < 2e-4, tag
+        if tag == "warp":
+            for k in ("w_edge", "w_llr", "wf_edge", "wf_llr"):
+                assert _rel(out[k].cpu().numpy(), o["g_" + k]) < 2e-4, k
+    assert np.array_equal(res["warp"][0], res["thread"][0][:small])           # same forward arithmetic, bit for bit
