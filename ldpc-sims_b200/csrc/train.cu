@@ -249,7 +249,7 @@ __global__ void __launch_bounds__(128) bp_train_backward_kernel(const TrainArgs 
     }
 }
 
-// ---- small batches: ONE WARP PER CODEWORD ---------------------------------------------------------------------------
+// ---- small batches (up to 16 384 codewords): ONE WARP PER CODEWORD ---------------------------------------------------------------------------
 // With a few hundred codewords (the reference trains on minibatches of 512, ofdm/ofdm_nn.py:262) one thread per
 // codeword leaves the GPU with 16 warps, each walking the whole graph serially.  Here the 32 lanes of a warp take the
 // nodes of ONE codeword (variable v = lane, lane + 32, ...), the working arrays are a per-warp slice of shared memory,
@@ -461,7 +461,7 @@ __global__ void __launch_bounds__(128) bp_train_backward_wpc_kernel(const TrainA
 
 // Which variant serves a batch: forward and backward MUST agree (the tape layout differs).
 static int wpc_warps(const TrainArgs &a) {
-    if (a.B > 8192) return 0;                                                  // large batches: one thread per codeword
+    if (a.B > 16384) return 0;             // measured crossover on B200 (default code): beyond it one thread per codeword wins
     const size_t per_warp = (size_t)a.g.E * 3 * sizeof(float);
     if (per_warp * 4 <= 96 * 1024) return 4;
     if (per_warp * 2 <= 200 * 1024) return 2;

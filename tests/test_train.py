@@ -243,7 +243,7 @@ def test_training_edge_cases():
 
 @pytest.mark.gpu
 def test_both_training_variants_and_isolated_variable():
-    """The warp-per-codeword pair (batches up to 8192) and the thread-per-codeword pair (larger) give the same result;
+    """The warp-per-codeword pair (batches up to 16384) and the thread-per-codeword pair (larger) give the same result;
     H here has a variable without any check (a degree the compile-time-degree switch has no case for)."""
     import torch
     import bp_oracle as O
@@ -264,7 +264,7 @@ def test_both_training_variants_and_isolated_variable():
     llr = (rng.randn(small, g.n)).astype(np.float32)
     gp = rng.randn(small, g.n).astype(np.float32)
     o = O.bp_weighted_grad(H, llr, iters, 20.0, w, gp, graph=g)
-    big = 8192 + 64                                           # same rows tiled past the variant threshold
+    big = 16384 + 64                                           # same rows tiled past the variant threshold
     reps = -(-big // small)
     llr_b, gp_b = np.tile(llr, (reps, 1))[:big], np.tile(gp, (reps, 1))[:big]
     res = {}
