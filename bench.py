@@ -475,6 +475,29 @@ def main():
                       "d2h_bytes_per_step": Be * code.packed_bytes, "codewords_per_step": Be, "pinned_h2d_gbs": h2d_gbs,
                       "api": "ldpc_decode_host (C ABI behind ofdm_functions.decode_bits), pinned f32 LLRs in, packed bits out"}
         assert torch.equal(h_packed.to(dev), packed[:Be]), "e2e result differs from the device path"
+        # the same call with receiver-quantised int8 LLRs (LDPC_I8: a quarter of the PCIe bytes); NOT the headline - the
+        # reference's input is f32 - but it shows what bounds e2e.  Checked against the device path on the same values.
+        h_q = (llr[:Be] * (127.0 / 32.0)).round().clamp(-127, 127).to(torch.int8).cpu().pin_memory()
+
+        def e2e_i8_step():
+            N.check(lib.ldpc_decode_host(code._h, h_q.data_ptr(), N.I8, Be, a.iters, upd, a.clamp, 1.0,
+                                         None, h_packed.data_ptr(), None, None, 16384))
+        for _ in range(2):
+            e2e_i8_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(a.steps):
+            e2e_i8_step()
+        barrier()
+        dt = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        ref_q = code.decode(h_q.to(dev).float(), a.iters, a.clamp, update=a.update, want=("hard_packed",))["hard_packed"]
+        assert torch.equal(h_packed.to(dev), ref_q), "int8 e2e result differs from the device path on the same values"
+        out["e2e_int8_llr"] = {"value": Be * world * a.steps * K_CODE / float(dt.item()) / 1e9, "unit": "Gbit/s", "h2d_bytes_per_step": Be * qc.n,
+                               "d2h_bytes_per_step": Be * code.packed_bytes,
+                               "note": "same call, LLRs quantised to int8 on the host side of the receiver (llr * 127/32, clamp 20 unchanged => not the same "
+                                       "decisions as f32; a feature for callers whose demapper emits fixed-point LLRs)"}
 
     # ---- CPU baseline beside it (rank 0, N=1 only) ---------------------------------------------------
     if rank == 0 and world == 1 and not a.no_cpu_baseline:

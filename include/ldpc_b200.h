@@ -41,7 +41,8 @@ enum {
 };
 
 /* ---- element type of an LLR buffer --------------------------------------------------- */
-enum { LDPC_F32 = 0, LDPC_F64 = 1, LDPC_F16 = 2 };
+enum { LDPC_F32 = 0, LDPC_F64 = 1, LDPC_F16 = 2, LDPC_I8 = 3 };   /* I8: receiver-quantised LLRs, value = the integer (decoder
+                                                                      input only; a quarter of the f32 bytes over PCIe / HBM) */
 
 /* ---- which kernel a code handle dispatches to ---------------------------------------- */
 enum { LDPC_KERNEL_GENERIC = 0, LDPC_KERNEL_QC = 1, LDPC_KERNEL_TINY = 2 /* register-resident, one thread per codeword: the reference's default (64,32) code */,

@@ -50,6 +50,7 @@ struct GraphTables {        // device pointers
 __device__ __forceinline__ float load_llr(const void *p, int dtype, long long i) {
     if (dtype == LDPC_F32) return __ldg(reinterpret_cast<const float *>(p) + i);
     if (dtype == LDPC_F64) return static_cast<float>(__ldg(reinterpret_cast<const double *>(p) + i));
+    if (dtype == LDPC_I8) return static_cast<float>(__ldg(reinterpret_cast<const signed char *>(p) + i));
     return __half2float(__ldg(reinterpret_cast<const __half *>(p) + i));
 }
 

@@ -76,6 +76,7 @@ __global__ void __launch_bounds__((QcLayout<Code, CW>::THREADS), (QcLayout<Code,
         };
         if (a.llr_dtype == LDPC_F32) load_all([&](long long i) { return __ldg(reinterpret_cast<const float *>(a.llr) + i); });
         else if (a.llr_dtype == LDPC_F64) load_all([&](long long i) { return (float)__ldg(reinterpret_cast<const double *>(a.llr) + i); });
+        else if (a.llr_dtype == LDPC_I8) load_all([&](long long i) { return (float)__ldg(reinterpret_cast<const signed char *>(a.llr) + i); });
         else load_all([&](long long i) { return __half2float(__ldg(reinterpret_cast<const __half *>(a.llr) + i)); });
     }
     } else {

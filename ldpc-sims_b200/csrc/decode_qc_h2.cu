@@ -112,6 +112,7 @@ __global__ void __launch_bounds__((QcLayout<Code, CW>::THREADS)) decode_qc_h2_ke
         };
         if (a.llr_dtype == LDPC_F32) load_all([&](long long i) { return __ldg(reinterpret_cast<const float *>(a.llr) + i); });
         else if (a.llr_dtype == LDPC_F64) load_all([&](long long i) { return (float)__ldg(reinterpret_cast<const double *>(a.llr) + i); });
+        else if (a.llr_dtype == LDPC_I8) load_all([&](long long i) { return (float)__ldg(reinterpret_cast<const signed char *>(a.llr) + i); });
         else load_all([&](long long i) { return __half2float(__ldg(reinterpret_cast<const __half *>(a.llr) + i)); });
         static_for<NB>([&](auto cc) {
             constexpr int c = decltype(cc)::value;

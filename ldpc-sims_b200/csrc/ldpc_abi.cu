@@ -183,7 +183,7 @@ static int check_decode_args(const ldpc_code_t *code, const void *llr, int llr_d
     if (!code) { set_error("null code handle"); return LDPC_EINVAL; }
     if (B < 0 || iters < 0) { set_error("negative batch or iteration count"); return LDPC_EINVAL; }
     if (B > 0 && !llr) { set_error("null llr pointer"); return LDPC_EINVAL; }
-    if (llr_dtype < LDPC_F32 || llr_dtype > LDPC_F16) { set_error("bad llr_dtype %d", llr_dtype); return LDPC_EINVAL; }
+    if (llr_dtype < LDPC_F32 || llr_dtype > LDPC_I8) { set_error("bad llr_dtype %d", llr_dtype); return LDPC_EINVAL; }
     if (update < LDPC_UPDATE_SP || update > LDPC_UPDATE_OMS) { set_error("bad update rule %d", update); return LDPC_EINVAL; }
     if (!(clamp_value > 0.0f)) { set_error("clamp_value must be positive"); return LDPC_EINVAL; }
     return LDPC_OK;
@@ -305,7 +305,7 @@ int ldpc_decode_host(const ldpc_code_t *code, const void *llr_host, int llr_dtyp
     if (rc) return rc;
     if (N == 0) return LDPC_OK;
     const int n = code->n, nby = (n + 7) / 8;
-    const size_t esz = llr_dtype == LDPC_F64 ? 8 : (llr_dtype == LDPC_F16 ? 2 : 4);
+    const size_t esz = llr_dtype == LDPC_F64 ? 8 : (llr_dtype == LDPC_F16 ? 2 : (llr_dtype == LDPC_I8 ? 1 : 4));
     if (chunk <= 0) chunk = 16384;
     chunk = std::min<int64_t>(chunk, N);
     ldpc_code *mc = const_cast<ldpc_code *>(code);

@@ -205,7 +205,7 @@ int ldpc_decode_count(const ldpc_code_t *code, const void *llr, int llr_dtype, i
                       ldpc_stream_t stream) {
     if (!code || !llr || !ref_packed || !counters || B < 0) { set_error("ldpc_decode_count: null argument"); return LDPC_EINVAL; }
     if (iters < 0 || update < LDPC_UPDATE_SP || update > LDPC_UPDATE_OMS || !(clamp_value > 0.0f)) { set_error("ldpc_decode_count: bad decoder parameters"); return LDPC_EINVAL; }
-    if (llr_dtype != LDPC_F32 && llr_dtype != LDPC_F64 && llr_dtype != LDPC_F16) { set_error("ldpc_decode_count: bad llr dtype"); return LDPC_EINVAL; }
+    if (llr_dtype < LDPC_F32 || llr_dtype > LDPC_I8) { set_error("ldpc_decode_count: bad llr dtype"); return LDPC_EINVAL; }
     if (k_info <= 0 || k_info > code->n) { set_error("ldpc_decode_count: bad k"); return LDPC_EINVAL; }
     if (B == 0) return LDPC_OK;
     DecodeArgs a;

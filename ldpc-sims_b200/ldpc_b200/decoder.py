@@ -13,8 +13,8 @@ import torch
 from . import _native as N
 from .codes import EdgeTables, detect_qc
 
-_DTYPES = {torch.float32: N.F32, torch.float64: N.F64, torch.float16: N.F16}
-_NP_DTYPES = {np.dtype(np.float32): N.F32, np.dtype(np.float64): N.F64, np.dtype(np.float16): N.F16}
+_DTYPES = {torch.float32: N.F32, torch.float64: N.F64, torch.float16: N.F16, torch.int8: N.I8}
+_NP_DTYPES = {np.dtype(np.float32): N.F32, np.dtype(np.float64): N.F64, np.dtype(np.float16): N.F16, np.dtype(np.int8): N.I8}
 
 
 def _ptr(t):

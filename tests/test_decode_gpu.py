@@ -397,3 +397,34 @@ def test_runtime_qc_kernel_equals_generic(update, param):
             b = dec(gen, llr, iters, 20, update, param, want=want)
             for k in want:
                 assert np.array_equal(a[k], b[k]), (name, update, iters, k)
+
+
+@pytest.mark.gpu
+def test_int8_llr_input_equals_float_input():
+    """LDPC_I8: receiver-quantised LLRs (value = the integer).  Every kernel and the host-buffer pipeline must give the
+    bits of the same values passed as float32."""
+    import torch
+    from ldpc_b200.codes import ieee80211n_1944_r12, peg_64_32
+    from ldpc_b200.decoder import LdpcCode, decode_host
+    rng = np.random.RandomState(11)
+    qc = ieee80211n_1944_r12()
+    cases = [("qc", qc.H, dict(qc_Z=81, qc_proto=qc.proto), None), ("qc_rt", qc.H, dict(qc_Z=81, qc_proto=qc.proto), "qc_rt"),
+             ("generic", qc.H, dict(qc_Z=81, qc_proto=qc.proto), "generic"), ("tiny", peg_64_32()[0], {}, None)]
+    for name, H, kw, force in cases:
+        code = LdpcCode(H, **kw)
+        if force:
+            code.set_kernel(force)
+        q = np.clip(np.round(rng.randn(37, H.shape[1]) * 9 + 6), -127, 127).astype(np.int8)
+        a = code.decode(torch.as_tensor(q).cuda(), 6, 20.0, update="minsum", want=("llr_post", "hard_packed", "syndrome"))
+        b = code.decode(torch.as_tensor(q.astype(np.float32)).cuda(), 6, 20.0, update="minsum", want=("llr_post", "hard_packed", "syndrome"))
+        for k in a:
+            assert torch.equal(a[k], b[k]), (name, k)
+        if name == "qc":
+            code.set_precision("f16x2")
+            a = code.decode(torch.as_tensor(q).cuda(), 6, 20.0, update="minsum", want=("hard_packed",))
+            b = code.decode(torch.as_tensor(q.astype(np.float32)).cuda(), 6, 20.0, update="minsum", want=("hard_packed",))
+            assert torch.equal(a["hard_packed"], b["hard_packed"])
+            code.set_precision("f32")
+            ha = decode_host(code, q, 6, 20.0, update="minsum", want=("hard_packed", "syndrome"))
+            hb = decode_host(code, q.astype(np.float32), 6, 20.0, update="minsum", want=("hard_packed", "syndrome"))
+            assert np.array_equal(ha["hard_packed"], hb["hard_packed"]) and np.array_equal(ha["syndrome"], hb["syndrome"])
