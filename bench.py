@@ -494,6 +494,25 @@ def main():
             dist.all_reduce(dt, op=dist.ReduceOp.MAX)
         ref_q = code.decode(h_q.to(dev).float(), a.iters, a.clamp, update=a.update, want=("hard_packed",))["hard_packed"]
         assert torch.equal(h_packed.to(dev), ref_q), "int8 e2e result differs from the device path on the same values"
+        # the reference's decode_bits contract itself: ordinary (pageable) float64 ndarray in, float64 {0,1} ndarray out
+        from ldpc_b200.decoder import decode_bits_host
+        Bd = min(Be, 65536)
+        np_llr = h_llr[:Bd].numpy().astype(np.float64)
+        np_out = np.empty((Bd, qc.n), np.float64)
+        decode_bits_host(code, np_llr, a.iters, a.clamp, np_out, update=a.update)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(a.steps):
+            decode_bits_host(code, np_llr, a.iters, a.clamp, np_out, update=a.update)
+        barrier()
+        dtb = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(dtb, op=dist.ReduceOp.MAX)
+        assert np.array_equal(np.packbits(np_out.astype(np.uint8), axis=1), packed[:Bd].cpu().numpy()), "decode_bits result differs from the device path"
+        out["e2e_decode_bits_f64"] = {"value": Bd * world * a.steps * K_CODE / float(dtb.item()) / 1e9, "unit": "Gbit/s", "codewords_per_step": Bd,
+                                      "host_bytes_per_codeword": qc.n * 16,
+                                      "note": "ldpc_decode_bits_host behind ofdm_functions.decode_bits: pageable float64 ndarray in, float64 {0,1} ndarray out "
+                                              "(the reference's own formats, 31 KB of host memory per codeword); host threads cast/expand around the GPU"}
         out["e2e_int8_llr"] = {"value": Be * world * a.steps * K_CODE / float(dt.item()) / 1e9, "unit": "Gbit/s", "h2d_bytes_per_step": Be * qc.n,
                                "d2h_bytes_per_step": Be * code.packed_bytes,
                                "note": "same call, LLRs quantised to int8 on the host side of the receiver (llr * 127/32, clamp 20 unchanged => not the same "

@@ -178,6 +178,15 @@ int ldpc_decode_host(const ldpc_code_t *code, const void *llr_host, int llr_dtyp
                      uint8_t *hard_host, uint8_t *hard_packed_host, float *llr_post_host,
                      int32_t *syndrome_host, int64_t chunk_codewords);
 
+/* ldpc_decode_bits_host - decode_bits (ofdm/ofdm_functions.py:131-163) for ORDINARY (pageable) host arrays: llr_host
+ * [N,n] of llr_dtype (the reference passes float64 and casts it to f32, :156), bits_out [N,n] of {0,1} as out_dtype
+ * (LDPC_F64 = the reference's float64 result, :161; LDPC_F32; LDPC_I8 = one byte per bit).  Host threads cast / copy each
+ * chunk into pinned staging while the previous chunk is on the GPU, only packed bits return over PCIe, and host threads
+ * expand them into bits_out while the next chunk decodes.  threads <= 0: min(16, hardware threads).  Synchronous. */
+int ldpc_decode_bits_host(const ldpc_code_t *code, const void *llr_host, int llr_dtype, int64_t N, int iters,
+                          int update, float clamp_value, float param, void *bits_out, int out_dtype,
+                          int64_t chunk_codewords, int threads);
+
 /* ldpc_count_errors - exact integer link metrics, accumulated (+=) into counters[5] (i64):
  *   {uncoded bit errors over n, decoded info-bit errors over the first k, frame errors
  *    (any of n decoded bits wrong), bits = B*n, frames = B}

@@ -84,6 +84,8 @@ def lib():
     L.ldpc_decode_ex.argtypes = [vp, ctypes.POINTER(DecodeParams), vp]
     L.ldpc_decode_host.restype = ctypes.c_int
     L.ldpc_decode_host.argtypes = [vp, vp, i32, i64, i32, i32, f32, f32, vp, vp, vp, vp, i64]
+    L.ldpc_decode_bits_host.restype = ctypes.c_int
+    L.ldpc_decode_bits_host.argtypes = [vp, vp, i32, i64, i32, i32, f32, f32, vp, i32, i64, i32]
     L.ldpc_count_errors.restype = ctypes.c_int
     L.ldpc_count_errors.argtypes = [vp, i32, vp, vp, i64, i32, i32, vp, vp]
     u64, sz = ctypes.c_uint64, ctypes.c_size_t

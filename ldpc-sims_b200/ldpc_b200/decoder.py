@@ -262,3 +262,21 @@ def decode_host(code: LdpcCode, llrs: np.ndarray, iterations, clamp_value, updat
         if v is not None:
             out[k] = v
     return out
+
+
+def decode_bits_host(code: LdpcCode, llrs: np.ndarray, iterations, clamp_value, out: np.ndarray, update="sp", param=1.0, chunk=16384, threads=0):
+    """llrs [N,n] (ordinary numpy memory, float64/float32/float16/int8) -> out [N,n] filled with {0,1} (float64, float32 or
+    uint8) through ldpc_decode_bits_host: threaded cast/copy into pinned staging, packed bits back, threaded expansion."""
+    llrs = np.ascontiguousarray(llrs)
+    if llrs.dtype not in _NP_DTYPES:
+        llrs = llrs.astype(np.float32)
+    Nn, n = llrs.shape
+    if n != code.n or out.shape != (Nn, n) or not out.flags.c_contiguous:
+        raise ValueError(f"llrs and out must be C-contiguous [N,{code.n}]")
+    kinds = {np.dtype(np.float64): N.F64, np.dtype(np.float32): N.F32, np.dtype(np.uint8): N.I8}
+    if out.dtype not in kinds:
+        raise ValueError("out must be float64, float32 or uint8")
+    with torch.cuda.device(code.device):
+        N.check(N.lib().ldpc_decode_bits_host(code._h, llrs.ctypes.data, _NP_DTYPES[llrs.dtype], Nn, int(iterations), _update_id(update),
+                                              float(clamp_value), float(param), out.ctypes.data, kinds[out.dtype], int(chunk), int(threads)))
+    return out

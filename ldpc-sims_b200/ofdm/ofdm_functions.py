@@ -22,7 +22,7 @@ import torch.nn as nn  # noqa: F401
 
 from bp.bp import *  # noqa: F401,F403
 from ldpc_b200 import _native
-from ldpc_b200.decoder import LdpcCode, decode_host
+from ldpc_b200.decoder import LdpcCode, decode_bits_host, decode_host
 from ldpc_b200.linksim import encode_bits, modulate_bits, transmit_symbols, quantizer, demodulate_signal  # noqa: F401
 
 _CODE_CACHE = {}
@@ -47,11 +47,16 @@ def decode_bits(llrs, H, bp_iterations, batch_size, clamp_value, *, update="sp",
     One native handle per distinct H is cached instead of rebuilding the model per call.
     """
     llrs = np.asarray(llrs)
-    output_bits = np.zeros(llrs.shape, dtype=out_dtype)
     used = (llrs.shape[0] // int(batch_size)) * int(batch_size)
     if used == 0:
-        return output_bits
+        return np.zeros(llrs.shape, dtype=out_dtype)
     code = _code_for(H, qc_Z)
+    if np.dtype(out_dtype) in (np.dtype(np.float64), np.dtype(np.float32), np.dtype(np.uint8)):
+        output_bits = np.empty(llrs.shape, dtype=out_dtype)          # every decoded row is written by the native call
+        output_bits[used:] = 0
+        decode_bits_host(code, llrs[:used], bp_iterations, clamp_value, output_bits[:used], update=update, param=param)
+        return output_bits
+    output_bits = np.zeros(llrs.shape, dtype=out_dtype)
     out = decode_host(code, llrs[:used], bp_iterations, clamp_value, update=update, param=param, want=("hard",))
     output_bits[:used] = out["hard"]
     return output_bits

@@ -56,3 +56,32 @@ def test_legacy_constructor_and_cpu_tensors():
     x = torch.zeros(32, 96)
     a, b = m5(x, llr, 20), m2(x, llr, 20)
     assert not a.is_cuda and torch.equal(a, b)
+
+
+@pytest.mark.gpu
+def test_decode_bits_staged_pipeline_formats():
+    """ldpc_decode_bits_host (behind decode_bits): float64 / float32 / int8 LLR arrays in ordinary memory, float64 /
+    float32 / uint8 {0,1} out, several chunks, ragged tail left zero - all equal to the device path."""
+    import torch
+    from ldpc_b200.codes import ieee80211n_1944_r12
+    from ldpc_b200.decoder import LdpcCode, decode_bits_host
+    from ofdm.ofdm_functions import decode_bits
+    qc = ieee80211n_1944_r12()
+    rng = np.random.RandomState(4)
+    N = 300
+    llr = rng.randn(N, qc.n) * 2.5 + 2.0
+    code = LdpcCode(qc.H, qc_Z=81, qc_proto=qc.proto)
+    ref = code.decode(torch.as_tensor(llr.astype(np.float32)).cuda(), 5, 20.0, update="minsum", want=("hard",))["hard"].cpu().numpy()
+    for in_dt in (np.float64, np.float32):
+        for out_dt in (np.float64, np.float32, np.uint8):
+            out = np.full((N, qc.n), 7, out_dt)
+            decode_bits_host(code, llr.astype(in_dt), 5, 20.0, out, update="minsum", chunk=64, threads=3)
+            assert np.array_equal(out, ref.astype(out_dt)), (in_dt, out_dt)
+    q = np.clip(np.round(llr * 4), -127, 127).astype(np.int8)
+    refq = code.decode(torch.as_tensor(q).cuda(), 5, 20.0, update="minsum", want=("hard",))["hard"].cpu().numpy()
+    out = np.empty((N, qc.n), np.uint8)
+    assert np.array_equal(decode_bits_host(code, q, 5, 20.0, out, update="minsum", chunk=128), refq)
+    got = decode_bits(llr, qc.H, 5, 128, 20.0, update="minsum", qc_Z=81)           # 300 // 128 * 128 = 256 rows decoded
+    assert got.dtype == np.float64 and np.array_equal(got[:256], ref[:256].astype(np.float64)) and not got[256:].any()
+    with pytest.raises(ValueError):
+        decode_bits_host(code, llr, 5, 20.0, np.empty((N, qc.n), np.int32))
