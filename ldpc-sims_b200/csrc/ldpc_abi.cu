@@ -8,6 +8,9 @@
 #include <new>
 #include <thread>
 #include <vector>
+#if defined(__SSE2__)
+#include <emmintrin.h>
+#endif
 
 #include "common.cuh"
 
@@ -402,6 +405,9 @@ static void parallel_for(int64_t n, int threads, F f) {          // f(begin, end
     for (auto &th : pool) th.join();
 }
 
+// Both host loops below are memory-bound (31 KB of caller memory per n=1944 codeword): the float64 results and the
+// staged float32 LLRs are written with non-temporal stores where SSE2 is available, which saves the read-for-ownership
+// of every destination line.
 template <class T>
 static void expand_bits(const uint8_t *packed, int64_t rows, int n, int nby, T *out, int threads) {
     parallel_for(rows, threads, [=](int64_t b, int64_t e) {
@@ -416,6 +422,54 @@ static void expand_bits(const uint8_t *packed, int64_t rows, int n, int nby, T *
                 v += lim;
             }
         }
+    });
+}
+
+#if defined(__SSE2__)
+template <>
+void expand_bits<double>(const uint8_t *packed, int64_t rows, int n, int nby, double *out, int threads) {
+    static double lut[256][8];
+    static std::once_flag once;
+    std::call_once(once, [] {
+        for (int b = 0; b < 256; ++b)
+            for (int k = 0; k < 8; ++k) lut[b][k] = (double)((b >> (7 - k)) & 1);
+    });
+    parallel_for(rows, threads, [=](int64_t b, int64_t e) {
+        for (int64_t r = b; r < e; ++r) {
+            const uint8_t *p = packed + r * nby;
+            double *o = out + r * n;
+            const bool aligned = (reinterpret_cast<uintptr_t>(o) & 15) == 0;
+            int v = 0;
+            for (int j = 0; j < nby; ++j, v += 8) {
+                const double *l = lut[p[j]];
+                if (aligned && v + 8 <= n) {
+                    _mm_stream_pd(o + v, _mm_loadu_pd(l));
+                    _mm_stream_pd(o + v + 2, _mm_loadu_pd(l + 2));
+                    _mm_stream_pd(o + v + 4, _mm_loadu_pd(l + 4));
+                    _mm_stream_pd(o + v + 6, _mm_loadu_pd(l + 6));
+                } else {
+                    for (int k = 0; k < std::min(8, n - v); ++k) o[v + k] = l[k];
+                }
+            }
+        }
+        _mm_sfence();
+    });
+}
+#endif
+
+// dst (16-byte aligned pinned staging) = (float)src
+static void cast_f64_to_f32(const double *src, float *dst, int64_t elems, int threads) {
+    parallel_for((elems + 3) / 4, threads, [=](int64_t lo4, int64_t hi4) {
+        const int64_t lo = lo4 * 4, hi = std::min(elems, hi4 * 4);
+        int64_t k = lo;
+#if defined(__SSE2__)
+        for (; k + 4 <= hi; k += 4) {
+            const __m128 a = _mm_cvtpd_ps(_mm_loadu_pd(src + k)), b = _mm_cvtpd_ps(_mm_loadu_pd(src + k + 2));   // round to nearest even
+            _mm_stream_ps(dst + k, _mm_movelh_ps(a, b));
+        }
+        _mm_sfence();
+#endif
+        for (; k < hi; ++k) dst[k] = (float)src[k];
     });
 }
 
@@ -477,9 +531,7 @@ int ldpc_decode_bits_host(const ldpc_code_t *code, const void *llr_host, int llr
         const int64_t cnt = std::min<int64_t>(chunk, N - done);
         const int64_t elems = cnt * n;
         if (llr_dtype == LDPC_F64) {
-            const double *src = (const double *)llr_host + (size_t)done * n;
-            float *dst = (float *)b.h_llr;
-            parallel_for(elems, threads, [=](int64_t lo, int64_t hi) { for (int64_t k = lo; k < hi; ++k) dst[k] = (float)src[k]; });
+            cast_f64_to_f32((const double *)llr_host + (size_t)done * n, (float *)b.h_llr, elems, threads);
         } else {
             const char *src = (const char *)llr_host + (size_t)done * n * src_esz;
             char *dst = (char *)b.h_llr;
