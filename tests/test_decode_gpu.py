@@ -382,6 +382,12 @@ def test_runtime_qc_kernel_equals_generic(update, param):
         if (proto[:, c] < 0).all():
             proto[rng.randint(mb), c] = rng.randint(Z)
     cases.append(("random-qc", expand_qc(proto, Z), Z, proto, 301))
+    # high-rate shape (check degree 20: the <12,24> degree caps) and a dense shape (variable degree 14, check degree 16:
+    # the <16,32> caps; the generic cross-check then runs its run-time-degree <32,32> instantiation)
+    for tag, Zs, mbs, nbs, fill in (("wide", 16, 3, 20, 1.0), ("dense", 8, 14, 16, 1.0)):
+        pr = rng.randint(0, Zs, size=(mbs, nbs)).astype(np.int16)
+        pr[rng.rand(mbs, nbs) > fill] = -1
+        cases.append((tag, expand_qc(pr, Zs), Zs, pr, 45))
     for name, H, Zc, pr, B in cases:
         rt = LdpcCode(H, qc_Z=Zc, qc_proto=pr)
         rt.set_kernel("qc_rt")
