@@ -59,7 +59,7 @@ class BeliefPropagation(nn.Module):
     otherwise (model.eval() / torch.no_grad(), as ofdm_functions.py:147 does) the inference kernels run - the
     unweighted fast paths while every weight is still 1."""
 
-    def __init__(self, H, iterations, *legacy, update="sp", param=1.0, warm_start=False, qc_Z=0):
+    def __init__(self, H, iterations, *legacy, update="sp", param=1.0, warm_start=False, qc_Z="auto"):
         super().__init__()
         if len(legacy) == 3:                       # (mask_vc, mask_cv, mask_v_final, llr_expander, iterations)
             mask_v, mask_c, mask_v_final, llr_expander, iterations = H, iterations, legacy[0], legacy[1], legacy[2]
@@ -68,7 +68,7 @@ class BeliefPropagation(nn.Module):
             raise TypeError("BeliefPropagation(H, iterations) or the legacy 5-argument form")
         self._H = (np.asarray(_np(H)) != 0).astype(np.uint8)
         self.iterations = int(iterations)
-        self.update, self.param, self.warm_start, self._qc_Z = update, float(param), bool(warm_start), int(qc_Z)
+        self.update, self.param, self.warm_start, self._qc_Z = update, float(param), bool(warm_start), qc_Z
         self._tables = EdgeTables.from_H(self._H)
         self.layer_size_val = int(self._tables.E)
         E, n, mdv = self._tables.E, self._tables.n, self._tables.max_dv

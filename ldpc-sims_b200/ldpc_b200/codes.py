@@ -402,6 +402,21 @@ def load_mat(path, key=None) -> np.ndarray:
     return (M != 0).astype(np.uint8)
 
 
+def auto_qc_block_size(H: np.ndarray, min_Z=24):
+    """Largest block size Z >= min_Z (a common divisor of both dimensions) for which H is block-circulant, else 0.  Used
+    when a caller hands over a bare H, as every reference call site does (BeliefPropagation(H, iterations),
+    decode_bits(llrs, H, ...)): a quasi-cyclic H then gets the QC kernels without being told."""
+    H = np.asarray(H)
+    m, n = H.shape
+    g = int(np.gcd(m, n))
+    for Z in sorted((z for z in range(min_Z, g + 1) if g % z == 0), reverse=True):
+        if (m // Z) * (n // Z) > 4096:                       # not a prototype-sized block grid
+            break
+        if detect_qc(H, Z) is not None:
+            return Z
+    return 0
+
+
 def qc_block_size(H: np.ndarray, candidates=(81, 54, 27, 96, 64, 48, 32, 24, 16, 8)):
     """Largest candidate Z for which H is block-circulant (so LdpcCode(H, qc_Z=Z) can pick a compiled kernel), else 0."""
     for Z in candidates:

@@ -11,7 +11,7 @@ import numpy as np
 import torch
 
 from . import _native as N
-from .codes import EdgeTables, detect_qc
+from .codes import EdgeTables, auto_qc_block_size, detect_qc
 
 _DTYPES = {torch.float32: N.F32, torch.float64: N.F64, torch.float16: N.F16, torch.int8: N.I8}
 _NP_DTYPES = {np.dtype(np.float32): N.F32, np.dtype(np.float64): N.F64, np.dtype(np.float16): N.F16, np.dtype(np.int8): N.I8}
@@ -33,11 +33,17 @@ def _update_id(update):
 class LdpcCode:
     """H compiled to device edge tables (replaces generate_masks, bp/masking.py:12-147)."""
 
-    def __init__(self, H, qc_Z=0, qc_proto=None, device=None):
+    def __init__(self, H, qc_Z="auto", qc_proto=None, device=None):
+        """qc_Z: block size of a quasi-cyclic H (with qc_proto, or detected from H), 0 = treat H as unstructured,
+        "auto" (default) = look for a block-circulant structure with Z >= 24 (codes.auto_qc_block_size)."""
         N.require_cuda()
         H = np.asarray(H)
         if H.ndim != 2:
             raise ValueError("H must be 2-D")
+        if isinstance(qc_Z, str):
+            if qc_Z != "auto":
+                raise ValueError("qc_Z must be an integer or 'auto'")
+            qc_Z = auto_qc_block_size(H) if qc_proto is None else 0
         self.tables = EdgeTables.from_H(H)
         self.m, self.n, self.E = self.tables.m, self.tables.n, self.tables.E
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)

@@ -28,17 +28,17 @@ from ldpc_b200.linksim import encode_bits, modulate_bits, transmit_symbols, quan
 _CODE_CACHE = {}
 
 
-def _code_for(H, qc_Z=0):
+def _code_for(H, qc_Z="auto"):
     _native.require_cuda()                      # fail loudly: there is no CPU fallback
     Hb = np.ascontiguousarray((np.asarray(H) != 0).astype(np.uint8))
-    key = (Hb.shape, hashlib.sha1(Hb.tobytes()).hexdigest(), int(qc_Z), torch.cuda.current_device())
+    key = (Hb.shape, hashlib.sha1(Hb.tobytes()).hexdigest(), qc_Z, torch.cuda.current_device())
     if key not in _CODE_CACHE:
         _CODE_CACHE[key] = LdpcCode(Hb, qc_Z=qc_Z)
     return _CODE_CACHE[key]
 
 
 # batch_size must be divisible! (reference comment, ofdm_functions.py:130)
-def decode_bits(llrs, H, bp_iterations, batch_size, clamp_value, *, update="sp", param=1.0, qc_Z=0,
+def decode_bits(llrs, H, bp_iterations, batch_size, clamp_value, *, update="sp", param=1.0, qc_Z="auto",
                 out_dtype=np.float64):
     """llrs [N,n] float64 log(P1/P0) -> [N,n] array of {0,1} (float64 like the reference).
 

@@ -86,3 +86,15 @@ def test_alist_and_mat_round_trip(tmp_path):
     Hw = ieee80211n_1944_r12().H
     assert np.array_equal(load_alist(save_alist(Hw)), Hw != 0)
     assert qc_block_size(Hw) == 81 and qc_block_size(H) in (0, 8, 16, 32)
+
+
+def test_auto_qc_block_size():
+    """A bare H (what every reference call site passes) is recognised as quasi-cyclic."""
+    from ldpc_b200.codes import auto_qc_block_size, expand_qc, ieee80211n_1944_r12, peg_64_32
+    assert auto_qc_block_size(ieee80211n_1944_r12().H) == 81
+    assert auto_qc_block_size(peg_64_32()[0]) == 0
+    rng = np.random.RandomState(0)
+    proto = rng.randint(-1, 27, size=(4, 8)).astype(np.int16)
+    assert auto_qc_block_size(expand_qc(proto, 27)) == 27
+    H = (rng.rand(48, 96) < 0.1).astype(np.uint8)
+    assert auto_qc_block_size(H) == 0

@@ -48,7 +48,7 @@ def wcode():
 @pytest.fixture(scope="module")
 def wcode_generic():
     from ldpc_b200.decoder import LdpcCode
-    return LdpcCode(ieee80211n_1944_r12().H)
+    return LdpcCode(ieee80211n_1944_r12().H, qc_Z=0)        # unstructured: the generic kernel
 
 
 def dec(code, llr, iters, clamp, update="sp", param=1.0, x0=None,

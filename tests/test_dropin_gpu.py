@@ -85,3 +85,22 @@ def test_decode_bits_staged_pipeline_formats():
     assert got.dtype == np.float64 and np.array_equal(got[:256], ref[:256].astype(np.float64)) and not got[256:].any()
     with pytest.raises(ValueError):
         decode_bits_host(code, llr, 5, 20.0, np.empty((N, qc.n), np.int32))
+
+
+@pytest.mark.gpu
+def test_bare_H_selects_the_qc_kernels():
+    """BeliefPropagation(H, iterations) / decode_bits(llrs, H, ...) carry no structure hint in the reference: the n=1944
+    code must still land on the compiled QC kernel, a quasi-cyclic H without a specialisation on the run-time QC kernel."""
+    from bp.bp import BeliefPropagation
+    from ldpc_b200.codes import expand_qc, ieee80211n_1944_r12
+    from ldpc_b200.decoder import LdpcCode
+    qc = ieee80211n_1944_r12()
+    m = BeliefPropagation(qc.H, 5).eval()
+    llr = torch.randn(8, qc.n, device="cuda") * 3 + 2
+    p = m(None, llr, 20)
+    assert m._code(llr.device).kernel == 1
+    ref = LdpcCode(qc.H, qc_Z=0).decode(llr, 5, 20, want=("prob",))["prob"]
+    assert torch.equal(p, ref)                                    # same bits as the generic kernel
+    rng = np.random.RandomState(1)
+    proto = rng.randint(-1, 32, size=(5, 10)).astype(np.int16)
+    assert LdpcCode(expand_qc(proto, 32)).kernel == 3
