@@ -4,11 +4,12 @@
 // (bp/bp_vc.py:16-58) and BeliefPropagationCV_Function (bp/bp_cv.py:22-96; its backward materialises a
 // [B,E,E,E] tensor) unrolled by BeliefPropagation.forward (bp/bp.py:43-51).  Sum-product only (the reference's rule).
 //
-// Mapping: ONE THREAD PER CODEWORD.  Every per-edge array (the tape of C->V messages entering each iteration, the
+// Two kernel pairs, chosen by batch size (wpc_warps below).
+// Large batches: ONE THREAD PER CODEWORD.  Every per-edge array (the tape of C->V messages entering each iteration, the
 // recomputed tanh values, the message gradients) lives in global memory as [edge][B], so a warp's 32 codewords read
 // and write 128 contiguous bytes per edge and walk the Tanner graph in lock step (node tables are warp-uniform
 // loads).  That makes the weight gradients - sums over the batch - a warp shuffle reduction followed by one atomic per
-// warp and weight.  The forward arithmetic is node_math.cuh in the generic kernel's order, so prob equals
+// warp and weight.  Batches up to 16 384: ONE WARP PER CODEWORD (further down).  In both, the forward arithmetic is node_math.cuh in the generic kernel's order, so prob equals
 // ldpc_decode_weighted bit for bit; the backward is the derivative of exactly that forward (clamps pass the gradient
 // where the clamped value is inside or on the bound, as torch.clamp does; a saturated product therefore has zero
 // gradient, where the reference's hand-written backward keeps 2/(1-q^2) ~ 1e7 - a documented deviation).
