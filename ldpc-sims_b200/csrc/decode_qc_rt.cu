@@ -19,6 +19,14 @@
 
 namespace ldpc {
 
+// volatile: never moved across a barrier or each other; "memory" on the store orders it against the plain accesses
+__device__ __forceinline__ float lds_f32(int addr) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts_f32(int addr, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory"); }
+
 struct QcRtParams {
     DecodeArgs a;
     int Z, MB, NB, nblk, CW;
@@ -38,8 +46,11 @@ __global__ void __launch_bounds__(512) decode_qc_rt_kernel(const QcRtParams p) {
                   *blk_shift = col_blk + nblk, *blk_col = blk_shift + nblk;
     // per-CTA derived tables (word offsets for this CW): a block's base, and for the rotated access base - shift and the
     // wrap threshold, so an edge address is one add and one select on the thread index
-    int32_t *row_base = tab_s + ((ntab + 3) & ~3), *col_off = row_base + nblk, *col_thr = col_off + nblk;
-    float *msg = reinterpret_cast<float *>(col_thr + ((nblk + 3) & ~3));          // [nblk][Z][CW]
+    // (shared-window BYTE addresses, so that an edge access is one table load, one add and - in the variable phase - one
+    // select on the thread index; the accesses below are ld/st.shared on those addresses)
+    int2 *col_tab = reinterpret_cast<int2 *>(tab_s + ((ntab + 3) & ~3));          // {address of block - shift, wrap threshold}
+    int32_t *row_base = reinterpret_cast<int32_t *>(col_tab + nblk);
+    float *msg = reinterpret_cast<float *>(row_base + ((nblk + 3) & ~3));         // [nblk][Z][CW]
     float *llr_s = msg + (size_t)nblk * Z * CW;                                    // [NB][Z][CW]
     uint8_t *hard_s = reinterpret_cast<uint8_t *>(llr_s + (size_t)n * CW);        // [CW][hard_stride]
     int *scratch = reinterpret_cast<int *>(hard_s + (size_t)CW * p.hard_stride);  // [4 + CW]
@@ -49,16 +60,16 @@ __global__ void __launch_bounds__(512) decode_qc_rt_kernel(const QcRtParams p) {
     const int ncw = (int)min((long long)CW, a.B - cw0);
     const int z = tid / CW, cw = tid - z * CW;
     const bool active = z < Z && cw < ncw;
-    const int ZCW = Z * CW;
+    const int tid4 = tid * 4, ZCW4 = Z * CW * 4;
+    const uint32_t msg_a = (uint32_t)__cvta_generic_to_shared(msg);
 
     for (int i = tid; i < ntab; i += T) tab_s[i] = __ldg(p.tab + i);
     {
         const int32_t *g_row_blk = p.tab + MB + 1, *g_col_blk = g_row_blk + nblk + NB + 1, *g_shift = g_col_blk + nblk;
         for (int i = tid; i < nblk; i += T) {
-            row_base[i] = __ldg(g_row_blk + i) * Z * CW;
+            row_base[i] = msg_a + __ldg(g_row_blk + i) * ZCW4;
             const int b = __ldg(g_col_blk + i), sh = __ldg(g_shift + b);
-            col_off[i] = (b * Z - sh) * CW;
-            col_thr[i] = sh * CW;
+            col_tab[i] = make_int2((int)(msg_a + b * ZCW4 - sh * CW * 4), sh * CW);
         }
     }
     for (int i = tid; i < nblk * Z * CW; i += T) msg[i] = 0.0f;                   // the zeros every reference caller passes
@@ -81,12 +92,13 @@ __global__ void __launch_bounds__(512) decode_qc_rt_kernel(const QcRtParams p) {
                     float in[D], out[D];
 #pragma unroll
                     for (int k = 0; k < D; ++k) {
-                        slot[k] = col_off[b0 + k] + tid + (tid < col_thr[b0 + k] ? ZCW : 0);
-                        in[k] = msg[slot[k]];
+                        const int2 ct = col_tab[b0 + k];
+                        slot[k] = ct.x + tid4 + (tid < ct.y ? ZCW4 : 0);
+                        in[k] = lds_f32(slot[k]);
                     }
                     var_node<D, IS_SP>(in, D, l, out);
 #pragma unroll
-                    for (int k = 0; k < D; ++k) msg[slot[k]] = out[k];
+                    for (int k = 0; k < D; ++k) sts_f32(slot[k], out[k]);
                 });
             }
         }
@@ -103,13 +115,13 @@ __global__ void __launch_bounds__(512) decode_qc_rt_kernel(const QcRtParams p) {
                     float in[D], out[D];
 #pragma unroll
                     for (int j = 0; j < D; ++j) {
-                        slot[j] = row_base[b0 + j] + tid;
-                        in[j] = msg[slot[j]];
+                        slot[j] = row_base[b0 + j] + tid4;
+                        in[j] = lds_f32(slot[j]);
                     }
                     if constexpr (IS_SP) check_node_sp<D>(in, D, a.clampv, out);
                     else check_node_ms_ct<D, UPD>(in, a.clampv, a.param, out);      // box-min tree: same bits as check_node_ms
 #pragma unroll
-                    for (int j = 0; j < D; ++j) msg[slot[j]] = out[j];
+                    for (int j = 0; j < D; ++j) sts_f32(slot[j], out[j]);
                 });
             }
         }
@@ -127,7 +139,10 @@ __global__ void __launch_bounds__(512) decode_qc_rt_kernel(const QcRtParams p) {
                 constexpr int D = decltype(dd)::value;
                 float in[D];
 #pragma unroll
-                for (int k = 0; k < D; ++k) in[k] = msg[col_off[b0 + k] + tid + (tid < col_thr[b0 + k] ? ZCW : 0)];
+                for (int k = 0; k < D; ++k) {
+                    const int2 ct = col_tab[b0 + k];
+                    in[k] = lds_f32(ct.x + tid4 + (tid < ct.y ? ZCW4 : 0));
+                }
                 t = marginal_t<D>(in, D, l);
             });
             const uint8_t hb = hard_bit(t);
