@@ -278,3 +278,32 @@ def test_both_training_variants_and_isolated_variable():
             for k in ("w_edge", "w_llr", "wf_edge", "wf_llr"):
                 assert _rel(out[k].cpu().numpy(), o["g_" + k]) < 2e-4, k
     assert np.array_equal(res["warp"][0], res["thread"][0][:small])           # same forward arithmetic, bit for bit
+
+
+def test_joint_module_and_state_dict_on_cpu():
+    """Host logic only (no GPU): Joint's three constructor forms, the sparse parameters, loading a reference
+    state_dict (with the DataParallel / Joint prefixes) and exporting it again in the reference's dense layout."""
+    import torch
+    from bp.bp import BeliefPropagation
+    from bp.masking import generate_masks
+    from bp.parity import H
+    from nn.joint import Joint
+    iters = int(G["iters"])
+    j = Joint(32, 3.16, H, iters)
+    assert j.layer_size() == 96 and Joint(H, iters).BP.iterations == iters
+    mask_c, mask_v, mask_v_final, llr_expander = generate_masks(H)
+    assert Joint(32, 3.16, mask_v, mask_c, mask_v_final, llr_expander, iters).BP.layer_size() == 96
+    names = {k for k, _ in j.named_parameters()}
+    assert {"BP.w_edge", "BP.w_llr", "BP.wf_edge", "BP.wf_llr", "LLRest.final.weight"} <= names
+    assert all(p.requires_grad for p in j.BP.parameters()) and j.BP._all_ones()
+    bp = BeliefPropagation(H, iters)
+    bp.load_state_dict({"module.BP." + k: torch.tensor(v) for k, v in STATE.items()})
+    assert not bp._all_ones() and tuple(bp.w_edge.shape) == (iters, 96, 2)
+    back = bp.reference_state_dict()
+    for k, v in STATE.items():
+        assert np.array_equal(back[k].numpy(), v), k
+    bp2 = BeliefPropagation(H, iters)
+    bp2.load_state_dict(bp.state_dict())                      # its own (sparse) format
+    assert all(torch.equal(a, b) for a, b in zip(bp.parameters(), bp2.parameters()))
+    with pytest.raises(TypeError):
+        Joint(32, 3.16, H)
