@@ -294,6 +294,15 @@ int ldpc_sim_generate(const ldpc_code_t *code, const ldpc_sim_params_t *params, 
 int ldpc_sim_generate_ex(const ldpc_code_t *code, const ldpc_sim_params_t *params, uint8_t *cw_packed,
                          float *llr, float *samples, ldpc_stream_t stream);
 
+/* The same link chain on CALLER-SUPPLIED transmitted codewords (MSB-first packed, device) and, when `noise` is
+ * non-NULL, caller-supplied additive noise: f32 (re, im) pairs [n_codewords][ceil((n/2)/ofdm_size)][ofdm_size]
+ * (device), one pair per received time sample, already scaled (the reference's own draw,
+ * ofdm/ofdm_functions.py:30-33).  With noise == NULL the Philox stream of ldpc_sim_generate is used.  This is the
+ * identical-input form of the AGC-scaled quantizer front end (evaluate_quantized_snr.py:96-133): everything after
+ * the addition - AGC, ADC, rescale, FFT, LLR - is the simulator's own device code. */
+int ldpc_sim_frontend(const ldpc_code_t *code, const ldpc_sim_params_t *params, const uint8_t *cw_packed,
+                      const float *noise, float *llr, float *samples, ldpc_stream_t stream);
+
 /* ldpc_decode_count - ldpc_decode with the exact link metrics fused at its tail
  * (evaluate_quantized_snr.py:169-188): decodes llr [B,n] and ADDS {uncoded bit errors, info-bit errors,
  * frame errors, bits, frames} into counters[5] (i64, device) against ref_packed (transmitted

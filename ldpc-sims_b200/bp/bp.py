@@ -116,6 +116,9 @@ class BeliefPropagation(nn.Module):
         if return_hard: want.append("hard")
         if return_syndrome: want.append("syndrome")
         if not self._all_ones():                   # trained weights: weighted kernels
+            if self.warm_start and x is not None:
+                raise NotImplementedError("warm_start with trained weights is only available in training mode "
+                                          "(ldpc_decode_weighted takes no initial messages)")
             w = {k: p.detach().to(dev) for k, p in zip(_PARAMS, ps)}
             w.update(iterations=self.iterations, stride=int(self.w_edge.shape[2]))
             out = code.decode_weighted(llr.detach().to(dev), w, clamp_value, update=self.update, param=self.param, want=tuple(want))
@@ -128,30 +131,45 @@ class BeliefPropagation(nn.Module):
     def layer_size(self):
         return self.layer_size_val
 
-    def load_state_dict(self, state_dict, strict=True):
+    def _load_from_state_dict(self, state_dict, prefix, local_metadata, strict, missing_keys, unexpected_keys, error_msgs):
+        """nn.Module loads a PARENT's state_dict by recursing through this hook (never through a child's
+        load_state_dict), so the conversion of a REFERENCE BeliefPropagation state (bp/bp.py:26-39: per-iteration dense
+        `layers.{i}.0.input_weight` [E,E] / `llr_weight` [1,n] and `final_layer.0.*`, plus the mask buffers) lives here: the
+        reference pattern `nn.DataParallel(Joint(...)).load_state_dict(ckpt['model_state_dict'])` (joint_evaluate.py:62-67,
+        keys `module.BP.layers...`) then loads into the sparse tables.  The dense tensors are converted, the masks dropped."""
+        ref_keys = [k for k in state_dict if k.startswith(prefix + "layers.") or k.startswith(prefix + "final_layer.")]
+        if ref_keys:
+            st = {k[len(prefix):]: state_dict[k] for k in ref_keys}
+            need = [f"layers.{i}.0.{w}" for i in range(self.iterations) for w in ("input_weight", "llr_weight")]
+            need += ["final_layer.0.input_weight", "final_layer.0.llr_weight"]
+            lacking = [k for k in need if k not in st]
+            if lacking:                                    # e.g. a checkpoint trained with another iteration count: reported as
+                missing_keys.extend(prefix + k for k in lacking)   # missing keys (strict loading raises, non-strict returns them)
+            else:
+                w = sparse_weights_from_reference_state(self._tables, st, self.iterations)
+                for k in _PARAMS:
+                    state_dict[prefix + k] = torch.as_tensor(w[k])
+            for k in ref_keys:                             # consumed (or rejected above): never "unexpected"
+                del state_dict[k]
+        super()._load_from_state_dict(state_dict, prefix, local_metadata, strict, missing_keys, unexpected_keys, error_msgs)
+
+    def load_state_dict(self, state_dict, strict=True, **kw):
         """Accepts this module's own state_dict (the four sparse tables) or the state_dict of a REFERENCE
-        BeliefPropagation (bp/bp.py:26-39, optionally with the 'module.' / 'BP.' prefixes of DataParallel /
-        nn/joint.py): its dense input_weight / llr_weight tensors are converted to the sparse tables; the masks are
-        not kept."""
+        BeliefPropagation (bp/bp.py:26-39), optionally with the 'module.' / 'BP.' prefixes of DataParallel /
+        nn/joint.py when it is loaded DIRECTLY into this module; nested loading (through Joint / DataParallel) goes
+        through _load_from_state_dict with the parent's own prefixes."""
         st = {}
         for k, v in state_dict.items():
             for pre in ("module.", "BP."):
                 if k.startswith(pre):
                     k = k[len(pre):]
             st[k] = v
-        if all(k in st for k in _PARAMS):
-            return super().load_state_dict({k: st[k] for k in _PARAMS}, strict=True)
-        need = [f"layers.{i}.0.{w}" for i in range(self.iterations) for w in ("input_weight", "llr_weight")]
-        need += ["final_layer.0.input_weight", "final_layer.0.llr_weight"]
-        missing = [k for k in need if k not in st]
-        if missing and strict:
-            raise KeyError(f"not a reference BeliefPropagation state_dict for {self.iterations} iterations: missing {missing[:3]}...")
-        if not missing:
-            w = sparse_weights_from_reference_state(self._tables, st, self.iterations)
-            with torch.no_grad():
-                for k in _PARAMS:
-                    getattr(self, k).copy_(torch.as_tensor(w[k]))
-        return self
+        return super().load_state_dict(st, strict=strict, **kw)
+
+    def invalidate(self):
+        """Forget the cached "every weight is 1" decision (use after editing the weights through `.data`, which bumps
+        neither data_ptr nor _version)."""
+        self._trivial = (None, True)
 
     def reference_state_dict(self):
         """The trainable tensors in the REFERENCE's dense layout and key names (layers.{i}.0.input_weight [E,E], ...),

@@ -23,6 +23,7 @@
 #include "node_math.cuh"
 #include "linksim_device.cuh"
 #include "qc_plan.cuh"
+#include "decode_qc_pers.cuh"
 
 namespace ldpc {
 

@@ -17,60 +17,11 @@
 #include "common.cuh"
 #include "epilogue.cuh"
 #include "node_math.cuh"
+#include "node_math_h2.cuh"
 #include "qc_plan.cuh"
+#include "decode_qc_pers.cuh"
 
 namespace ldpc {
-
-__device__ __forceinline__ __half2 h2_add(__half2 a, __half2 b) { return __hadd2_rn(a, b); }
-
-__device__ __forceinline__ __half2 h2_boxmin(__half2 a, __half2 b) {
-    unsigned d;
-    asm("min.xorsign.abs.f16x2 %0, %1, %2;" : "=r"(d) : "r"(*reinterpret_cast<unsigned *>(&a)), "r"(*reinterpret_cast<unsigned *>(&b)));
-    return *reinterpret_cast<__half2 *>(&d);
-}
-
-template <int D>
-__device__ __forceinline__ void h2_sum_others(const __half2 (&in)[D], __half2 (&out)[D]) {
-    if constexpr (D == 1) { out[0] = __float2half2_rn(0.0f); return; }
-    __half2 pre[D];
-    __half2 acc = in[0];
-#pragma unroll
-    for (int k = 1; k < D; ++k) { pre[k] = acc; acc = h2_add(acc, in[k]); }
-    acc = in[D - 1];
-    out[D - 1] = pre[D - 1];
-#pragma unroll
-    for (int k = D - 2; k >= 1; --k) { out[k] = h2_add(pre[k], acc); acc = h2_add(in[k], acc); }
-    out[0] = acc;
-}
-
-template <int D>
-__device__ __forceinline__ void h2_boxmin_others_clamped(const __half2 (&v)[D], __half2 c, __half2 (&out)[D]) {
-    if constexpr (D == 8) {
-        const __half2 p01 = h2_boxmin(v[0], v[1]), p23 = h2_boxmin(v[2], v[3]), p45 = h2_boxmin(v[4], v[5]), p67 = h2_boxmin(v[6], v[7]);
-        const __half2 qL = h2_boxmin(h2_boxmin(p01, p23), c), qR = h2_boxmin(h2_boxmin(p45, p67), c);
-        out[0] = h2_boxmin(h2_boxmin(v[1], p23), qR); out[1] = h2_boxmin(h2_boxmin(v[0], p23), qR);
-        out[2] = h2_boxmin(h2_boxmin(v[3], p01), qR); out[3] = h2_boxmin(h2_boxmin(v[2], p01), qR);
-        out[4] = h2_boxmin(h2_boxmin(v[5], p67), qL); out[5] = h2_boxmin(h2_boxmin(v[4], p67), qL);
-        out[6] = h2_boxmin(h2_boxmin(v[7], p45), qL); out[7] = h2_boxmin(h2_boxmin(v[6], p45), qL);
-    } else if constexpr (D == 7) {
-        const __half2 p01 = h2_boxmin(v[0], v[1]), p23 = h2_boxmin(v[2], v[3]), p45 = h2_boxmin(v[4], v[5]);
-        const __half2 qL = h2_boxmin(h2_boxmin(p01, p23), c), qR = h2_boxmin(h2_boxmin(p45, v[6]), c);
-        out[0] = h2_boxmin(h2_boxmin(v[1], p23), qR); out[1] = h2_boxmin(h2_boxmin(v[0], p23), qR);
-        out[2] = h2_boxmin(h2_boxmin(v[3], p01), qR); out[3] = h2_boxmin(h2_boxmin(v[2], p01), qR);
-        out[4] = h2_boxmin(h2_boxmin(v[5], v[6]), qL); out[5] = h2_boxmin(h2_boxmin(v[4], v[6]), qL);
-        out[6] = h2_boxmin(p45, qL);
-    } else {
-        __half2 pre[D];
-        __half2 acc = c;
-#pragma unroll
-        for (int j = 0; j < D; ++j) { pre[j] = acc; acc = h2_boxmin(acc, v[j]); }
-        acc = c;
-#pragma unroll
-        for (int j = D - 1; j >= 0; --j) { out[j] = h2_boxmin(pre[j], acc); acc = h2_boxmin(acc, v[j]); }
-    }
-}
-
-__device__ __forceinline__ float sat_llr(float v) { return fminf(fmaxf(v, -32768.0f), 32768.0f); }
 
 template <class Code, int CW /* codeword PAIRS per CTA */, int UPD>
 __global__ void __launch_bounds__((QcLayout<Code, CW>::THREADS)) decode_qc_h2_kernel(const DecodeArgs a) {

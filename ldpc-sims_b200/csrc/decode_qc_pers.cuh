@@ -1,0 +1,607 @@
+// decode_qc_pers.cuh - the persistent, TMA-fed form of the code-specialised decoder (fp32 and f16x2).
+//
+// Same plan (qc_plan.cuh), same node arithmetic (node_math*.cuh) and therefore the same bits as
+// decode_qc_kernel; what changes is the schedule around the two node phases:
+//   * ONE CTA per SM, two codeword GROUPS of TG threads each (a group = CWT codeword slots x Z lanes,
+//     codewords interleaved by lane exactly as in decode_qc.cu).  The CTA is persistent: group g of
+//     CTA b decodes tiles  (b*2 + g) + k * 2*gridDim.x.
+//   * the channel-LLR tile of the NEXT tile is fetched by one elected thread with a bulk copy
+//     (cp.async.bulk, completion on an mbarrier) into a per-group staging buffer while the current
+//     tile decodes (the per-batch host->device tensor of ofdm_functions.py:156 is the tile being staged);
+//     dtypes other than f32 / unaligned pointers take a cooperative convert-and-stage path.
+//   * a tile is a sequence of P = 2*iters + 1 SLOTS separated by barriers:
+//       slot 0      tail of the previous tile (bit packing, syndrome, counters) + LLR -> registers +
+//                   first variable phase (C->V messages are the zeros every caller passes)
+//       slot 2i-1   check phase i,   slot 2i  variable phase i+1        (i = 1 .. iters)
+//       slot 2*iters  marginal, hard decision, posterior store
+//     LOCK = true: the barriers are CTA-wide and group 1 runs ONE SLOT BEHIND group 0, so in every
+//     slot one group's ALU-bound check phase (FMNMX) overlaps the other's FMA/LSU-bound variable phase
+//     (anti-phase by construction).  LOCK = false: each group synchronises on its own named barrier
+//     and the two run free.
+#pragma once
+#include <type_traits>
+
+#include "common.cuh"
+#include "epilogue.cuh"
+#include "node_math.cuh"
+#include "node_math_h2.cuh"
+#include "qc_plan.cuh"
+
+namespace ldpc {
+
+// ---- mbarrier / bulk-copy wrappers (PTX ISA: mbarrier, cp.async.bulk) -----------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *b, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *b, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *b) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(b))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *b, uint32_t parity) {
+    const uint32_t addr = smem_u32(b);
+    uint32_t ok;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok)
+                     : "r"(addr), "r"(parity)
+                     : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void named_bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+
+template <class T> struct cpt_of { static constexpr int value = 1; };
+template <> struct cpt_of<__half2> { static constexpr int value = 2; };
+
+template <class Code, int CWT, int CPT, int NG = 2>
+struct PersLayout {
+    static constexpr int Z = Code::Z, N = Code::NB * Z;
+    static constexpr int NLOC = kQc<Code>.n_local, NSM = kQc<Code>.n_smem;
+    static constexpr int G = NG;                                   // codeword groups per CTA (2: one CTA per SM; 1: two CTAs per SM)
+    static constexpr int CWG = CWT * CPT;                          // codewords per group tile
+    static constexpr int TG = ((CWT * Z + 31) / 32) * 32;          // threads per group (warp multiple: the group index is warp-uniform)
+    static constexpr int THREADS = G * TG;
+    static constexpr int HARD_STRIDE = (N + 15) & ~15;
+    static constexpr size_t MSG_BYTES = (4 * (size_t)NSM * Z * CWT + 15) & ~size_t(15);
+    static constexpr size_t STAGE_BYTES = (size_t)CWG * N * 4;    // f32 rows
+    static constexpr size_t HARD_BYTES = (size_t)CWG * HARD_STRIDE;
+    static constexpr int SCR_INTS = 3 + 2 * CWG;                  // {uncoded, info, -} + frame flags [CWG] + syndrome weights [CWG]
+    static constexpr size_t SCR_BYTES = (SCR_INTS * 4 + 15) & ~size_t(15);
+    static constexpr size_t GROUP_BYTES = MSG_BYTES + STAGE_BYTES + HARD_BYTES + SCR_BYTES;
+    static constexpr size_t SMEM = 16 + G * GROUP_BYTES;          // two mbarriers in front
+    static_assert(N % 4 == 0, "bulk copies move whole 16-byte units: the f32 row must be a multiple of 16 bytes");
+};
+
+// ---- node arithmetic adaptors: one spelling for both number formats ----------------------------------------
+struct NodeParams {
+    float clampv, param;
+    __half2 clamp_h, alpha_h;
+};
+
+template <int D, int UPD>
+__device__ __forceinline__ void vnode(const float (&in)[D], float llr, float (&out)[D]) { var_node<D, UPD == UPD_SP>(in, D, llr, out); }
+template <int D, int UPD>
+__device__ __forceinline__ void vnode(const __half2 (&in)[D], __half2 llr, __half2 (&out)[D]) {
+    __half2 s[D];
+    h2_sum_others<D>(in, s);
+    const __half2 Lp = __hneg2(llr);
+#pragma unroll
+    for (int k = 0; k < D; ++k) out[k] = h2_add(Lp, s[k]);
+}
+template <int D, int UPD>
+__device__ __forceinline__ void cnode(const float (&in)[D], const NodeParams &p, float (&out)[D]) {
+    if constexpr (UPD == UPD_SP) check_node_sp<D>(in, D, p.clampv, out);
+    else check_node_ms_ct<D, UPD>(in, p.clampv, p.param, out);
+}
+template <int D, int UPD>
+__device__ __forceinline__ void cnode(const __half2 (&in)[D], const NodeParams &p, __half2 (&out)[D]) {
+    if constexpr (UPD == UPD_NMS) {
+        __half2 v[D];
+#pragma unroll
+        for (int j = 0; j < D; ++j) v[j] = __hmul2_rn(p.alpha_h, in[j]);
+        h2_boxmin_others_clamped<D>(v, p.clamp_h, out);
+    } else {
+        h2_boxmin_others_clamped<D>(in, p.clamp_h, out);
+    }
+}
+template <int D>
+__device__ __forceinline__ float mnode(const float (&in)[D], int d, float llr) { return marginal_t<D>(in, d, llr); }
+template <int D>
+__device__ __forceinline__ __half2 mnode(const __half2 (&in)[D], int d, __half2 llr) {
+    __half2 acc = __float2half2_rn(0.0f);
+#pragma unroll
+    for (int k = 0; k < D; ++k)
+        if (k < d) acc = (k == 0) ? in[0] : h2_add(acc, in[k]);
+    return __hmul2_rn(__float2half2_rn(0.5f), h2_add(__hneg2(llr), acc));
+}
+__device__ __forceinline__ float zero_of(float) { return 0.0f; }
+__device__ __forceinline__ __half2 zero_of(__half2) { return __float2half2_rn(0.0f); }
+
+// ---- software-pipelined variable phase (see VarBatches in qc_plan.cuh) ---------------------------------------
+template <class Code, int CWT, int UPD, class T, int VBM>
+struct VarPipe {
+    static constexpr int Z = Code::Z, NB = Code::NB;
+    static constexpr int VBW = kVarBatches<Code, VBM>.width, NBATCH = kVarBatches<Code, VBM>.n;
+    static constexpr int NLOCA = kQc<Code>.n_local > 0 ? kQc<Code>.n_local : 1;
+
+    template <int B>
+    static __device__ __forceinline__ void load(int t, T *lo, T *hi, T (&in)[VBW], T *(&ptr)[VBW]) {
+        constexpr int c0 = kVarBatches<Code, VBM>.first[B], c1 = kVarBatches<Code, VBM>.first[B + 1];
+        static_for<c1 - c0>([&](auto ci) {
+            constexpr int c = c0 + decltype(ci)::value;
+            static_for<kQc<Code>.col_deg[c]>([&](auto kk) {
+                constexpr int k = decltype(kk)::value;
+                if constexpr (!kQc<Code>.col_loc[c][k]) {
+                    constexpr int s = kQc<Code>.col_eff[c][k];
+                    constexpr int off = (kQc<Code>.col_slot[c][k] * Z - s) * CWT;
+                    constexpr int i = kVarBatches<Code, VBM>.idx[c][k];
+                    ptr[i] = (t < s ? hi : lo) + off;
+                    in[i] = *ptr[i];
+                }
+            });
+        });
+    }
+    template <int B>
+    static __device__ __forceinline__ void finish(const T (&llr)[NB], T (&loc)[NLOCA], T (&in)[VBW], T *(&ptr)[VBW]) {
+        constexpr int c0 = kVarBatches<Code, VBM>.first[B], c1 = kVarBatches<Code, VBM>.first[B + 1];
+        static_for<c1 - c0>([&](auto ci) {
+            constexpr int c = c0 + decltype(ci)::value;
+            constexpr int D = kQc<Code>.col_deg[c];
+            if constexpr (D > 0) {
+                T x[D], y[D];
+                static_for<D>([&](auto kk) {
+                    constexpr int k = decltype(kk)::value;
+                    constexpr int slot = kQc<Code>.col_slot[c][k], i = kVarBatches<Code, VBM>.idx[c][k];
+                    if constexpr (kQc<Code>.col_loc[c][k]) x[k] = loc[slot];
+                    else x[k] = in[i];
+                });
+                vnode<D, UPD>(x, llr[c], y);
+                static_for<D>([&](auto kk) {
+                    constexpr int k = decltype(kk)::value;
+                    constexpr int slot = kQc<Code>.col_slot[c][k], i = kVarBatches<Code, VBM>.idx[c][k];
+                    if constexpr (kQc<Code>.col_loc[c][k]) loc[slot] = y[k];
+                    else *ptr[i] = y[k];
+                });
+            }
+        });
+    }
+    // batch B is in (cur, pcur): prefetch B+1 into (nxt, pnxt), finish B, recurse with the buffers swapped
+    template <int B>
+    static __device__ __forceinline__ void run(int t, T *lo, T *hi, const T (&llr)[NB], T (&loc)[NLOCA], T (&cur)[VBW], T *(&pcur)[VBW],
+                                               T (&nxt)[VBW], T *(&pnxt)[VBW]) {
+        if constexpr (B < NBATCH) {
+            if constexpr (B + 1 < NBATCH) load<B + 1>(t, lo, hi, nxt, pnxt);
+            finish<B>(llr, loc, cur, pcur);
+            run<B + 1>(t, lo, hi, llr, loc, nxt, pnxt, cur, pcur);
+        }
+    }
+};
+
+// ---- group-scoped tails (the CTA-scoped forms live in epilogue.cuh) ---------------------------------------
+__device__ __forceinline__ void pack_hard_group(const uint8_t *hard_s, int hs_stride, int ncw, int n, uint8_t *packed_g, int tid, int nthr) {
+    const int nbytes = (n + 7) >> 3;
+    const int nfull = n >> 3;                                       // hard_s rows are 16-byte aligned (PersLayout)
+    for (int i = tid; i < ncw * nbytes; i += nthr) {
+        const int cw = i / nbytes, by = i - cw * nbytes;
+        const uint8_t *h = hard_s + cw * hs_stride + by * 8;
+        unsigned v = 0;
+        if (by < nfull) {
+            const unsigned long long y = *reinterpret_cast<const unsigned long long *>(h) & 0x0101010101010101ull;
+            v = (unsigned)((y * 0x8040201008040201ull) >> 56);
+        } else {
+#pragma unroll
+            for (int b = 0; b < 8; ++b) {
+                const int idx = by * 8 + b;
+                v |= (idx < n ? (unsigned)(h[b] & 1) : 0u) << (7 - b);
+            }
+        }
+        packed_g[(long long)cw * nbytes + by] = (uint8_t)v;
+    }
+}
+
+// accumulate into scr[0] (uncoded bit errors), scr[1] (information-bit errors), scr[3 + cw] (frame error flag);
+// flushed one barrier later by count_flush_group
+__device__ __forceinline__ void count_accumulate_group(const uint8_t *hard_s, int hs_stride, int ncw, int n, int k_info,
+                                                       const uint8_t *ref_packed_g, int *scr, int tid, int nthr) {
+    const int nbytes = (n + 7) >> 3;
+    int unc = 0, inf = 0;
+    for (int i = tid; i < ncw * n; i += nthr) {
+        const int cw = i / n, v = i - cw * n;
+        const int hv = hard_s[cw * hs_stride + v];
+        const int ref = (ref_packed_g[(long long)cw * nbytes + (v >> 3)] >> (7 - (v & 7))) & 1;
+        const int hb = hv & 1, ub = (hv >> 1) & 1;
+        unc += (ub != ref);
+        const int e = (hb != ref);
+        inf += e & (v < k_info);
+        if (e) scr[3 + cw] = 1;                                    // benign race: everyone writes 1
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        unc += __shfl_xor_sync(0xffffffffu, unc, o);
+        inf += __shfl_xor_sync(0xffffffffu, inf, o);
+    }
+    if ((tid & 31) == 0) {
+        if (unc) atomicAdd(&scr[0], unc);
+        if (inf) atomicAdd(&scr[1], inf);
+    }
+}
+__device__ __forceinline__ void count_flush_group(int ncw, int n, unsigned long long *counters, int *scr) {   // one thread
+    int fe = 0;
+    for (int c = 0; c < ncw; ++c) { fe += scr[3 + c]; scr[3 + c] = 0; }
+    if (scr[0]) atomicAdd(&counters[0], (unsigned long long)scr[0]);
+    if (scr[1]) atomicAdd(&counters[1], (unsigned long long)scr[1]);
+    if (fe) atomicAdd(&counters[2], (unsigned long long)fe);
+    atomicAdd(&counters[3], (unsigned long long)ncw * (unsigned long long)n);
+    atomicAdd(&counters[4], (unsigned long long)ncw);
+    scr[0] = 0;
+    scr[1] = 0;
+}
+
+// =========================================================================================================
+template <class Code, int CWT, int UPD, class T, bool LOCK, int VB, int NG>
+__global__ void __launch_bounds__((PersLayout<Code, CWT, cpt_of<T>::value, NG>::THREADS), (NG == 1 ? 2 : 1)) decode_qc_pers_kernel(const DecodeArgs a) {
+    constexpr int CPT = cpt_of<T>::value;
+    using L = PersLayout<Code, CWT, CPT, NG>;
+    static_assert(NG == 2 || !LOCK, "the lock-step schedule pairs two groups of one CTA");
+    constexpr int Z = Code::Z, NB = Code::NB, MB = Code::MB, N = L::N, TG = L::TG, CWG = L::CWG;
+    static_assert(CPT == 1 || UPD == UPD_MINSUM || UPD == UPD_NMS, "the f16x2 format implements min-sum and normalized min-sum");
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+
+    const int g = threadIdx.x / TG;                                  // codeword group of this warp
+    const int tid = threadIdx.x - g * TG;
+    uint64_t *const mbar = reinterpret_cast<uint64_t *>(smem_raw) + g;
+    unsigned char *const grp = smem_raw + 16 + (size_t)g * L::GROUP_BYTES;
+    T *const msg_s = reinterpret_cast<T *>(grp);
+    float *const stage = reinterpret_cast<float *>(grp + L::MSG_BYTES);
+    uint8_t *const hard_s = grp + L::MSG_BYTES + L::STAGE_BYTES;
+    int *const scr = reinterpret_cast<int *>(hard_s + L::HARD_BYTES);
+
+    // codewords interleaved by lane: thread = t * CWT + slot; message word (blk, z) of slot sl at (blk * Z + z) * CWT + sl
+    const int t = tid / CWT, sl = tid - t * CWT;
+    T *const msg = msg_s + ((t < Z) ? tid : 0);
+    T *const lo = msg;
+    T *const hi = msg + Z * CWT;
+
+    const long long ntiles = (a.B + CWG - 1) / CWG;
+    const long long tstride = (long long)gridDim.x * L::G;
+    const long long tfirst = (long long)blockIdx.x * L::G + g;
+    const int K = (int)((ntiles + tstride - 1) / tstride);           // tiles per group, the same for every group (trailing ones may be empty)
+    const int P = 2 * a.iters + 1;                                   // slots per tile
+    const bool tma_ok = a.llr_dtype == LDPC_F32 && (reinterpret_cast<uintptr_t>(a.llr) & 15u) == 0;
+    const int nbytes = (N + 7) >> 3;
+
+    NodeParams np;
+    np.clampv = a.clampv; np.param = a.param;
+    np.clamp_h = __float2half2_rn(a.clampv); np.alpha_h = __float2half2_rn(a.param);
+
+    auto tile_ncw = [&](long long j) -> int {
+        const long long r = a.B - j * CWG;
+        return r <= 0 ? 0 : (int)(r < CWG ? r : CWG);
+    };
+    auto issue_tma = [&](long long j) {                              // one thread
+        const int n = tile_ncw(j);
+        if (n > 0) {
+            const uint32_t bytes = (uint32_t)n * N * 4u;
+            mbar_expect_tx(mbar, bytes);
+            bulk_g2s(stage, reinterpret_cast<const float *>(a.llr) + j * CWG * (long long)N, bytes, mbar);
+        }
+    };
+    auto fill_sync = [&](long long j) {                              // whole group: any dtype, any alignment
+        const int n = tile_ncw(j);
+        const long long src = j * CWG * (long long)N;
+        for (int i = tid; i < n * N; i += TG) stage[i] = load_llr(a.llr, a.llr_dtype, src + i);
+    };
+
+    T llr[NB];
+    T loc[L::NLOC > 0 ? L::NLOC : 1];
+
+    // ---- phases (bodies as in decode_qc.cu) -------------------------------------------------------------
+    auto var_phase = [&](auto first_tag) {
+        constexpr bool FIRST = decltype(first_tag)::value;
+        static_for<NB>([&](auto cc) {
+            constexpr int c = decltype(cc)::value;
+            constexpr int D = kQc<Code>.col_deg[c];
+            if constexpr (D > 0) {
+                T in[D], out[D];
+                T *ptr[D];
+                static_for<D>([&](auto kk) {
+                    constexpr int k = decltype(kk)::value;
+                    constexpr bool is_loc = kQc<Code>.col_loc[c][k];
+                    constexpr int slot = kQc<Code>.col_slot[c][k];
+                    if constexpr (is_loc) {
+                        ptr[k] = nullptr;
+                        in[k] = FIRST ? zero_of(T()) : loc[slot];
+                    } else {
+                        constexpr int s = kQc<Code>.col_eff[c][k];
+                        constexpr int off = (slot * Z - s) * CWT;
+                        ptr[k] = (t < s ? hi : lo) + off;
+                        in[k] = FIRST ? zero_of(T()) : *ptr[k];
+                    }
+                });
+                vnode<D, UPD>(in, llr[c], out);
+                static_for<D>([&](auto kk) {
+                    constexpr int k = decltype(kk)::value;
+                    constexpr bool is_loc = kQc<Code>.col_loc[c][k];
+                    constexpr int slot = kQc<Code>.col_slot[c][k];
+                    if constexpr (is_loc) loc[slot] = out[k];
+                    else *ptr[k] = out[k];
+                });
+            }
+        });
+    };
+    // the same phase with the shared-memory loads of batch b+1 issued before batch b is computed and stored (VarBatches)
+    auto var_phase_pipe = [&]() {
+        using VP = VarPipe<Code, CWT, UPD, T, (VB > 0 ? VB : 0)>;
+        T inA[VP::VBW], inB[VP::VBW];
+        T *pA[VP::VBW], *pB[VP::VBW];
+        VP::template load<0>(t, lo, hi, inA, pA);
+        VP::template run<0>(t, lo, hi, llr, loc, inA, pA, inB, pB);
+    };
+    auto check_phase = [&]() {
+        static_for<MB>([&](auto rr) {
+            constexpr int r = decltype(rr)::value;
+            constexpr int D = kQc<Code>.row_deg[r];
+            if constexpr (D > 0) {
+                T in[D], out[D];
+                static_for<D>([&](auto jj) {
+                    constexpr int j = decltype(jj)::value;
+                    constexpr bool is_loc = kQc<Code>.row_loc[r][j];
+                    constexpr int slot = kQc<Code>.row_slot[r][j];
+                    if constexpr (is_loc) in[j] = loc[slot];
+                    else in[j] = msg[slot * Z * CWT];
+                });
+                cnode<D, UPD>(in, np, out);
+                static_for<D>([&](auto jj) {
+                    constexpr int j = decltype(jj)::value;
+                    constexpr bool is_loc = kQc<Code>.row_loc[r][j];
+                    constexpr int slot = kQc<Code>.row_slot[r][j];
+                    if constexpr (is_loc) loc[slot] = out[j];
+                    else msg[slot * Z * CWT] = out[j];
+                });
+            }
+        });
+    };
+    // LLR tile (staging buffer, f32 rows) -> registers, in this thread's lane relabelling
+    auto load_llr_regs = [&](bool second) {
+        const float *row0 = stage + (sl * CPT) * N;
+        static_for<NB>([&](auto cc) {
+            constexpr int c = decltype(cc)::value;
+            constexpr int rho = kQc<Code>.rho[c];
+            int zv = t + rho;
+            if (zv >= Z) zv -= Z;
+            if constexpr (CPT == 1) llr[c] = row0[c * Z + zv];
+            else llr[c] = __floats2half2_rn(sat_llr(row0[c * Z + zv]), second ? sat_llr(row0[N + c * Z + zv]) : 0.0f);
+        });
+    };
+    // marginal, hard decision (hard_s: bit 0 decoded bit, bit 1 channel decision), posterior / probability / byte outputs
+    auto marginal_phase = [&](long long cw0, bool second) {
+        T tm[NB];
+        static_for<NB>([&](auto cc) {
+            constexpr int c = decltype(cc)::value;
+            constexpr int D = kQc<Code>.col_deg[c];
+            T in[D > 0 ? D : 1];
+            static_for<D>([&](auto kk) {
+                constexpr int k = decltype(kk)::value;
+                constexpr bool is_loc = kQc<Code>.col_loc[c][k];
+                constexpr int slot = kQc<Code>.col_slot[c][k];
+                if constexpr (is_loc) in[k] = loc[slot];
+                else {
+                    constexpr int s = kQc<Code>.col_eff[c][k];
+                    constexpr int off = (slot * Z - s) * CWT;
+                    in[k] = ((t < s ? hi : lo) + off)[0];
+                }
+            });
+            tm[c] = mnode<(D > 0 ? D : 1)>(in, D, llr[c]);
+        });
+        auto tf = [&](int c, int h) -> float {                        // marginal of codeword h of this thread as a float
+            if constexpr (CPT == 1) return tm[c];
+            else return h == 0 ? __low2float(tm[c]) : __high2float(tm[c]);
+        };
+        auto lf = [&](int c, int h) -> float {
+            if constexpr (CPT == 1) return llr[c];
+            else return h == 0 ? __low2float(llr[c]) : __high2float(llr[c]);
+        };
+        unsigned hb[CPT];
+        float tmin = CUDART_INF_F;
+#pragma unroll
+        for (int h = 0; h < CPT; ++h) {
+            hb[h] = 0;
+            static_for<NB>([&](auto cc) {
+                constexpr int c = decltype(cc)::value;
+                const float v = tf(c, h);
+                hb[h] |= (v < 0.0f ? 1u : 0u) << c;
+                tmin = fminf(tmin, fabsf(v));
+            });
+        }
+        if (!(tmin > 1e-5f)) {                                       // tie band (rare): round the way the reference does (node_math.cuh)
+#pragma unroll
+            for (int h = 0; h < CPT; ++h) {
+                hb[h] = 0;
+                static_for<NB>([&](auto cc) {
+                    constexpr int c = decltype(cc)::value;
+                    hb[h] |= (unsigned)hard_bit(tf(c, h)) << c;
+                });
+            }
+        }
+        const long long gbase = (cw0 + sl * CPT) * N;
+        uint8_t *const hrow = hard_s + (sl * CPT) * L::HARD_STRIDE;
+        float *const post = a.llr_post ? a.llr_post + gbase : nullptr;
+        static_for<NB>([&](auto cc) {
+            constexpr int c = decltype(cc)::value;
+            constexpr int rho = kQc<Code>.rho[c];
+            int zv = t + rho;
+            if (zv >= Z) zv -= Z;
+            const int idx = c * Z + zv;
+#pragma unroll
+            for (int h = 0; h < CPT; ++h) {
+                if (h == 1 && !second) break;
+                hrow[h * L::HARD_STRIDE + idx] = (uint8_t)(((hb[h] >> c) & 1u) | ((lf(c, h) > 0.0f) ? 2u : 0u));
+                if (post) post[h * N + idx] = __fmul_rn(-2.0f, tf(c, h));
+            }
+        });
+        if (a.prob || a.hard) {                                      // byte / probability outputs: cold path
+#pragma unroll 1
+            for (int c = 0; c < NB; ++c) {
+                float tv[CPT];
+                int rho = 0;
+                static_for<NB>([&](auto cc) {
+                    constexpr int c2 = decltype(cc)::value;
+                    constexpr int rho2 = kQc<Code>.rho[c2];
+                    if (c == c2) {
+                        rho = rho2;
+#pragma unroll
+                        for (int h = 0; h < CPT; ++h) tv[h] = tf(c2, h);
+                    }
+                });
+                int zv = t + rho;
+                if (zv >= Z) zv -= Z;
+#pragma unroll
+                for (int h = 0; h < CPT; ++h) {
+                    if (h == 1 && !second) break;
+                    const long long o = gbase + (long long)h * N + c * Z + zv;
+                    if (a.prob) a.prob[o] = prob_one(tv[h]);
+                    if (a.hard) a.hard[o] = (uint8_t)((hb[h] >> c) & 1u);
+                }
+            }
+        }
+    };
+    auto syndrome_phase = [&](bool second) {                        // adds this thread's unsatisfied checks
+#pragma unroll
+        for (int h = 0; h < CPT; ++h) {
+            if (h == 1 && !second) break;
+            int w = 0;
+            const uint8_t *hs = hard_s + (sl * CPT + h) * L::HARD_STRIDE;
+            static_for<MB>([&](auto rr) {
+                constexpr int r = decltype(rr)::value;
+                constexpr int D = kQc<Code>.row_deg[r];
+                constexpr int sg = kQc<Code>.sigma[r];
+                int zc = t + sg;
+                if (zc >= Z) zc -= Z;
+                unsigned par = 0;
+                static_for<D>([&](auto jj) {
+                    constexpr int j = decltype(jj)::value;
+                    constexpr int s = kQc<Code>.row_shift[r][j];
+                    constexpr int cbase = kQc<Code>.row_col[r][j] * Z;
+                    int zv = zc + s;
+                    if (zv >= Z) zv -= Z;
+                    par ^= hs[cbase + zv] & 1u;
+                });
+                w += (int)par;
+            });
+            if (w) atomicAdd(&scr[3 + CWG + sl * CPT + h], w);
+        }
+    };
+
+    // ---- set-up: barrier object, scratch, first tile -----------------------------------------------------
+    if (tid == 0) {
+        mbar_init(mbar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (int i = tid; i < L::SCR_INTS; i += TG) scr[i] = 0;
+    __syncthreads();
+    if (tma_ok) { if (tid == 0) issue_tma(tfirst); }
+    else fill_sync(tfirst);
+    __syncthreads();
+
+#ifdef LDPC_EXP_DELAY
+    if (g == 1) { const long long t0 = clock64(); while (clock64() - t0 < LDPC_EXP_DELAY) {} }   // timing experiment: start group 1 out of phase
+#endif
+    // ---- the slot loop -----------------------------------------------------------------------------------
+    int k = 0, s = 0;                                                // tile ordinal / slot of this group
+    long long jcur = tfirst;
+    int ncw = tile_ncw(jcur), ncw_prev = 0;
+    const int nsteps = K * P + 2 + (LOCK ? 1 : 0);
+#pragma unroll 1
+    for (int step = 0; step < nsteps; ++step) {
+        const bool run = !LOCK || step >= g;                         // LOCK: group 1 is one slot behind group 0
+        if (run && (k < K || s <= 1)) {
+            const bool act = (sl * CPT < ncw) && (t < Z);            // this thread holds a codeword of the current tile
+            const bool sec = sl * CPT + 1 < ncw;                     // (f16x2) the .y half holds one too
+            if (s == 0) {
+                if (ncw_prev > 0) {                                  // tail of the previous tile, part 1: reads hard_s
+                    const long long cwp = (jcur - tstride) * CWG;
+                    if (a.syndrome && (sl * CPT < ncw_prev) && (t < Z)) syndrome_phase(sl * CPT + 1 < ncw_prev);
+                    if (a.hard_packed) pack_hard_group(hard_s, L::HARD_STRIDE, ncw_prev, N, a.hard_packed + cwp * nbytes, tid, TG);
+                    if (a.counters) count_accumulate_group(hard_s, L::HARD_STRIDE, ncw_prev, N, a.k_info, a.ref_packed + cwp * nbytes, scr, tid, TG);
+                }
+                if (ncw > 0) {
+                    if (tma_ok) mbar_wait(mbar, (uint32_t)(k & 1));
+                    if (act) {
+                        load_llr_regs(sec);
+                        var_phase(std::true_type{});
+                    }
+                }
+            } else if (s == P - 1) {
+                if (ncw > 0) {
+                    if (act) marginal_phase(jcur * CWG, sec);
+                    if (!tma_ok) fill_sync(jcur + tstride);
+                }
+            } else {
+                if (s == 1) {
+                    if (ncw_prev > 0) {                              // tail of the previous tile, part 2: per-codeword words
+                        const long long cwp = (jcur - tstride) * CWG;
+                        if (tid < ncw_prev) {
+                            if (a.syndrome) { a.syndrome[cwp + tid] = scr[3 + CWG + tid]; scr[3 + CWG + tid] = 0; }
+                            if (a.iters_used) a.iters_used[cwp + tid] = a.iters;
+                        }
+                        if (a.counters && tid == 32) count_flush_group(ncw_prev, N, a.counters, scr);
+                    }
+                    if (tma_ok && tid == 0 && ncw > 0) issue_tma(jcur + tstride);   // every thread has taken its LLRs (barrier of slot 0)
+                }
+                if (act) {
+                    if (s & 1) check_phase();
+                    else if constexpr (VB >= 0) var_phase_pipe();
+                    else var_phase(std::false_type{});
+                }
+            }
+        }
+#ifdef LDPC_EXP_NOBAR
+        if (step < 0) named_bar_sync(1 + g, TG);                    // timing experiment only: phases not separated (results wrong)
+#else
+        if constexpr (LOCK) __syncthreads();
+        else named_bar_sync(1 + g, TG);
+#endif
+        if (run) {
+            if (++s == P && k < K) {
+                s = 0;
+                ++k;
+                ncw_prev = ncw;
+                jcur += tstride;
+                ncw = (k < K) ? tile_ncw(jcur) : 0;
+            }
+        }
+    }
+}
+
+// ---- host launcher -------------------------------------------------------------------------------------
+inline int device_sm_count() {
+    static int cached[64] = {};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+    if (!cached[dev]) {
+        int n = 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+        cached[dev] = n;
+    }
+    return cached[dev];
+}
+
+template <class Code, int CWT, int UPD, class T, bool LOCK, int VB, int NG = 2>
+int launch_qc_pers(const DecodeArgs &a, cudaStream_t s) {
+    using L = PersLayout<Code, CWT, cpt_of<T>::value, NG>;
+    const long long ntiles = (a.B + L::CWG - 1) / L::CWG;
+    const long long want = (ntiles + L::G - 1) / L::G;
+    const long long slots = (long long)device_sm_count() * (NG == 1 ? 2 : 1);   // persistent CTAs: one (two groups) or two (one group) per SM
+    const int grid = (int)(want < slots ? want : slots);
+    auto k = decode_qc_pers_kernel<Code, CWT, UPD, T, LOCK, VB, NG>;
+    LDPC_CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::SMEM));
+    k<<<grid, L::THREADS, L::SMEM, s>>>(a);
+    LDPC_CUDA_TRY(cudaGetLastError());
+    return LDPC_OK;
+}
+
+}  // namespace ldpc

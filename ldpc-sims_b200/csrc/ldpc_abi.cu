@@ -193,6 +193,15 @@ static int check_decode_args(const ldpc_code_t *code, const void *llr, int llr_d
     return LDPC_OK;
 }
 
+// device-pointer entry points: the handle's tables live on code->device; a launch from another current device would
+// read them through an invalid context
+static int check_current_device(const ldpc_code_t *code) {
+    int dev = -1;
+    if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); set_error("no CUDA device: libldpc_b200 has no CPU fallback"); return LDPC_ECUDA; }
+    if (dev != code->device) { set_error("code handle belongs to device %d but device %d is current", code->device, dev); return LDPC_EINVAL; }
+    return LDPC_OK;
+}
+
 }  // extern "C"
 
 namespace ldpc {
@@ -230,6 +239,7 @@ int ldpc_decode(const ldpc_code_t *code, const void *llr, int llr_dtype, int64_t
                 uint8_t *hard, uint8_t *hard_packed, int32_t *syndrome, float *x_out, ldpc_stream_t stream) {
     int rc = check_decode_args(code, llr, llr_dtype, B, iters, update, clamp_value);
     if (rc) return rc;
+    if ((rc = check_current_device(code))) return rc;
     DecodeArgs a;
     memset(&a, 0, sizeof(a));
     a.llr = llr; a.llr_dtype = llr_dtype; a.B = B; a.iters = iters; a.update = update;
@@ -245,6 +255,7 @@ int ldpc_decode_weighted(const ldpc_code_t *code, const void *llr, int llr_dtype
                          int32_t *syndrome, float *x_out, ldpc_stream_t stream) {
     int rc = check_decode_args(code, llr, llr_dtype, B, iters, update, clamp_value);
     if (rc) return rc;
+    if ((rc = check_current_device(code))) return rc;
     if (!w_edge || !w_llr || !wf_edge || !wf_llr || w_stride < code->max_dv) { set_error("ldpc_decode_weighted: weight tables missing or w_stride < max_dv (%d)", code->max_dv); return LDPC_EINVAL; }
     DecodeArgs a;
     memset(&a, 0, sizeof(a));
@@ -260,6 +271,7 @@ int ldpc_decode_ex(const ldpc_code_t *code, const ldpc_decode_params_t *p, ldpc_
     if (!p || p->struct_size != (int32_t)sizeof(ldpc_decode_params_t)) { set_error("ldpc_decode_ex: bad params struct"); return LDPC_EINVAL; }
     int rc = check_decode_args(code, p->llr, p->llr_dtype, p->B, p->iters, p->update, p->clamp_value);
     if (rc) return rc;
+    if ((rc = check_current_device(code))) return rc;
     DecodeArgs a;
     memset(&a, 0, sizeof(a));
     a.llr = p->llr; a.llr_dtype = p->llr_dtype; a.B = p->B; a.iters = p->iters; a.update = p->update;
@@ -311,6 +323,25 @@ struct HostPipe {
 };
 }  // namespace
 
+// One mutex for the lazy creation of a handle's HostPipe, shared by every entry point that creates it (two
+// function-local mutexes let concurrent first calls of ldpc_decode_host and ldpc_decode_bits_host both allocate).
+static std::mutex g_host_pipe_create_mu;
+
+// The host pipelines own device buffers and streams: they run on the handle's device whatever device is current in the
+// calling thread, and restore the caller's device on return.
+namespace {
+struct DeviceGuard {
+    int prev = -1;
+    bool switched = false;
+    cudaError_t err = cudaSuccess;
+    explicit DeviceGuard(int dev) {
+        err = cudaGetDevice(&prev);
+        if (err == cudaSuccess && prev != dev) { err = cudaSetDevice(dev); switched = (err == cudaSuccess); }
+    }
+    ~DeviceGuard() { if (switched) cudaSetDevice(prev); }
+};
+}  // namespace
+
 extern "C" void ldpc_host_pipe_free(void *p) {
     HostPipe *hp = static_cast<HostPipe *>(p);
     if (!hp) return;
@@ -330,9 +361,10 @@ int ldpc_decode_host(const ldpc_code_t *code, const void *llr_host, int llr_dtyp
     if (chunk <= 0) chunk = 16384;
     chunk = std::min<int64_t>(chunk, N);
     ldpc_code *mc = const_cast<ldpc_code *>(code);
+    DeviceGuard dev_guard(code->device);
+    if (dev_guard.err != cudaSuccess) return cuda_fail(dev_guard.err, "cudaSetDevice(code->device)");
     {
-        static std::mutex create_mu;
-        std::lock_guard<std::mutex> g(create_mu);
+        std::lock_guard<std::mutex> g(g_host_pipe_create_mu);
         if (!mc->host_pipe) mc->host_pipe = new (std::nothrow) HostPipe();
         if (!mc->host_pipe) { set_error("out of host memory"); return LDPC_ENOMEM; }
     }
@@ -490,9 +522,10 @@ int ldpc_decode_bits_host(const ldpc_code_t *code, const void *llr_host, int llr
     chunk = std::min<int64_t>(chunk, N);
     if (threads <= 0) threads = (int)std::min(16u, std::max(1u, std::thread::hardware_concurrency()));   // host-memory-bound: scales to 16 on the test box
     ldpc_code *mc = const_cast<ldpc_code *>(code);
+    DeviceGuard dev_guard(code->device);
+    if (dev_guard.err != cudaSuccess) return cuda_fail(dev_guard.err, "cudaSetDevice(code->device)");
     {
-        static std::mutex create_mu;
-        std::lock_guard<std::mutex> g(create_mu);
+        std::lock_guard<std::mutex> g(g_host_pipe_create_mu);
         if (!mc->host_pipe) mc->host_pipe = new (std::nothrow) HostPipe();
         if (!mc->host_pipe) { set_error("out of host memory"); return LDPC_ENOMEM; }
     }

@@ -19,6 +19,7 @@ struct LinkParams {
     float agc_clip, clip_ratio;
     unsigned long long seed;
     long long cw_first;
+    const float2 *noise = nullptr;   // ldpc_sim_frontend only: caller-supplied noise samples [codeword][ofdm symbol][time sample] instead of Philox
 };
 
 struct LinkConsts {
@@ -55,7 +56,9 @@ __device__ __forceinline__ void fill_twiddles_f(cplx<T> *tw, int N) {
 // Per-symbol arithmetic does not depend on S.
 struct NoSamples { __device__ __forceinline__ void operator()(int, int, float, float) const {} };
 
-template <int N, int S, class BitFn, class OutFn, class SampFn = NoSamples>
+// EXT_NOISE: the additive noise comes from p.noise (identical-input parity tests against the reference's own
+// noise realisation, evaluate_quantized_snr.py:96-133); everything after the addition is the same code.
+template <int N, int S, class BitFn, class OutFn, class SampFn = NoSamples, bool EXT_NOISE = false>
 __device__ __forceinline__ void ofdm_symbols_llr(int lane, const int (&os)[S], const unsigned long long (&gcw)[S],
                                                  const bool (&valid)[S], int nsym, const LinkParams &p, const LinkConsts &k,
                                                  const cplx<float> *tw, BitFn bit, OutFn out, SampFn samp = SampFn()) {
@@ -82,15 +85,22 @@ __device__ __forceinline__ void ofdm_symbols_llr(int lane, const int (&os)[S], c
 #pragma unroll
             for (int r = 0; r < P / 2; ++r) {
                 const int t0 = bitrev(r * 32 + lane, LOGN);                   // even
-                uint32_t rnd[4];
-                rng((uint32_t)gcw[s], (uint32_t)(gcw[s] >> 32), RNG_NOISE, (uint32_t)((os[s] * N + t0) >> 1), rnd);
                 float z[4];
-                box_muller<float>(rnd[0], rnd[1], z[0], z[1]);
-                box_muller<float>(rnd[2], rnd[3], z[2], z[3]);
+                if constexpr (EXT_NOISE) {
+                    const float2 *nz = p.noise + ((long long)(gcw[s] - (unsigned long long)p.cw_first) * p.n_ofdm_per_cw + os[s]) * N + t0;
+                    const float2 n0 = valid[s] ? nz[0] : make_float2(0.f, 0.f), n1 = valid[s] ? nz[1] : make_float2(0.f, 0.f);
+                    z[0] = n0.x; z[1] = n0.y; z[2] = n1.x; z[3] = n1.y;
+                } else {
+                    uint32_t rnd[4];
+                    rng((uint32_t)gcw[s], (uint32_t)(gcw[s] >> 32), RNG_NOISE, (uint32_t)((os[s] * N + t0) >> 1), rnd);
+                    box_muller<float>(rnd[0], rnd[1], z[0], z[1]);
+                    box_muller<float>(rnd[2], rnd[3], z[2], z[3]);
+                }
+                const float nscale = EXT_NOISE ? 1.0f : k.nstd;
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
                     const int rr = r + h * (P / 2);
-                    float re = x[s][rr].re + k.nstd * z[2 * h], im = x[s][rr].im + k.nstd * z[2 * h + 1];
+                    float re = x[s][rr].re + nscale * z[2 * h], im = x[s][rr].im + nscale * z[2 * h + 1];
                     if (p.qbits > 0) { re = div_rn_nochk(quant(k.factor * re), k.factor); im = div_rn_nochk(quant(k.factor * im), k.factor); }
                     x[s][rr] = {re, im};
                     if (valid[s]) samp(s, t0 + h, re, im);
@@ -98,11 +108,17 @@ __device__ __forceinline__ void ofdm_symbols_llr(int lane, const int (&os)[S], c
             }
         } else {
             const int t = bitrev(lane, LOGN);
-            uint32_t rnd[4];
-            rng((uint32_t)gcw[s], (uint32_t)(gcw[s] >> 32), RNG_NOISE, (uint32_t)((os[s] * N + t) >> 1), rnd);
             float z0, z1;
-            box_muller<float>(rnd[2 * (t & 1)], rnd[2 * (t & 1) + 1], z0, z1);
-            float re = x[s][0].re + k.nstd * z0, im = x[s][0].im + k.nstd * z1;
+            if constexpr (EXT_NOISE) {
+                const float2 nz = valid[s] ? p.noise[((long long)(gcw[s] - (unsigned long long)p.cw_first) * p.n_ofdm_per_cw + os[s]) * N + t] : make_float2(0.f, 0.f);
+                z0 = nz.x; z1 = nz.y;
+            } else {
+                uint32_t rnd[4];
+                rng((uint32_t)gcw[s], (uint32_t)(gcw[s] >> 32), RNG_NOISE, (uint32_t)((os[s] * N + t) >> 1), rnd);
+                box_muller<float>(rnd[2 * (t & 1)], rnd[2 * (t & 1) + 1], z0, z1);
+            }
+            const float nscale = EXT_NOISE ? 1.0f : k.nstd;
+            float re = x[s][0].re + nscale * z0, im = x[s][0].im + nscale * z1;
             if (p.qbits > 0) { re = div_rn_nochk(quant(k.factor * re), k.factor); im = div_rn_nochk(quant(k.factor * im), k.factor); }
             x[s][0] = {re, im};
             if (valid[s]) samp(s, t, re, im);

@@ -27,6 +27,7 @@
 
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <vector>
 
 #include "common.cuh"
@@ -418,6 +419,7 @@ struct ldpc_mlp {
     int maxw = 0;              // widest layer (elements per row)
     std::vector<ldpc::mlp::Layer> layers;
     __half *d_act[2] = {nullptr, nullptr};   // ping-pong activation planes [NS][chunk][maxw]
+    std::mutex mu;             // ldpc_mlp_forward grows and reuses the activation buffers: one call at a time per handle
 };
 
 using namespace ldpc;
@@ -550,6 +552,7 @@ int ldpc_mlp_forward(ldpc_mlp_t *h, const float *x, int64_t B, float *y, ldpc_st
     cudaStream_t s = (cudaStream_t)stream;
     if (B == 0) return LDPC_OK;
     if (reinterpret_cast<uintptr_t>(y) & 15) { set_error("ldpc_mlp_forward: y must be 16-byte aligned"); return LDPC_EINVAL; }
+    std::lock_guard<std::mutex> lock(h->mu);   // host-side serialisation; work of different calls is still ordered per stream by the caller
     {
         const int rc0 = ensure_activation_buffers(h, B, s);
         if (rc0) return rc0;

@@ -117,6 +117,32 @@ __device__ __forceinline__ void static_for(F &&f) {
     static_for_impl(static_cast<F &&>(f), std::make_integer_sequence<int, N>{});
 }
 
+// Variable-phase batches of the persistent kernel (decode_qc_pers.cuh): consecutive block columns whose
+// shared-memory edges are loaded TOGETHER, one batch ahead of the batch being computed.  The rotated-window
+// pointers of the variable phase are run-time selections, so the compiler cannot prove that a store of one
+// node and a load of the next do not alias and keeps them in program order; issuing the loads of batch b+1
+// before the stores of batch b in the SOURCE is what lets the shared-memory latency overlap the additions.
+template <class Code, int VB_MAX>
+struct VarBatches {
+    static constexpr int MB = Code::MB, NB = Code::NB;
+    int n = 0, first[NB + 1] = {}, width = 1;
+    int idx[NB][MB] = {};                                // (column, edge) -> index inside its batch (shared-memory edges only)
+    constexpr VarBatches() {
+        int cnt = 0;
+        for (int c = 0; c < NB; ++c) {
+            int nsm = 0;
+            for (int k = 0; k < kQc<Code>.col_deg[c]; ++k) nsm += kQc<Code>.col_loc[c][k] ? 0 : 1;
+            if (c > 0 && (cnt + nsm > VB_MAX || VB_MAX <= 0)) { first[++n] = c; cnt = 0; }
+            for (int k = 0; k < kQc<Code>.col_deg[c]; ++k)
+                if (!kQc<Code>.col_loc[c][k]) idx[c][k] = cnt++;
+            if (cnt > width) width = cnt;
+        }
+        first[++n] = NB;
+    }
+};
+template <class Code, int VB_MAX>
+inline constexpr VarBatches<Code, VB_MAX> kVarBatches{};
+
 template <class Code, int CW>
 struct QcLayout {
     static constexpr int Z = Code::Z;

@@ -74,7 +74,7 @@ __device__ __forceinline__ int cw_bit(const uint8_t *row, int i) { return (row[i
 
 // samples (nullable): [ncw * n_ofdm_per_cw][2N + 1] f32 rows (Re t = 0..N-1, Im t = 0..N-1, linear SNR): the
 // input_samples of the MLP demappers (evaluate_quantized_snr.py:135-140)
-template <int N>
+template <int N, bool EXT_NOISE = false>
 __global__ void __launch_bounds__(256) linksim_llr_kernel(const uint8_t *cw_packed, long long ncw, LinkParams p, float *llr,
                                                           float *samples) {
     __shared__ cplx<float> tw[N / 2];
@@ -112,10 +112,10 @@ __global__ void __launch_bounds__(256) linksim_llr_kernel(const uint8_t *cw_pack
                 srow[s] = samples + (o0 + s) * (2 * N + 1);
                 if (valid[s] && lane == 0) srow[s][2 * N] = p.snr;
             }
-            ofdm_symbols_llr<N, S>(lane, os, gcw, valid, nsym, p, k, tw, bitf, outf,
-                                   [&](int s, int t, float re, float im) { srow[s][t] = re; srow[s][N + t] = im; });
+            auto sampf = [&](int s, int t, float re, float im) { srow[s][t] = re; srow[s][N + t] = im; };
+            ofdm_symbols_llr<N, S, decltype(bitf), decltype(outf), decltype(sampf), EXT_NOISE>(lane, os, gcw, valid, nsym, p, k, tw, bitf, outf, sampf);
         } else {
-            ofdm_symbols_llr<N, S>(lane, os, gcw, valid, nsym, p, k, tw, bitf, outf);
+            ofdm_symbols_llr<N, S, decltype(bitf), decltype(outf), NoSamples, EXT_NOISE>(lane, os, gcw, valid, nsym, p, k, tw, bitf, outf);
         }
     }
 }
@@ -155,10 +155,13 @@ static int check_sim(const ldpc_code_t *code, const ldpc_sim_params_t *sp) {
 }
 
 static int launch_frontend(const ldpc_code_t *code, const ldpc_sim_params_t *sp, long long first, long long cnt,
-                           uint8_t *cw_packed, float *llr, cudaStream_t s, float *samples = nullptr) {
+                           uint8_t *cw_packed, float *llr, cudaStream_t s, float *samples = nullptr, bool given_codewords = false,
+                           const float2 *noise = nullptr) {
     const int n = code->n, k = code->k_info, kw = (k + 31) / 32;
     const size_t sm = (size_t)kw * 4 + ((n + 3) & ~3);
-    if (n <= 64 && k <= 32) {
+    if (given_codewords) {
+        // ldpc_sim_frontend: the caller supplies the transmitted codewords
+    } else if (n <= 64 && k <= 32) {
         gen_codewords_small_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, s>>>(code->d_gen, n, k, first, cnt, sp->seed, cw_packed);
     } else {
         const int g1 = (int)std::min<long long>(cnt, 148LL * 8);
@@ -169,9 +172,19 @@ static int launch_frontend(const ldpc_code_t *code, const ldpc_sim_params_t *sp,
     lp.n = n; lp.n_ofdm_per_cw = (n / 2 + sp->ofdm_size - 1) / sp->ofdm_size; lp.ofdm_size = sp->ofdm_size;
     lp.snr = powf(10.0f, sp->snr_db / 10.0f);
     lp.qbits = sp->qbits; lp.agc_mode = sp->agc_mode; lp.agc_clip = sp->agc_clip; lp.clip_ratio = sp->clip_ratio;
-    lp.seed = sp->seed; lp.cw_first = first;
+    lp.seed = sp->seed; lp.cw_first = first; lp.noise = noise;
     const long long warps = cnt * lp.n_ofdm_per_cw;
     const int g2 = (int)std::min<long long>((warps + 7) / 8, 148LL * 16);
+    if (noise) {
+        switch (sp->ofdm_size) {
+            case 32: linksim_llr_kernel<32, true><<<g2, 256, 0, s>>>(cw_packed, cnt, lp, llr, samples); break;
+            case 64: linksim_llr_kernel<64, true><<<g2, 256, 0, s>>>(cw_packed, cnt, lp, llr, samples); break;
+            case 128: linksim_llr_kernel<128, true><<<g2, 256, 0, s>>>(cw_packed, cnt, lp, llr, samples); break;
+            default: linksim_llr_kernel<256, true><<<g2, 256, 0, s>>>(cw_packed, cnt, lp, llr, samples); break;
+        }
+        LDPC_CUDA_TRY(cudaGetLastError());
+        return LDPC_OK;
+    }
     switch (sp->ofdm_size) {
         case 32: linksim_llr_kernel<32><<<g2, 256, 0, s>>>(cw_packed, cnt, lp, llr, samples); break;
         case 64: linksim_llr_kernel<64><<<g2, 256, 0, s>>>(cw_packed, cnt, lp, llr, samples); break;
@@ -198,6 +211,20 @@ int ldpc_sim_generate_ex(const ldpc_code_t *code, const ldpc_sim_params_t *sp, u
     if (!cw_packed || !llr) { set_error("ldpc_sim_generate_ex: null output"); return LDPC_EINVAL; }
     if (sp->n_codewords == 0) return LDPC_OK;
     return launch_frontend(code, sp, sp->first_codeword, sp->n_codewords, cw_packed, llr, (cudaStream_t)stream, samples);
+}
+
+int ldpc_sim_frontend(const ldpc_code_t *code, const ldpc_sim_params_t *sp, const uint8_t *cw_packed, const float *noise,
+                      float *llr, float *samples, ldpc_stream_t stream) {
+    if (!code || !sp) { set_error("ldpc_sim_frontend: null argument"); return LDPC_EINVAL; }
+    if (sp->struct_size != (int32_t)sizeof(ldpc_sim_params_t)) { set_error("ldpc_sim_params_t size mismatch"); return LDPC_EINVAL; }
+    if (code->n % 2) { set_error("QPSK needs an even code length"); return LDPC_EUNSUPPORTED; }
+    if (sp->ofdm_size != 32 && sp->ofdm_size != 64 && sp->ofdm_size != 128 && sp->ofdm_size != 256) { set_error("ofdm_size must be 32, 64, 128 or 256"); return LDPC_EUNSUPPORTED; }
+    if (sp->n_codewords < 0 || sp->qbits < 0 || sp->qbits > 16) { set_error("bad n_codewords / qbits"); return LDPC_EINVAL; }
+    if (sp->qbits > 0 && sp->agc_mode != 1 && sp->agc_mode != 2) { set_error("agc_mode must be 1 (script AGC) or 2 (gen_qdata) when qbits > 0"); return LDPC_EINVAL; }
+    if (!cw_packed || !llr) { set_error("ldpc_sim_frontend: null codewords / output"); return LDPC_EINVAL; }
+    if (sp->n_codewords == 0) return LDPC_OK;
+    return launch_frontend(code, sp, sp->first_codeword, sp->n_codewords, const_cast<uint8_t *>(cw_packed), llr, (cudaStream_t)stream, samples,
+                           true, reinterpret_cast<const float2 *>(noise));
 }
 
 int ldpc_decode_count(const ldpc_code_t *code, const void *llr, int llr_dtype, int64_t B, int iters, int update,

@@ -108,6 +108,8 @@ def lib():
     L.ldpc_sim_generate.argtypes = [vp, vp, vp, vp, vp]
     L.ldpc_sim_generate_ex.restype = ctypes.c_int
     L.ldpc_sim_generate_ex.argtypes = [vp, vp, vp, vp, vp, vp]
+    L.ldpc_sim_frontend.restype = ctypes.c_int
+    L.ldpc_sim_frontend.argtypes = [vp, vp, vp, vp, vp, vp, vp]
     L.ldpc_decode_count.restype = ctypes.c_int
     L.ldpc_decode_count.argtypes = [vp, vp, i32, i64, i32, i32, f32, f32, vp, i32, vp, vp]
     L.ldpc_mlp_create.restype = ctypes.c_int

@@ -204,6 +204,29 @@ def sim_generate(code, cfg: LinkConfig, first, count, want_samples=False):
     return (cwp, llr, smp) if want_samples else (cwp, llr)
 
 
+def sim_frontend(code, cfg: LinkConfig, cw_packed, noise=None, want_samples=False):
+    """The simulator's link chain (QPSK, IFFT, + noise, AGC / ADC / rescale, FFT, exact LLR - float32) on
+    CALLER-SUPPLIED codewords (packed MSB-first [count, ceil(n/8)] u8 CUDA tensor) and, optionally, caller-supplied
+    noise (complex64 CUDA tensor [count, symbols_per_codeword, ofdm_size], already scaled): the identical-input
+    form of evaluate_quantized_snr.py:96-133.  Returns llr f32 [count, n] (and the MLP input rows)."""
+    dev = code.device
+    count = cw_packed.shape[0]
+    per_cw = (code.n // 2 + cfg.ofdm_size - 1) // cfg.ofdm_size
+    llr = torch.empty(count, code.n, dtype=torch.float32, device=dev)
+    smp = torch.zeros(count * per_cw, 2 * cfg.ofdm_size + 1, dtype=torch.float32, device=dev) if want_samples else None
+    nz = None
+    if noise is not None:
+        nz = torch.view_as_real(noise.to(torch.complex64).contiguous()).contiguous()
+        if nz.numel() != count * per_cw * cfg.ofdm_size * 2:
+            raise ValueError("noise must be [count, symbols_per_codeword, ofdm_size] complex")
+    sp = cfg.to_struct(0, count)
+    with torch.cuda.device(dev):
+        N.check(N.lib().ldpc_sim_frontend(code._h, ctypes.byref(sp), cw_packed.contiguous().data_ptr(),
+                                          None if nz is None else nz.data_ptr(), llr.data_ptr(),
+                                          None if smp is None else smp.data_ptr(), _stream()))
+    return (llr, smp) if want_samples else llr
+
+
 def decode_count(code, llr, ref_packed, cfg: LinkConfig, counters=None):
     """Decode llr [B,n] and add the exact link metrics against the transmitted codewords (packed) into
     `counters` (int64[5] CUDA tensor): one launch, ldpc_decode_count."""

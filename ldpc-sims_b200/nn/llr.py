@@ -33,34 +33,52 @@ class _NativeChain(nn.Module):
         self._splits = int(splits)
         self._native = {}                          # device index -> (parameter versions, NativeMLP)
 
+    def _tensors(self):
+        """The weight / bias tensors the forward actually uses, read as ATTRIBUTES of the layers: on nn.DataParallel
+        replicas `parameters()` is empty (replicate() fills `_parameters` with plain tensors under the same names),
+        but attribute access works on the original and on every replica."""
+        out = []
+        for name in self._chain:
+            layer = getattr(self, name)
+            out.append(layer.weight)
+            b = getattr(layer, "bias", None)
+            if b is not None:
+                out.append(b)
+        return out
+
     def _handle(self, device):
         layers = [getattr(self, n) for n in self._chain]
-        params = [p for l in layers for p in l.parameters()]
-        versions = tuple(p._version for p in params) + tuple(p.data_ptr() for p in params)
+        params = self._tensors()
         key = device.index if device.index is not None else torch.cuda.current_device()
+        # The native handle is rebuilt whenever the VALUES change.  Tensor identity / _version cannot tell: DataParallel
+        # hands every forward fresh replica tensors with the same values, and 2019-style `p.data.copy_(...)` edits change the
+        # values without bumping _version - so the key is a checksum of the values themselves (two multi-tensor reductions
+        # and one host read per forward; the reference's own loops read every batch back to the host anyway).
+        chk = self._checksum(params)
         hit = self._native.get(key)
-        if hit is not None and hit[0] != versions:
-            # nn.DataParallel re-broadcasts the parameters on every forward (new tensors, same values): compare a cheap
-            # checksum of the values before rebuilding the native handle (weight upload + plane split)
-            chk = self._checksum(params)
-            hit = (versions, hit[1], chk) if (len(hit) > 2 and hit[2] == chk) else None
-            if hit is not None:
-                self._native[key] = hit
-        if hit is None:
-            hit = (versions, NativeMLP([l.weight for l in layers], [l.bias for l in layers], list(self._acts),
-                                       splits=self._splits, device=torch.device("cuda", key)), self._checksum(params))
+        if hit is None or hit[0] != chk:
+            hit = (chk, NativeMLP([l.weight for l in layers], [getattr(l, "bias", None) for l in layers], list(self._acts),
+                                  splits=self._splits, device=torch.device("cuda", key)))
             self._native[key] = hit
         return hit[1]
 
     @staticmethod
     def _checksum(params):
         with torch.no_grad():
-            return tuple(float(v) for p in params for v in (p.double().sum(), (p.double() ** 2).sum()))
+            ps = [p.detach() for p in params]
+            l2 = torch._foreach_norm(ps, 2)
+            l1 = torch._foreach_norm(ps, 1)
+            first = [p.reshape(-1)[:1].to(l2[0].dtype).reshape(()) for p in ps]
+            return tuple(torch.stack(list(l2) + list(l1) + first).double().tolist())
+
+    def invalidate(self):
+        """Drop the cached native handles (they are rebuilt from the current parameter values on the next forward)."""
+        self._native.clear()
 
     def forward(self, x):
         src = x.device
         dev = src if src.type == "cuda" else torch.device("cuda", torch.cuda.current_device())
-        if self.training and torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters())):
+        if self.training and torch.is_grad_enabled() and (x.requires_grad or any(t.requires_grad for t in self._tensors())):
             y = x.to(device=dev, dtype=torch.float32)        # training: library GEMMs under autograd (parameters must be on dev)
             for name, act in zip(self._chain, self._acts):
                 y = getattr(self, name)(y)

@@ -131,6 +131,28 @@ def agc_quantized_frontend(rx_signal, snrdb_val, qbits, clip_ratio, ofdm_size, a
     return qpsk_llrs(deofdm, snr_single), qrx_signal_rescaled
 
 
+def framed_link_llrs(enc_bits, snrdb, ofdm_size, qbits=0, clip_ratio=1.0, agc_clip=10, noise=None):
+    """The reference chain for a code whose length is NOT 2 * ofdm_size (the reference itself only works for
+    n = 2 * ofdm_size, SURVEY hard part 6): every codeword is framed into ceil((n/2)/N) OFDM symbols, null
+    subcarriers after its last QPSK symbol; each OFDM symbol then goes through exactly the reference's per-symbol
+    steps (ofdm_functions.py:17-35,63-78; with qbits > 0 the AGC-scaled quantizer of
+    evaluate_quantized_snr.py:96-133).  With n = 2 * ofdm_size this IS gen_data / agc_quantized_frontend.
+    enc_bits [B, n] of 0/1; returns (llrs float64 [B, n], rx_signal [1, B*S*N], noise [N, B*S])."""
+    enc_bits = np.asarray(enc_bits)
+    B, n = enc_bits.shape
+    nsym = n // 2
+    S = (nsym + ofdm_size - 1) // ofdm_size
+    sym = np.zeros((B, S * ofdm_size), dtype=complex)
+    sym[:, :nsym] = modulate_bits(enc_bits.reshape((1, -1))).reshape(B, nsym)
+    snr = np.power(10, snrdb / 10)
+    rx_signal, _ = transmit_symbols(sym.reshape((1, -1)), ofdm_size, snr, noise=noise)
+    if qbits > 0:
+        llr, _ = agc_quantized_frontend(rx_signal, snrdb, qbits, clip_ratio, ofdm_size, agc_clip=agc_clip)
+    else:
+        llr, _ = demodulate_signal(rx_signal, ofdm_size, snr)
+    return llr.reshape(B, S * ofdm_size * 2)[:, :n].copy(), rx_signal
+
+
 def error_metrics(llrs, decoded_bits, enc_bits, k):
     """evaluate_quantized_snr.py:169-188 as exact integer counters.
     llrs, decoded_bits, enc_bits: [N,n].  Returns dict of int64 counts:

@@ -22,16 +22,25 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 REF = "/root/reference/pytorch"
 np.complex = complex            # ofdm_functions.py:47,87 use the removed aliases
 np.float = float
-sys.path.insert(0, REF)
 sys.path.insert(0, os.path.join(ROOT, "oracle"))
-sys.path.insert(0, os.path.join(ROOT, "ldpc-sims_b200"))
+sys.path.insert(0, REF)
+# The product package is NOT put on sys.path: its bp/ ofdm/ nn/ drop-ins are regular packages and would win over the
+# reference's __init__-less directories of the same names whatever the path order.  The one module needed from it
+# (the n=1944 prototype and encoder, plain numpy) is loaded by file name.
 
 from bp.bp import BeliefPropagation                      # noqa: E402  (the reference)
 from bp.parity import H as H_REF, G as G_REF             # noqa: E402
 import ofdm.ofdm_functions as REFOF                      # noqa: E402
 import bp_oracle as O                                    # noqa: E402
 import linksim_oracle as LO                              # noqa: E402
-from ldpc_b200.codes import ieee80211n_1944_r12          # noqa: E402
+import importlib.util                                    # noqa: E402
+_spec = importlib.util.spec_from_file_location("_b200_codes", os.path.join(ROOT, "ldpc-sims_b200", "ldpc_b200", "codes.py"))
+_codes = importlib.util.module_from_spec(_spec)
+sys.modules["_b200_codes"] = _codes
+_spec.loader.exec_module(_codes)
+ieee80211n_1944_r12 = _codes.ieee80211n_1944_r12
+for _m in (sys.modules["bp.bp"], sys.modules["bp.parity"], REFOF):      # the modules under test really are the reference's
+    assert os.path.abspath(_m.__file__).startswith(REF + os.sep), _m.__file__
 
 GOLD = os.path.join(ROOT, "tests", "golden")
 os.makedirs(GOLD, exist_ok=True)
@@ -108,13 +117,47 @@ def default_code_cases():
         print(f"  default-code case {name:12s} iters={iters} clamp={clamp}: oracle == reference (x, t, prob, hard)")
     out["names"] = np.array([c[0] for c in cases])
     np.savez_compressed(os.path.join(GOLD, "bp_default_code.npz"), **out)
+    # B = 4096 from the dense reference.  To keep the fixture small only the bit-exact outputs are kept for
+    # all 4096 codewords (packed hard bits, syndrome weights) plus the marginals of the first 512; gaussian LLRs are
+    # regenerated from their seed by the test, link LLRs (the reference's own gen_data draw) are stored.
+    big = {}
+    B4 = 4096
+    big_cases = []
+    for ci, (seed, scale, iters, clamp) in enumerate([(21, 4.0, 5, 10), (22, 10.0, 10, 100), (23, 2.0, 3, 20)]):
+        llr = (np.random.RandomState(seed).randn(B4, 64) * scale).astype(np.float32)
+        big_cases.append((f"gauss{ci}", llr, iters, clamp, dict(seed=np.int64(seed), scale=np.float64(scale))))
+    for snrdb in (4.0, 8.0):
+        np.random.seed(int(200 + snrdb))
+        enc = REFOF.encode_bits(REFOF.create_bits(B4 * 32), G_REF)
+        _, _, rx_llrs, _ = REFOF.gen_data(REFOF.modulate_bits(enc), snrdb, 32)
+        big_cases.append((f"link{int(snrdb)}dB", rx_llrs.reshape(-1, 64).astype(np.float32), 3, 20, dict(store_llr=True)))
+    for name, llr, iters, clamp, extra in big_cases:
+        if iters not in models:
+            models[iters] = BeliefPropagation(H_REF, iters).eval()
+        prob, t, x = ref_forward(models[iters], llr, clamp)
+        o = O.bp_decode(H_REF, llr, iters, clamp)
+        assert np.array_equal(o["x"], x) and np.array_equal(o["t"], t) and np.array_equal(o["prob"], prob), name
+        hard = np.round(prob).astype(np.uint8)
+        assert np.array_equal(o["hard"], hard)
+        # decode_bits (the batching wrapper) on the same LLRs agrees with the module's own rounding
+        assert np.array_equal(REFOF.decode_bits(llr.astype(np.float64), H_REF, iters, 1024, clamp).astype(np.uint8), hard)
+        big[name + "_iters"] = np.int64(iters); big[name + "_clamp"] = np.float64(clamp)
+        big[name + "_hard"] = np.packbits(hard, axis=1); big[name + "_syndrome"] = o["syndrome"].astype(np.int16)
+        big[name + "_t512"] = t[:512]
+        if extra.pop("store_llr", False):
+            big[name + "_llr"] = llr
+        for k, v in extra.items():
+            big[name + "_" + k] = v
+        print(f"  default-code B=4096 case {name:10s} iters={iters} clamp={clamp}: oracle == reference (x, t, prob, hard)")
+    big["names"] = np.array([c[0] for c in big_cases])
+    np.savez_compressed(os.path.join(GOLD, "bp_default_code_4096.npz"), **big)
 
 
 def wifi_dense_case():
     """n=1944 dense reference at tiny batch: tolerance pin (association order differs)."""
     code = ieee80211n_1944_r12()
     Hw = code.H.astype(np.int64)
-    B, iters, clamp = 8, 10, 20
+    B, iters, clamp = 16, 10, 20                               # SURVEY 8(c): B = 16 from the dense reference
     rng = np.random.RandomState(2024)
     u = rng.randint(0, 2, size=(B, code.k)).astype(np.uint8)
     c = code.encode(u)

@@ -2,9 +2,12 @@
 reference's golden vectors.  Bars:
   * hard decisions, syndrome weights, error counters: bit-exact
   * min-sum family marginals / messages: bit-exact against the oracle (add/min/abs/sign only)
-  * sum-product marginals: fp32 tolerance - >= 99.9 % of values within 1e-4 relative (the
-    2*atanh step amplifies 1-ulp tanh/log differences between CUDA libm and ATen's CPU
-    kernels, SURVEY.md section 7 hard part 2); every value within 2e-2 relative or 2e-3 abs.
+  * sum-product marginals: fp32 tolerance (SURVEY.md section 7 hard part 2): >= 99.9 % of values within 1e-4
+    relative, and EVERY value within 1e-4 * max(|t|, 16.64) unless it is a saturation outlier: the 2*atanh step
+    log((1+p)/(1-p)) of the reference (bp_cv.py:44-50) turns a 1-ulp difference of tanhf / the product into up to
+    ln(3/2) = 0.405 of a message once |p| is within a few ulps of the clamp 1 - 2^-23, so a marginal fed by k
+    messages with |x| >= 9 may move by up to 0.21 k (t = 0.5 * sum).  sp_check enforces exactly that and returns the
+    histogram of |dt| / max(|t|, 16.64) by decade (profiles/r02_sp_histogram.txt keeps the measured ones).
 """
 import os
 
@@ -24,12 +27,40 @@ REL_TOL = 1e-4          # north_star: LLRs within 1e-4 relative in fp32
 FRAC_OK = 0.999
 
 
-def sp_close(t_gpu, t_ref):
-    rel = np.abs(t_gpu - t_ref) / np.maximum(np.abs(t_ref), 1e-30)
+H64 = peg_64_32()[0]
+SCALE_FLOOR = 16.64     # the largest message the reference can produce (2 atanh(1 - 2^-23) = 16.6355)
+SAT_MSG = 9.0           # messages beyond this are ill-conditioned in the reference's own formula
+HIST_EDGES = np.array([0, 1e-7, 1e-6, 1e-5, 1e-4, 1e-3, 1e-2, 1e-1, np.inf])
+
+
+def sp_check(t_gpu, t_ref, n_sat=None):
+    """Returns (frac within 1e-4 relative, worst |dt| / max(|t|, 16.64), ok, histogram).  n_sat [B,n] = number of
+    incoming C->V messages with |x| >= SAT_MSG per variable (from the oracle); None = unknown (column degree cap)."""
+    t_gpu = np.asarray(t_gpu, np.float64); t_ref = np.asarray(t_ref, np.float64)
     ab = np.abs(t_gpu - t_ref)
-    frac = np.mean((rel <= REL_TOL) | (ab <= 1e-6))
-    worst_ok = np.all((rel <= 2e-2) | (ab <= 2e-3))
-    return frac, worst_ok, rel.max()
+    rel = ab / np.maximum(np.abs(t_ref), 1e-30)
+    frac = float(np.mean((rel <= REL_TOL) | (ab <= 1e-6)))
+    e = ab / np.maximum(np.abs(t_ref), SCALE_FLOOR)
+    hist = np.histogram(e, bins=HIST_EDGES)[0]
+    out = e > 1e-4
+    if n_sat is None:
+        n_sat = np.full(t_ref.shape, 11)
+    ok = bool(np.all(ab[out] <= 0.21 * n_sat[out] + 1e-3))          # outliers only where the formula is saturated
+    return frac, float(e.max()), ok, hist
+
+
+def sat_count(H, x_cm):
+    """Per-variable number of final C->V messages with |x| >= SAT_MSG; x_cm [B,E] in check-major edge order."""
+    cols = np.nonzero(np.asarray(H) != 0)[1]
+    big = (np.abs(x_cm) >= SAT_MSG).astype(np.int64)
+    out = np.zeros((x_cm.shape[0], H.shape[1]), np.int64)
+    np.add.at(out, (slice(None), cols), big)
+    return out
+
+
+def sp_close(t_gpu, t_ref, n_sat=None):
+    frac, worst, ok, _ = sp_check(t_gpu, t_ref, n_sat)
+    return frac, ok, worst
 
 
 @pytest.fixture(scope="module")
@@ -69,12 +100,17 @@ def test_default_code_against_reference_golden(dcode, golden_dir):
         assert np.array_equal(o["hard_packed"], g[f"{name}_hard"]), f"{name}: hard bits differ from the reference"
         assert np.array_equal(np.packbits(o["hard"], axis=1), g[f"{name}_hard"])
         assert np.array_equal(o["syndrome"], g[f"{name}_syndrome"]), name
-        frac, worst_ok, mx = sp_close(o["llr_post"] / -2.0, g[f"{name}_t"])
+        ns_all = sat_count(H64, O.bp_decode(H64, llr, iters, clamp)["x"])       # the oracle is bit-identical to the reference here
+        frac, worst_ok, mx = sp_close(o["llr_post"] / -2.0, g[f"{name}_t"], ns_all)
         assert frac >= FRAC_OK and worst_ok, (name, frac, mx)
         dp = np.abs(o["prob"][:64] - g[f"{name}_prob"])
         assert np.mean(dp <= 1e-5) >= FRAC_OK and dp.max() <= 5e-3, (name, dp.max())
-        fx, wx, _ = sp_close(o["x"][:64], g[f"{name}_x"])
+        fx, wx, _ = sp_close(o["x"][:64], g[f"{name}_x"], np.ones(g[f"{name}_x"].shape, np.int64) * 2)
         assert fx >= FRAC_OK and wx, name
+        # first 64 codewords: the stored reference messages say which marginals may be saturation outliers
+        ns = sat_count(peg_64_32()[0], g[f"{name}_x"])
+        f64, w64, m64 = sp_close(o["llr_post"][:64] / -2.0, g[f"{name}_t"][:64], ns)
+        assert f64 >= 0.998 and w64, (name, f64, m64)
 
 
 def test_default_code_tiny_kernel_against_reference_golden(dcode, golden_dir):
@@ -87,7 +123,8 @@ def test_default_code_tiny_kernel_against_reference_golden(dcode, golden_dir):
         assert np.array_equal(o["hard_packed"], g[f"{name}_hard"]), f"{name}: hard bits differ from the reference"
         assert np.array_equal(np.packbits(o["hard"], axis=1), g[f"{name}_hard"])
         assert np.array_equal(o["syndrome"], g[f"{name}_syndrome"]), name
-        frac, worst_ok, mx = sp_close(o["llr_post"] / -2.0, g[f"{name}_t"])
+        ns_all = sat_count(H64, O.bp_decode(H64, llr, iters, clamp)["x"])       # the oracle is bit-identical to the reference here
+        frac, worst_ok, mx = sp_close(o["llr_post"] / -2.0, g[f"{name}_t"], ns_all)
         assert frac >= FRAC_OK and worst_ok, (name, frac, mx)
         dp = np.abs(o["prob"][:64] - g[f"{name}_prob"])
         assert np.mean(dp <= 1e-5) >= FRAC_OK and dp.max() <= 5e-3, (name, dp.max())
@@ -191,8 +228,10 @@ def test_wifi_sum_product_against_oracle_and_dense_reference(wcode, golden_dir):
     g = np.load(os.path.join(golden_dir, "bp_wifi1944_dense.npz"))
     o = dec(wcode, g["llr"], int(g["iters"]), float(g["clamp"]), want=("llr_post", "hard_packed", "prob"))
     assert np.array_equal(o["hard_packed"], g["hard"]), "hard bits differ from the dense reference"
-    f_ref, w_ref, mx_ref = sp_close(o["llr_post"] / -2.0, g["t"])              # vs dense reference
-    f_ora, w_ora, mx_ora = sp_close(o["llr_post"] / -2.0, g["oracle_t"])       # vs sparse oracle
+    qc0 = ieee80211n_1944_r12()
+    ns = sat_count(qc0.H, C.decode(C.CGraph(qc0.H), g["llr"], int(g["iters"]), float(g["clamp"]), "sp", want=("x",))["x"])
+    f_ref, w_ref, mx_ref = sp_close(o["llr_post"] / -2.0, g["t"], ns)          # vs dense reference
+    f_ora, w_ora, mx_ora = sp_close(o["llr_post"] / -2.0, g["oracle_t"], ns)   # vs sparse oracle
     assert f_ref >= FRAC_OK and w_ref, (f_ref, mx_ref)
     assert f_ora >= FRAC_OK and w_ora, (f_ora, mx_ora)
     # a bigger batch against the sparse oracle (torch CPU transcendentals)
@@ -205,8 +244,46 @@ def test_wifi_sum_product_against_oracle_and_dense_reference(wcode, golden_dir):
     a = O.bp_decode(qc.H, llr, 10, 20)
     o = dec(wcode, llr, 10, 20, want=("llr_post", "hard", "syndrome"))
     assert np.array_equal(o["hard"], a["hard"]) and np.array_equal(o["syndrome"], a["syndrome"])
-    frac, worst_ok, mx = sp_close(o["llr_post"] / -2.0, a["t"])
+    frac, worst_ok, mx = sp_close(o["llr_post"] / -2.0, a["t"], sat_count(qc.H, a["x"]))
     assert frac >= FRAC_OK and worst_ok, (frac, mx)
+
+
+def test_wifi_4096_codewords_against_c_oracle(wcode):
+    """SURVEY 8(d) config 3 parity subset: the first 4096 codewords of the headline workload (BPSK/AWGN at Eb/N0 = 2 dB)
+    against the sparse oracle, sum-product AND min-sum.  Min-sum: everything bit-exact.  Sum-product: hard bits and
+    syndrome weights exact, marginals inside the sp_check bar with the oracle's own messages naming the saturated ones."""
+    qc = ieee80211n_1944_r12()
+    g = C.CGraph(qc.H)
+    rng = np.random.RandomState(1234)
+    B = 4096
+    c = qc.encode(rng.randint(0, 2, (B, qc.k)).astype(np.uint8))
+    sigma = (1.0 / (2 * 0.5 * 10 ** 0.2)) ** 0.5
+    llr = (-2.0 * ((1.0 - 2.0 * c) + sigma * rng.randn(B, qc.n)) / sigma ** 2).astype(np.float32)
+    ms = C.decode(g, llr, 10, 20.0, "minsum", want=("t", "hard", "syndrome"))
+    o = dec(wcode, llr, 10, 20, "minsum", want=("llr_post", "hard", "syndrome"))
+    assert np.array_equal(o["hard"], ms["hard"]) and np.array_equal(o["syndrome"], ms["syndrome"])
+    assert np.array_equal(o["llr_post"], -2.0 * ms["t"])
+    sp = C.decode(g, llr, 10, 20.0, "sp", want=("t", "hard", "syndrome", "x"))
+    o = dec(wcode, llr, 10, 20, "sp", want=("llr_post", "hard", "syndrome"))
+    assert np.array_equal(o["hard"], sp["hard"]) and np.array_equal(o["syndrome"], sp["syndrome"])
+    frac, worst, ok, hist = sp_check(o["llr_post"] / -2.0, sp["t"], sat_count(qc.H, sp["x"]))
+    assert frac >= FRAC_OK and ok, (frac, worst, hist.tolist())
+
+
+def test_default_code_4096_golden(dcode, golden_dir):
+    """B = 4096 vectors minted from the dense reference (oracle/make_golden.py): packed hard bits and
+    syndrome weights of all 4096 codewords bit-exact, marginals of the first 512 inside the sum-product bar."""
+    g = np.load(os.path.join(golden_dir, "bp_default_code_4096.npz"))
+    for name in g["names"]:
+        if f"{name}_llr" in g.files:
+            llr = g[f"{name}_llr"]
+        else:
+            llr = (np.random.RandomState(int(g[f"{name}_seed"])).randn(4096, 64) * float(g[f"{name}_scale"])).astype(np.float32)
+        o = dec(dcode, llr, int(g[f"{name}_iters"]), float(g[f"{name}_clamp"]), want=("llr_post", "hard_packed", "syndrome"))
+        assert np.array_equal(o["hard_packed"], g[f"{name}_hard"]), name
+        assert np.array_equal(o["syndrome"], g[f"{name}_syndrome"].astype(np.int32)), name
+        frac, ok, worst = sp_close(o["llr_post"][:512] / -2.0, g[f"{name}_t512"])
+        assert frac >= FRAC_OK and ok, (name, frac, worst)
 
 
 def test_input_dtypes_and_edge_batches(dcode, wcode):

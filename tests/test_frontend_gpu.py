@@ -93,3 +93,49 @@ def test_device_rng_noise_statistics():
     assert abs(k4 - 3.0) < 0.05                                            # gaussian kurtosis
     rx2, _ = transmit_symbols(sym, 64, snr, device_rng=True, seed=5)
     assert np.array_equal(rx, rx2)                                         # counter-based: reproducible
+
+
+@pytest.mark.parametrize("snr", [4, 15])
+def test_agc_quantizer_frontend_identical_inputs(g, snr):
+    """SURVEY 8(a) row a14, evaluate_quantized_snr.py:96-133, on the reference's OWN received samples
+    (frontend.npz snr*_rx_signal / snr*_noise) against its own LLRs (snr*_agc_llrs):
+    (i) the float64 drop-in functions (device quantizer + device DFT / LLR) to 1e-10;
+    (ii) the float32 simulator chain (the code the fused single-launch kernel runs) fed the same transmitted bits
+         and the same noise realisation: ADC levels identical, LLRs to single precision."""
+    import ofdm.ofdm_functions as F
+    from ldpc_b200.decoder import LdpcCode
+    from ldpc_b200.linksim import LinkConfig, sim_frontend
+    tag = f"snr{snr}"
+    ref = g[tag + "_agc_llrs"]
+    rx = g[tag + "_rx_signal"]
+    snr_lin = np.power(10, snr / 10)
+    # (i) the script's lines with the drop-in functions
+    factor = 10 / (.5 * (1 + 1 / snr_lin)) * 1.0
+    scaled = (factor * rx.reshape((-1, 32)).T).T.reshape((1, -1))
+    q = F.quantizer(scaled, 3, 10)
+    resc = q.reshape((-1, 32)).T / factor
+    llr64, _ = F.demodulate_signal(resc.T.reshape((1, -1)), 32, snr_lin)
+    assert llr64.shape == ref.shape
+    assert np.abs(llr64 - ref).max() < TOL * max(1.0, np.abs(ref).max())
+    # (ii) the simulator's float32 chain on the same bits and the same noise
+    H, _ = peg_64_32()
+    code = LdpcCode(H)
+    enc = g["enc"].reshape(-1, 64)
+    cwp = torch.as_tensor(np.packbits(enc, axis=1)).cuda()
+    noise = torch.as_tensor(g[tag + "_noise"].reshape(-1, 1, 32).astype(np.complex64)).cuda()
+    cfg = LinkConfig(snr_db=float(snr), ofdm_size=32, qbits=3, agc_mode=1, agc_clip=10.0, clip_ratio=1.0)
+    llr32, smp = sim_frontend(code, cfg, cwp, noise, want_samples=True)
+    llr32 = llr32.cpu().numpy().reshape(1, -1).astype(np.float64)
+    smp = smp.cpu().numpy().astype(np.float64)
+    _, qresc = LO.agc_quantized_frontend(rx, float(snr), 3, 1.0, 32, agc_clip=10)        # [32, n_ofdm] complex
+    step = 2 * 10 / (2 ** 3 - 1)
+    lev_ref = np.concatenate([qresc.real.T, qresc.imag.T], axis=1) * factor / step        # [n_ofdm, 64] ADC output in steps
+    lev_gpu = smp[:, :64] * factor / step
+    assert np.abs(lev_gpu - lev_ref).max() < 1e-4, "ADC output levels differ"          # same level for every sample
+    assert np.allclose(smp[:, 64], snr_lin, rtol=1e-6)
+    err = np.abs(llr32 - ref).max() / np.abs(ref).max()
+    assert err < 3e-6, err
+    # without a noise array the same entry point uses the simulator's Philox stream: statistics only
+    llr_rng = sim_frontend(code, cfg, cwp).cpu().numpy()
+    hard_ok = np.mean((llr_rng > 0) == (enc > 0))
+    assert hard_ok > (0.9 if snr == 4 else 0.97)

@@ -118,6 +118,54 @@ def test_quantized_link_matches_oracle_statistics(dsim):
     assert 0.008 < float(r["uncoded_ber"]) < 0.02                      # survey probe: 1.35e-2
 
 
+def _wilson(k, n, z=3.9):
+    """Wilson score interval of a binomial proportion (z = 3.9: 1e-4 two-sided)."""
+    p = k / n
+    d = 1 + z * z / n
+    c = (p + z * z / (2 * n)) / d
+    h = z * np.sqrt(p * (1 - p) / n + z * z / (4 * n * n)) / d
+    return c - h, c + h
+
+
+@pytest.mark.parametrize("qbits", [0, 3])
+def test_wifi1944_link_matches_oracle_chain(wsim, qbits):
+    """BASELINE config 4 at the oracle's size: n=1944 over OFDM-64 (16 symbols per codeword, 52 null subcarriers
+    in the last one), min-sum x10, 2^14 codewords per point at three SNRs.  The GPU counters (Philox noise) and
+    the oracle chain (numpy noise -> oracle/linksim_oracle.framed_link_llrs -> C oracle decoder) are independent
+    Monte-Carlo estimates of the same curve: uncoded BER, coded BER and BLER must agree inside binomial
+    confidence intervals."""
+    import c_oracle as C
+    from ldpc_b200.codes import ieee80211n_1944_r12
+    from ldpc_b200.linksim import LinkConfig, sim_run
+    qc = ieee80211n_1944_r12()
+    g = C.CGraph(qc.H)
+    Ncw = 1 << 14
+    rng = np.random.RandomState(2024 + qbits)
+    enc = qc.encode(rng.randint(0, 2, (Ncw, qc.k)).astype(np.uint8)).astype(np.float64)
+    for snr_db in ((1.75, 2.25, 2.75) if qbits == 0 else (3.0, 3.75, 4.5)):
+        np.random.seed(int(snr_db * 100) + qbits)
+        llr, _ = LO.framed_link_llrs(enc, snr_db, 64, qbits=qbits)
+        dec = C.decode(g, llr.astype(np.float32), 10, 20.0, "minsum", want=("hard",))["hard"]
+        m = LO.error_metrics(llr, dec, enc, qc.k)
+        c = sim_run(wsim, LinkConfig(snr_db=snr_db, ofdm_size=64, qbits=qbits, agc_mode=1, iters=10, update="minsum",
+                                     clamp_value=20.0, seed=31 + qbits), 0, Ncw).cpu().numpy()
+        assert c[3] == m["bits"] and c[4] == m["frames"]
+        # uncoded bit errors are independent per bit
+        lo, hi = _wilson(m["uncoded_errs"], m["bits"])
+        lo2, hi2 = _wilson(int(c[0]), int(c[3]))
+        assert lo <= hi2 and lo2 <= hi, (snr_db, "uncoded", m["uncoded_errs"], int(c[0]))
+        # frame errors are independent per frame
+        lo, hi = _wilson(m["frame_errs"], m["frames"])
+        lo2, hi2 = _wilson(int(c[2]), int(c[4]))
+        assert lo <= hi2 and lo2 <= hi, (snr_db, "bler", m["frame_errs"], int(c[2]))
+        # information-bit errors come in bursts of one frame: compare the mean burst size given the frame counts
+        if m["frame_errs"] >= 50 and c[2] >= 50:
+            b_o, b_g = m["info_errs"] / m["frame_errs"], c[1] / c[2]
+            assert abs(b_o - b_g) < 0.25 * max(b_o, b_g), (snr_db, "errors per bad frame", b_o, b_g)
+        else:
+            assert abs(m["info_errs"] - int(c[1])) < 60 * 50
+
+
 def test_sweep_single_rank(wsim):
     from ldpc_b200.linksim import LinkConfig, rates, sweep
     cfgs = [LinkConfig(snr_db=s, ofdm_size=64, iters=10, update="minsum", clamp_value=20.0, seed=1) for s in (0.0, 2.0, 4.0)]
