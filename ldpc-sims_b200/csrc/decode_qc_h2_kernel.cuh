@@ -1,25 +1,15 @@
-// decode_qc_h2.cu - f16x2 variant of the code-specialised min-sum decoder: every thread
+// decode_qc_h2_kernel.cuh - f16x2 variant of the code-specialised min-sum decoder: every thread
 // carries TWO codewords packed in one 32-bit register (half2), so each shared-memory word,
 // each HADD2 and each HMNMX2.XORSIGN serves two codewords.  Same plan (qc_plan.cuh), same
-// schedule and phases as decode_qc.cu; only the number format differs.
-//
-// Arithmetic ("min-sum f16", defined bit-exactly by oracle/bp_oracle.py::bp_decode_f16 - the
-// reference has neither min-sum nor half precision, bp/bp.py:27-31):
-//   Lh   = fp16_rn(clip(llr, +-32768)),  L' = -Lh
-//   V->C y_k = fp16(L' + S_k), S_k = P_k + Q_k two-sweep, every add rounded to fp16 (RN)
-//   C->V x_j = c (+) (+)_{i!=j} g(y_i), a (+) b = sign(a)sign(b) min(|a|,|b|), c = fp16_rn(clamp),
-//        g = identity (min-sum) | fp16(alpha_h * y) (normalized min-sum)
-//   t    = fp16(0.5 * fp16(L' + ((x_0 + x_1) + ...)));  outputs from float(t) exactly as fp32 path.
+// schedule and phases as decode_qc_kernel.cuh; only the number format differs (node_math_h2.cuh).
+#pragma once
 #include <cuda_fp16.h>
-
-#include <cstdlib>
 
 #include "common.cuh"
 #include "epilogue.cuh"
 #include "node_math.cuh"
 #include "node_math_h2.cuh"
 #include "qc_plan.cuh"
-#include "decode_qc_pers.cuh"
 
 namespace ldpc {
 
@@ -277,30 +267,6 @@ __global__ void __launch_bounds__((QcLayout<Code, CW>::THREADS)) decode_qc_h2_ke
         count_errors(hard_s, L::HARD_STRIDE, ncw, N, a.k_info, a.ref_packed + cw0 * ((N + 7) >> 3), a.counters,
                      scratch + 1);
     }
-}
-
-template <class Code, int CW, int UPD>
-static int launch_h2_one(const DecodeArgs &a, cudaStream_t s) {
-    using L = QcLayout<Code, CW>;
-    const size_t smem = L::MSG_BYTES + (size_t)2 * CW * L::HARD_STRIDE + sizeof(int) * (8 + 2 * CW);
-    const long long grid = (a.B + 2 * CW - 1) / (2 * CW);
-    if (grid > 0x7fffffffLL) { set_error("batch too large"); return LDPC_EINVAL; }
-    auto k = decode_qc_h2_kernel<Code, CW, UPD>;
-    LDPC_CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k<<<(int)grid, L::THREADS, smem, s>>>(a);
-    LDPC_CUDA_TRY(cudaGetLastError());
-    return LDPC_OK;
-}
-
-int launch_decode_qc_h2(int qc_id, const DecodeArgs &a, cudaStream_t s) {
-    if (a.B <= 0) return LDPC_OK;
-    if (qc_id != 0) { set_error("unknown QC specialisation %d", qc_id); return LDPC_EINVAL; }
-    static const int cw = [] { const char *e = getenv("LDPC_QC_H2_CW"); return e ? atoi(e) : 3; }();
-    if (a.update == UPD_MINSUM && cw == 6) return launch_h2_one<Wifi1944R12, 6, UPD_MINSUM>(a, s);
-    if (a.update == UPD_MINSUM) return launch_h2_one<Wifi1944R12, 3, UPD_MINSUM>(a, s);
-    if (a.update == UPD_NMS) return launch_h2_one<Wifi1944R12, 3, UPD_NMS>(a, s);
-    set_error("the f16x2 kernel implements min-sum and normalized min-sum only");
-    return LDPC_EUNSUPPORTED;
 }
 
 }  // namespace ldpc

@@ -1,23 +1,19 @@
 // decode_qc_pers.cuh - the persistent, TMA-fed form of the code-specialised decoder (fp32 and f16x2).
 //
-// Same plan (qc_plan.cuh), same node arithmetic (node_math*.cuh) and therefore the same bits as
-// decode_qc_kernel; what changes is the schedule around the two node phases:
-//   * ONE CTA per SM, two codeword GROUPS of TG threads each (a group = CWT codeword slots x Z lanes,
-//     codewords interleaved by lane exactly as in decode_qc.cu).  The CTA is persistent: group g of
-//     CTA b decodes tiles  (b*2 + g) + k * 2*gridDim.x.
-//   * the channel-LLR tile of the NEXT tile is fetched by one elected thread with a bulk copy
-//     (cp.async.bulk, completion on an mbarrier) into a per-group staging buffer while the current
-//     tile decodes (the per-batch host->device tensor of ofdm_functions.py:156 is the tile being staged);
-//     dtypes other than f32 / unaligned pointers take a cooperative convert-and-stage path.
-//   * a tile is a sequence of P = 2*iters + 1 SLOTS separated by barriers:
-//       slot 0      tail of the previous tile (bit packing, syndrome, counters) + LLR -> registers +
-//                   first variable phase (C->V messages are the zeros every caller passes)
-//       slot 2i-1   check phase i,   slot 2i  variable phase i+1        (i = 1 .. iters)
-//       slot 2*iters  marginal, hard decision, posterior store
-//     LOCK = true: the barriers are CTA-wide and group 1 runs ONE SLOT BEHIND group 0, so in every
-//     slot one group's ALU-bound check phase (FMNMX) overlaps the other's FMA/LSU-bound variable phase
-//     (anti-phase by construction).  LOCK = false: each group synchronises on its own named barrier
-//     and the two run free.
+// Same plan (qc_plan.cuh), same node arithmetic (node_math*.cuh) and therefore the same bits as decode_qc_kernel; what
+// changes is how a CTA gets its data and how the variable phase is ordered:
+//   * CTAs are persistent (two per SM): CTA b decodes tiles b, b + gridDim.x, ...
+//   * the channel-LLR tile of the NEXT tile is fetched by one elected thread with a bulk copy (cp.async.bulk, completion
+//     on an mbarrier -> SASS UBLKCP / SYNCS) into a staging buffer while the current tile decodes (the per-batch
+//     host->device tensor of ofdm_functions.py:156 is the tile being staged); threads then take their NB LLRs from shared
+//     memory with immediate offsets instead of 64-bit global address arithmetic.  Dtypes other than f32 / unaligned
+//     pointers take a cooperative convert-and-stage path through the same buffer.
+//   * the variable phase issues the shared-memory loads of the next batch of block columns before it computes and
+//     stores the current one (VarBatches, qc_plan.cuh): its pointers are run-time selections, so the compiler cannot
+//     reorder a load above a store by itself.
+// Schedules measured and REJECTED on B200 (profiles/r02_decoder_schedule_experiments.md): one 512-thread CTA per SM
+// with two codeword groups in lock-step anti-phase (CTA-wide barrier per half iteration, one group's check phase
+// against the other's variable phase), the same two groups free-running on named barriers, and a generic slot loop.
 #pragma once
 #include <type_traits>
 
@@ -57,14 +53,13 @@ __device__ __forceinline__ void named_bar_sync(int id, int count) { asm volatile
 template <class T> struct cpt_of { static constexpr int value = 1; };
 template <> struct cpt_of<__half2> { static constexpr int value = 2; };
 
-template <class Code, int CWT, int CPT, int NG = 2>
+template <class Code, int CWT, int CPT>
 struct PersLayout {
     static constexpr int Z = Code::Z, N = Code::NB * Z;
     static constexpr int NLOC = kQc<Code>.n_local, NSM = kQc<Code>.n_smem;
-    static constexpr int G = NG;                                   // codeword groups per CTA (2: one CTA per SM; 1: two CTAs per SM)
-    static constexpr int CWG = CWT * CPT;                          // codewords per group tile
-    static constexpr int TG = ((CWT * Z + 31) / 32) * 32;          // threads per group (warp multiple: the group index is warp-uniform)
-    static constexpr int THREADS = G * TG;
+    static constexpr int CWG = CWT * CPT;                          // codewords per tile
+    static constexpr int THREADS = ((CWT * Z + 31) / 32) * 32;
+    static constexpr int MIN_CTAS = THREADS <= 256 ? 2 : 1;
     static constexpr int HARD_STRIDE = (N + 15) & ~15;
     static constexpr size_t MSG_BYTES = (4 * (size_t)NSM * Z * CWT + 15) & ~size_t(15);
     static constexpr size_t STAGE_BYTES = (size_t)CWG * N * 4;    // f32 rows
@@ -72,7 +67,7 @@ struct PersLayout {
     static constexpr int SCR_INTS = 3 + 2 * CWG;                  // {uncoded, info, -} + frame flags [CWG] + syndrome weights [CWG]
     static constexpr size_t SCR_BYTES = (SCR_INTS * 4 + 15) & ~size_t(15);
     static constexpr size_t GROUP_BYTES = MSG_BYTES + STAGE_BYTES + HARD_BYTES + SCR_BYTES;
-    static constexpr size_t SMEM = 16 + G * GROUP_BYTES;          // two mbarriers in front
+    static constexpr size_t SMEM = 16 + GROUP_BYTES;              // the mbarrier in front
     static_assert(N % 4 == 0, "bulk copies move whole 16-byte units: the f32 row must be a multiple of 16 bytes");
 };
 
@@ -242,19 +237,21 @@ __device__ __forceinline__ void count_flush_group(int ncw, int n, unsigned long 
 }
 
 // =========================================================================================================
-template <class Code, int CWT, int UPD, class T, bool LOCK, int VB, int NG>
-__global__ void __launch_bounds__((PersLayout<Code, CWT, cpt_of<T>::value, NG>::THREADS), (NG == 1 ? 2 : 1)) decode_qc_pers_kernel(const DecodeArgs a) {
+// Persistent form of decode_qc_kernel (fixed iteration count, channel LLRs from global memory): the same phases in the
+// same order, but a CTA walks tiles  blockIdx.x, blockIdx.x + gridDim.x, ...  and the LLR tile of its NEXT tile is in
+// flight (bulk copy into `stage`) while the current one decodes.
+template <class Code, int CWT, int UPD, class T, int VB>
+__global__ void __launch_bounds__((PersLayout<Code, CWT, cpt_of<T>::value>::THREADS), (PersLayout<Code, CWT, cpt_of<T>::value>::MIN_CTAS))
+decode_qc_pers_kernel(const DecodeArgs a) {
     constexpr int CPT = cpt_of<T>::value;
-    using L = PersLayout<Code, CWT, CPT, NG>;
-    static_assert(NG == 2 || !LOCK, "the lock-step schedule pairs two groups of one CTA");
-    constexpr int Z = Code::Z, NB = Code::NB, MB = Code::MB, N = L::N, TG = L::TG, CWG = L::CWG;
+    using L = PersLayout<Code, CWT, CPT>;
+    constexpr int Z = Code::Z, NB = Code::NB, MB = Code::MB, N = L::N, TG = L::THREADS, CWG = L::CWG;
     static_assert(CPT == 1 || UPD == UPD_MINSUM || UPD == UPD_NMS, "the f16x2 format implements min-sum and normalized min-sum");
     extern __shared__ __align__(128) unsigned char smem_raw[];
 
-    const int g = threadIdx.x / TG;                                  // codeword group of this warp
-    const int tid = threadIdx.x - g * TG;
-    uint64_t *const mbar = reinterpret_cast<uint64_t *>(smem_raw) + g;
-    unsigned char *const grp = smem_raw + 16 + (size_t)g * L::GROUP_BYTES;
+    const int tid = threadIdx.x;
+    uint64_t *const mbar = reinterpret_cast<uint64_t *>(smem_raw);
+    unsigned char *const grp = smem_raw + 16;
     T *const msg_s = reinterpret_cast<T *>(grp);
     float *const stage = reinterpret_cast<float *>(grp + L::MSG_BYTES);
     uint8_t *const hard_s = grp + L::MSG_BYTES + L::STAGE_BYTES;
@@ -267,10 +264,6 @@ __global__ void __launch_bounds__((PersLayout<Code, CWT, cpt_of<T>::value, NG>::
     T *const hi = msg + Z * CWT;
 
     const long long ntiles = (a.B + CWG - 1) / CWG;
-    const long long tstride = (long long)gridDim.x * L::G;
-    const long long tfirst = (long long)blockIdx.x * L::G + g;
-    const int K = (int)((ntiles + tstride - 1) / tstride);           // tiles per group, the same for every group (trailing ones may be empty)
-    const int P = 2 * a.iters + 1;                                   // slots per tile
     const bool tma_ok = a.llr_dtype == LDPC_F32 && (reinterpret_cast<uintptr_t>(a.llr) & 15u) == 0;
     const int nbytes = (N + 7) >> 3;
 
@@ -290,7 +283,7 @@ __global__ void __launch_bounds__((PersLayout<Code, CWT, cpt_of<T>::value, NG>::
             bulk_g2s(stage, reinterpret_cast<const float *>(a.llr) + j * CWG * (long long)N, bytes, mbar);
         }
     };
-    auto fill_sync = [&](long long j) {                              // whole group: any dtype, any alignment
+    auto fill_sync = [&](long long j) {                              // whole CTA: any dtype, any alignment
         const int n = tile_ncw(j);
         const long long src = j * CWG * (long long)N;
         for (int i = tid; i < n * N; i += TG) stage[i] = load_llr(a.llr, a.llr_dtype, src + i);
@@ -299,42 +292,30 @@ __global__ void __launch_bounds__((PersLayout<Code, CWT, cpt_of<T>::value, NG>::
     T llr[NB];
     T loc[L::NLOC > 0 ? L::NLOC : 1];
 
-    // ---- phases (bodies as in decode_qc.cu) -------------------------------------------------------------
-    auto var_phase = [&](auto first_tag) {
-        constexpr bool FIRST = decltype(first_tag)::value;
+    auto var_phase_first = [&]() {                                  // C->V messages are the zeros every caller passes (ofdm_functions.py:157)
         static_for<NB>([&](auto cc) {
             constexpr int c = decltype(cc)::value;
             constexpr int D = kQc<Code>.col_deg[c];
             if constexpr (D > 0) {
                 T in[D], out[D];
-                T *ptr[D];
-                static_for<D>([&](auto kk) {
-                    constexpr int k = decltype(kk)::value;
-                    constexpr bool is_loc = kQc<Code>.col_loc[c][k];
-                    constexpr int slot = kQc<Code>.col_slot[c][k];
-                    if constexpr (is_loc) {
-                        ptr[k] = nullptr;
-                        in[k] = FIRST ? zero_of(T()) : loc[slot];
-                    } else {
-                        constexpr int s = kQc<Code>.col_eff[c][k];
-                        constexpr int off = (slot * Z - s) * CWT;
-                        ptr[k] = (t < s ? hi : lo) + off;
-                        in[k] = FIRST ? zero_of(T()) : *ptr[k];
-                    }
-                });
+                static_for<D>([&](auto kk) { in[decltype(kk)::value] = zero_of(T()); });
                 vnode<D, UPD>(in, llr[c], out);
                 static_for<D>([&](auto kk) {
                     constexpr int k = decltype(kk)::value;
                     constexpr bool is_loc = kQc<Code>.col_loc[c][k];
                     constexpr int slot = kQc<Code>.col_slot[c][k];
                     if constexpr (is_loc) loc[slot] = out[k];
-                    else *ptr[k] = out[k];
+                    else {
+                        constexpr int s = kQc<Code>.col_eff[c][k];
+                        constexpr int off = (slot * Z - s) * CWT;
+                        ((t < s ? hi : lo) + off)[0] = out[k];
+                    }
                 });
             }
         });
     };
-    // the same phase with the shared-memory loads of batch b+1 issued before batch b is computed and stored (VarBatches)
-    auto var_phase_pipe = [&]() {
+    // shared-memory loads of batch b+1 issued before batch b is computed and stored (VarBatches, qc_plan.cuh)
+    auto var_phase = [&]() {
         using VP = VarPipe<Code, CWT, UPD, T, (VB > 0 ? VB : 0)>;
         T inA[VP::VBW], inB[VP::VBW];
         T *pA[VP::VBW], *pB[VP::VBW];
@@ -397,23 +378,24 @@ __global__ void __launch_bounds__((PersLayout<Code, CWT, cpt_of<T>::value, NG>::
             });
             tm[c] = mnode<(D > 0 ? D : 1)>(in, D, llr[c]);
         });
-        auto tf = [&](int c, int h) -> float {                        // marginal of codeword h of this thread as a float
+        auto tfv = [&](auto cc, int h) -> float {                    // marginal of codeword h of this thread as a float
+            constexpr int c = decltype(cc)::value;
             if constexpr (CPT == 1) return tm[c];
             else return h == 0 ? __low2float(tm[c]) : __high2float(tm[c]);
         };
-        auto lf = [&](int c, int h) -> float {
-            if constexpr (CPT == 1) return llr[c];
-            else return h == 0 ? __low2float(llr[c]) : __high2float(llr[c]);
-        };
-        unsigned hb[CPT];
+        unsigned hb[CPT], cb[CPT];
         float tmin = CUDART_INF_F;
 #pragma unroll
         for (int h = 0; h < CPT; ++h) {
-            hb[h] = 0;
+            hb[h] = 0; cb[h] = 0;
             static_for<NB>([&](auto cc) {
                 constexpr int c = decltype(cc)::value;
-                const float v = tf(c, h);
+                const float v = tfv(cc, h);
+                float l;
+                if constexpr (CPT == 1) l = llr[c];
+                else l = h == 0 ? __low2float(llr[c]) : __high2float(llr[c]);
                 hb[h] |= (v < 0.0f ? 1u : 0u) << c;
+                cb[h] |= (l > 0.0f ? 1u : 0u) << c;
                 tmin = fminf(tmin, fabsf(v));
             });
         }
@@ -423,26 +405,31 @@ __global__ void __launch_bounds__((PersLayout<Code, CWT, cpt_of<T>::value, NG>::
                 hb[h] = 0;
                 static_for<NB>([&](auto cc) {
                     constexpr int c = decltype(cc)::value;
-                    hb[h] |= (unsigned)hard_bit(tf(c, h)) << c;
+                    hb[h] |= (unsigned)hard_bit(tfv(cc, h)) << c;
                 });
             }
         }
         const long long gbase = (cw0 + sl * CPT) * N;
         uint8_t *const hrow = hard_s + (sl * CPT) * L::HARD_STRIDE;
-        float *const post = a.llr_post ? a.llr_post + gbase : nullptr;
-        static_for<NB>([&](auto cc) {
-            constexpr int c = decltype(cc)::value;
-            constexpr int rho = kQc<Code>.rho[c];
-            int zv = t + rho;
-            if (zv >= Z) zv -= Z;
-            const int idx = c * Z + zv;
+        auto stores = [&](auto with_post) {                         // the output pointer is tested ONCE around the store loop
+            constexpr bool POST = decltype(with_post)::value;
+            float *const post = a.llr_post + gbase;
+            static_for<NB>([&](auto cc) {
+                constexpr int c = decltype(cc)::value;
+                constexpr int rho = kQc<Code>.rho[c];
+                int zv = t + rho;
+                if (zv >= Z) zv -= Z;
+                const int idx = c * Z + zv;
 #pragma unroll
-            for (int h = 0; h < CPT; ++h) {
-                if (h == 1 && !second) break;
-                hrow[h * L::HARD_STRIDE + idx] = (uint8_t)(((hb[h] >> c) & 1u) | ((lf(c, h) > 0.0f) ? 2u : 0u));
-                if (post) post[h * N + idx] = __fmul_rn(-2.0f, tf(c, h));
-            }
-        });
+                for (int h = 0; h < CPT; ++h) {
+                    if (h == 1 && !second) break;
+                    hrow[h * L::HARD_STRIDE + idx] = (uint8_t)(((hb[h] >> c) & 1u) | (((cb[h] >> c) & 1u) << 1));
+                    if constexpr (POST) post[h * N + idx] = __fmul_rn(-2.0f, tfv(cc, h));
+                }
+            });
+        };
+        if (a.llr_post) stores(std::true_type{});
+        else stores(std::false_type{});
         if (a.prob || a.hard) {                                      // byte / probability outputs: cold path
 #pragma unroll 1
             for (int c = 0; c < NB; ++c) {
@@ -454,7 +441,7 @@ __global__ void __launch_bounds__((PersLayout<Code, CWT, cpt_of<T>::value, NG>::
                     if (c == c2) {
                         rho = rho2;
 #pragma unroll
-                        for (int h = 0; h < CPT; ++h) tv[h] = tf(c2, h);
+                        for (int h = 0; h < CPT; ++h) tv[h] = tfv(cc, h);
                     }
                 });
                 int zv = t + rho;
@@ -503,76 +490,45 @@ __global__ void __launch_bounds__((PersLayout<Code, CWT, cpt_of<T>::value, NG>::
     }
     for (int i = tid; i < L::SCR_INTS; i += TG) scr[i] = 0;
     __syncthreads();
-    if (tma_ok) { if (tid == 0) issue_tma(tfirst); }
-    else fill_sync(tfirst);
+    if (tma_ok) { if (tid == 0) issue_tma(blockIdx.x); }
+    else fill_sync(blockIdx.x);
     __syncthreads();
 
-#ifdef LDPC_EXP_DELAY
-    if (g == 1) { const long long t0 = clock64(); while (clock64() - t0 < LDPC_EXP_DELAY) {} }   // timing experiment: start group 1 out of phase
-#endif
-    // ---- the slot loop -----------------------------------------------------------------------------------
-    int k = 0, s = 0;                                                // tile ordinal / slot of this group
-    long long jcur = tfirst;
-    int ncw = tile_ncw(jcur), ncw_prev = 0;
-    const int nsteps = K * P + 2 + (LOCK ? 1 : 0);
+    uint32_t parity = 0;
 #pragma unroll 1
-    for (int step = 0; step < nsteps; ++step) {
-        const bool run = !LOCK || step >= g;                         // LOCK: group 1 is one slot behind group 0
-        if (run && (k < K || s <= 1)) {
-            const bool act = (sl * CPT < ncw) && (t < Z);            // this thread holds a codeword of the current tile
-            const bool sec = sl * CPT + 1 < ncw;                     // (f16x2) the .y half holds one too
-            if (s == 0) {
-                if (ncw_prev > 0) {                                  // tail of the previous tile, part 1: reads hard_s
-                    const long long cwp = (jcur - tstride) * CWG;
-                    if (a.syndrome && (sl * CPT < ncw_prev) && (t < Z)) syndrome_phase(sl * CPT + 1 < ncw_prev);
-                    if (a.hard_packed) pack_hard_group(hard_s, L::HARD_STRIDE, ncw_prev, N, a.hard_packed + cwp * nbytes, tid, TG);
-                    if (a.counters) count_accumulate_group(hard_s, L::HARD_STRIDE, ncw_prev, N, a.k_info, a.ref_packed + cwp * nbytes, scr, tid, TG);
-                }
-                if (ncw > 0) {
-                    if (tma_ok) mbar_wait(mbar, (uint32_t)(k & 1));
-                    if (act) {
-                        load_llr_regs(sec);
-                        var_phase(std::true_type{});
-                    }
-                }
-            } else if (s == P - 1) {
-                if (ncw > 0) {
-                    if (act) marginal_phase(jcur * CWG, sec);
-                    if (!tma_ok) fill_sync(jcur + tstride);
-                }
-            } else {
-                if (s == 1) {
-                    if (ncw_prev > 0) {                              // tail of the previous tile, part 2: per-codeword words
-                        const long long cwp = (jcur - tstride) * CWG;
-                        if (tid < ncw_prev) {
-                            if (a.syndrome) { a.syndrome[cwp + tid] = scr[3 + CWG + tid]; scr[3 + CWG + tid] = 0; }
-                            if (a.iters_used) a.iters_used[cwp + tid] = a.iters;
-                        }
-                        if (a.counters && tid == 32) count_flush_group(ncw_prev, N, a.counters, scr);
-                    }
-                    if (tma_ok && tid == 0 && ncw > 0) issue_tma(jcur + tstride);   // every thread has taken its LLRs (barrier of slot 0)
-                }
-                if (act) {
-                    if (s & 1) check_phase();
-                    else if constexpr (VB >= 0) var_phase_pipe();
-                    else var_phase(std::false_type{});
-                }
-            }
+    for (long long j = blockIdx.x; j < ntiles; j += gridDim.x) {
+        const int ncw = tile_ncw(j);
+        const long long cw0 = j * CWG;
+        const bool act = (sl * CPT < ncw) && (t < Z);                // this thread holds a codeword of the tile
+        const bool sec = sl * CPT + 1 < ncw;                         // (f16x2) the .y half holds one too
+        if (tma_ok) { mbar_wait(mbar, parity); parity ^= 1u; }
+        if (act) {
+            load_llr_regs(sec);
+            var_phase_first();
         }
-#ifdef LDPC_EXP_NOBAR
-        if (step < 0) named_bar_sync(1 + g, TG);                    // timing experiment only: phases not separated (results wrong)
-#else
-        if constexpr (LOCK) __syncthreads();
-        else named_bar_sync(1 + g, TG);
-#endif
-        if (run) {
-            if (++s == P && k < K) {
-                s = 0;
-                ++k;
-                ncw_prev = ncw;
-                jcur += tstride;
-                ncw = (k < K) ? tile_ncw(jcur) : 0;
-            }
+        __syncthreads();                                             // every thread has taken its LLRs: the staging buffer is free
+        if (tma_ok && tid == 0) issue_tma(j + gridDim.x);
+        if (act) check_phase();
+        __syncthreads();
+#pragma unroll 1
+        for (int it = 1; it < a.iters; ++it) {
+            if (act) var_phase();
+            __syncthreads();
+            if (act) check_phase();
+            __syncthreads();
+        }
+        if (act) marginal_phase(cw0, sec);
+        if (!tma_ok) fill_sync(j + gridDim.x);
+        __syncthreads();
+        // ---- tail: everything that reads the tile's hard decisions from shared memory ------------------------
+        if (a.hard_packed) pack_hard_group(hard_s, L::HARD_STRIDE, ncw, N, a.hard_packed + cw0 * nbytes, tid, TG);
+        if (a.iters_used && tid < ncw) a.iters_used[cw0 + tid] = a.iters;
+        if (a.syndrome || a.counters) {
+            if (a.syndrome && act) syndrome_phase(sec);
+            if (a.counters) count_accumulate_group(hard_s, L::HARD_STRIDE, ncw, N, a.k_info, a.ref_packed + cw0 * nbytes, scr, tid, TG);
+            __syncthreads();
+            if (a.syndrome && tid < ncw) { a.syndrome[cw0 + tid] = scr[3 + CWG + tid]; scr[3 + CWG + tid] = 0; }
+            if (a.counters && tid == 32) count_flush_group(ncw, N, a.counters, scr);
         }
     }
 }
@@ -590,14 +546,13 @@ inline int device_sm_count() {
     return cached[dev];
 }
 
-template <class Code, int CWT, int UPD, class T, bool LOCK, int VB, int NG = 2>
+template <class Code, int CWT, int UPD, class T, int VB>
 int launch_qc_pers(const DecodeArgs &a, cudaStream_t s) {
-    using L = PersLayout<Code, CWT, cpt_of<T>::value, NG>;
+    using L = PersLayout<Code, CWT, cpt_of<T>::value>;
     const long long ntiles = (a.B + L::CWG - 1) / L::CWG;
-    const long long want = (ntiles + L::G - 1) / L::G;
-    const long long slots = (long long)device_sm_count() * (NG == 1 ? 2 : 1);   // persistent CTAs: one (two groups) or two (one group) per SM
-    const int grid = (int)(want < slots ? want : slots);
-    auto k = decode_qc_pers_kernel<Code, CWT, UPD, T, LOCK, VB, NG>;
+    const long long slots = (long long)device_sm_count() * L::MIN_CTAS;      // persistent CTAs: as many as are resident at once
+    const int grid = (int)(ntiles < slots ? ntiles : slots);
+    auto k = decode_qc_pers_kernel<Code, CWT, UPD, T, VB>;
     LDPC_CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::SMEM));
     k<<<grid, L::THREADS, L::SMEM, s>>>(a);
     LDPC_CUDA_TRY(cudaGetLastError());

@@ -222,7 +222,8 @@ int decode_dispatch(const ldpc_code *code, const DecodeArgs &a, cudaStream_t s) 
         if (code->precision == LDPC_PREC_F16X2 && (a.update == LDPC_UPDATE_MINSUM || a.update == LDPC_UPDATE_NMS) &&
             !a.early_exit && !a.iters_used)
             return launch_decode_qc_h2(code->qc_id, a, s);
-        return launch_decode_qc(code->qc_id, a, s);
+        const int rc = launch_decode_qc(code->qc_id, a, s);
+        if (rc != LDPC_EUNSUPPORTED) return rc;            // a combination this code was not compiled for: generic kernel below
     }
     if (code->kernel == LDPC_KERNEL_QC_RT && a.x0 == nullptr && a.x_out == nullptr && !a.early_exit)
         return launch_decode_qc_rt(code->d_qc_rt, code->qc_Z, code->qc_mb, code->qc_nb, code->qc_nblk, code->max_dv, code->max_dc, a, s);

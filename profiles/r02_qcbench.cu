@@ -11,8 +11,8 @@
 #include <cstring>
 #include <vector>
 
-#include "decode_qc.cu"
-#include "decode_qc_h2.cu"
+#include "decode_qc_code.cuh"
+#include "decode_qc_pers.cuh"
 
 namespace ldpc {
 void set_error(const char *fmt, ...) {
@@ -134,17 +134,21 @@ int main(int argc, char **argv) {
         // ---- reference: the round-1 kernels -------------------------------------------------------------------
         DecodeArgs ar = make_args(b, iters, UPD_MINSUM, true);
         if (fmt == 0) {
-            const float ms = time_ms([&] { launch_decode_qc(0, ar, 0); }, reps);
+            const float ms = time_ms([&] { QcCodeImpl<Wifi1944R12, 3, true>::decode(ar, 0); }, reps);
             printf("%-44s %8.3f ms  %7.2f Gbit/s\n", "round-1 decode_qc_kernel<CW=3> fp32", ms, b.B * 972.0 / (ms * 1e-3) / 1e9);
         } else {
-            const float ms = time_ms([&] { launch_decode_qc_h2(0, ar, 0); }, reps);
+            const float ms = time_ms([&] { QcCodeImpl<Wifi1944R12, 3, true>::decode_h2(ar, 0); }, reps);
             printf("%-44s %8.3f ms  %7.2f Gbit/s\n", "round-1 decode_qc_h2_kernel<3 pairs> f16x2", ms, b.B * 972.0 / (ms * 1e-3) / 1e9);
         }
         CK(cudaDeviceSynchronize());
         DecodeArgs av = make_args(b, iters, UPD_MINSUM, false);
         if (fmt == 0) {
-            run_variant("pers fp32 G2 free VB=6", b, reps, [&] { launch_qc_pers<Wifi1944R12, 3, UPD_MINSUM, float, false, 6, 2>(av, 0); });
-            run_variant("pers fp32 G1 VB=6", b, reps, [&] { launch_qc_pers<Wifi1944R12, 3, UPD_MINSUM, float, false, 6, 1>(av, 0); });
+            run_variant("pers fp32 VB=0", b, reps, [&] { launch_qc_pers<Wifi1944R12, 3, UPD_MINSUM, float, 0>(av, 0); });
+            run_variant("pers fp32 VB=6", b, reps, [&] { launch_qc_pers<Wifi1944R12, 3, UPD_MINSUM, float, 6>(av, 0); });
+            run_variant("pers fp32 VB=11", b, reps, [&] { launch_qc_pers<Wifi1944R12, 3, UPD_MINSUM, float, 11>(av, 0); });
+        } else {
+            run_variant("pers f16x2 VB=0", b, reps, [&] { launch_qc_pers<Wifi1944R12, 3, UPD_MINSUM, __half2, 0>(av, 0); });
+            run_variant("pers f16x2 VB=6", b, reps, [&] { launch_qc_pers<Wifi1944R12, 3, UPD_MINSUM, __half2, 6>(av, 0); });
         }
     }
     return 0;

@@ -35,6 +35,60 @@ def test_wifi_structure():
     assert detect_qc(H, 80) is None
 
 
+def test_wifi_family_structure():
+    """All twelve IEEE 802.11n prototypes (Z in {27, 54, 81}, rates 1/2 .. 5/6).  The shift values are
+    transcribed from memory (see ldpc_b200/codes.py); these are the structural invariants the kernels and the
+    linear-time encoder rely on, and they hold for every table shipped."""
+    from ldpc_b200.codes import WIFI_LENGTHS, WIFI_RATES, ieee80211n, ieee80211n_family
+    fam = ieee80211n_family()
+    assert len(fam) == 12 and len({q.name for q in fam}) == 12
+    rate_mb = {"1/2": 12, "2/3": 8, "3/4": 6, "5/6": 4}
+    for n in WIFI_LENGTHS:
+        for rate in WIFI_RATES:
+            qc = ieee80211n(n, rate)
+            P, Z, mb, nb = qc.proto, qc.Z, qc.mb, qc.nb
+            assert (nb, mb, Z) == (24, rate_mb[rate], n // 24) and qc.n == n and qc.k == n - mb * Z
+            assert P.min() >= -1 and P.max() < Z
+            kb = nb - mb
+            # information part: every block column carries at least two blocks, every row has the same degree +-1
+            deg_r = (P >= 0).sum(1)
+            assert deg_r.max() - deg_r.min() <= 1 and (P[:, :kb] >= 0).sum(0).min() >= 2
+            # parity part [h | T]: T dual-diagonal with shift 0, h = (1, 0, 1) at the top row, one middle row, the bottom row
+            for j in range(mb - 1):
+                col = P[:, kb + 1 + j]
+                assert col[j] == 0 and col[j + 1] == 0 and (np.delete(col, [j, j + 1]) == -1).all()
+            hr = [r for r in range(mb) if P[r, kb] >= 0]
+            assert len(hr) == 3 and hr[0] == 0 and hr[2] == mb - 1 and [int(P[r, kb]) for r in hr] == [1, 0, 1]
+            H = qc.H
+            assert H.shape == (mb * Z, n) and int(H.sum()) == int((P >= 0).sum()) * Z
+            assert gf2_rank(H) == mb * Z
+            assert np.array_equal(detect_qc(H, Z), P)
+            u = np.random.RandomState(n + mb).randint(0, 2, (8, qc.k)).astype(np.uint8)
+            c = qc.encode(u)                                       # linear-time dual-diagonal encoder
+            assert np.array_equal(c[:, :qc.k], u) and not ((H.astype(np.int64) @ c.T.astype(np.int64)) % 2).any()
+    with pytest.raises(ValueError):
+        ieee80211n(1944, "7/8")
+    assert np.array_equal(ieee80211n(1944, "1/2").proto, ieee80211n_1944_r12().proto)
+
+
+def test_compiled_prototype_header_matches_code_library():
+    """csrc/qc_protos.cuh (+ qc_plan.cuh for the headline code) is generated from ldpc_b200/codes.py: the compiled tables are
+    the library's tables (ldpc_code_create only selects a compiled kernel when they agree entry by entry)."""
+    import os, re
+    from ldpc_b200.codes import ieee80211n
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    txt = open(os.path.join(root, "ldpc-sims_b200", "csrc", "qc_protos.cuh")).read() + \
+        open(os.path.join(root, "ldpc-sims_b200", "csrc", "qc_plan.cuh")).read()
+    found = 0
+    for m in re.finditer(r"struct Wifi(\d+)R(\d)(\d) \{.*?proto\[MB\]\[NB\] = \{(.*?)\};", txt, re.S):
+        n, a, b, body = int(m.group(1)), m.group(2), m.group(3), m.group(4)
+        vals = np.array([int(v) for v in re.findall(r"-?\d+", body)], dtype=np.int16)
+        qc = ieee80211n(n, f"{a}/{b}")
+        assert np.array_equal(vals.reshape(qc.proto.shape), qc.proto), m.group(0)[:40]
+        found += 1
+    assert found == 12
+
+
 def test_wifi_encoder_matches_dense_generator():
     qc = ieee80211n_1944_r12()
     rng = np.random.RandomState(0)

@@ -512,3 +512,57 @@ def test_int8_llr_input_equals_float_input():
             ha = decode_host(code, q, 6, 20.0, update="minsum", want=("hard_packed", "syndrome"))
             hb = decode_host(code, q.astype(np.float32), 6, 20.0, update="minsum", want=("hard_packed", "syndrome"))
             assert np.array_equal(ha["hard_packed"], hb["hard_packed"]) and np.array_equal(ha["syndrome"], hb["syndrome"])
+
+
+FAMILY = [(n, r) for n in (648, 1296, 1944) for r in ("1/2", "2/3", "3/4", "5/6")]
+
+
+@pytest.mark.parametrize("n,rate", FAMILY)
+def test_wifi_family_compiled_kernels_against_oracle(n, rate):
+    """every IEEE 802.11n prototype runs on the code-compiled kernel (kernel == qc) and matches the
+    sparse oracle: min-sum family bit-exact (marginals, hard bits, syndrome weights - ragged batch, every update rule),
+    sum-product hard bits / syndromes exact and marginals inside the sum-product bar, early termination (min-sum) equal
+    to the oracle's frozen-codeword schedule, f16x2 bit-exact against its own oracle."""
+    from ldpc_b200.codes import ieee80211n
+    qc = ieee80211n(n, rate)
+    code = LdpcCode(qc.H, qc_Z=qc.Z, qc_proto=qc.proto)
+    assert code.kernel == 1, "no compiled specialisation selected"
+    g = C.CGraph(qc.H)
+    rng = np.random.RandomState(n + int(rate[0]))
+    B = 301
+    c = qc.encode(rng.randint(0, 2, (B, qc.k)).astype(np.uint8))
+    R = qc.k / qc.n
+    sigma = (1.0 / (2 * R * 10 ** (0.1 * (1.5 + 2.5 * R)))) ** 0.5          # around each code's waterfall
+    llr = (-2.0 * ((1.0 - 2.0 * c) + sigma * rng.randn(B, qc.n)) / sigma ** 2).astype(np.float32)
+    for update, param in (("minsum", 1.0), ("nms", 0.8125), ("oms", 0.35)):
+        ref = C.decode(g, llr, 6, 20.0, update, param, want=("t", "hard", "syndrome"))
+        o = dec(code, llr, 6, 20, update, param, want=("llr_post", "hard", "hard_packed", "syndrome"))
+        assert np.array_equal(o["llr_post"], -2.0 * ref["t"]), (update, "marginals")
+        assert np.array_equal(o["hard"], ref["hard"]) and np.array_equal(o["syndrome"], ref["syndrome"]), update
+        assert np.array_equal(o["hard_packed"], np.packbits(ref["hard"], axis=1)), update
+    sp = C.decode(g, llr, 6, 20.0, "sp", want=("t", "hard", "syndrome", "x"))
+    o = dec(code, llr, 6, 20, "sp", want=("llr_post", "hard", "syndrome"))
+    assert np.mean(o["hard"] != sp["hard"]) < 2e-5 and np.mean(o["syndrome"] != sp["syndrome"]) < 0.02
+    frac, ok, worst = sp_close(o["llr_post"] / -2.0, sp["t"], sat_count(qc.H, sp["x"]))
+    assert frac >= FRAC_OK and ok, (frac, worst)
+    # the generic kernel (no structure given) produces the same bits as the compiled one
+    gen = LdpcCode(qc.H, qc_Z=0)
+    assert gen.kernel == 0
+    a = dec(code, llr[:64], 4, 20, "minsum", want=("llr_post", "syndrome"))
+    b = dec(gen, llr[:64], 4, 20, "minsum", want=("llr_post", "syndrome"))
+    assert np.array_equal(a["llr_post"], b["llr_post"]) and np.array_equal(a["syndrome"], b["syndrome"])
+    # early termination, min-sum (compiled for every code) and another rule (generic-kernel fall-back off the headline code)
+    for update in ("minsum", "oms"):
+        ee = code.decode(torch.as_tensor(llr).cuda(), 20, 20.0, update=update, param=0.35 if update == "oms" else 1.0,
+                         early_exit=True, want=("hard", "syndrome", "iters_used"))
+        full = dec(code, llr, 20, 20, update, 0.35 if update == "oms" else 1.0, want=("hard", "syndrome"))
+        it = ee["iters_used"].cpu().numpy()
+        conv = it < 20
+        assert conv.any() and (ee["syndrome"].cpu().numpy()[conv] == 0).all()
+        assert np.array_equal(ee["hard"].cpu().numpy()[~conv], full["hard"][~conv])
+    # f16x2
+    code.set_precision("f16")
+    f = O.bp_decode_f16(qc.H, llr[:96], 5, 20.0, update="minsum")
+    o = dec(code, llr[:96], 5, 20, "minsum", want=("llr_post", "hard"))
+    assert np.array_equal(o["hard"], f["hard"]) and np.array_equal(o["llr_post"], (-2.0 * f["t"]).astype(np.float32))
+    code.set_precision("f32")

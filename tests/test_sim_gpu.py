@@ -188,3 +188,26 @@ def test_single_launch_simulator_equals_three_launch_chain(wsim, N, update, qbit
     chain = sim_run(wsim, LinkConfig(force_unfused=True, **kw), 12345, 1000).cpu().numpy()
     assert fused.tolist() == chain.tolist()
     assert fused[4] == 1000 and fused[0] > 0
+
+
+@pytest.mark.parametrize("n,rate", [(648, "1/2"), (648, "5/6"), (1296, "3/4"), (1944, "2/3"), (1944, "5/6")])
+def test_wifi_family_single_launch_simulator(n, rate):
+    """The other compiled 802.11n codes in the single-launch simulator (device dual-diagonal encoder of that prototype,
+    OFDM-64, min-sum): counters equal to the three-launch chain, transmitted words are codewords of H."""
+    from ldpc_b200.codes import ieee80211n
+    from ldpc_b200.decoder import LdpcCode
+    from ldpc_b200.linksim import LinkConfig, attach_generator, sim_generate, sim_run
+    qc = ieee80211n(n, rate)
+    code = attach_generator(LdpcCode(qc.H, qc_Z=qc.Z, qc_proto=qc.proto))
+    assert code.kernel == 1
+    R = qc.k / qc.n
+    kw = dict(snr_db=10 * np.log10(2 * R) + 1.5 + 2.5 * R, ofdm_size=64, qbits=0, iters=8, update="minsum", clamp_value=20.0, seed=5 + n)
+    fused = sim_run(code, LinkConfig(**kw), 777, 1001).cpu().numpy()
+    chain = sim_run(code, LinkConfig(force_unfused=True, **kw), 777, 1001).cpu().numpy()
+    assert fused.tolist() == chain.tolist()
+    assert fused[4] == 1001 and fused[3] == 1001 * n and 0 < fused[0] < fused[3] // 4 and fused[2] < 1001
+    cwp, _ = sim_generate(code, LinkConfig(**kw), 777, 64)
+    cw = np.unpackbits(cwp.cpu().numpy(), axis=1)[:, :n]
+    assert not ((qc.H.astype(np.int64) @ cw.T.astype(np.int64)) % 2).any()
+    u = cw[:, :qc.k]
+    assert np.array_equal(qc.encode(u), cw)                      # the device encoder is the library's linear-time encoder
