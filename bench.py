@@ -44,6 +44,8 @@ def parse():
     ap.add_argument("--no-sp", action="store_true", help="skip the sum-product measurement")
     ap.add_argument("--no-nn", action="store_true", help="skip the NN-demapper link (BASELINE.json configs[4])")
     ap.add_argument("--no-train", action="store_true", help="skip the weighted-BP training step (SURVEY 8f rank 2)")
+    ap.add_argument("--no-numa-bind", action="store_true", help="do not pin the rank to the NUMA node of its GPU")
+    ap.add_argument("--e2e-chunk", type=int, default=16384, help="codewords per H2D / decode / D2H chunk of the host pipeline")
     ap.add_argument("--no-sweep", action="store_true", help="skip the sharded BER/FER sweep with its all-reduce (BASELINE.json configs[3])")
     ap.add_argument("--sweep-codewords", type=int, default=1 << 19, help="codewords per SNR point of the sweep, TOTAL over all GPUs (strong scaling)")
     ap.add_argument("--nn-symbols", type=int, default=1 << 20, help="OFDM symbols per GPU of the NN-demapper measurement")
@@ -159,6 +161,37 @@ class Clocks:
     def summary(self):
         s = sorted(self.samples)
         return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+
+
+def bind_to_gpu_numa(index):
+    """Pin this rank's host threads (and therefore its first-touch pinned allocations) to the NUMA node its GPU hangs off:
+    with 8 ranks on a two-socket box a staging buffer on the far socket crosses the inter-socket link on every H2D copy.
+    Returns a small record for the JSON line; never fails the run."""
+    rec = {"bound": False}
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(index)).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        dom, rest = bus.split(":", 1)
+        sysfs = f"/sys/bus/pci/devices/{dom[-4:].lower()}:{rest.lower()}/numa_node"
+        node = int(open(sysfs).read().strip())
+        rec["pci"] = bus
+        rec["numa_node"] = node
+        if node >= 0:
+            cpus = set()
+            for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+                lo, _, hi = part.partition("-")
+                cpus.update(range(int(lo), int(hi or lo) + 1))
+            allowed = os.sched_getaffinity(0)
+            use = cpus & allowed
+            if use:
+                os.sched_setaffinity(0, use)
+                rec["bound"] = True
+                rec["cpus"] = len(use)
+    except Exception as e:                                  # no NVML / no sysfs (containers): run unbound
+        rec["error"] = str(e)[:80]
+    return rec
 
 
 def bench_nn(a, dev, world, barrier, peaks):
@@ -355,6 +388,7 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     # NCCL_DEBUG is left exactly as the launcher set it: NCCL writes its log lines to stdout, this script prints ONE
     # line that starts with '{' - a consumer takes that line (torchrun interleaves the ranks' output anyway).
+    numa = bind_to_gpu_numa(local) if not a.no_numa_bind else {"bound": False}
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
@@ -540,14 +574,19 @@ def main():
 
         def e2e_step():
             N.check(lib.ldpc_decode_host(code._h, h_llr.data_ptr(), N.F32, Be, a.iters, upd, a.clamp, 1.0,
-                                         None, h_packed.data_ptr(), None, None, 16384))
+                                         None, h_packed.data_ptr(), None, None, a.e2e_chunk))
         # raw pinned H2D bandwidth of this box, for context
         d_tmp = torch.empty_like(h_llr, device=dev)
-        torch.cuda.synchronize()
+        barrier()                                            # all ranks copy at the same time: the rate the box sustains under load
         t0 = time.perf_counter()
-        d_tmp.copy_(h_llr, non_blocking=True)
+        for _ in range(3):
+            d_tmp.copy_(h_llr, non_blocking=True)
         torch.cuda.synchronize()
-        h2d_gbs = h_llr.numel() * 4 / (time.perf_counter() - t0) / 1e9
+        h2d_gbs = 3 * h_llr.numel() * 4 / (time.perf_counter() - t0) / 1e9
+        if world > 1:
+            hb = torch.tensor([h2d_gbs], device=dev, dtype=torch.float64)
+            dist.all_reduce(hb, op=dist.ReduceOp.MIN)
+            h2d_gbs = float(hb.item())
         del d_tmp
         for _ in range(2):
             e2e_step()
@@ -562,6 +601,8 @@ def main():
         e2e = Be * world * a.steps * K_CODE / float(dt.item()) / 1e9
         out["e2e"] = {"value": e2e, "unit": "Gbit/s", "h2d_bytes_per_step": Be * qc.n * 4,
                       "d2h_bytes_per_step": Be * code.packed_bytes, "codewords_per_step": Be, "pinned_h2d_gbs": h2d_gbs,
+                      "pinned_h2d_note": "slowest rank, all ranks copying concurrently", "chunk_codewords": a.e2e_chunk, "numa": numa,
+                      "pcie_ceiling_gbps": h2d_gbs * 1e9 / (qc.n * 4) * K_CODE / 1e9 * world,
                       "api": "ldpc_decode_host (C ABI behind ofdm_functions.decode_bits), pinned f32 LLRs in, packed bits out"}
         assert torch.equal(h_packed.to(dev), packed[:Be]), "e2e result differs from the device path"
         # the same call with receiver-quantised int8 LLRs (LDPC_I8: a quarter of the PCIe bytes); NOT the headline - the

@@ -46,7 +46,10 @@ enum { LDPC_F32 = 0, LDPC_F64 = 1, LDPC_F16 = 2, LDPC_I8 = 3 };   /* I8: receive
 
 /* ---- which kernel a code handle dispatches to ---------------------------------------- */
 enum { LDPC_KERNEL_GENERIC = 0, LDPC_KERNEL_QC = 1, LDPC_KERNEL_TINY = 2 /* register-resident, one thread per codeword: the reference's default (64,32) code */,
-       LDPC_KERNEL_QC_RT = 3 /* any quasi-cyclic code, prototype matrix at run time (qc_Z / qc_proto without a compiled specialisation) */ };
+       LDPC_KERNEL_QC_RT = 3 /* any quasi-cyclic code, prototype matrix at run time (qc_Z / qc_proto without a compiled specialisation) */,
+       LDPC_KERNEL_QC_TMA = 4 /* opt-in (ldpc_code_set_kernel): the persistent form of the compiled kernel - CTAs loop over codeword tiles,
+                                 the next tile's LLRs arrive by cp.async.bulk while the current one decodes; same bits as LDPC_KERNEL_QC,
+                                 measured 2 % slower on B200 (HBM is at 9 % of its bandwidth: there is no load latency left to hide) */ };
 
 typedef struct ldpc_code ldpc_code_t;
 typedef void *ldpc_stream_t;             /* a cudaStream_t (CUstream); NULL = default stream */

@@ -91,6 +91,7 @@ int launch_decode_generic(const GraphTables &g, int max_dv, int max_dc, const De
 bool qc_kernel_available(int Z, int mb, int nb, const int16_t *proto);
 int launch_decode_qc(int qc_id, const DecodeArgs &a, cudaStream_t s);
 int launch_decode_qc_h2(int qc_id, const DecodeArgs &a, cudaStream_t s);
+int launch_decode_qc_tma(int qc_id, const DecodeArgs &a, cudaStream_t s);   // LDPC_EUNSUPPORTED -> launch_decode_qc
 struct LinkParams;
 int launch_sim_fused_qc(int qc_id, const DecodeArgs &a, const LinkParams &lp, cudaStream_t s);   // LDPC_EUNSUPPORTED -> use the 3-launch chain
 int qc_lookup(int Z, int mb, int nb, const int16_t *proto);   // -1 if no compiled specialisation

@@ -5,6 +5,7 @@
 #pragma once
 #include "decode_qc_kernel.cuh"
 #include "decode_qc_h2_kernel.cuh"
+#include "decode_qc_pers.cuh"
 #include "qc_protos.cuh"
 
 namespace ldpc {
@@ -15,6 +16,7 @@ struct QcCodeEntry {
     int (*decode)(const DecodeArgs &, cudaStream_t);
     int (*decode_h2)(const DecodeArgs &, cudaStream_t);                        // f16x2: min-sum / normalized min-sum
     int (*sim_fused)(const DecodeArgs &, const LinkParams &, cudaStream_t);    // LDPC_EUNSUPPORTED -> three-launch chain
+    int (*decode_tma)(const DecodeArgs &, cudaStream_t);                       // persistent / bulk-copy form (LDPC_KERNEL_QC_TMA); LDPC_EUNSUPPORTED -> decode
     void (*plan_info)(int out[4]);
 };
 
@@ -112,7 +114,21 @@ struct QcCodeImpl {
         return LDPC_EUNSUPPORTED;
     }
 
-    static QcCodeEntry entry(const char *name) { return QcCodeEntry{name, matches, decode, decode_h2, sim_fused, plan_info}; }
+    // persistent, bulk-copy-fed form (decode_qc_pers.cuh): fixed iteration count >= 1, compiled for the headline code
+    static int decode_tma(const DecodeArgs &a, cudaStream_t s) {
+        if constexpr (FULL) {
+            if (a.B <= 0) return LDPC_OK;
+            if (a.early_exit || a.iters < 1) return LDPC_EUNSUPPORTED;
+            switch (a.update) {
+                case UPD_SP: return launch_qc_pers<Code, CW, UPD_SP, float, 6>(a, s);
+                case UPD_MINSUM: return launch_qc_pers<Code, CW, UPD_MINSUM, float, 6>(a, s);
+                default: return LDPC_EUNSUPPORTED;
+            }
+        }
+        return LDPC_EUNSUPPORTED;
+    }
+
+    static QcCodeEntry entry(const char *name) { return QcCodeEntry{name, matches, decode, decode_h2, sim_fused, decode_tma, plan_info}; }
 };
 
 // codewords (fp32) / codeword pairs (f16x2) per CTA: as close to 256 threads as Z allows (two CTAs per SM)

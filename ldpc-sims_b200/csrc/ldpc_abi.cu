@@ -175,7 +175,7 @@ int ldpc_code_set_precision(ldpc_code_t *code, int precision) {
 int ldpc_code_set_kernel(ldpc_code_t *code, int kernel) {
     if (!code) { set_error("null code"); return LDPC_EINVAL; }
     if (kernel == LDPC_KERNEL_GENERIC) { code->kernel = kernel; return LDPC_OK; }
-    if (kernel == LDPC_KERNEL_QC && code->qc_id >= 0) { code->kernel = kernel; return LDPC_OK; }
+    if ((kernel == LDPC_KERNEL_QC || kernel == LDPC_KERNEL_QC_TMA) && code->qc_id >= 0) { code->kernel = kernel; return LDPC_OK; }
     if (kernel == LDPC_KERNEL_TINY && code->tiny_id >= 0) { code->kernel = kernel; return LDPC_OK; }
     if (kernel == LDPC_KERNEL_QC_RT && code->d_qc_rt) { code->kernel = kernel; return LDPC_OK; }
     set_error("kernel %d not available for this code", kernel);
@@ -218,7 +218,11 @@ int decode_dispatch(const ldpc_code *code, const DecodeArgs &a, cudaStream_t s) 
             return launch_decode_tiny(code->tiny_id, a, s);
         return launch_decode_generic(code->g, code->max_dv, code->max_dc, a, s);
     }
-    if (code->kernel == LDPC_KERNEL_QC && a.x0 == nullptr && a.x_out == nullptr) {
+    if ((code->kernel == LDPC_KERNEL_QC || code->kernel == LDPC_KERNEL_QC_TMA) && a.x0 == nullptr && a.x_out == nullptr) {
+        if (code->kernel == LDPC_KERNEL_QC_TMA && code->precision == LDPC_PREC_F32) {
+            const int rc = launch_decode_qc_tma(code->qc_id, a, s);
+            if (rc != LDPC_EUNSUPPORTED) return rc;        // early termination, other update rules, other codes: the one-tile-per-CTA kernel
+        }
         if (code->precision == LDPC_PREC_F16X2 && (a.update == LDPC_UPDATE_MINSUM || a.update == LDPC_UPDATE_NMS) &&
             !a.early_exit && !a.iters_used)
             return launch_decode_qc_h2(code->qc_id, a, s);

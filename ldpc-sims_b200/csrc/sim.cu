@@ -253,7 +253,7 @@ int ldpc_sim_run(const ldpc_code_t *code, const ldpc_sim_params_t *sp, void *wor
     const int n = code->n, nby = (n + 7) / 8;
     cudaStream_t s = (cudaStream_t)stream;
     // ---- single launch: front end fused into the code-specialised decoder kernel -------------------
-    if (code->kernel == LDPC_KERNEL_QC && code->precision == LDPC_PREC_F32 && !(sp->reserved & 1)) {
+    if ((code->kernel == LDPC_KERNEL_QC || code->kernel == LDPC_KERNEL_QC_TMA) && code->precision == LDPC_PREC_F32 && !(sp->reserved & 1)) {
         DecodeArgs a;
         memset(&a, 0, sizeof(a));
         a.llr_dtype = LDPC_F32; a.B = sp->n_codewords; a.iters = sp->iters; a.update = sp->update;

@@ -16,7 +16,7 @@ LIB_PATH = os.path.join(_PKG, "lib", "libldpc_b200.so")
 OK, EINVAL, ECUDA, ENOMEM, EUNSUPPORTED = 0, -1, -2, -3, -4
 UPDATE_SP, UPDATE_MINSUM, UPDATE_NMS, UPDATE_OMS = 0, 1, 2, 3
 F32, F64, F16, I8 = 0, 1, 2, 3
-KERNEL_GENERIC, KERNEL_QC, KERNEL_TINY, KERNEL_QC_RT = 0, 1, 2, 3
+KERNEL_GENERIC, KERNEL_QC, KERNEL_TINY, KERNEL_QC_RT, KERNEL_QC_TMA = 0, 1, 2, 3, 4
 PREC_F32, PREC_F16X2 = 0, 1
 ABI_VERSION = 1
 

@@ -74,7 +74,8 @@ class LdpcCode:
             self._h = None
 
     def set_kernel(self, kernel):
-        kid = {"generic": N.KERNEL_GENERIC, "qc": N.KERNEL_QC, "tiny": N.KERNEL_TINY, "qc_rt": N.KERNEL_QC_RT}.get(kernel, kernel)
+        kid = {"generic": N.KERNEL_GENERIC, "qc": N.KERNEL_QC, "tiny": N.KERNEL_TINY, "qc_rt": N.KERNEL_QC_RT,
+               "qc_tma": N.KERNEL_QC_TMA}.get(kernel, kernel)
         N.check(N.lib().ldpc_code_set_kernel(self._h, int(kid)))
         self.kernel = int(kid)
 

@@ -142,6 +142,13 @@ int main(int argc, char **argv) {
         }
         CK(cudaDeviceSynchronize());
         DecodeArgs av = make_args(b, iters, UPD_MINSUM, false);
+        if (fmt == 0) {   // occupancy experiment: the round-1 kernel with ONE CTA per SM (extra dynamic shared memory), i.e. half the warps
+            using L1 = QcLayout<Wifi1944R12, 3>;
+            auto k1 = decode_qc_kernel<Wifi1944R12, 3, UPD_MINSUM, 0, false>;
+            CK(cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, 120 * 1024));
+            run_variant("round-1 kernel, 1 CTA/SM (8 warps)", b, reps, [&] { k1<<<(int)((b.B + 2) / 3), L1::THREADS, 120 * 1024>>>(av, LinkParams()); });
+            CK(cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L1::SMEM));
+        }
         if (fmt == 0) {
             run_variant("pers fp32 VB=0", b, reps, [&] { launch_qc_pers<Wifi1944R12, 3, UPD_MINSUM, float, 0>(av, 0); });
             run_variant("pers fp32 VB=6", b, reps, [&] { launch_qc_pers<Wifi1944R12, 3, UPD_MINSUM, float, 6>(av, 0); });

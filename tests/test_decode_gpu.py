@@ -566,3 +566,44 @@ def test_wifi_family_compiled_kernels_against_oracle(n, rate):
     o = dec(code, llr[:96], 5, 20, "minsum", want=("llr_post", "hard"))
     assert np.array_equal(o["hard"], f["hard"]) and np.array_equal(o["llr_post"], (-2.0 * f["t"]).astype(np.float32))
     code.set_precision("f32")
+
+
+def test_persistent_tma_kernel_equals_default(wcode):
+    """LDPC_KERNEL_QC_TMA (decode_qc_pers.cuh: persistent CTAs, next tile's LLRs by cp.async.bulk, software-pipelined
+    variable phase) produces the bits of the default compiled kernel: min-sum and sum-product, ragged batch (partial last
+    tile, fewer tiles than CTAs and more), f32 (bulk-copy path), f64 / f16 / misaligned f32 (staging path), every output."""
+    qc = ieee80211n_1944_r12()
+    tma = LdpcCode(qc.H, qc_Z=81, qc_proto=qc.proto)
+    tma.set_kernel("qc_tma")
+    assert tma.kernel == 4
+    rng = np.random.RandomState(77)
+    want = ("prob", "llr_post", "hard", "hard_packed", "syndrome")
+    for B in (1, 2, 1000, 3001):
+        llr = (rng.randn(B, qc.n) * 2.5 + 1.0).astype(np.float32)
+        for update, iters in (("minsum", 10), ("sp", 3), ("minsum", 1)):
+            a = dec(wcode, llr, iters, 20, update, want=want)
+            b = dec(tma, llr, iters, 20, update, want=want)
+            for k in want:
+                assert np.array_equal(a[k], b[k]), (B, update, iters, k)
+    llr = (rng.randn(257, qc.n) * 3).astype(np.float32)
+    ref = dec(wcode, llr, 4, 20, "minsum", want=("llr_post", "hard_packed"))
+    for dt in (torch.float64, torch.float16):
+        x = torch.as_tensor(llr).cuda().to(dt)
+        a = wcode.decode(x, 4, 20.0, update="minsum", want=("llr_post", "hard_packed"))
+        b = tma.decode(x, 4, 20.0, update="minsum", want=("llr_post", "hard_packed"))
+        assert torch.equal(a["llr_post"], b["llr_post"]) and torch.equal(a["hard_packed"], b["hard_packed"])
+    buf = torch.zeros(257 * qc.n + 1, device="cuda")
+    mis = buf[1:].view(257, qc.n)                                  # 4-byte aligned only: no bulk copy possible
+    mis.copy_(torch.as_tensor(llr))
+    b = tma.decode(mis, 4, 20.0, update="minsum", want=("llr_post", "hard_packed"))
+    assert np.array_equal(b["llr_post"].cpu().numpy(), ref["llr_post"]) and np.array_equal(b["hard_packed"].cpu().numpy(), ref["hard_packed"])
+    # falls back to the default kernel where it is not compiled (early termination, other rules): same results
+    o = tma.decode(torch.as_tensor(llr).cuda(), 4, 20.0, update="oms", param=0.3, want=("hard_packed",))
+    r = wcode.decode(torch.as_tensor(llr).cuda(), 4, 20.0, update="oms", param=0.3, want=("hard_packed",))
+    assert torch.equal(o["hard_packed"], r["hard_packed"])
+    # fused counters through the persistent kernel
+    from ldpc_b200.linksim import LinkConfig, attach_generator, decode_count, sim_generate
+    attach_generator(tma); attach_generator(wcode)
+    cfg = LinkConfig(snr_db=1.8, ofdm_size=64, iters=6, update="minsum", clamp_value=20.0, seed=3)
+    cwp, l2 = sim_generate(wcode, cfg, 0, 1001)
+    assert torch.equal(decode_count(tma, l2, cwp, cfg), decode_count(wcode, l2, cwp, cfg))
