@@ -46,6 +46,7 @@ def parse():
     ap.add_argument("--no-train", action="store_true", help="skip the weighted-BP training step (SURVEY 8f rank 2)")
     ap.add_argument("--no-numa-bind", action="store_true", help="do not pin the rank to the NUMA node of its GPU")
     ap.add_argument("--e2e-chunk", type=int, default=16384, help="codewords per H2D / decode / D2H chunk of the host pipeline")
+    ap.add_argument("--no-family", action="store_true", help="skip the per-code table of the 802.11n family")
     ap.add_argument("--no-sweep", action="store_true", help="skip the sharded BER/FER sweep with its all-reduce (BASELINE.json configs[3])")
     ap.add_argument("--sweep-codewords", type=int, default=1 << 19, help="codewords per SNR point of the sweep, TOTAL over all GPUs (strong scaling)")
     ap.add_argument("--nn-symbols", type=int, default=1 << 20, help="OFDM symbols per GPU of the NN-demapper measurement")
@@ -334,6 +335,59 @@ def bench_sweep(a, dev, world, rank, barrier):
             "coded_bler": [float(v) for v in r["coded_bler"]], "counters": got.tolist()}
 
 
+def bench_family(a, dev, world, barrier, headline_updates_per_s):
+    """every IEEE 802.11n prototype on its code-compiled kernel - decoded information rate and directed
+    edge-updates per second (the roofline quantity) next to the headline code's, same decoder settings, LLRs in HBM."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from ldpc_b200.codes import WIFI_LENGTHS, WIFI_RATES, ieee80211n
+    from ldpc_b200.decoder import LdpcCode
+    from ldpc_b200 import _native as N
+    lib = N.lib()
+    stream = torch.cuda.current_stream(dev)
+    out = []
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for n in WIFI_LENGTHS:
+        for rate in WIFI_RATES:
+            qc = ieee80211n(n, rate)
+            code = LdpcCode(qc.H, qc_Z=qc.Z, qc_proto=qc.proto, device=dev)
+            B = int(2.0e8 // n)                                   # ~0.8 GB of f32 LLRs per launch: larger than L2
+            R = qc.k / qc.n
+            sigma = (1.0 / (2 * R * 10 ** (0.1 * (1.5 + 2.5 * R)))) ** 0.5
+            cw = torch.as_tensor(qc.encode(np.random.RandomState(n).randint(0, 2, (64, qc.k)).astype(np.uint8))).to(dev)
+            llr = torch.empty(B, n, dtype=torch.float32, device=dev)
+            for s0 in range(0, B, 32768):
+                s1 = min(B, s0 + 32768)
+                y = (1.0 - 2.0 * cw[torch.arange(s0, s1, device=dev) % 64].float()) + sigma * torch.randn(s1 - s0, n, device=dev)
+                llr[s0:s1] = -2.0 * y / sigma ** 2
+            post = torch.empty(B, n, dtype=torch.float32, device=dev)
+            packed = torch.empty(B, code.packed_bytes, dtype=torch.uint8, device=dev)
+
+            def step():
+                N.check(lib.ldpc_decode(code._h, llr.data_ptr(), N.F32, B, a.iters, N.UPDATE_IDS[a.update], a.clamp, 1.0, None, None,
+                                        post.data_ptr(), None, packed.data_ptr(), None, None, ctypes.c_void_p(stream.cuda_stream)))
+            step(); step()
+            barrier()
+            e0.record(stream)
+            for _ in range(3):
+                step()
+            e1.record(stream)
+            barrier()
+            t = torch.tensor([e0.elapsed_time(e1) / 3], device=dev, dtype=torch.float64)
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+            E = int(qc.H.sum())
+            ups = B / (ms * 1e-3) * 2 * E * a.iters
+            out.append({"code": qc.name, "Z": qc.Z, "k": qc.k, "edges": E, "kernel": ("generic", "qc", "tiny", "qc_rt", "qc_tma")[code.kernel],
+                        "codewords_per_gpu": B, "ms": ms, "info_gbps": B * world * qc.k / (ms * 1e-3) / 1e9,
+                        "edge_updates_per_s": ups * world,
+                        "edge_update_rate_vs_headline": ups / headline_updates_per_s if headline_updates_per_s else None})
+            del llr, post, packed, code
+    return out
+
+
 def bench_train(dev, world, barrier):
     """ofdm/ofdm_nn.py:281-343 in miniature: BCE through the weighted decoder on the default code, loss.backward() on
     the native sparse backward, at the reference's minibatch (512) and at a GPU-sized batch."""
@@ -564,6 +618,10 @@ def main():
     # ---- BASELINE.json configs[3]: sharded BER/FER sweep, fixed total, one all-reduce of the counters in the timed region ----
     if not a.no_sweep:
         out["sweep"] = bench_sweep(a, dev, world, rank, barrier)
+
+    # ---- the whole IEEE 802.11n family on compiled kernels ----------------------------------------------
+    if not a.no_family:
+        out["wifi_family"] = bench_family(a, dev, world, barrier, upd_s)
 
     # ---- e2e: the C-ABI host call (decode_bits path): pinned host LLRs in, packed bits out ---------
     if not a.no_e2e:
