@@ -10,6 +10,7 @@
 #include "node_math.cuh"
 #include "node_math_h2.cuh"
 #include "qc_plan.cuh"
+#include "qc_var_pipe.cuh"
 
 namespace ldpc {
 
@@ -65,38 +66,59 @@ __global__ void __launch_bounds__((QcLayout<Code, CW>::THREADS)) decode_qc_h2_ke
 
     auto var_phase = [&](auto first_tag) {
         constexpr bool FIRST = decltype(first_tag)::value;
-        static_for<NB>([&](auto cc) {
-            constexpr int c = decltype(cc)::value;
-            constexpr int D = kQc<Code>.col_deg[c];
-            if constexpr (D > 0) {
-                __half2 in[D], s[D];
-                __half2 *ptr[D];
-                static_for<D>([&](auto kk) {
-                    constexpr int k = decltype(kk)::value;
-                    constexpr bool is_loc = kQc<Code>.col_loc[c][k];
-                    constexpr int slot = kQc<Code>.col_slot[c][k];
-                    if constexpr (is_loc) {
-                        ptr[k] = nullptr;
-                        in[k] = FIRST ? __float2half2_rn(0.0f) : loc[slot];
-                    } else {
-                        constexpr int sh = kQc<Code>.col_eff[c][k];
-                        constexpr int off = (slot * Z - sh) * CW;
-                        ptr[k] = (t < sh ? hi : lo) + off;
-                        in[k] = FIRST ? __float2half2_rn(0.0f) : *ptr[k];
-                    }
-                });
-                h2_sum_others<D>(in, s);
-                const __half2 Lp = __hneg2(llr[c]);
-                static_for<D>([&](auto kk) {
-                    constexpr int k = decltype(kk)::value;
-                    constexpr bool is_loc = kQc<Code>.col_loc[c][k];
-                    constexpr int slot = kQc<Code>.col_slot[c][k];
-                    const __half2 y = h2_add(Lp, s[k]);
-                    if constexpr (is_loc) loc[slot] = y;
-                    else *ptr[k] = y;
-                });
-            }
-        });
+        if constexpr (FIRST) {
+            static_for<NB>([&](auto cc) {
+                constexpr int c = decltype(cc)::value;
+                constexpr int D = kQc<Code>.col_deg[c];
+                if constexpr (D > 0) {
+                    const __half2 y = h2_add(__hneg2(llr[c]), __float2half2_rn(0.0f));       // every C->V message is still zero
+                    static_for<D>([&](auto kk) {
+                        constexpr int k = decltype(kk)::value;
+                        constexpr bool is_loc = kQc<Code>.col_loc[c][k];
+                        constexpr int slot = kQc<Code>.col_slot[c][k];
+                        if constexpr (is_loc) loc[slot] = y;
+                        else {
+                            constexpr int sh = kQc<Code>.col_eff[c][k];
+                            constexpr int off = (slot * Z - sh) * CW;
+                            ((t < sh ? hi : lo) + off)[0] = y;
+                        }
+                    });
+                }
+            });
+        } else {
+            // in-order (the software-pipelined form of qc_var_pipe.cuh measured 2.8 % SLOWER here: two codewords per thread
+            // already double the independent work between a load and its use, and the extra live registers cost more)
+            static_for<NB>([&](auto cc) {
+                constexpr int c = decltype(cc)::value;
+                constexpr int D = kQc<Code>.col_deg[c];
+                if constexpr (D > 0) {
+                    __half2 in[D], out[D];
+                    __half2 *ptr[D];
+                    static_for<D>([&](auto kk) {
+                        constexpr int k = decltype(kk)::value;
+                        constexpr bool is_loc = kQc<Code>.col_loc[c][k];
+                        constexpr int slot = kQc<Code>.col_slot[c][k];
+                        if constexpr (is_loc) {
+                            ptr[k] = nullptr;
+                            in[k] = loc[slot];
+                        } else {
+                            constexpr int sh = kQc<Code>.col_eff[c][k];
+                            constexpr int off = (slot * Z - sh) * CW;
+                            ptr[k] = (t < sh ? hi : lo) + off;
+                            in[k] = *ptr[k];
+                        }
+                    });
+                    vnode<D, UPD>(in, llr[c], out);
+                    static_for<D>([&](auto kk) {
+                        constexpr int k = decltype(kk)::value;
+                        constexpr bool is_loc = kQc<Code>.col_loc[c][k];
+                        constexpr int slot = kQc<Code>.col_slot[c][k];
+                        if constexpr (is_loc) loc[slot] = out[k];
+                        else *ptr[k] = out[k];
+                    });
+                }
+            });
+        }
     };
     auto check_phase = [&]() {
         static_for<MB>([&](auto rr) {

@@ -24,6 +24,7 @@
 #include "node_math.cuh"
 #include "linksim_device.cuh"
 #include "qc_plan.cuh"
+#include "qc_var_pipe.cuh"
 
 namespace ldpc {
 
@@ -178,40 +179,40 @@ __global__ void __launch_bounds__((QcLayout<Code, CW>::THREADS), (QcLayout<Code,
         __syncthreads();                                                   // the message region is free again
     }
 
-    // V -> C for all NB block columns of this thread.  FIRST: the C->V messages are still the
-    // zeros every reference caller passes (ofdm_functions.py:157) - nothing is loaded.
+    // V -> C for all NB block columns of this thread.  FIRST: the C->V messages are still the zeros every reference
+    // caller passes (ofdm_functions.py:157) - nothing is loaded.  Otherwise the shared-memory loads of the next batch of
+    // block columns are issued before the current batch is computed and stored (VarPipe, qc_var_pipe.cuh): the rotated-
+    // window pointers are run-time selections, so the compiler cannot move a load above a store of another block itself.
     auto var_phase = [&](auto first_tag) {
         constexpr bool FIRST = decltype(first_tag)::value;
-        static_for<NB>([&](auto cc) {
-            constexpr int c = decltype(cc)::value;
-            constexpr int D = kQc<Code>.col_deg[c];
-            if constexpr (D > 0) {
-                float in[D], out[D];
-                float *ptr[D];
-                static_for<D>([&](auto kk) {
-                    constexpr int k = decltype(kk)::value;
-                    constexpr bool is_loc = kQc<Code>.col_loc[c][k];
-                    constexpr int slot = kQc<Code>.col_slot[c][k];
-                    if constexpr (is_loc) {
-                        ptr[k] = nullptr;
-                        in[k] = FIRST ? 0.0f : loc[slot];
-                    } else {
-                        constexpr int s = kQc<Code>.col_eff[c][k];
-                        constexpr int off = (slot * Z - s) * CW;
-                        ptr[k] = (t < s ? hi : lo) + off;
-                        in[k] = FIRST ? 0.0f : *ptr[k];
-                    }
-                });
-                var_node<D, IS_SP>(in, D, llr[c], out);
-                static_for<D>([&](auto kk) {
-                    constexpr int k = decltype(kk)::value;
-                    constexpr bool is_loc = kQc<Code>.col_loc[c][k];
-                    constexpr int slot = kQc<Code>.col_slot[c][k];
-                    if constexpr (is_loc) loc[slot] = out[k];
-                    else *ptr[k] = out[k];
-                });
-            }
-        });
+        if constexpr (FIRST) {
+            static_for<NB>([&](auto cc) {
+                constexpr int c = decltype(cc)::value;
+                constexpr int D = kQc<Code>.col_deg[c];
+                if constexpr (D > 0) {
+                    float in[D], out[D];
+                    static_for<D>([&](auto kk) { in[decltype(kk)::value] = 0.0f; });
+                    var_node<D, IS_SP>(in, D, llr[c], out);
+                    static_for<D>([&](auto kk) {
+                        constexpr int k = decltype(kk)::value;
+                        constexpr bool is_loc = kQc<Code>.col_loc[c][k];
+                        constexpr int slot = kQc<Code>.col_slot[c][k];
+                        if constexpr (is_loc) loc[slot] = out[k];
+                        else {
+                            constexpr int s = kQc<Code>.col_eff[c][k];
+                            constexpr int off = (slot * Z - s) * CW;
+                            ((t < s ? hi : lo) + off)[0] = out[k];
+                        }
+                    });
+                }
+            });
+        } else {
+            using VP = VarPipe<Code, CW, UPD, float, 6>;
+            float inA[VP::VBW], inB[VP::VBW];
+            float *pA[VP::VBW], *pB[VP::VBW];
+            VP::template load<0>(t, lo, hi, inA, pA);
+            VP::template run<0>(t, lo, hi, llr, loc, inA, pA, inB, pB);
+        }
     };
     auto check_phase = [&]() {
         static_for<MB>([&](auto rr) {

@@ -12,7 +12,7 @@ __global__ void __launch_bounds__(1024) k(float *out, int iters, long long *clk)
     for (int i = tid; i < 16384; i += blockDim.x) sm[i] = (float)i;
     __syncthreads();
     const unsigned base0 = (unsigned)__cvta_generic_to_shared(sm);
-    float acc0 = 0, acc1 = 0, acc2 = 0, acc3 = 0;
+    float acc0 = 0, acc1 = 0, acc2 = 0, acc3 = 0, bcc0 = 0, bcc1 = 0, bcc2 = 0, bcc3 = 0;
     const long long t0 = clock64();
     for (int it = 0; it < iters; ++it) {
         const unsigned base = base0 + ((unsigned)it & 1u) * 32768u;   // loop-variant address: nothing can be hoisted
@@ -65,6 +65,23 @@ __global__ void __launch_bounds__(1024) k(float *out, int iters, long long *clk)
                 acc3 = __fadd_rn(acc3, v);
                 acc0 = __fadd_rn(m2, acc3);
                 asm volatile("st.shared.f32 [%0], %1;" ::"r"(base + (unsigned)(tid * 4 + (u ^ 5) * 4096 % 32768)), "f"(m2) : "memory");
+            } else if (MODE == 14) { // TWO independent dependent-chain edge mixes per thread, interleaved (intra-thread anti-phase probe)
+                float v, w;
+                asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(base + (unsigned)(tid * 4 + u * 4096 % 32768)) : "memory");
+                asm volatile("ld.shared.f32 %0, [%1];" : "=f"(w) : "r"(base + (unsigned)(tid * 4 + (u ^ 3) * 4096 % 32768)) : "memory");
+                float m0, m1, m2;
+                asm volatile("min.xorsign.abs.f32 %0, %1, %2;" : "=f"(m0) : "f"(acc0), "f"(v));
+                asm volatile("min.xorsign.abs.f32 %0, %1, %2;" : "=f"(m1) : "f"(m0), "f"(acc1));
+                if (u & 1) asm volatile("min.xorsign.abs.f32 %0, %1, %2;" : "=f"(m2) : "f"(m1), "f"(acc2)); else m2 = m1;
+                // second stream: the variable-node side (adds only), independent of the first
+                bcc0 = __fadd_rn(bcc0, w);
+                bcc1 = __fadd_rn(bcc1, bcc0);
+                bcc2 = __fadd_rn(bcc2, w);
+                bcc3 = __fadd_rn(bcc1, bcc2);
+                acc3 = __fadd_rn(acc3, v);
+                acc0 = __fadd_rn(m2, acc3);
+                asm volatile("st.shared.f32 [%0], %1;" ::"r"(base + (unsigned)(tid * 4 + (u ^ 5) * 4096 % 32768)), "f"(m2) : "memory");
+                asm volatile("st.shared.f32 [%0], %1;" ::"r"(base + (unsigned)(tid * 4 + (u ^ 6) * 4096 % 32768)), "f"(bcc3) : "memory");
             } else if (MODE == 11 || MODE == 12) { // bursts: a whole loop iteration of loads, then one of stores (12: CTA-wide barrier between them)
                 if (it & 1) {
                     asm volatile("st.shared.f32 [%0], %1;" ::"r"(base + (unsigned)(tid * 4 + u * 4096 % 32768)), "f"(acc0) : "memory");
@@ -97,7 +114,7 @@ __global__ void __launch_bounds__(1024) k(float *out, int iters, long long *clk)
     }
     const long long t1 = clock64();
     if (tid == 0) clk[blockIdx.x] = t1 - t0;
-    out[blockIdx.x * blockDim.x + tid] = acc0 + acc1 + acc2 + acc3;
+    out[blockIdx.x * blockDim.x + tid] = acc0 + acc1 + acc2 + acc3 + bcc3;
 }
 
 template <int MODE>
@@ -137,6 +154,7 @@ int main() {
     run<11>("16 LDS.32 then 16 STS.32 per warp", 1);
     run<12>("16 LDS.32 | barrier | 16 STS.32 | barrier", 1);
     run<13>("LDS.32 : STS.32 3:1", 1);
+    run<14>("two interleaved streams/thread: check-like + var-like (instr = 2 LDS + 2 STS)", 4);
     run<9>("edge mix, dependent chain (instr = LDS+STS)", 2);
     run<10>("edge mix, dependent chain + 8-warp barriers", 2);
     run<8>("edge mix LDS+2.5FMNMX+2FADD+STS (instr = LDS+STS)", 2);
