@@ -38,7 +38,7 @@ namespace ldpc {
 template <class Code, int CW, int UPD, int SIM, bool EE>
 __global__ void __launch_bounds__((QcLayout<Code, CW>::THREADS), (QcLayout<Code, CW>::MIN_CTAS)) decode_qc_kernel(const DecodeArgs a, const LinkParams lp) {
     using L = QcLayout<Code, CW>;
-    constexpr bool IS_SP = (UPD == UPD_SP);
+    constexpr bool IS_SP = (UPD == UPD_SP || UPD == UPD_SPF);
     constexpr int Z = Code::Z, NB = Code::NB, MB = Code::MB, N = L::N;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float *msg_s = reinterpret_cast<float *>(smem_raw);
@@ -192,7 +192,7 @@ __global__ void __launch_bounds__((QcLayout<Code, CW>::THREADS), (QcLayout<Code,
                 if constexpr (D > 0) {
                     float in[D], out[D];
                     static_for<D>([&](auto kk) { in[decltype(kk)::value] = 0.0f; });
-                    var_node<D, IS_SP>(in, D, llr[c], out);
+                    vnode<D, UPD>(in, llr[c], out);
                     static_for<D>([&](auto kk) {
                         constexpr int k = decltype(kk)::value;
                         constexpr bool is_loc = kQc<Code>.col_loc[c][k];
@@ -227,7 +227,7 @@ __global__ void __launch_bounds__((QcLayout<Code, CW>::THREADS), (QcLayout<Code,
                     if constexpr (is_loc) in[j] = loc[slot];
                     else in[j] = msg[slot * Z * CW];
                 });
-                if constexpr (IS_SP) check_node_sp<D>(in, D, a.clampv, out);
+                if constexpr (IS_SP) check_node_sp<D, UPD == UPD_SPF>(in, D, a.clampv, out);
                 else check_node_ms_ct<D, UPD>(in, a.clampv, a.param, out);
                 static_for<D>([&](auto jj) {
                     constexpr int j = decltype(jj)::value;

@@ -16,7 +16,9 @@ struct NodeParams {
 };
 
 template <int D, int UPD>
-__device__ __forceinline__ void vnode(const float (&in)[D], float llr, float (&out)[D]) { var_node<D, UPD == UPD_SP>(in, D, llr, out); }
+__device__ __forceinline__ void vnode(const float (&in)[D], float llr, float (&out)[D]) {
+    var_node_m<D, (UPD == UPD_SP ? 1 : (UPD == UPD_SPF ? 2 : 0))>(in, D, llr, out);
+}
 template <int D, int UPD>
 __device__ __forceinline__ void vnode(const __half2 (&in)[D], __half2 llr, __half2 (&out)[D]) {
     __half2 s[D];
@@ -27,7 +29,7 @@ __device__ __forceinline__ void vnode(const __half2 (&in)[D], __half2 llr, __hal
 }
 template <int D, int UPD>
 __device__ __forceinline__ void cnode(const float (&in)[D], const NodeParams &p, float (&out)[D]) {
-    if constexpr (UPD == UPD_SP) check_node_sp<D>(in, D, p.clampv, out);
+    if constexpr (UPD == UPD_SP || UPD == UPD_SPF) check_node_sp<D, UPD == UPD_SPF>(in, D, p.clampv, out);
     else check_node_ms_ct<D, UPD>(in, p.clampv, p.param, out);
 }
 template <int D, int UPD>

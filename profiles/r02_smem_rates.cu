@@ -65,6 +65,33 @@ __global__ void __launch_bounds__(1024) k(float *out, int iters, long long *clk)
                 acc3 = __fadd_rn(acc3, v);
                 acc0 = __fadd_rn(m2, acc3);
                 asm volatile("st.shared.f32 [%0], %1;" ::"r"(base + (unsigned)(tid * 4 + (u ^ 5) * 4096 % 32768)), "f"(m2) : "memory");
+            } else if (MODE == 15 || MODE == 16) {
+                // the decoder's two phases with their real per-exchanged-edge ratios: check-like unit = LDS + 5 dependent FMNMX + STS
+                // (248 / 51), variable-like unit = LDS + 4 FADD + ISETP/SEL + STS.  15: PHASED - a whole loop iteration of one kind,
+                // 8-warp barrier, then the other (16 warps = two groups, as the kernel).  16: both units INTERLEAVED in one thread.
+                const bool do_check = (MODE == 16) || !(it & 1), do_var = (MODE == 16) || (it & 1);
+                if (do_check) {
+                    float v;
+                    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(base + (unsigned)(tid * 4 + u * 4096 % 32768)) : "memory");
+                    float m0, m1, m2, m3, m4;
+                    asm volatile("min.xorsign.abs.f32 %0, %1, %2;" : "=f"(m0) : "f"(acc0), "f"(v));
+                    asm volatile("min.xorsign.abs.f32 %0, %1, %2;" : "=f"(m1) : "f"(acc1), "f"(v));
+                    asm volatile("min.xorsign.abs.f32 %0, %1, %2;" : "=f"(m2) : "f"(m0), "f"(acc2));
+                    asm volatile("min.xorsign.abs.f32 %0, %1, %2;" : "=f"(m3) : "f"(m1), "f"(m2));
+                    asm volatile("min.xorsign.abs.f32 %0, %1, %2;" : "=f"(m4) : "f"(m3), "f"(acc3));
+                    acc0 = m1; acc1 = m2; acc2 = m4; acc3 = v;
+                    asm volatile("st.shared.f32 [%0], %1;" ::"r"(base + (unsigned)(tid * 4 + (u ^ 5) * 4096 % 32768)), "f"(m4) : "memory");
+                }
+                if (do_var) {
+                    float w;
+                    const unsigned sel = (tid < 7 * u + 3) ? 12u : 0u;                  // the rotated-window select
+                    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(w) : "r"(base + sel + (unsigned)(tid * 4 + (u ^ 3) * 4096 % 32768)) : "memory");
+                    bcc0 = __fadd_rn(bcc0, w);
+                    bcc1 = __fadd_rn(bcc1, bcc0);
+                    bcc2 = __fadd_rn(bcc2, w);
+                    bcc3 = __fadd_rn(bcc1, bcc2);
+                    asm volatile("st.shared.f32 [%0], %1;" ::"r"(base + sel + (unsigned)(tid * 4 + (u ^ 6) * 4096 % 32768)), "f"(bcc3) : "memory");
+                }
             } else if (MODE == 14) { // TWO independent dependent-chain edge mixes per thread, interleaved (intra-thread anti-phase probe)
                 float v, w;
                 asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(base + (unsigned)(tid * 4 + u * 4096 % 32768)) : "memory");
@@ -110,6 +137,7 @@ __global__ void __launch_bounds__(1024) k(float *out, int iters, long long *clk)
             }
         }
         if (MODE == 12) __syncthreads();
+        if (MODE == 15 || MODE == 16) asm volatile("bar.sync %0, 256;" ::"r"(1 + tid / 256) : "memory");
         if (MODE == 10 && (it & 1)) asm volatile("bar.sync %0, 256;" ::"r"(1 + tid / 256) : "memory");   // 8-warp groups, every ~230 instructions
     }
     const long long t1 = clock64();
@@ -154,6 +182,8 @@ int main() {
     run<11>("16 LDS.32 then 16 STS.32 per warp", 1);
     run<12>("16 LDS.32 | barrier | 16 STS.32 | barrier", 1);
     run<13>("LDS.32 : STS.32 3:1", 1);
+    run<15>("PHASED check-like / variable-like iterations, 8-warp barriers (instr = LDS+STS)", 2);
+    run<16>("INTERLEAVED check-like + variable-like in one thread (instr = 2 LDS + 2 STS)", 4);
     run<14>("two interleaved streams/thread: check-like + var-like (instr = 2 LDS + 2 STS)", 4);
     run<9>("edge mix, dependent chain (instr = LDS+STS)", 2);
     run<10>("edge mix, dependent chain + 8-warp barriers", 2);
