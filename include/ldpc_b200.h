@@ -266,7 +266,12 @@ typedef struct {
     int32_t update;         /* LDPC_UPDATE_* */
     float clamp_value;
     float param;
-    int32_t reserved;       /* bit 0: force the three-launch chain (A/B test of the single-launch kernel) */
+    int32_t reserved;       /* option bits.  bit 0: force the three-launch chain (A/B test of the single-launch kernel);
+                               bit 1: flat Rayleigh block fading - one CN(0,1) gain per OFDM symbol (Philox stream 2), coherent
+                                      receiver with perfect channel knowledge: r = h x + n, z = r / h, LLR noise power sigma^2 / |h|^2
+                                      (north star "AWGN/fading channel"; the reference has AWGN only, ofdm_functions.py:30-33);
+                               bit 2: tanh compander clip * tanh(x / clip) in front of the uniform ADC (north star "uniform/tanh
+                                      quantizer"; the reference's quantizer is ofdm_functions.py:37-51) */
     uint64_t seed;          /* Philox key */
     int64_t first_codeword; /* global index of the first codeword (Philox subsequence) */
     int64_t n_codewords;

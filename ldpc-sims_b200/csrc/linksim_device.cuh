@@ -19,6 +19,9 @@ struct LinkParams {
     float agc_clip, clip_ratio;
     unsigned long long seed;
     long long cw_first;
+    int channel = 0;       // 0 = AWGN (the reference, ofdm_functions.py:30-33); 1 = flat Rayleigh block fading, one CN(0,1) gain per OFDM
+                           //     symbol, coherent receiver with perfect channel knowledge (north star: "AWGN/fading channel"; not in the reference)
+    int compander = 0;     // 1 = tanh compander (soft clipping clip * tanh(x / clip)) in front of the uniform ADC (north star: "uniform/tanh quantizer")
     const float2 *noise = nullptr;   // ldpc_sim_frontend only: caller-supplied noise samples [codeword][ofdm symbol][time sample] instead of Philox
 };
 
@@ -76,6 +79,29 @@ __device__ __forceinline__ void ofdm_symbols_llr(int lane, const int (&os)[S], c
         }
 #pragma unroll
     for (int s = 0; s < S; ++s) warp_fft<N, float, true>(x[s], lane, tw, k.scale);   // time sample t = bitrev(r*32+lane)
+    // flat block fading: one complex gain per OFDM symbol (Philox stream RNG_FADE, counter = symbol index: every lane draws the same)
+    cplx<float> hg[S];
+    float inv_h2[S];
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+        hg[s] = {1.0f, 0.0f};
+        inv_h2[s] = 1.0f;
+        if (p.channel == 1) {
+            uint32_t rnd[4];
+            rng((uint32_t)gcw[s], (uint32_t)(gcw[s] >> 32), RNG_FADE, (uint32_t)os[s], rnd);
+            float g0, g1;
+            box_muller<float>(rnd[0], rnd[1], g0, g1);
+            hg[s] = {k.a * g0, k.a * g1};                                              // CN(0, 1)
+            inv_h2[s] = 1.0f / fmaxf(hg[s].re * hg[s].re + hg[s].im * hg[s].im, 1e-12f);
+#pragma unroll
+            for (int r = 0; r < P; ++r) x[s][r] = {x[s][r].re * hg[s].re - x[s][r].im * hg[s].im, x[s][r].re * hg[s].im + x[s][r].im * hg[s].re};
+        }
+    }
+    auto adc = [&](float v) -> float {                                                 // AGC scale, optional compander, uniform ADC, rescale
+        float w = k.factor * v;
+        if (p.compander) w = k.clip * tanhf(w / k.clip);
+        return div_rn_nochk(quant(w), k.factor);
+    };
     // AWGN: one Philox block serves the two time samples 2j, 2j+1 (counter = j, words {0,1} / {2,3}).
     // With i = r*32 + lane the sample index t = bitrev(i) has bit 0 = bit LOGN-1 of i, so for N >= 64
     // registers r and r + P/2 of a lane hold exactly such a pair and share one Philox call.
@@ -101,7 +127,7 @@ __device__ __forceinline__ void ofdm_symbols_llr(int lane, const int (&os)[S], c
                 for (int h = 0; h < 2; ++h) {
                     const int rr = r + h * (P / 2);
                     float re = x[s][rr].re + nscale * z[2 * h], im = x[s][rr].im + nscale * z[2 * h + 1];
-                    if (p.qbits > 0) { re = div_rn_nochk(quant(k.factor * re), k.factor); im = div_rn_nochk(quant(k.factor * im), k.factor); }
+                    if (p.qbits > 0) { re = adc(re); im = adc(im); }
                     x[s][rr] = {re, im};
                     if (valid[s]) samp(s, t0 + h, re, im);
                 }
@@ -119,11 +145,19 @@ __device__ __forceinline__ void ofdm_symbols_llr(int lane, const int (&os)[S], c
             }
             const float nscale = EXT_NOISE ? 1.0f : k.nstd;
             float re = x[s][0].re + nscale * z0, im = x[s][0].im + nscale * z1;
-            if (p.qbits > 0) { re = div_rn_nochk(quant(k.factor * re), k.factor); im = div_rn_nochk(quant(k.factor * im), k.factor); }
+            if (p.qbits > 0) { re = adc(re); im = adc(im); }
             x[s][0] = {re, im};
             if (valid[s]) samp(s, t, re, im);
         }
     }
+    // coherent receiver: divide by the (flat) channel gain before the FFT; the noise power seen by the demapper is sigma^2 / |h|^2
+#pragma unroll
+    for (int s = 0; s < S; ++s)
+        if (p.channel == 1) {
+#pragma unroll
+            for (int r = 0; r < P; ++r)
+                x[s][r] = {(x[s][r].re * hg[s].re + x[s][r].im * hg[s].im) * inv_h2[s], (x[s][r].im * hg[s].re - x[s][r].re * hg[s].im) * inv_h2[s]};
+        }
 #pragma unroll
     for (int s = 0; s < S; ++s) warp_fft_dit<N, float, false>(x[s], lane, tw, k.scale);  // back to natural subcarrier order
 #pragma unroll
@@ -131,7 +165,8 @@ __device__ __forceinline__ void ofdm_symbols_llr(int lane, const int (&os)[S], c
 #pragma unroll
         for (int r = 0; r < P; ++r) {
             const int sidx = os[s] * N + r * 32 + lane;
-            if (valid[s] && sidx < nsym) out(s, sidx, qpsk_llr<float>(x[s][r].re, k.a, k.two_np), qpsk_llr<float>(x[s][r].im, k.a, k.two_np));
+            const float tnp = k.two_np * inv_h2[s];
+            if (valid[s] && sidx < nsym) out(s, sidx, qpsk_llr<float>(x[s][r].re, k.a, tnp), qpsk_llr<float>(x[s][r].im, k.a, tnp));
         }
 }
 

@@ -172,6 +172,7 @@ static int launch_frontend(const ldpc_code_t *code, const ldpc_sim_params_t *sp,
     lp.n = n; lp.n_ofdm_per_cw = (n / 2 + sp->ofdm_size - 1) / sp->ofdm_size; lp.ofdm_size = sp->ofdm_size;
     lp.snr = powf(10.0f, sp->snr_db / 10.0f);
     lp.qbits = sp->qbits; lp.agc_mode = sp->agc_mode; lp.agc_clip = sp->agc_clip; lp.clip_ratio = sp->clip_ratio;
+    lp.channel = (sp->reserved >> 1) & 1; lp.compander = (sp->reserved >> 2) & 1;
     lp.seed = sp->seed; lp.cw_first = first; lp.noise = noise;
     const long long warps = cnt * lp.n_ofdm_per_cw;
     const int g2 = (int)std::min<long long>((warps + 7) / 8, 148LL * 16);
@@ -263,6 +264,7 @@ int ldpc_sim_run(const ldpc_code_t *code, const ldpc_sim_params_t *sp, void *wor
         lp.n = n; lp.n_ofdm_per_cw = (n / 2 + sp->ofdm_size - 1) / sp->ofdm_size; lp.ofdm_size = sp->ofdm_size;
         lp.snr = powf(10.0f, sp->snr_db / 10.0f);
         lp.qbits = sp->qbits; lp.agc_mode = sp->agc_mode; lp.agc_clip = sp->agc_clip; lp.clip_ratio = sp->clip_ratio;
+    lp.channel = (sp->reserved >> 1) & 1; lp.compander = (sp->reserved >> 2) & 1;
         lp.seed = sp->seed; lp.cw_first = sp->first_codeword;
         rc = launch_sim_fused_qc(code->qc_id, a, lp, s);
         if (rc != LDPC_EUNSUPPORTED) return rc;

@@ -156,12 +156,17 @@ class LinkConfig:
     param: float = 1.0
     seed: int = 1234
     force_unfused: bool = False      # A/B: three-launch chain instead of the single-launch kernel
+    channel: str = "awgn"            # "awgn" (the reference) or "rayleigh": flat block fading per OFDM symbol, coherent receiver
+    compander: bool = False          # tanh compander clip * tanh(x / clip) in front of the uniform ADC
 
     def to_struct(self, first, count):
         from .decoder import _update_id
+        if self.channel not in ("awgn", "rayleigh"):
+            raise ValueError("channel must be 'awgn' or 'rayleigh'")
         return SimParams(ctypes.sizeof(SimParams), self.ofdm_size, self.qbits, self.agc_mode, self.agc_clip,
                          self.clip_ratio, self.snr_db, self.iters, _update_id(self.update), self.clamp_value,
-                         self.param, 1 if self.force_unfused else 0, self.seed, first, count)
+                         self.param, (1 if self.force_unfused else 0) | (2 if self.channel == "rayleigh" else 0) | (4 if self.compander else 0),
+                         self.seed, first, count)
 
 
 COUNTER_NAMES = ("uncoded_bit_errors", "info_bit_errors", "frame_errors", "bits", "frames")

@@ -131,13 +131,17 @@ def agc_quantized_frontend(rx_signal, snrdb_val, qbits, clip_ratio, ofdm_size, a
     return qpsk_llrs(deofdm, snr_single), qrx_signal_rescaled
 
 
-def framed_link_llrs(enc_bits, snrdb, ofdm_size, qbits=0, clip_ratio=1.0, agc_clip=10, noise=None):
+def framed_link_llrs(enc_bits, snrdb, ofdm_size, qbits=0, clip_ratio=1.0, agc_clip=10, noise=None, channel="awgn", compander=False,
+                     fading=None):
     """The reference chain for a code whose length is NOT 2 * ofdm_size (the reference itself only works for
     n = 2 * ofdm_size, SURVEY hard part 6): every codeword is framed into ceil((n/2)/N) OFDM symbols, null
     subcarriers after its last QPSK symbol; each OFDM symbol then goes through exactly the reference's per-symbol
     steps (ofdm_functions.py:17-35,63-78; with qbits > 0 the AGC-scaled quantizer of
     evaluate_quantized_snr.py:96-133).  With n = 2 * ofdm_size this IS gen_data / agc_quantized_frontend.
-    enc_bits [B, n] of 0/1; returns (llrs float64 [B, n], rx_signal [1, B*S*N], noise [N, B*S])."""
+    channel='rayleigh' (not in the reference; defined here as in include/ldpc_b200.h): one CN(0,1) gain h per OFDM symbol,
+    r = h x + n, the receiver divides by h and demaps with the noise power 0.5 / (snr |h|^2).  compander: the ADC input
+    goes through agc_clip * tanh(. / agc_clip) first.
+    enc_bits [B, n] of 0/1; returns (llrs float64 [B, n], rx_signal [1, B*S*N])."""
     enc_bits = np.asarray(enc_bits)
     B, n = enc_bits.shape
     nsym = n // 2
@@ -145,12 +149,37 @@ def framed_link_llrs(enc_bits, snrdb, ofdm_size, qbits=0, clip_ratio=1.0, agc_cl
     sym = np.zeros((B, S * ofdm_size), dtype=complex)
     sym[:, :nsym] = modulate_bits(enc_bits.reshape((1, -1))).reshape(B, nsym)
     snr = np.power(10, snrdb / 10)
-    rx_signal, _ = transmit_symbols(sym.reshape((1, -1)), ofdm_size, snr, noise=noise)
-    if qbits > 0:
-        llr, _ = agc_quantized_frontend(rx_signal, snrdb, qbits, clip_ratio, ofdm_size, agc_clip=agc_clip)
+    if channel == "awgn" and not compander:
+        rx_signal, _ = transmit_symbols(sym.reshape((1, -1)), ofdm_size, snr, noise=noise)
+        if qbits > 0:
+            llr, _ = agc_quantized_frontend(rx_signal, snrdb, qbits, clip_ratio, ofdm_size, agc_clip=agc_clip)
+        else:
+            llr, _ = demodulate_signal(rx_signal, ofdm_size, snr)
+        return llr.reshape(B, S * ofdm_size * 2)[:, :n].copy(), rx_signal
+    W = _dft_cached(int(ofdm_size))
+    cols = sym.reshape((-1, ofdm_size)).T                          # [N, B*S]: columns = OFDM symbols
+    x = np.matmul(W.conj().T, cols)
+    if channel == "rayleigh":
+        h = fading if fading is not None else (np.random.normal(0, 1, cols.shape[1]) + 1j * np.random.normal(0, 1, cols.shape[1])) / np.sqrt(2)
+    elif channel == "awgn":
+        h = np.ones(cols.shape[1], dtype=complex)
     else:
-        llr, _ = demodulate_signal(rx_signal, ofdm_size, snr)
-    return llr.reshape(B, S * ofdm_size * 2)[:, :n].copy(), rx_signal
+        raise ValueError(channel)
+    if noise is None:
+        noise = (np.random.normal(0, 1 / np.sqrt(snr), x.shape) + 1j * np.random.normal(0, 1 / np.sqrt(snr), x.shape)) / np.sqrt(2)
+    r = x * h[None, :] + noise
+    if qbits > 0:
+        factor = agc_clip / (.5 * (1 + 1 / snr)) * clip_ratio
+        v = factor * r
+        if compander:
+            v = agc_clip * np.tanh(v.real / agc_clip) + 1j * agc_clip * np.tanh(v.imag / agc_clip)
+        r = quantizer(v, qbits, agc_clip) / factor
+    elif compander:
+        raise ValueError("the compander belongs to the ADC model: qbits > 0")
+    z = r * np.conj(h)[None, :] / (np.abs(h) ** 2)[None, :]
+    R = np.matmul(W, z)
+    llr = qpsk_llrs(R, snr * (np.abs(h) ** 2)[None, :])
+    return llr.reshape(B, S * ofdm_size * 2)[:, :n].copy(), r.T.reshape((1, -1))
 
 
 def error_metrics(llrs, decoded_bits, enc_bits, k):

@@ -211,3 +211,46 @@ def test_wifi_family_single_launch_simulator(n, rate):
     assert not ((qc.H.astype(np.int64) @ cw.T.astype(np.int64)) % 2).any()
     u = cw[:, :qc.k]
     assert np.array_equal(qc.encode(u), cw)                      # the device encoder is the library's linear-time encoder
+
+
+def test_rayleigh_fading_channel_and_tanh_compander(wsim):
+    """North-star extras that the reference does not have (it is AWGN + uniform quantizer only): flat Rayleigh block fading
+    with a coherent receiver, and a tanh compander in front of the ADC.  Defined in include/ldpc_b200.h and restated in
+    oracle/linksim_oracle.framed_link_llrs.  (i) uncoded BER against the closed form 0.5 (1 - sqrt(g / (1 + g))), g = snr / 2;
+    (ii) the single-launch simulator and the three-launch chain give identical counters with both options on;
+    (iii) coded curves against the oracle chain (numpy fading + noise, C oracle decoder) inside binomial intervals."""
+    import c_oracle as C
+    from ldpc_b200.codes import ieee80211n_1944_r12
+    from ldpc_b200.linksim import LinkConfig, sim_run
+    qc = ieee80211n_1944_r12()
+    for snr_db in (5.0, 12.0):
+        c = sim_run(wsim, LinkConfig(snr_db=snr_db, ofdm_size=64, iters=1, update="minsum", clamp_value=20.0, seed=9, channel="rayleigh"),
+                    0, 4096).cpu().numpy()
+        g = 10 ** (snr_db / 10) / 2
+        pb = 0.5 * (1 - np.sqrt(g / (1 + g)))
+        # 4096 codewords x 16 OFDM symbols = 65 536 independent fades: the BER estimate has the fades' variance, not the bits'
+        assert abs(c[0] / c[3] - pb) < 6 * np.sqrt(pb / (4096 * 16)) + 2e-3, (snr_db, c[0] / c[3], pb)
+    kw = dict(snr_db=9.0, ofdm_size=64, qbits=3, agc_mode=1, iters=6, update="minsum", clamp_value=20.0, seed=13, channel="rayleigh", compander=True)
+    fused = sim_run(wsim, LinkConfig(**kw), 100, 1000).cpu().numpy()
+    chain = sim_run(wsim, LinkConfig(force_unfused=True, **kw), 100, 1000).cpu().numpy()
+    assert fused.tolist() == chain.tolist() and fused[0] > 0
+    awgn = sim_run(wsim, LinkConfig(**{**kw, "channel": "awgn", "compander": False}), 100, 1000).cpu().numpy()
+    assert awgn[0] != fused[0]                                          # the options do something
+    # (iii) against the oracle chain
+    gph = C.CGraph(qc.H)
+    Ncw = 1 << 13
+    rng = np.random.RandomState(77)
+    enc = qc.encode(rng.randint(0, 2, (Ncw, qc.k)).astype(np.uint8)).astype(np.float64)
+    for snr_db, qbits, comp in ((7.0, 0, False), (9.0, 3, True)):                      # BLER ~ 6 % and ~ 12 % (oracle probe)
+        np.random.seed(int(snr_db))
+        llr, _ = LO.framed_link_llrs(enc, snr_db, 64, qbits=qbits, channel="rayleigh", compander=comp)
+        dec = C.decode(gph, llr.astype(np.float32), 10, 20.0, "minsum", want=("hard",))["hard"]
+        m = LO.error_metrics(llr, dec, enc, qc.k)
+        c = sim_run(wsim, LinkConfig(snr_db=snr_db, ofdm_size=64, qbits=qbits, agc_mode=1, iters=10, update="minsum", clamp_value=20.0,
+                                     seed=21, channel="rayleigh", compander=comp), 0, Ncw).cpu().numpy()
+        # uncoded errors are correlated inside an OFDM symbol (one fade): interval from the number of symbols
+        p_o, p_g = m["uncoded_errs"] / m["bits"], c[0] / c[3]
+        assert abs(p_o - p_g) < 6 * np.sqrt(2 * max(p_o, p_g) / (Ncw * 16)) + 1e-3, (snr_db, p_o, p_g)
+        lo, hi = _wilson(m["frame_errs"], m["frames"])
+        lo2, hi2 = _wilson(int(c[2]), int(c[4]))
+        assert lo <= hi2 and lo2 <= hi, (snr_db, "bler", m["frame_errs"], int(c[2]))
