@@ -78,6 +78,15 @@ typedef struct {
 } ldpc_code_info_t;
 int ldpc_code_info(const ldpc_code_t *code, ldpc_code_info_t *info);
 
+/* Register a quasi-cyclic code that was specialised at RUN TIME: `so_path` is a shared object built from one generated
+ * translation unit (ldpc_b200/jit.py writes it from the caller's prototype matrix and compiles it with the system nvcc
+ * against the library's own kernel templates, csrc/decode_qc_code.cuh).  After registration ldpc_code_create selects the
+ * code-compiled kernel (LDPC_KERNEL_QC) for that prototype exactly as for the built-in IEEE 802.11n family; without it
+ * the prototype runs on LDPC_KERNEL_QC_RT.  Returns the registry id (>= 0) or a negative LDPC_E* code (file not loadable,
+ * not a plug-in, built against other headers).  Replaces nothing in the reference: it has one hard-wired code
+ * (bp/parity.py:7-47) and mentions a parity.mat it does not ship (bp/masking.py:151-153). */
+int ldpc_qc_register_plugin(const char *so_path);
+
 /* Execution plan of the code-specialised kernel (zeros for the generic kernel):
  * out = {blocks whose messages stay in registers, blocks exchanged through shared memory,
  *        threads per CTA, codewords per CTA}.  Used by bench.py for the roofline arithmetic. */

@@ -95,6 +95,7 @@ int launch_decode_qc_tma(int qc_id, const DecodeArgs &a, cudaStream_t s);   // L
 struct LinkParams;
 int launch_sim_fused_qc(int qc_id, const DecodeArgs &a, const LinkParams &lp, cudaStream_t s);   // LDPC_EUNSUPPORTED -> use the 3-launch chain
 int qc_lookup(int Z, int mb, int nb, const int16_t *proto);   // -1 if no compiled specialisation
+int qc_register_plugin(const char *so_path);                   // -> registry id (>= 0) or a negative LDPC_E* code
 int tiny_lookup(int m, int n, const int32_t *row_ptr, const int32_t *col_idx);   // -1 if no compiled register-resident specialisation
 int launch_decode_tiny(int tiny_id, const DecodeArgs &a, cudaStream_t s);
 int launch_decode_qc_rt(const int32_t *d_tab, int Z, int mb, int nb, int nblk, int max_dv, int max_dc, const DecodeArgs &a, cudaStream_t s);

@@ -93,6 +93,10 @@ struct QcCodeImpl {
         return LDPC_OK;
     }
     static int sim_fused(const DecodeArgs &a, const LinkParams &lp, cudaStream_t s) {
+        if constexpr (!kQc<Code>.dual_diagonal) return LDPC_EUNSUPPORTED;   // the in-kernel encoder needs the 802.11n-style parity part
+        else return sim_fused_dd(a, lp, s);
+    }
+    static int sim_fused_dd(const DecodeArgs &a, const LinkParams &lp, cudaStream_t s) {
         if (a.B <= 0) return LDPC_OK;
         if (lp.ofdm_size == 64) {
             if (a.update == UPD_MINSUM) return launch_sim<UPD_MINSUM, 64>(a, lp, s);
@@ -133,5 +137,29 @@ struct QcCodeImpl {
 
 // codewords (fp32) / codeword pairs (f16x2) per CTA: as close to 256 threads as Z allows (two CTAs per SM)
 template <int Z> struct QcTile { static constexpr int CW = (256 / Z) > 0 ? (256 / Z) : 1; };
+
+// The minimal set for a code specialised at RUN TIME (ldpc_b200/jit.py compiles one translation unit with the system nvcc
+// and registers it through ldpc_qc_register_plugin): the four update rules with a fixed iteration count.  Everything else
+// (early termination, f16x2, the single-launch simulator) falls through to the kernels that take the prototype at run time.
+template <class Code, int CW>
+struct QcCodeImplLite {
+    using F = QcCodeImpl<Code, CW, false>;
+    static int decode(const DecodeArgs &a, cudaStream_t s) {
+        if (a.early_exit) return LDPC_EUNSUPPORTED;
+        return F::decode(a, s);
+    }
+    static int no_h2(const DecodeArgs &, cudaStream_t) {
+        set_error("the f16x2 kernel is not part of a run-time specialised code: use LDPC_PREC_F32");
+        return LDPC_EUNSUPPORTED;
+    }
+    static int no_tma(const DecodeArgs &, cudaStream_t) { return LDPC_EUNSUPPORTED; }
+    static int no_sim(const DecodeArgs &, const LinkParams &, cudaStream_t) { return LDPC_EUNSUPPORTED; }
+    static QcCodeEntry entry(const char *name) { return QcCodeEntry{name, F::matches, decode, no_h2, no_sim, no_tma, F::plan_info}; }
+};
+
+// what a plug-in and the library must agree on before any entry point is called through a QcCodeEntry
+inline unsigned qc_plugin_abi_tag() {
+    return (unsigned)(sizeof(DecodeArgs) * 1000003u + sizeof(LinkParams) * 10007u + sizeof(QcCodeEntry) * 101u + 2u /* revision */);
+}
 
 }  // namespace ldpc

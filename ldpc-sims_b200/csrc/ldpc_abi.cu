@@ -156,6 +156,8 @@ int ldpc_code_info(const ldpc_code_t *code, ldpc_code_info_t *info) {
     return LDPC_OK;
 }
 
+int ldpc_qc_register_plugin(const char *so_path) { return qc_register_plugin(so_path); }
+
 int ldpc_code_plan_info(const ldpc_code_t *code, int32_t out[4]) {
     if (!code || !out) { set_error("ldpc_code_plan_info: null argument"); return LDPC_EINVAL; }
     int v[4] = {0, 0, 0, 0};

@@ -68,6 +68,8 @@ def lib():
     L.ldpc_code_info.argtypes = [vp, ctypes.POINTER(CodeInfo)]
     L.ldpc_code_plan_info.restype = ctypes.c_int
     L.ldpc_code_plan_info.argtypes = [vp, vp]
+    L.ldpc_qc_register_plugin.restype = ctypes.c_int
+    L.ldpc_qc_register_plugin.argtypes = [ctypes.c_char_p]
     L.ldpc_code_set_precision.restype = ctypes.c_int
     L.ldpc_code_set_precision.argtypes = [vp, i32]
     L.ldpc_code_set_kernel.restype = ctypes.c_int

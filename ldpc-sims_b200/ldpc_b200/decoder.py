@@ -33,9 +33,12 @@ def _update_id(update):
 class LdpcCode:
     """H compiled to device edge tables (replaces generate_masks, bp/masking.py:12-147)."""
 
-    def __init__(self, H, qc_Z="auto", qc_proto=None, device=None):
+    def __init__(self, H, qc_Z="auto", qc_proto=None, device=None, specialize=False):
         """qc_Z: block size of a quasi-cyclic H (with qc_proto, or detected from H), 0 = treat H as unstructured,
-        "auto" (default) = look for a block-circulant structure with Z >= 24 (codes.auto_qc_block_size)."""
+        "auto" (default) = look for a block-circulant structure with Z >= 24 (codes.auto_qc_block_size).
+        specialize=True: a quasi-cyclic code outside the built-in IEEE 802.11n family is compiled at run time into the
+        code-specialised kernel (ldpc_b200.jit: one nvcc invocation per new prototype, cached) instead of running on the
+        run-time-table kernel; raises jit.SpecializeError if the prototype does not fit the mapping or nvcc is missing."""
         N.require_cuda()
         H = np.asarray(H)
         if H.ndim != 2:
@@ -54,6 +57,9 @@ class LdpcCode:
             if qc_proto is None:
                 qc_Z = 0
         proto = None if qc_proto is None else np.ascontiguousarray(qc_proto, dtype=np.int16)
+        if specialize and proto is not None and qc_Z:
+            from . import jit
+            jit.specialize_qc(proto, int(qc_Z))               # registers the plug-in: ldpc_code_create below finds it
         h = ctypes.c_void_p()
         with torch.cuda.device(self.device):
             N.check(N.lib().ldpc_code_create(

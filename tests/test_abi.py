@@ -73,3 +73,29 @@ def test_product_never_imports_oracle():
             for line in txt.splitlines():
                 if "sys.path" in line:
                     assert "oracle" not in line, (path, line)
+
+
+def test_runtime_specialisation_builds_and_registers(tmp_path):
+    """ldpc_b200.jit: a quasi-cyclic prototype outside the built-in family is compiled with the system nvcc into a plug-in
+    and registered (no device needed for either step); unsupported shapes and non-plug-ins are refused with a message."""
+    import numpy as np
+    from ldpc_b200 import jit, _native as N
+    if jit.find_nvcc() is None:
+        import pytest
+        pytest.skip("no nvcc")
+    rng = np.random.RandomState(3)
+    proto = rng.randint(-1, 31, size=(5, 10)).astype(np.int16)
+    proto[:, :2] = rng.randint(0, 31, size=(5, 2))
+    src = jit.source_for(proto, 31)
+    assert "QcCodeImplLite" in src and "static constexpr int Z = 31, MB = 5, NB = 10;" in src
+    so = jit.build(proto, 31, cache_dir=str(tmp_path))
+    assert so == jit.build(proto, 31, cache_dir=str(tmp_path))                       # cached by content
+    rid = N.lib().ldpc_qc_register_plugin(so.encode())
+    assert rid >= 12 and N.lib().ldpc_qc_register_plugin(so.encode()) == rid          # after the twelve built-in codes; idempotent
+    assert N.lib().ldpc_qc_register_plugin(b"/no/such/file.so") < 0 and b"ldpc_qc_register_plugin" in N.lib().ldpc_last_error()
+    bogus = tmp_path / "bogus.so"
+    import shutil, ctypes.util
+    shutil.copy(ctypes.util.find_library("m") and "/lib/x86_64-linux-gnu/libm.so.6" or so, bogus)
+    assert N.lib().ldpc_qc_register_plugin(str(bogus).encode()) < 0                  # a shared object, but not a plug-in
+    ok, why = jit.supported(np.zeros((40, 68), np.int16), 384)
+    assert not ok and "block columns" in why

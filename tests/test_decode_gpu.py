@@ -607,3 +607,45 @@ def test_persistent_tma_kernel_equals_default(wcode):
     cfg = LinkConfig(snr_db=1.8, ofdm_size=64, iters=6, update="minsum", clamp_value=20.0, seed=3)
     cwp, l2 = sim_generate(wcode, cfg, 0, 1001)
     assert torch.equal(decode_count(tma, l2, cwp, cfg), decode_count(wcode, l2, cwp, cfg))
+
+
+def test_runtime_specialised_code_equals_oracle_and_runtime_table_kernel():
+    """A quasi-cyclic prototype the library has never seen, compiled at run time into the code-specialised kernel
+    (LdpcCode(..., specialize=True) -> ldpc_b200.jit -> ldpc_qc_register_plugin): selected as LDPC_KERNEL_QC, every update
+    rule bit-exact against the oracle (min-sum family) / inside the sum-product bar, identical to the run-time-table kernel;
+    early termination falls through to the generic kernel."""
+    from ldpc_b200 import jit
+    from ldpc_b200.codes import expand_qc
+    if jit.find_nvcc() is None:
+        pytest.skip("no nvcc on this box")
+    rng = np.random.RandomState(31)
+    Z, mb, nb = 31, 5, 10
+    proto = rng.randint(-1, Z, size=(mb, nb)).astype(np.int16)
+    proto[:, :3] = rng.randint(0, Z, size=(mb, 3))                 # every row and column populated
+    proto[np.arange(mb), nb - mb + np.arange(mb)] = 0
+    H = expand_qc(proto, Z)
+    rt = LdpcCode(H, qc_Z=Z, qc_proto=proto)
+    assert rt.kernel == 3                                          # run-time-table kernel
+    jc = LdpcCode(H, qc_Z=Z, qc_proto=proto, specialize=True)
+    assert jc.kernel == 1                                          # compiled
+    g = C.CGraph(H)
+    llr = (rng.randn(1001, H.shape[1]) * 2.0 + 0.8).astype(np.float32)
+    for update, param in (("minsum", 1.0), ("nms", 0.75), ("oms", 0.25)):
+        ref = C.decode(g, llr, 7, 20.0, update, param, want=("t", "hard", "syndrome"))
+        a = dec(jc, llr, 7, 20, update, param, want=("llr_post", "hard", "hard_packed", "syndrome"))
+        b = dec(rt, llr, 7, 20, update, param, want=("llr_post", "hard", "hard_packed", "syndrome"))
+        assert np.array_equal(a["llr_post"], -2.0 * ref["t"]) and np.array_equal(a["hard"], ref["hard"]) and np.array_equal(a["syndrome"], ref["syndrome"])
+        for k in a:
+            assert np.array_equal(a[k], b[k]), (update, k)
+    sp = C.decode(g, llr, 5, 20.0, "sp", want=("t", "hard", "x"))
+    a = dec(jc, llr, 5, 20, "sp", want=("llr_post", "hard"))
+    assert np.mean(a["hard"] != sp["hard"]) < 2e-5
+    frac, ok, worst = sp_close(a["llr_post"] / -2.0, sp["t"], sat_count(H, sp["x"]))
+    assert frac >= FRAC_OK and ok, (frac, worst)
+    llr0 = (-(3.0 + 1.5 * rng.randn(500, H.shape[1]))).astype(np.float32)      # noisy all-zero codeword: converges
+    ee = jc.decode(torch.as_tensor(llr0).cuda(), 15, 20.0, update="minsum", early_exit=True, want=("hard", "iters_used", "syndrome"))
+    it = ee["iters_used"].cpu().numpy()
+    assert (it < 15).any() and (ee["syndrome"].cpu().numpy()[it < 15] == 0).all() and not ee["hard"].cpu().numpy()[it < 15].any()
+    with pytest.raises(Exception):
+        jc.set_precision("f16"); dec(jc, llr[:8], 2, 20, "minsum", want=("hard",))
+    jc.set_precision("f32")
