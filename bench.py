@@ -335,6 +335,43 @@ def bench_sweep(a, dev, world, rank, barrier):
             "coded_bler": [float(v) for v in r["coded_bler"]], "counters": got.tolist()}
 
 
+def bench_quantized_link(a, dev, world, rank, barrier):
+    """BASELINE.json configs[1] (evaluate_quantized_snr.py:14-23,91-188 at one SNR): the reference's default (64,32) code over
+    32-point OFDM, 3-bit ADC with the script's AGC (clip 10), 15 dB, sum-product x10, clamp 100 - 2^24 codewords in total,
+    sharded by batch, one all-reduce of the 5 counters.  The survey's CPU run of the reference script at 2^14 codewords gave
+    uncoded 1.35e-2, coded 1.9e-4, BLER 2.1e-2."""
+    import torch
+    import torch.distributed as dist
+    from ldpc_b200.codes import peg_64_32
+    from ldpc_b200.decoder import LdpcCode
+    from ldpc_b200.linksim import LinkConfig, attach_generator, rates, shard_range, sim_run
+    H, G = peg_64_32()
+    code = attach_generator(LdpcCode(H, device=dev), G)
+    cfg = LinkConfig(snr_db=15.0, ofdm_size=32, qbits=3, agc_mode=1, agc_clip=10.0, clip_ratio=1.0, iters=10, update="sp",
+                     clamp_value=100.0, seed=15)
+    total = 1 << 24
+    first, count = shard_range(total, rank, world)
+    c = torch.zeros(5, dtype=torch.int64, device=dev)
+    sim_run(code, cfg, first, min(count, 1 << 20), c)                # warm-up
+    c.zero_()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    sim_run(code, cfg, first, count, c)
+    if world > 1:
+        dist.all_reduce(c, op=dist.ReduceOp.SUM)
+    e1.record()
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    r = rates(c.cpu().numpy(), 64, 32)
+    return {"workload": "default (64,32) code, OFDM-32, 3-bit ADC (script AGC, clip 10), 15 dB, sum-product x10, clamp 100", "codewords_total": total,
+            "ms": ms, "codewords_per_s": total / (ms * 1e-3), "uncoded_ber": float(r["uncoded_ber"]), "coded_ber": float(r["coded_ber"]),
+            "coded_bler": float(r["coded_bler"]), "reference_script_probe_2e14_codewords": {"uncoded_ber": 1.35e-2, "coded_ber": 1.87e-4, "coded_bler": 2.09e-2}}
+
+
 def bench_family(a, dev, world, barrier, headline_updates_per_s):
     """every IEEE 802.11n prototype on its code-compiled kernel - decoded information rate and directed
     edge-updates per second (the roofline quantity) next to the headline code's, same decoder settings, LLRs in HBM."""
@@ -659,6 +696,10 @@ def main():
     # ---- BASELINE.json configs[3]: sharded BER/FER sweep, fixed total, one all-reduce of the counters in the timed region ----
     if not a.no_sweep:
         out["sweep"] = bench_sweep(a, dev, world, rank, barrier)
+
+    # ---- BASELINE.json configs[1]: the quantized link on the reference's own code at one SNR -------------------------------
+    if not a.no_sweep:
+        out["quantized_link"] = bench_quantized_link(a, dev, world, rank, barrier)
 
     # ---- the whole IEEE 802.11n family on compiled kernels ----------------------------------------------
     if not a.no_family:

@@ -99,3 +99,24 @@ def test_runtime_specialisation_builds_and_registers(tmp_path):
     assert N.lib().ldpc_qc_register_plugin(str(bogus).encode()) < 0                  # a shared object, but not a plug-in
     ok, why = jit.supported(np.zeros((40, 68), np.int16), 384)
     assert not ok and "block columns" in why
+
+
+def test_header_is_plain_c_and_reference_arm_prints_the_contract_line(tmp_path):
+    """include/ldpc_b200.h must be consumable from C (the drop-in boundary is a C ABI), and `bench.py --impl reference`
+    (the CPU arm: oracle port on host cores, no GPU) must print one JSON line with the contract's keys."""
+    import json, os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = tmp_path / "use.c"
+    src.write_text('#include "ldpc_b200.h"\nint main(void) { ldpc_sim_params_t p; ldpc_decode_params_t d; (void)p; (void)d; return ldpc_abi_version() < 0; }\n')
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", "-I", os.path.join(root, "include"), "-c", str(src), "-o", str(tmp_path / "use.o")])
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0", "--cpu-seconds", "0.3"],
+                         capture_output=True, text=True, timeout=300, env={**os.environ, "RANK": "0"})
+    assert out.returncode == 0, out.stderr[-500:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["unit"] == "Gbit/s" and line["higher_is_better"] is True and line["value"] > 0
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1 and "workload" in line["config"]
+    assert line["e2e"] == {"value": line["value"], "unit": "Gbit/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    # ranks other than 0 of a torchrun launch exit without work
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                         capture_output=True, text=True, timeout=60, env={**os.environ, "RANK": "1", "WORLD_SIZE": "2"})
+    assert out.returncode == 0 and out.stdout.strip() == ""
