@@ -601,13 +601,13 @@ def main():
     # n_sm blocks exchanged through shared memory (the other n_loc blocks and the LLRs are registers)
     smem_bytes_per_update = 4 * n_sm * 81 * 4 / (2 * E_CODE) if n_sm else (4 * E_CODE + N_CODE) * 4 / (2 * E_CODE)
     smem_peak = 148 * 128 * sm_mhz * 1e6 / smem_bytes_per_update
-    # issue ceiling of the instruction stream: 734 SASS instructions per thread-iteration (378 variable
-    # phase + 356 check phase, profiles/r01_sass_loop.txt), thr_cta/cw_cta thread slots per codeword,
-    # 2*E updates per iteration; ALU-pipe ceiling: 248 FMNMX.XORSIGN + 66 ISETP/SEL per thread-iteration on
-    # the half-rate ALU pipe (measured 0.5 warp-instr/clk/SMSP, profiles/r01_pipe_rates.txt)
-    lane_instr_per_update = 734 * (thr_cta / max(cw_cta, 1)) / (2 * E_CODE) if n_sm else None
+    # issue ceiling of the instruction stream: 705 SASS instructions per thread-iteration (371 variable phase + 334 check
+    # phase, profiles/r02_sass_loop.txt), thr_cta/cw_cta thread slots per codeword, 2*E updates per iteration; ALU-pipe
+    # ceiling: 210 FMNMX.XORSIGN + 66 ISETP/SEL per thread-iteration on the half-rate ALU pipe (measured 0.5
+    # warp-instr/clk/SMSP, profiles/r01_pipe_rates.txt)
+    lane_instr_per_update = 705 * (thr_cta / max(cw_cta, 1)) / (2 * E_CODE) if n_sm else None
     issue_peak = 148 * 4 * 32 * sm_mhz * 1e6 / lane_instr_per_update if lane_instr_per_update else None
-    alu_peak = 148 * 4 * 16 * sm_mhz * 1e6 / (314 * (thr_cta / max(cw_cta, 1)) / (2 * E_CODE)) if n_sm else None
+    alu_peak = 148 * 4 * 16 * sm_mhz * 1e6 / (276 * (thr_cta / max(cw_cta, 1)) / (2 * E_CODE)) if n_sm else None
     out = {
         "metric": METRIC, "value": value, "unit": "Gbit/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

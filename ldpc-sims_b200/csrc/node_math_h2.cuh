@@ -33,30 +33,23 @@ __device__ __forceinline__ void h2_sum_others(const __half2 (&in)[D], __half2 (&
     out[0] = acc;
 }
 
+// prefix / suffix form, 3D - 4 operations (see boxmin_others_clamped in node_math.cuh)
 template <int D>
 __device__ __forceinline__ void h2_boxmin_others_clamped(const __half2 (&v)[D], __half2 c, __half2 (&out)[D]) {
-    if constexpr (D == 8) {
-        const __half2 p01 = h2_boxmin(v[0], v[1]), p23 = h2_boxmin(v[2], v[3]), p45 = h2_boxmin(v[4], v[5]), p67 = h2_boxmin(v[6], v[7]);
-        const __half2 qL = h2_boxmin(h2_boxmin(p01, p23), c), qR = h2_boxmin(h2_boxmin(p45, p67), c);
-        out[0] = h2_boxmin(h2_boxmin(v[1], p23), qR); out[1] = h2_boxmin(h2_boxmin(v[0], p23), qR);
-        out[2] = h2_boxmin(h2_boxmin(v[3], p01), qR); out[3] = h2_boxmin(h2_boxmin(v[2], p01), qR);
-        out[4] = h2_boxmin(h2_boxmin(v[5], p67), qL); out[5] = h2_boxmin(h2_boxmin(v[4], p67), qL);
-        out[6] = h2_boxmin(h2_boxmin(v[7], p45), qL); out[7] = h2_boxmin(h2_boxmin(v[6], p45), qL);
-    } else if constexpr (D == 7) {
-        const __half2 p01 = h2_boxmin(v[0], v[1]), p23 = h2_boxmin(v[2], v[3]), p45 = h2_boxmin(v[4], v[5]);
-        const __half2 qL = h2_boxmin(h2_boxmin(p01, p23), c), qR = h2_boxmin(h2_boxmin(p45, v[6]), c);
-        out[0] = h2_boxmin(h2_boxmin(v[1], p23), qR); out[1] = h2_boxmin(h2_boxmin(v[0], p23), qR);
-        out[2] = h2_boxmin(h2_boxmin(v[3], p01), qR); out[3] = h2_boxmin(h2_boxmin(v[2], p01), qR);
-        out[4] = h2_boxmin(h2_boxmin(v[5], v[6]), qL); out[5] = h2_boxmin(h2_boxmin(v[4], v[6]), qL);
-        out[6] = h2_boxmin(p45, qL);
+    if constexpr (D == 1) {
+        out[0] = c;
     } else {
         __half2 pre[D];
-        __half2 acc = c;
+        pre[0] = c;
 #pragma unroll
-        for (int j = 0; j < D; ++j) { pre[j] = acc; acc = h2_boxmin(acc, v[j]); }
-        acc = c;
+        for (int j = 1; j < D; ++j) pre[j] = h2_boxmin(pre[j - 1], v[j - 1]);
+        out[D - 1] = pre[D - 1];
+        __half2 suf = v[D - 1];
 #pragma unroll
-        for (int j = D - 1; j >= 0; --j) { out[j] = h2_boxmin(pre[j], acc); acc = h2_boxmin(acc, v[j]); }
+        for (int j = D - 2; j >= 0; --j) {
+            out[j] = h2_boxmin(pre[j], suf);
+            if (j > 0) suf = h2_boxmin(v[j], suf);
+        }
     }
 }
 
