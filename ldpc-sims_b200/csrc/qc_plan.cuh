@@ -2,6 +2,7 @@
 // code-specialised decoder kernels (fp32 and f16x2 variants).
 #pragma once
 #include <stdint.h>
+#include <type_traits>
 #include <utility>
 
 namespace ldpc {
@@ -22,6 +23,12 @@ struct Wifi1944R12 {
         {-1, 45, -1, 70, 0, -1, -1, -1, 77, 9, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, 0, 0, -1},
         {2, 56, -1, 57, 35, -1, -1, -1, -1, -1, 12, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, 0, 0},
         {24, -1, 61, -1, 60, -1, -1, 27, 51, -1, -1, 16, 1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, 0}};
+    // Spanning tree (block row, block column) that fixes the lane relabelling (QcPlan below).  ANY spanning tree makes
+    // MB + NB - 1 = 35 blocks thread-local; this one (hill-climbing over edge swaps, scratch search recorded in
+    // profiles/r02_decoder_schedule_experiments.md) additionally leaves only 24 DISTINCT effective shifts among the 51
+    // exchanged blocks instead of the 33 of the breadth-first tree: the variable phase needs one ISETP + one SEL per
+    // distinct shift for its rotated-window pointers.
+    static constexpr int forest[35][2] = {{6, 18}, {9, 8}, {9, 4}, {2, 14}, {1, 8}, {6, 1}, {11, 0}, {5, 11}, {10, 23}, {1, 9}, {6, 8}, {3, 0}, {9, 3}, {10, 22}, {3, 7}, {0, 4}, {8, 20}, {11, 8}, {10, 10}, {2, 15}, {2, 5}, {0, 13}, {7, 20}, {8, 11}, {11, 23}, {9, 21}, {4, 4}, {11, 12}, {6, 6}, {8, 8}, {4, 17}, {6, 2}, {8, 5}, {7, 19}, {3, 16}};
 };
 
 // ---- compile-time plan ------------------------------------------------------------------------------
@@ -34,6 +41,11 @@ struct Wifi1944R12 {
 // MB + NB - 1 blocks (35 of the 86 for 802.11n n=1944) become thread-local; only the remaining
 // blocks are exchanged through shared memory.  Which node a thread computes does not change
 // the node's arithmetic, so results stay bit-identical to the generic kernel.
+template <class Code, class = void>
+struct has_forest : std::false_type {};
+template <class Code>
+struct has_forest<Code, std::void_t<decltype(Code::forest)>> : std::true_type {};
+
 template <class Code>
 struct QcPlan {
     static constexpr int Z = Code::Z, MB = Code::MB, NB = Code::NB;
@@ -62,8 +74,25 @@ struct QcPlan {
             for (int r = 0; r < MB; ++r) if (hcol[r] >= 0) { ++cnt; if (r != 0 && r != MB - 1) mid = r; }
             if (cnt != 3 || hcol[0] < 0 || hcol[MB - 1] < 0 || hcol[0] != hcol[MB - 1] || mid < 0 || hcol[mid] != 0) dual_diagonal = false;
         }
-        // breadth-first spanning tree over block rows / block columns
         bool row_seen[MB] = {}, col_seen[NB] = {};
+        if constexpr (has_forest<Code>::value) {
+            // the code brings its own spanning forest: propagate sigma / rho along its edges
+            constexpr int NE = (int)(sizeof(Code::forest) / sizeof(Code::forest[0]));
+            for (int pass = 0; pass < MB + NB; ++pass) {
+                bool any = false;
+                for (int e = 0; e < NE; ++e) {
+                    const int r = Code::forest[e][0], c = Code::forest[e][1];
+                    if (row_seen[r] && !col_seen[c]) { rho[c] = (Code::proto[r][c] + sigma[r]) % Z; col_seen[c] = true; any = true; }
+                    else if (col_seen[c] && !row_seen[r]) { sigma[r] = ((rho[c] - Code::proto[r][c]) % Z + Z) % Z; row_seen[r] = true; any = true; }
+                }
+                if (!any) {                              // start (the next) component at the first forest edge not reached yet
+                    for (int e = 0; e < NE && !any; ++e)
+                        if (!row_seen[Code::forest[e][0]] && !col_seen[Code::forest[e][1]]) { row_seen[Code::forest[e][0]] = true; sigma[Code::forest[e][0]] = 0; any = true; }
+                    if (!any) break;
+                }
+            }
+        }
+        // breadth-first spanning tree over whatever block rows / block columns are still unassigned
         int queue[MB + NB] = {}, head = 0, tail = 0;     // entries: r (>=0) or -(c+1)
         for (int root = 0; root < MB; ++root) {
             if (row_seen[root]) continue;
