@@ -49,7 +49,6 @@ __device__ __forceinline__ void mbar_wait(uint64_t *b, uint32_t parity) {
                      : "memory");
     } while (!ok);
 }
-__device__ __forceinline__ void named_bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 
 template <class T> struct cpt_of { static constexpr int value = 1; };
 template <> struct cpt_of<__half2> { static constexpr int value = 2; };
@@ -67,8 +66,8 @@ struct PersLayout {
     static constexpr size_t HARD_BYTES = (size_t)CWG * HARD_STRIDE;
     static constexpr int SCR_INTS = 3 + 2 * CWG;                  // {uncoded, info, -} + frame flags [CWG] + syndrome weights [CWG]
     static constexpr size_t SCR_BYTES = (SCR_INTS * 4 + 15) & ~size_t(15);
-    static constexpr size_t GROUP_BYTES = MSG_BYTES + STAGE_BYTES + HARD_BYTES + SCR_BYTES;
-    static constexpr size_t SMEM = 16 + GROUP_BYTES;              // the mbarrier in front
+    static constexpr size_t TILE_BYTES = MSG_BYTES + STAGE_BYTES + HARD_BYTES + SCR_BYTES;
+    static constexpr size_t SMEM = 16 + TILE_BYTES;               // the mbarrier in front
     static_assert(N % 4 == 0, "bulk copies move whole 16-byte units: the f32 row must be a multiple of 16 bytes");
 };
 
@@ -147,10 +146,10 @@ decode_qc_pers_kernel(const DecodeArgs a) {
 
     const int tid = threadIdx.x;
     uint64_t *const mbar = reinterpret_cast<uint64_t *>(smem_raw);
-    unsigned char *const grp = smem_raw + 16;
-    T *const msg_s = reinterpret_cast<T *>(grp);
-    float *const stage = reinterpret_cast<float *>(grp + L::MSG_BYTES);
-    uint8_t *const hard_s = grp + L::MSG_BYTES + L::STAGE_BYTES;
+    unsigned char *const tile_s = smem_raw + 16;
+    T *const msg_s = reinterpret_cast<T *>(tile_s);
+    float *const stage = reinterpret_cast<float *>(tile_s + L::MSG_BYTES);
+    uint8_t *const hard_s = tile_s + L::MSG_BYTES + L::STAGE_BYTES;
     int *const scr = reinterpret_cast<int *>(hard_s + L::HARD_BYTES);
 
     // codewords interleaved by lane: thread = t * CWT + slot; message word (blk, z) of slot sl at (blk * Z + z) * CWT + sl
