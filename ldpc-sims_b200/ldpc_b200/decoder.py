@@ -6,6 +6,7 @@ keeps the graph as sparse device tables inside an opaque native handle.
 from __future__ import annotations
 
 import ctypes
+import os
 
 import numpy as np
 import torch
@@ -289,6 +290,15 @@ def decode_bits_host(code: LdpcCode, llrs: np.ndarray, iterations, clamp_value, 
     kinds = {np.dtype(np.float64): N.F64, np.dtype(np.float32): N.F32, np.dtype(np.uint8): N.I8}
     if out.dtype not in kinds:
         raise ValueError("out must be float64, float32 or uint8")
+    if threads <= 0:
+        # the cast / expand threads are host-memory-bound and scale to ~16; under torchrun the ranks of a node share its
+        # cores, so each takes its share (16 threads x 8 ranks on 32 cores measured SLOWER than one rank alone)
+        try:
+            cores = len(os.sched_getaffinity(0))
+        except AttributeError:
+            cores = os.cpu_count() or 1
+        ranks = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1") or 1))
+        threads = max(1, min(16, cores // ranks))
     with torch.cuda.device(code.device):
         N.check(N.lib().ldpc_decode_bits_host(code._h, llrs.ctypes.data, _NP_DTYPES[llrs.dtype], Nn, int(iterations), _update_id(update),
                                               float(clamp_value), float(param), out.ctypes.data, kinds[out.dtype], int(chunk), int(threads)))
