@@ -42,20 +42,23 @@ __global__ void __launch_bounds__((QcLayout<Code, CW>::THREADS)) decode_qc_h2_ke
         // issue all 2*NB independent global loads first (they overlap in flight), convert afterwards
         float raw0[NB], raw1[NB];
         const long long g1 = second ? gbase + N : gbase;                 // half-empty last pair: re-read row 0, discard
-        auto load_all = [&](auto ld) {                                    // one uniform dtype branch, then 2*NB straight loads
+        // one uniform dtype branch, then 2*NB straight loads from two per-thread lane bases with compile-time offsets
+        // (the wrapped position of a column is Z elements lower: a 32-bit select, see decode_qc_kernel.cuh)
+        auto load_all = [&](auto *base, auto conv) {
+            const auto *b0 = base + gbase + t, *b1 = base + g1 + t;
             static_for<NB>([&](auto cc) {
                 constexpr int c = decltype(cc)::value;
                 constexpr int rho = kQc<Code>.rho[c];
-                int zv = t + rho;
-                if (zv >= Z) zv -= Z;
-                raw0[c] = ld(gbase + c * Z + zv);
-                raw1[c] = ld(g1 + c * Z + zv);
+                constexpr int o0 = c * Z + rho;
+                const int off = (rho != 0 && t >= Z - rho) ? (o0 - Z) : o0;
+                raw0[c] = conv(__ldg(b0 + off));
+                raw1[c] = conv(__ldg(b1 + off));
             });
         };
-        if (a.llr_dtype == LDPC_F32) load_all([&](long long i) { return __ldg(reinterpret_cast<const float *>(a.llr) + i); });
-        else if (a.llr_dtype == LDPC_F64) load_all([&](long long i) { return (float)__ldg(reinterpret_cast<const double *>(a.llr) + i); });
-        else if (a.llr_dtype == LDPC_I8) load_all([&](long long i) { return (float)__ldg(reinterpret_cast<const signed char *>(a.llr) + i); });
-        else load_all([&](long long i) { return __half2float(__ldg(reinterpret_cast<const __half *>(a.llr) + i)); });
+        if (a.llr_dtype == LDPC_F32) load_all(reinterpret_cast<const float *>(a.llr), [](float v) { return v; });
+        else if (a.llr_dtype == LDPC_F64) load_all(reinterpret_cast<const double *>(a.llr), [](double v) { return (float)v; });
+        else if (a.llr_dtype == LDPC_I8) load_all(reinterpret_cast<const signed char *>(a.llr), [](signed char v) { return (float)v; });
+        else load_all(reinterpret_cast<const __half *>(a.llr), [](__half v) { return __half2float(v); });
         static_for<NB>([&](auto cc) {
             constexpr int c = decltype(cc)::value;
             llr[c] = __floats2half2_rn(sat_llr(raw0[c]), second ? sat_llr(raw1[c]) : 0.0f);
@@ -208,26 +211,31 @@ __global__ void __launch_bounds__((QcLayout<Code, CW>::THREADS)) decode_qc_h2_ke
                 hb1 |= (unsigned)hard_bit(tf.y) << c;
             });
         }
-        uint8_t *const hrow = hard_s + (2 * pr) * L::HARD_STRIDE;
+        uint8_t *const hrow = hard_s + (2 * pr) * L::HARD_STRIDE + t;     // lane base + compile-time offsets (wrapped: Z lower)
         static_for<NB>([&](auto cc) {
             constexpr int c = decltype(cc)::value;
             constexpr int rho = kQc<Code>.rho[c];
-            int zv = t + rho;
-            if (zv >= Z) zv -= Z;
+            constexpr int o0 = c * Z + rho;
+            const int off = (rho != 0 && t >= Z - rho) ? (o0 - Z) : o0;
             const float2 lf = __half22float2(llr[c]);
-            hrow[c * Z + zv] = (uint8_t)(((hb0 >> c) & 1u) | ((lf.x > 0.0f) ? 2u : 0u));
-            if (second) hrow[L::HARD_STRIDE + c * Z + zv] = (uint8_t)(((hb1 >> c) & 1u) | ((lf.y > 0.0f) ? 2u : 0u));
+            hrow[off] = (uint8_t)(((hb0 >> c) & 1u) | ((lf.x > 0.0f) ? 2u : 0u));
+            if (second) hrow[L::HARD_STRIDE + off] = (uint8_t)(((hb1 >> c) & 1u) | ((lf.y > 0.0f) ? 2u : 0u));
         });
         if (a.llr_post) {
-            float *const post = a.llr_post + gbase;
+            float *const post = a.llr_post + gbase + t;
             static_for<NB>([&](auto cc) {
                 constexpr int c = decltype(cc)::value;
                 constexpr int rho = kQc<Code>.rho[c];
-                int zv = t + rho;
-                if (zv >= Z) zv -= Z;
+                constexpr int o0 = c * Z + rho;
                 const float2 tf = __half22float2(th[c]);
-                post[c * Z + zv] = __fmul_rn(-2.0f, tf.x);
-                if (second) post[N + c * Z + zv] = __fmul_rn(-2.0f, tf.y);
+                const float v0 = __fmul_rn(-2.0f, tf.x), v1 = __fmul_rn(-2.0f, tf.y);
+                if (rho != 0 && t >= Z - rho) {
+                    post[o0 - Z] = v0;
+                    if (second) post[N + o0 - Z] = v1;
+                } else {
+                    post[o0] = v0;
+                    if (second) post[N + o0] = v1;
+                }
             });
         }
         if (a.prob || a.hard) {                                            // byte / probability outputs: cold path

@@ -67,19 +67,23 @@ __global__ void __launch_bounds__((QcLayout<Code, CW>::THREADS), (QcLayout<Code,
     const long long gbase = (cw0 + (active ? cw : 0)) * N;
     if constexpr (SIM == 0) {
     if (active) {
-        auto load_all = [&](auto ld) {                                    // one uniform dtype branch, then NB straight loads
+        // One uniform dtype branch, then NB straight loads.  Variable (c, (t + rho_c) mod Z) sits at lane-base + c Z + rho_c,
+        // or Z elements lower once t + rho_c wraps: two COMPILE-TIME offsets from one per-thread base pointer, selected by
+        // a predicate.
+        auto load_all = [&](auto *base, auto conv) {
+            const auto *bp = base + gbase + t;
             static_for<NB>([&](auto cc) {
                 constexpr int c = decltype(cc)::value;
                 constexpr int rho = kQc<Code>.rho[c];
-                int zv = t + rho;
-                if (zv >= Z) zv -= Z;
-                llr[c] = ld(gbase + c * Z + zv);
+                constexpr int o0 = c * Z + rho;
+                const int off = (rho != 0 && t >= Z - rho) ? (o0 - Z) : o0;            // a 32-bit select, then one widening add
+                llr[c] = conv(__ldg(bp + off));
             });
         };
-        if (a.llr_dtype == LDPC_F32) load_all([&](long long i) { return __ldg(reinterpret_cast<const float *>(a.llr) + i); });
-        else if (a.llr_dtype == LDPC_F64) load_all([&](long long i) { return (float)__ldg(reinterpret_cast<const double *>(a.llr) + i); });
-        else if (a.llr_dtype == LDPC_I8) load_all([&](long long i) { return (float)__ldg(reinterpret_cast<const signed char *>(a.llr) + i); });
-        else load_all([&](long long i) { return __half2float(__ldg(reinterpret_cast<const __half *>(a.llr) + i)); });
+        if (a.llr_dtype == LDPC_F32) load_all(reinterpret_cast<const float *>(a.llr), [](float v) { return v; });
+        else if (a.llr_dtype == LDPC_F64) load_all(reinterpret_cast<const double *>(a.llr), [](double v) { return (float)v; });
+        else if (a.llr_dtype == LDPC_I8) load_all(reinterpret_cast<const signed char *>(a.llr), [](signed char v) { return (float)v; });
+        else load_all(reinterpret_cast<const __half *>(a.llr), [](__half v) { return __half2float(v); });
     }
     } else {
         static_assert(SIM == 0 || kQc<Code>.dual_diagonal, "the fused simulator needs the dual-diagonal encoder structure");
@@ -279,25 +283,26 @@ __global__ void __launch_bounds__((QcLayout<Code, CW>::THREADS), (QcLayout<Code,
                 hbits |= (unsigned)hard_bit(tm[c]) << c;
             });
         }
-        uint8_t *const hrow = hard_s + cw * L::HARD_STRIDE;
+        uint8_t *const hrow = hard_s + cw * L::HARD_STRIDE + t;           // lane base: two compile-time offsets per column (see the LLR loads)
         static_for<NB>([&](auto cc) {
             constexpr int c = decltype(cc)::value;
             constexpr int rho = kQc<Code>.rho[c];
-            int zv = t + rho;
-            if (zv >= Z) zv -= Z;
+            constexpr int o0 = c * Z + rho;
             const unsigned v = ((hbits >> c) & 1u) | ((llr[c] > 0.0f) ? 2u : 0u);
-            uint8_t *hp = hrow + c * Z + zv;
+            uint8_t *hp = (rho != 0 && t >= Z - rho) ? hrow + (o0 - Z) : hrow + o0;
             *hp = (uint8_t)(SIM ? ((*hp & 4u) | v) : v);
         });
         if (final_pass) {
             if (a.llr_post) {
-                float *const post = a.llr_post + gbase;
+                float *const post = a.llr_post + gbase + t;
                 static_for<NB>([&](auto cc) {
                     constexpr int c = decltype(cc)::value;
                     constexpr int rho = kQc<Code>.rho[c];
-                    int zv = t + rho;
-                    if (zv >= Z) zv -= Z;
-                    post[c * Z + zv] = __fmul_rn(-2.0f, tm[c]);
+                    constexpr int o0 = c * Z + rho;
+                    const float v = __fmul_rn(-2.0f, tm[c]);
+                    if constexpr (rho == 0) post[o0] = v;
+                    else if (t >= Z - rho) post[o0 - Z] = v;
+                    else post[o0] = v;
                 });
             }
             if (a.prob || a.hard) {                                          // byte / probability outputs: cold path
