@@ -228,7 +228,10 @@ def bench_nn(a, dev, world, barrier, peaks):
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
-    ms_mlp = timed(lambda: net(x), 3)
+    ms_mlp = timed(lambda: net(x), 3)                   # default schedule: the single-launch L2-resident chain
+    net.set_mode("per_layer")
+    ms_mlp_pl = timed(lambda: net(x), 3)                # round-1 schedule: one launch per layer, activations through HBM
+    net.set_mode("auto")
     counters = torch.zeros(5, dtype=torch.int64, device=dev)
     ms_link = timed(lambda: sim_run_nn(code, cfg, net, 0, S, counters), 2)
     # the reference's default code alone (BASELINE.json configs[0]/[1]): register-resident kernel, LLRs resident in HBM
@@ -243,12 +246,15 @@ def bench_nn(a, dev, world, barrier, peaks):
     c = counters.cpu().numpy().astype(np.float64)
     return {"workload": "LLRestimator_withSNR(32) 65-512-512-512-64 tanh (reference checkpoint) + (64,32) code, sum-product x10, 15 dB, 3-bit ADC",
             "ofdm_symbols_per_gpu": S, "link_ms": ms_link, "link_symbols_per_s": S * world / (ms_link * 1e-3),
-            "link_info_gbps": S * world * 32 / (ms_link * 1e-3) / 1e9, "mlp_ms": ms_mlp,
+            "link_info_gbps": S * world * 32 / (ms_link * 1e-3) / 1e9, "mlp_ms": ms_mlp, "mlp_ms_per_layer_launches": ms_mlp_pl,
+            "mlp_schedule": "one cooperative launch per 303 104-row chunk: groups of 4 SMs carry 128-row blocks through all layers, activation "
+                            "planes handed over through L2 (DRAM traffic 3.4 KB/row against 10.6 KB/row of the per-layer launches, ncu: "
+                            "profiles/r02_mlp_experiments.md)",
             "mlp_fp32_equivalent_tflops": flops / (ms_mlp * 1e-3) / 1e12,
             "roofline": {"bound": "tensor", "achieved": 3 * flops / (ms_mlp * 1e-3) / 1e12, "peak": tf_peak, "unit": "TFLOP/s",
                          "frac": 3 * flops / (ms_mlp * 1e-3) / 1e12 / tf_peak, "traffic": None,
                          "note": "16-bit tcgen05.mma flops issued: 3 plane pairs per fp32 product (2 exact binary16 planes per operand)"},
-            "coded_ber_nn": c[1] / max(c[4] * 32, 1), "uncoded_ber_nn": c[0] / max(c[3], 1), "gpu_launches_per_chunk": 8,
+            "coded_ber_nn": c[1] / max(c[4] * 32, 1), "uncoded_ber_nn": c[0] / max(c[3], 1), "gpu_launches_per_chunk": 5,
             "default_code_decode": {"codewords_per_gpu": S, "kernel": ("generic", "qc", "tiny", "qc_rt")[code.kernel],
                                     "sum_product_x10_info_gbps": S * world * 32 / (ms_sp * 1e-3) / 1e9, "sum_product_ms": ms_sp,
                                     "min_sum_x10_info_gbps": S * world * 32 / (ms_ms * 1e-3) / 1e9, "min_sum_ms": ms_ms,

@@ -346,6 +346,14 @@ int ldpc_mlp_create(int n_layers, const int32_t *dims, const float *const *weigh
                     int64_t chunk_rows, ldpc_mlp_t **out);
 int ldpc_mlp_forward(ldpc_mlp_t *mlp, const float *x, int64_t B, float *y, ldpc_stream_t stream);
 void ldpc_mlp_destroy(ldpc_mlp_t *mlp);
+/* How ldpc_mlp_forward schedules the chain (results are bit-identical):
+ * LDPC_MLP_PER_LAYER - one launch per layer, activation planes of a chunk ping-pong through device memory;
+ * LDPC_MLP_CHAIN     - one cooperative launch per chunk: groups of 4 SMs carry blocks of 128 rows through all layers while
+ *                      their activation planes are still in L2 (splits = 2, at most 6 layers of at most 512 outputs;
+ *                      LDPC_EUNSUPPORTED otherwise);
+ * LDPC_MLP_AUTO      - the chain where it applies (default). */
+enum { LDPC_MLP_AUTO = 0, LDPC_MLP_PER_LAYER = 1, LDPC_MLP_CHAIN = 2 };
+int ldpc_mlp_set_mode(ldpc_mlp_t *mlp, int mode);
 
 #ifdef __cplusplus
 }

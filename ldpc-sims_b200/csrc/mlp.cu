@@ -20,7 +20,8 @@
 //           every store instruction writes 8 rows x 64 contiguous bytes (or the fp32 result of the last
 //           layer); TMEM holds two accumulator sets, so the epilogue of a tile overlaps the loads and MMAs
 //           of the next one
-// Activations of a chunk of rows ping-pong between two plane buffers that stay L2-resident.
+// Activations of a chunk of rows ping-pong between two plane buffers (LDPC_MLP_PER_LAYER); where the shape allows, the whole
+// chain runs in ONE cooperative launch per chunk instead (chain_kernel below, LDPC_MLP_CHAIN, the default).
 #include <cuda.h>
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
@@ -64,6 +65,15 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *map
     asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
                  ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
+// the same load with an L2 eviction-priority hint (the fixed createpolicy encodings CUTLASS uses: cute/arch/copy_sm90_desc.hpp)
+constexpr uint64_t L2_EVICT_FIRST = 0x12F0000000000000ull, L2_EVICT_LAST = 0x14F0000000000000ull;
+__device__ __forceinline__ void tma_load_3d_hint(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1, int c2, uint64_t policy) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4, %5}], [%2], %6;"
+                 ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "l"(policy) : "memory");
+}
+__device__ __forceinline__ void st_global_v4_hint(void *p, const uint4 &v, uint64_t policy) {
+    asm volatile("st.global.L2::cache_hint.v4.b32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "l"(policy) : "memory");
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
@@ -96,9 +106,21 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-// libm tanhf (~1 ulp): measured FASTER in this epilogue than an ex2.approx/rcp.approx formulation (twice, on two
-// kernel generations) and it keeps the activations within an ulp of the reference's ATen tanh.
-__device__ __forceinline__ float tanh_act(float x) { return tanhf(x); }
+// tanh(x) = sign(x) (1 - e) / (1 + e) with e = 2^(-2 log2(e) |x|): two MUFU (ex2, rcp) + five ALU instructions, no branch.
+// Absolute error <= ~3e-7 over the whole range (the cancellation in 1 - e near 0 costs relative, not absolute, accuracy, and the
+// next layer consumes absolute values): the error of the whole chain against float64 is unchanged (2.2e-6 of the output scale,
+// profiles/r02_mlp_experiments.md).  libm tanhf is ~25 instructions with both range branches predicated, and the epilogue warps
+// are issue/latency-bound: 4.67 -> 4.50 ms per 2^20 rows.  -DMLP_EXP_NOTANH (timing experiments only) removes the activation.
+#ifdef MLP_EXP_NOTANH
+__device__ __forceinline__ float tanh_act(float x) { return x * 0.01f; }
+#else
+__device__ __forceinline__ float tanh_act(float x) {
+    float e, r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(fabsf(x) * -2.885390082f));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
+    return copysignf((1.0f - e) * r, x);
+}
+#endif
 
 // exact split of an fp32 value into binary16 planes
 template <int NS>
@@ -230,6 +252,10 @@ __global__ void __launch_bounds__(THREADS, 1) layer_kernel(const __grid_constant
                     const uint32_t ph = (it / STAGES) & 1;
                     mbar_wait(empty_bar(s), ph ^ 1);
                     TRACE(0);
+#ifdef MLP_EXP_NOLOAD
+                    mbar_arrive(full_bar(s));
+                    (void)m0; (void)n0;
+#else
                     mbar_expect_tx(full_bar(s), S::STAGE_BYTES);
                     const uint32_t st = base + s * S::STAGE_BYTES;
 #pragma unroll
@@ -237,6 +263,7 @@ __global__ void __launch_bounds__(THREADS, 1) layer_kernel(const __grid_constant
                         tma_load_3d(st + p * S::A_BYTES, &map_a, full_bar(s), kb * BK, m0, p);
                         tma_load_3d(st + NS * S::A_BYTES + p * S::B_BYTES, &map_w, full_bar(s), kb * BK, n0, p);
                     }
+#endif
                 }
             }
         }
@@ -257,6 +284,7 @@ __global__ void __launch_bounds__(THREADS, 1) layer_kernel(const __grid_constant
                 if (lane == 0) {
                     TRACE(1);
                     const uint32_t st = base + s * S::STAGE_BYTES;
+#ifndef MLP_EXP_NOMMA
 #pragma unroll
                     for (int k = 0; k < BK / UMMA_K; ++k) {
                         if constexpr (NS == 2) {
@@ -282,6 +310,7 @@ __global__ void __launch_bounds__(THREADS, 1) layer_kernel(const __grid_constant
                             }
                         }
                     }
+#endif
                     tc_commit(empty_bar(s));                               // stage free once these MMAs have read it
                     if (kb == args.k_blocks - 1) tc_commit(tfull_bar(acc)); // accumulator set complete
                 }
@@ -301,19 +330,24 @@ __global__ void __launch_bounds__(THREADS, 1) layer_kernel(const __grid_constant
             const long long m = (long long)m0 + row;
             mbar_wait(tfull_bar(acc), acc_ph);
             tc_fence_after();
+#ifdef MLP_EXP_NOEPI
+            if (lane == 0) mbar_arrive(tempty_bar(acc));
+            continue;
+#endif
             if (warp == 2 && lane == 0) TRACE(2);
             const uint32_t d_main = tmem_base + acc * ACC_COLS + ((uint32_t)(quad * 32) << 16);
 #pragma unroll 1
             for (int c0 = part * PART_COLS; c0 < (part + 1) * PART_COLS && c0 < BN; c0 += 32) {
                 uint32_t v[32], w[32];
+                float o[32];
+                const float bias_l = args.bias ? __ldg(args.bias + n0 + c0 + lane) : 0.0f;   // lane q holds the bias of column q: one load, in flight while the accumulators are read
                 tmem_ld32(d_main + (uint32_t)c0, v);
                 if (NS > 1) tmem_ld32(d_main + ACC2 + (uint32_t)c0, w);
-                float o[32];
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {
                     float f = __uint_as_float(v[j]);
                     if (NS > 1) f = __fadd_rn(f, __uint_as_float(w[j]));
-                    if (args.bias) f = __fadd_rn(f, __ldg(args.bias + n0 + c0 + j));
+                    if (args.bias) f = __fadd_rn(f, __shfl_sync(0xffffffffu, bias_l, j));
                     o[j] = args.act ? tanh_act(f) : f;
                 }
                 if (args.out_f32) {
@@ -353,6 +387,9 @@ __global__ void __launch_bounds__(THREADS, 1) layer_kernel(const __grid_constant
                             uint4 v;
                             asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
                                          : "r"(stg + (uint32_t)R * 64u + (uint32_t)((C ^ ((R >> 1) & 3)) << 4)) : "memory");
+#ifdef MLP_EXP_NOSTORE
+                            if (v.x == 0x12345678u && args.m_valid < 0)
+#endif
                             *reinterpret_cast<uint4 *>(plane + (long long)R * args.n_total + C * 8) = v;
                         }
                         __syncwarp();
@@ -364,6 +401,270 @@ __global__ void __launch_bounds__(THREADS, 1) layer_kernel(const __grid_constant
             if (warp == 2 && lane == 0) TRACE(2);
             if (lane == 0) mbar_arrive(tempty_bar(acc));                   // this warp is done with the accumulator set
         }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    }
+}
+
+// ---- the whole chain in ONE launch: row blocks flow through the layers while their activations are still in L2 ----------
+// The per-layer launches above stream every activation plane through HBM twice (write, then read by the next launch: 10.6 KB
+// per row measured, 20x the algorithmic 516 B).  Here GROUP = 4 persistent CTAs (one per SM) own a block of 128 rows for ALL
+// layers: CTA r computes one column tile of every layer (a narrower last layer rotates over the CTAs), writes its [128 x BN]
+// slice of the activation planes to a small ring in global memory (INFLIGHT row blocks per group, L2 evict_last stores) and a
+// signalling thread publishes it with fence + add on a per-(row block, layer) counter; the TMA producer of a tile of the
+// next layer acquires the counter (all GROUP slices of the previous layer present), crosses to the async proxy
+// (fence.proxy.async) and loads the full-width A operand from L2.  INFLIGHT row blocks are interleaved layer by layer, so the
+// epilogue and the cross-SM hand-over of one overlap the MMAs of the others.  Results are bit-identical to the per-layer
+// launches (same MMA order per tile, same epilogue arithmetic).  Measured on 2^20 rows (profiles/r02_mlp_experiments.md):
+// INFLIGHT = 4 (78 MB ring): 4.41 ms, 3.4 KB of DRAM traffic per row; 3 (58 MB): 4.64 ms, 1.6 KB; 2 (39 MB): 5.17 ms, 1.3 KB -
+// of which 0.6 KB is the input plane split, still a separate launch.  Launched cooperatively: the spin waits need every CTA of
+// a group resident.
+#ifndef MLP_INFLIGHT
+#define MLP_INFLIGHT 4
+#endif
+constexpr int MAX_CHAIN = 6, GROUP = 4, INFLIGHT = MLP_INFLIGHT;
+
+struct ChainLayer {
+    int k_blocks, n_total, bn, act;
+    const float *bias;
+};
+struct ChainArgs {
+    int n_layers, m_valid, row_blocks, n_groups;
+    ChainLayer L[MAX_CHAIN];
+    __half *ring[2];              // activation planes [NS][ring_rows][width of the producing layer]; layer l reads ring[l & 1]
+    long long ring_rows;          // n_groups * INFLIGHT * 128
+    float *out_f32;               // [m_valid][N of the last layer]
+    unsigned int *flags;          // [n_groups * INFLIGHT][MAX_CHAIN] epilogue-warp arrivals, monotonic within a launch
+};
+struct ChainMaps {
+    CUtensorMap a[MAX_CHAIN], w[MAX_CHAIN];
+};
+
+// Tiles of CTA r of group g, in issue order; every role of the CTA walks the same sequence.  Within a generation of INFLIGHT
+// row blocks the layers go round robin, except that the (short) layer-0 tiles of row blocks 2, 3, ... are slotted between the
+// layer-1 tiles of row blocks 0, 1, ...: a layer-0 tile has a quarter of the MMA work of a hidden tile but a full epilogue.
+template <class F>
+__device__ __forceinline__ void chain_tiles(const ChainArgs &a, int g, int r, F &&f) {
+    const int mine = (a.row_blocks - g + a.n_groups - 1) / a.n_groups;     // row blocks g, g + n_groups, ... of this group
+    auto tile = [&](int j, int l) {
+        const int nt = (r + GROUP - (j & (GROUP - 1))) & (GROUP - 1);      // a layer with fewer than GROUP tiles rotates over the CTAs
+        if (nt * a.L[l].bn < a.L[l].n_total) f(j, l, g + a.n_groups * j, nt);
+    };
+    for (int j0 = 0; j0 < mine; j0 += INFLIGHT) {
+        const int cnt = mine - j0 < INFLIGHT ? mine - j0 : INFLIGHT;
+        for (int s = 0; s < 2 && s < cnt; ++s) tile(j0 + s, 0);
+        for (int s = 0; s < cnt; ++s) {
+            tile(j0 + s, 1);
+            if (s + 2 < cnt) tile(j0 + s + 2, 0);
+        }
+        for (int l = 2; l < a.n_layers; ++l)
+            for (int s = 0; s < cnt; ++s) tile(j0 + s, l);
+    }
+}
+
+__device__ __forceinline__ void wait_counter(const unsigned int *p, unsigned int target) {
+    unsigned int v = 0;
+    for (unsigned spin = 0;; ++spin) {
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+        if (v >= target) break;
+        if (spin > (1u << 24)) __trap();
+        __nanosleep(64);
+    }
+    asm volatile("fence.proxy.async;" ::: "memory");       // the data was written through the generic proxy, TMA reads through the async proxy
+}
+
+constexpr int CHAIN_THREADS = THREADS + 32;          // + the signalling warp
+
+template <int NS>
+__global__ void __launch_bounds__(CHAIN_THREADS, 1) chain_kernel(const __grid_constant__ ChainMaps maps, const ChainArgs args) {
+    static_assert(NS == 2, "the chain kernel is the fp32-equivalent two-plane path");
+    constexpr int A_BYTES = BM * BK * 2, STAGE_MAX = NS * (A_BYTES + 128 * BK * 2), STAGES = 3;
+    constexpr uint32_t ACC_COLS = 256, TMEM_COLS = 512;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t bars = base + STAGES * STAGE_MAX;
+    auto full_bar = [&](int s) { return bars + 8u * s; };
+    auto empty_bar = [&](int s) { return bars + 8u * (STAGES + s); };
+    auto tfull_bar = [&](int a) { return bars + 8u * (2 * STAGES + a); };
+    auto tempty_bar = [&](int a) { return bars + 8u * (2 * STAGES + 2 + a); };
+    const uint32_t tmem_slot = bars + 8u * (2 * STAGES + 4);
+    auto stored_bar = [&](uint32_t t) { return bars + 8u * (2 * STAGES + 5 + (t & 3)); };   // the epilogue warps have issued the stores of tile t
+    const uint32_t store_staging = bars + 128u;
+    volatile uint32_t *tmem_slot_ptr = reinterpret_cast<volatile uint32_t *>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = blockIdx.x / GROUP, r = blockIdx.x % GROUP;
+    const int last = args.n_layers - 1;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), EPI_WARPS); }
+        for (uint32_t t = 0; t < 4; ++t) mbar_init(stored_bar(t), EPI_WARPS);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+
+    if (warp == 2 + EPI_WARPS) {
+        // ===== signaller: publishes a tile once its stores are visible device-wide.  The fence waits for the store
+        // acknowledgements (microseconds under load), so it lives here and not in the epilogue warps: they release (CTA scope)
+        // on an mbarrier and carry on; this thread acquires it, and its device-scope fence is cumulative over their stores.
+        if (lane == 0) {
+            uint32_t ti = 0;
+            chain_tiles(args, g, r, [&](int j, int l, int, int) {
+                mbar_wait(stored_bar(ti), (ti >> 2) & 1);
+                ++ti;
+                __threadfence();
+                atomicAdd(args.flags + (g * INFLIGHT + (j % INFLIGHT)) * MAX_CHAIN + l, (unsigned)EPI_WARPS);
+            });
+        }
+    } else if (warp == 0) {
+        if (lane == 0) {                                                   // ===== TMA producer =====
+            uint32_t it = 0;
+            chain_tiles(args, g, r, [&](int j, int l, int rb, int nt) {
+                const ChainLayer &L = args.L[l];
+                const int slot = g * INFLIGHT + (j % INFLIGHT);
+                const unsigned use = (unsigned)(j / INFLIGHT);             // earlier row blocks that went through this slot
+                int arow;
+                if (l == 0) {
+                    arow = rb * BM;
+                    // the first epilogue of this row block overwrites ring[1][slot]: the LAST layer of the previous occupant must have read it
+                    if (use) wait_counter(args.flags + slot * MAX_CHAIN + last, (unsigned)EPI_WARPS * (unsigned)(args.L[last].n_total / args.L[last].bn) * use);
+                } else {
+                    arow = slot * BM;
+                    wait_counter(args.flags + slot * MAX_CHAIN + (l - 1), (unsigned)EPI_WARPS * (unsigned)(args.L[l - 1].n_total / args.L[l - 1].bn) * (use + 1));
+                }
+                const uint32_t b_bytes = (uint32_t)L.bn * BK * 2;
+                TRACE(0);
+                for (int kb = 0; kb < L.k_blocks; ++kb, ++it) {
+                    const int s = it % STAGES;
+                    mbar_wait(empty_bar(s), ((it / STAGES) & 1) ^ 1);
+                    mbar_expect_tx(full_bar(s), NS * (A_BYTES + b_bytes));
+                    const uint32_t st = base + s * STAGE_MAX;
+#pragma unroll
+                    for (int p = 0; p < NS; ++p) {        // input planes stream through L2 once; ring and weights should stay
+                        tma_load_3d_hint(st + p * A_BYTES, &maps.a[l], full_bar(s), kb * BK, arow, p, l == 0 ? L2_EVICT_FIRST : L2_EVICT_LAST);
+                        tma_load_3d_hint(st + NS * A_BYTES + p * b_bytes, &maps.w[l], full_bar(s), kb * BK, nt * L.bn, p, L2_EVICT_LAST);
+                    }
+                }
+            });
+        }
+    } else if (warp == 1) {                                                // ===== MMA issuer =====
+        uint32_t it = 0, ti = 0;
+        chain_tiles(args, g, r, [&](int, int l, int, int) {
+            const ChainLayer &L = args.L[l];
+            const uint32_t acc = ti & 1, acc_ph = (ti >> 1) & 1;
+            ++ti;
+            mbar_wait(tempty_bar(acc), acc_ph ^ 1);
+            tc_fence_after();
+            if (lane == 0) TRACE(1);
+            const uint32_t d_main = tmem_base + acc * ACC_COLS;
+            const uint32_t idesc = (1u << 4) | ((uint32_t)(L.bn >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+            const uint32_t idesc2 = (1u << 4) | ((uint32_t)((2 * L.bn) >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+            for (int kb = 0; kb < L.k_blocks; ++kb, ++it) {
+                const int s = it % STAGES;
+                mbar_wait(full_bar(s), (it / STAGES) & 1);
+                tc_fence_after();
+                if (lane == 0) {
+                    const uint32_t st = base + s * STAGE_MAX;
+#pragma unroll
+                    for (int k = 0; k < BK / UMMA_K; ++k) {                // A0 [W0;W1]^T (N = 2 BN: pairs (0,0) | (0,1)), then A1 W0^T (pair (1,0))
+                        const uint64_t a0 = umma_desc_sw128(st + k * UMMA_K * 2), a1 = umma_desc_sw128(st + A_BYTES + k * UMMA_K * 2);
+                        const uint64_t b0 = umma_desc_sw128(st + NS * A_BYTES + k * UMMA_K * 2);
+                        umma_f16(d_main, a0, b0, idesc2, (kb | k) ? 1u : 0u);
+                        umma_f16(d_main + (uint32_t)L.bn, a1, b0, idesc, 1u);
+                    }
+                    tc_commit(empty_bar(s));
+                    if (kb == L.k_blocks - 1) { tc_commit(tfull_bar(acc)); TRACE(1); }
+                }
+                __syncwarp();
+            }
+        });
+    } else {                                                               // ===== epilogue warps =====
+        const int quad = warp & 3, part = (warp - 2) >> 2;                 // TMEM lane quadrant, 32-column slice
+        const int row = quad * 32 + lane;
+        uint32_t ti = 0;
+        chain_tiles(args, g, r, [&](int j, int l, int rb, int nt) {
+            const ChainLayer &L = args.L[l];
+            const int slot = g * INFLIGHT + (j % INFLIGHT);
+            const int n0 = nt * L.bn;
+            const uint32_t acc = ti & 1, acc_ph = (ti >> 1) & 1;
+            ++ti;
+            mbar_wait(tfull_bar(acc), acc_ph);
+            tc_fence_after();
+            if (warp == 2 && lane == 0) TRACE(2);
+            const uint32_t d_main = tmem_base + acc * ACC_COLS + ((uint32_t)(quad * 32) << 16);
+#pragma unroll 1
+            for (int c0 = part * 32; c0 < L.bn; c0 += 32 * (EPI_WARPS / 4)) {
+                uint32_t v[32], w[32];
+                float o[32];
+                const float bias_l = L.bias ? __ldg(L.bias + n0 + c0 + lane) : 0.0f;         // lane q holds the bias of column q: one load, in flight while the accumulators are read
+                tmem_ld32(d_main + (uint32_t)c0, v);
+                tmem_ld32(d_main + (uint32_t)(L.bn + c0), w);
+#pragma unroll
+                for (int q = 0; q < 32; ++q) {
+                    float f = __fadd_rn(__uint_as_float(v[q]), __uint_as_float(w[q]));
+                    if (L.bias) f = __fadd_rn(f, __shfl_sync(0xffffffffu, bias_l, q));
+                    o[q] = L.act ? tanh_act(f) : f;
+                }
+                if (l == last) {
+                    const long long m = (long long)rb * BM + row;
+                    if (m < args.m_valid) {
+                        float4 *dst = reinterpret_cast<float4 *>(args.out_f32 + m * L.n_total + n0 + c0);
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) __stcs(dst + q, make_float4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]));
+                    }
+                } else {
+                    const uint32_t stg = store_staging + (uint32_t)(warp - 2) * 2048u;
+#pragma unroll
+                    for (int s = 0; s < NS; ++s) {                         // exact plane split + transposed store (see layer_kernel)
+                        uint32_t pk[16];
+#pragma unroll
+                        for (int q = 0; q < 16; ++q) {
+                            const __half2 h = __floats2half2_rn(o[2 * q], o[2 * q + 1]);
+                            pk[q] = *reinterpret_cast<const uint32_t *>(&h);
+                            if (s + 1 < NS) {
+                                const float2 hf = __half22float2(h);
+                                o[2 * q] = __fsub_rn(o[2 * q], hf.x);
+                                o[2 * q + 1] = __fsub_rn(o[2 * q + 1], hf.y);
+                            }
+                        }
+#pragma unroll
+                        for (int q = 0; q < 4; ++q)
+                            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg + (uint32_t)lane * 64u + (uint32_t)((q ^ ((lane >> 1) & 3)) << 4)),
+                                         "r"(pk[4 * q]), "r"(pk[4 * q + 1]), "r"(pk[4 * q + 2]), "r"(pk[4 * q + 3]) : "memory");
+                        __syncwarp();
+                        __half *const plane = args.ring[(l + 1) & 1] + (long long)s * args.ring_rows * L.n_total +
+                                              ((long long)slot * BM + quad * 32) * L.n_total + n0 + c0;
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const int R = 8 * i + (lane >> 2), C = lane & 3;
+                            uint4 u;
+                            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(u.x), "=r"(u.y), "=r"(u.z), "=r"(u.w)
+                                         : "r"(stg + (uint32_t)R * 64u + (uint32_t)((C ^ ((R >> 1) & 3)) << 4)) : "memory");
+                            st_global_v4_hint(plane + (long long)R * L.n_total + C * 8, u, L2_EVICT_LAST);   // dirty ring lines stay in L2 until the slot is rewritten
+                        }
+                        __syncwarp();
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();                                                  // the lanes' stores happen before lane 0's (releasing) arrivals
+            if (lane == 0) {
+                mbar_arrive(tempty_bar(acc));
+                mbar_arrive(stored_bar(ti - 1));
+                if (warp == 2) TRACE(2);
+            }
+        });
     }
     tc_fence_before();
     __syncthreads();
@@ -415,10 +716,18 @@ struct Layer {
 struct ldpc_mlp {
     int ns, device;
     long long chunk = 0;       // rows the activation buffers currently hold (grown on demand up to chunk_max)
-    long long chunk_max = 0;
+    long long chunk_max = 0, chain_chunk_max = 0;
     int maxw = 0;              // widest layer (elements per row)
     std::vector<ldpc::mlp::Layer> layers;
-    __half *d_act[2] = {nullptr, nullptr};   // ping-pong activation planes [NS][chunk][maxw]
+    __half *d_act[2] = {nullptr, nullptr};   // ping-pong activation planes [NS][chunk][maxw] (one launch per layer)
+    // single-launch chain (chain_kernel): input planes of a chunk, the L2-resident activation ring, the arrival counters
+    int mode = 0;              // LDPC_MLP_AUTO / _PER_LAYER / _CHAIN
+    bool chain_ok = false;     // shape and device allow the chain kernel
+    int n_groups = 0;
+    long long x_rows = 0;
+    __half *d_x = nullptr, *d_ring[2] = {nullptr, nullptr};
+    unsigned int *d_flags = nullptr;
+    ldpc::mlp::ChainMaps cmaps;
     std::mutex mu;             // ldpc_mlp_forward grows and reuses the activation buffers: one call at a time per handle
 };
 
@@ -469,6 +778,7 @@ void ldpc_mlp_destroy(ldpc_mlp_t *h) {
     if (!h) return;
     for (auto &L : h->layers) { cudaFree(L.d_bias); cudaFree(L.d_w); }
     cudaFree(h->d_act[0]); cudaFree(h->d_act[1]);
+    cudaFree(h->d_x); cudaFree(h->d_ring[0]); cudaFree(h->d_ring[1]); cudaFree(h->d_flags);
     delete h;
 }
 
@@ -487,7 +797,10 @@ int ldpc_mlp_create(int n_layers, const int32_t *dims, const float *const *weigh
     ldpc_mlp *h = new ldpc_mlp();
     h->ns = splits;
     cudaGetDevice(&h->device);
-    if (chunk_rows <= 0) chunk_rows = 128 * 148 * 4;                      // 592 row tiles x 4 column tiles at N = 512: 16 tiles per persistent CTA (fill/drain amortised)
+    // default chunks: per-layer launches 592 row tiles (16 tiles per persistent CTA and layer amortise the fill/drain; both
+    // activation buffers of a chunk are 310 MB), the single-launch chain 4x that (its only per-chunk buffer is the input planes)
+    h->chain_chunk_max = chunk_rows > 0 ? ((chunk_rows + BM - 1) / BM) * BM : 128LL * 148 * 16;
+    if (chunk_rows <= 0) chunk_rows = 128 * 148 * 4;
     h->chunk_max = ((chunk_rows + BM - 1) / BM) * BM;
     int maxw = 0;
     h->layers.resize(n_layers);
@@ -520,6 +833,14 @@ int ldpc_mlp_create(int n_layers, const int32_t *dims, const float *const *weigh
         if ((rc = make_map(&L.map_w, L.d_w, L.Kp, L.N, h->ns, L.BN))) return fail(rc);
     }
     if (cudaGetLastError() != cudaSuccess) { set_error("ldpc_mlp_create: CUDA error while uploading the weights"); return fail(LDPC_ECUDA); }
+    {
+        int coop = 0, sms = 0;
+        cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, h->device);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
+        h->n_groups = sms / GROUP;
+        h->chain_ok = coop && h->ns == 2 && n_layers >= 2 && n_layers <= MAX_CHAIN && h->n_groups > 0;
+        for (const Layer &L : h->layers) h->chain_ok = h->chain_ok && L.N / L.BN <= GROUP;
+    }
     *out = h;
     return LDPC_OK;
 }
@@ -547,12 +868,66 @@ static int ensure_activation_buffers(ldpc_mlp *h, long long rows, cudaStream_t s
     return LDPC_OK;
 }
 
+// Single-launch chain: per chunk one plane-split launch of the input rows, one memset of the counters, one cooperative launch.
+static int ensure_chain_buffers(ldpc_mlp *h, long long rows, cudaStream_t s) {
+    const Layer &L0 = h->layers[0];
+    if (!h->d_ring[0]) {
+        const long long ring_rows = (long long)h->n_groups * INFLIGHT * BM;
+        for (int b = 0; b < 2; ++b)
+            if (cudaMalloc(&h->d_ring[b], (size_t)h->ns * ring_rows * h->maxw * sizeof(__half)) != cudaSuccess) { set_error("ldpc_mlp_forward: out of device memory (activation ring)"); return LDPC_ENOMEM; }
+        if (cudaMalloc(&h->d_flags, (size_t)h->n_groups * INFLIGHT * MAX_CHAIN * sizeof(unsigned int)) != cudaSuccess) { set_error("ldpc_mlp_forward: out of device memory"); return LDPC_ENOMEM; }
+        for (size_t l = 0; l < h->layers.size(); ++l) {
+            h->cmaps.w[l] = h->layers[l].map_w;
+            if (l) { const int rc = make_map(&h->cmaps.a[l], h->d_ring[l & 1], h->layers[l].Kp, ring_rows, h->ns, BM); if (rc) return rc; }
+        }
+    }
+    const long long want = std::min<long long>(h->chain_chunk_max, ((rows + BM - 1) / BM) * BM);
+    if (want > h->x_rows) {
+        if (h->x_rows) LDPC_CUDA_TRY(cudaStreamSynchronize(s));
+        cudaFree(h->d_x);
+        h->d_x = nullptr; h->x_rows = 0;
+        if (cudaMalloc(&h->d_x, (size_t)h->ns * want * L0.Kp * sizeof(__half)) != cudaSuccess) { set_error("ldpc_mlp_forward: out of device memory (%lld input rows)", want); return LDPC_ENOMEM; }
+        h->x_rows = want;
+        const int rc = make_map(&h->cmaps.a[0], h->d_x, L0.Kp, h->x_rows, h->ns, BM);
+        if (rc) return rc;
+    }
+    return LDPC_OK;
+}
+
+static int forward_chain(ldpc_mlp *h, const float *x, long long B, float *y, cudaStream_t s) {
+    { const int rc = ensure_chain_buffers(h, B, s); if (rc) return rc; }
+    const int nl = (int)h->layers.size();
+    const Layer &L0 = h->layers[0];
+    auto k = chain_kernel<2>;
+    constexpr int SMEM = 3 * 2 * (BM * BK * 2 + 128 * BK * 2) + 1024 + 128 + EPI_WARPS * 2048;
+    LDPC_CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    for (long long done = 0; done < B; done += h->x_rows) {
+        const long long rows = std::min<long long>(h->x_rows, B - done);
+        { const int rc = launch_split<2>(x + done * L0.K, L0.K, L0.K, rows, L0.Kp, h->d_x, h->x_rows * L0.Kp, s); if (rc) return rc; }
+        ChainArgs a;
+        memset(&a, 0, sizeof(a));
+        a.n_layers = nl; a.m_valid = (int)rows; a.row_blocks = (int)((rows + BM - 1) / BM);
+        a.n_groups = std::min(h->n_groups, a.row_blocks);
+        for (int l = 0; l < nl; ++l) { const Layer &L = h->layers[l]; a.L[l] = ChainLayer{L.Kp / BK, L.N, L.BN, L.act, L.d_bias}; }
+        a.ring[0] = h->d_ring[0]; a.ring[1] = h->d_ring[1];
+        a.ring_rows = (long long)h->n_groups * INFLIGHT * BM;
+        a.out_f32 = y + done * h->layers[nl - 1].N;
+        a.flags = h->d_flags;
+        LDPC_CUDA_TRY(cudaMemsetAsync(h->d_flags, 0, (size_t)h->n_groups * INFLIGHT * MAX_CHAIN * sizeof(unsigned int), s));
+        void *params[2] = {(void *)&h->cmaps, (void *)&a};
+        LDPC_CUDA_TRY(cudaLaunchCooperativeKernel((const void *)k, dim3((unsigned)(a.n_groups * GROUP)), dim3(CHAIN_THREADS), params, (size_t)SMEM, s));
+    }
+    return LDPC_OK;
+}
+
 int ldpc_mlp_forward(ldpc_mlp_t *h, const float *x, int64_t B, float *y, ldpc_stream_t stream) {
     if (!h || (B > 0 && (!x || !y)) || B < 0) { set_error("ldpc_mlp_forward: bad arguments"); return LDPC_EINVAL; }
     cudaStream_t s = (cudaStream_t)stream;
     if (B == 0) return LDPC_OK;
     if (reinterpret_cast<uintptr_t>(y) & 15) { set_error("ldpc_mlp_forward: y must be 16-byte aligned"); return LDPC_EINVAL; }
     std::lock_guard<std::mutex> lock(h->mu);   // host-side serialisation; work of different calls is still ordered per stream by the caller
+    if (h->mode == LDPC_MLP_CHAIN && !h->chain_ok) { set_error("ldpc_mlp_forward: the single-launch chain needs splits = 2, 2..%d layers of at most %d column tiles and cooperative launch", MAX_CHAIN, GROUP); return LDPC_EUNSUPPORTED; }
+    if (h->chain_ok && h->mode != LDPC_MLP_PER_LAYER) return forward_chain(h, x, B, y, s);
     {
         const int rc0 = ensure_activation_buffers(h, B, s);
         if (rc0) return rc0;
@@ -582,6 +957,14 @@ int ldpc_mlp_forward(ldpc_mlp_t *h, const float *x, int64_t B, float *y, ldpc_st
             if (rc) return rc;
         }
     }
+    return LDPC_OK;
+}
+
+int ldpc_mlp_set_mode(ldpc_mlp_t *h, int mode) {
+    if (!h || mode < LDPC_MLP_AUTO || mode > LDPC_MLP_CHAIN) { set_error("ldpc_mlp_set_mode: bad arguments"); return LDPC_EINVAL; }
+    if (mode == LDPC_MLP_CHAIN && !h->chain_ok) { set_error("ldpc_mlp_set_mode: this network / device cannot run the single-launch chain"); return LDPC_EUNSUPPORTED; }
+    std::lock_guard<std::mutex> lock(h->mu);
+    h->mode = mode;
     return LDPC_OK;
 }
 

@@ -120,6 +120,8 @@ def lib():
     L.ldpc_mlp_forward.argtypes = [vp, vp, i64, vp, vp]
     L.ldpc_mlp_destroy.restype = None
     L.ldpc_mlp_destroy.argtypes = [vp]
+    L.ldpc_mlp_set_mode.restype = ctypes.c_int
+    L.ldpc_mlp_set_mode.argtypes = [vp, i32]
     if L.ldpc_abi_version() != ABI_VERSION:
         raise ImportError(f"libldpc_b200.so ABI {L.ldpc_abi_version()} != binding {ABI_VERSION}; rebuild")
     _lib = L

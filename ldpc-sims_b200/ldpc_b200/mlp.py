@@ -11,11 +11,16 @@ import torch
 from . import _native as N
 
 
+MODES = {"auto": 0, "per_layer": 1, "chain": 2}       # LDPC_MLP_* of include/ldpc_b200.h
+
+
 class NativeMLP:
     """weights[l]: [out_l, in_l] float32 (nn.Linear.weight), biases[l]: [out_l] or None,
-    activations[l]: True -> tanh after layer l (default: every layer but the last)."""
+    activations[l]: True -> tanh after layer l (default: every layer but the last).
+    mode: "auto" (default: the single-launch L2-resident chain where the shape allows it), "per_layer" (one launch per
+    layer) or "chain" (raises if the network cannot run it); the results are bit-identical."""
 
-    def __init__(self, weights, biases=None, activations=None, splits=2, chunk_rows=0, device=None):
+    def __init__(self, weights, biases=None, activations=None, splits=2, chunk_rows=0, device=None, mode="auto"):
         N.require_cuda()
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         if self.device.index is None:
@@ -40,6 +45,15 @@ class NativeMLP:
         with torch.cuda.device(self.device):
             N.check(N.lib().ldpc_mlp_create(nl, dims_a, w_a, b_a, act_a, self.splits, int(chunk_rows), ctypes.byref(h)))
         self._h = h
+        self.mode = "auto"
+        if mode != "auto":
+            self.set_mode(mode)
+
+    def set_mode(self, mode):
+        if mode not in MODES:
+            raise ValueError(f"mode must be one of {sorted(MODES)}")
+        N.check(N.lib().ldpc_mlp_set_mode(self._h, MODES[mode]))
+        self.mode = mode
 
     def __call__(self, x, stream=None):
         """x: CUDA float32 [B, dims[0]] -> CUDA float32 [B, dims[-1]]."""

@@ -95,6 +95,37 @@ def test_native_mlp_matches_oracle_ragged_and_chunked():
 
 
 @pytest.mark.gpu
+def test_mlp_single_launch_chain_equals_per_layer_launches():
+    """LDPC_MLP_CHAIN (one cooperative launch per chunk, activations handed over through L2 between groups of 4 SMs) against
+    LDPC_MLP_PER_LAYER: same MMA order per tile and same epilogue arithmetic, so the results are bit-identical - on the
+    reference's two network shapes (nn/llr.py:46-73; a 64-wide first layer without bias or tanh rotates over the group), a
+    two-layer net, ragged row counts, several chunks per call and enough rows that every group wraps its ring many times."""
+    import torch
+    from ldpc_b200.mlp import NativeMLP
+    rng = np.random.RandomState(11)
+    shapes = (([65, 512, 512, 512, 64], None, True), ([64, 64, 512, 512, 512, 64], [0, 1, 1, 1, 0], False), ([64, 128, 64], None, True),
+              ([33, 256, 384, 64], None, True))
+    for dims, acts, bias in shapes:
+        W = [(rng.rand(dims[l + 1], dims[l]).astype(np.float32) * 2 - 1) / np.sqrt(dims[l]) for l in range(len(dims) - 1)]
+        Bs = [(rng.rand(d).astype(np.float32) - 0.5) for d in dims[1:]] if bias else None
+        for chunk in (0, 384):
+            a = NativeMLP(W, Bs, acts, chunk_rows=chunk, mode="chain")
+            b = NativeMLP(W, Bs, acts, chunk_rows=chunk, mode="per_layer")
+            for B in ((1, 127, 129, 1000, 150001) if chunk == 0 else (1, 385, 5000)):
+                x = torch.tensor(rng.randn(B, dims[0]).astype(np.float32) * 0.7).cuda()
+                ya, yb = a(x), b(x)
+                assert torch.equal(ya, yb), (dims, chunk, B, float((ya - yb).abs().max()))
+                assert torch.equal(a(x), ya)                      # and reproducible run to run (counters restart per launch)
+    # shapes the chain cannot run are refused in "chain" mode and served per layer in "auto"
+    W = [(rng.rand(1024, 64).astype(np.float32) - 0.5) / 8, (rng.rand(64, 1024).astype(np.float32) - 0.5) / 32]
+    with pytest.raises(RuntimeError, match="single-launch chain"):
+        NativeMLP(W, mode="chain")
+    with pytest.raises(RuntimeError, match="single-launch chain"):
+        NativeMLP([w[:64] for w in W[:1]] + [W[1][:, :64]], splits=3, mode="chain")
+    assert NativeMLP(W)(torch.zeros(5, 64, device="cuda")).shape == (5, 64)
+
+
+@pytest.mark.gpu
 def test_nn_demapper_then_decoder_matches_reference_bits():
     """evaluate_quantized_snr.py:150-173: llr_est = LLRest(x); bits_nn = decode_bits(llr_est, H, ...)."""
     import torch
