@@ -435,8 +435,9 @@ struct ChainLayer {
 struct ChainArgs {
     int n_layers, m_valid, row_blocks, n_groups;
     ChainLayer L[MAX_CHAIN];
-    __half *ring[2];              // activation planes [NS][ring_rows][width of the producing layer]; layer l reads ring[l & 1]
+    __half *ring[2];              // activation planes [NS][ring_rows][ring_pitch], the leading `width` columns used; layer l reads ring[l & 1]
     long long ring_rows;          // n_groups * INFLIGHT * 128
+    int ring_pitch;               // widest layer: one row pitch for every layer, so the slots of layers of different width cannot alias
     float *out_f32;               // [m_valid][N of the last layer]
     unsigned int *flags;          // [n_groups * INFLIGHT][MAX_CHAIN] epilogue-warp arrivals, monotonic within a launch
 };
@@ -643,15 +644,14 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 1) chain_kernel(const __grid_co
                             asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg + (uint32_t)lane * 64u + (uint32_t)((q ^ ((lane >> 1) & 3)) << 4)),
                                          "r"(pk[4 * q]), "r"(pk[4 * q + 1]), "r"(pk[4 * q + 2]), "r"(pk[4 * q + 3]) : "memory");
                         __syncwarp();
-                        __half *const plane = args.ring[(l + 1) & 1] + (long long)s * args.ring_rows * L.n_total +
-                                              ((long long)slot * BM + quad * 32) * L.n_total + n0 + c0;
+                        __half *const plane = args.ring[(l + 1) & 1] + ((long long)s * args.ring_rows + (long long)slot * BM + quad * 32) * args.ring_pitch + n0 + c0;
 #pragma unroll
                         for (int i = 0; i < 4; ++i) {
                             const int R = 8 * i + (lane >> 2), C = lane & 3;
                             uint4 u;
                             asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(u.x), "=r"(u.y), "=r"(u.z), "=r"(u.w)
                                          : "r"(stg + (uint32_t)R * 64u + (uint32_t)((C ^ ((R >> 1) & 3)) << 4)) : "memory");
-                            st_global_v4_hint(plane + (long long)R * L.n_total + C * 8, u, L2_EVICT_LAST);   // dirty ring lines stay in L2 until the slot is rewritten
+                            st_global_v4_hint(plane + (long long)R * args.ring_pitch + C * 8, u, L2_EVICT_LAST);   // dirty ring lines stay in L2 until the slot is rewritten
                         }
                         __syncwarp();
                     }
@@ -690,11 +690,13 @@ static EncodeTiledFn encode_fn() {
 }
 
 // planes [NS][rows][Kp] f16 -> 3-D map (k, row, plane), box [64 x box_rows x 1], 128-byte swizzle
-static int make_map(CUtensorMap *map, void *ptr, int Kp, long long rows, int ns, int box_rows) {
+// (pitch = elements between rows, 0 = dense: the activation ring keeps one row pitch for layers of different width)
+static int make_map(CUtensorMap *map, void *ptr, int Kp, long long rows, int ns, int box_rows, int pitch = 0) {
     EncodeTiledFn fn = encode_fn();
     if (!fn) { set_error("cuTensorMapEncodeTiled is not available from the driver"); return LDPC_ECUDA; }
+    if (pitch == 0) pitch = Kp;
     const cuuint64_t gdim[3] = {(cuuint64_t)Kp, (cuuint64_t)rows, (cuuint64_t)ns};
-    const cuuint64_t gstr[2] = {(cuuint64_t)Kp * 2, (cuuint64_t)rows * Kp * 2};
+    const cuuint64_t gstr[2] = {(cuuint64_t)pitch * 2, (cuuint64_t)rows * pitch * 2};
     const cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)box_rows, 1};
     const cuuint32_t est[3] = {1, 1, 1};
     const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, ptr, gdim, gstr, box, est, CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -878,7 +880,7 @@ static int ensure_chain_buffers(ldpc_mlp *h, long long rows, cudaStream_t s) {
         if (cudaMalloc(&h->d_flags, (size_t)h->n_groups * INFLIGHT * MAX_CHAIN * sizeof(unsigned int)) != cudaSuccess) { set_error("ldpc_mlp_forward: out of device memory"); return LDPC_ENOMEM; }
         for (size_t l = 0; l < h->layers.size(); ++l) {
             h->cmaps.w[l] = h->layers[l].map_w;
-            if (l) { const int rc = make_map(&h->cmaps.a[l], h->d_ring[l & 1], h->layers[l].Kp, ring_rows, h->ns, BM); if (rc) return rc; }
+            if (l) { const int rc = make_map(&h->cmaps.a[l], h->d_ring[l & 1], h->layers[l].Kp, ring_rows, h->ns, BM, h->maxw); if (rc) return rc; }
         }
     }
     const long long want = std::min<long long>(h->chain_chunk_max, ((rows + BM - 1) / BM) * BM);
@@ -911,6 +913,7 @@ static int forward_chain(ldpc_mlp *h, const float *x, long long B, float *y, cud
         for (int l = 0; l < nl; ++l) { const Layer &L = h->layers[l]; a.L[l] = ChainLayer{L.Kp / BK, L.N, L.BN, L.act, L.d_bias}; }
         a.ring[0] = h->d_ring[0]; a.ring[1] = h->d_ring[1];
         a.ring_rows = (long long)h->n_groups * INFLIGHT * BM;
+        a.ring_pitch = h->maxw;
         a.out_f32 = y + done * h->layers[nl - 1].N;
         a.flags = h->d_flags;
         LDPC_CUDA_TRY(cudaMemsetAsync(h->d_flags, 0, (size_t)h->n_groups * INFLIGHT * MAX_CHAIN * sizeof(unsigned int), s));
