@@ -94,6 +94,17 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
     d |= (uint64_t)2 << 61;                            // SWIZZLE_128B
     return d;
 }
+__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+        "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
@@ -110,7 +121,7 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
 // Absolute error <= ~3e-7 over the whole range (the cancellation in 1 - e near 0 costs relative, not absolute, accuracy, and the
 // next layer consumes absolute values): the error of the whole chain against float64 is unchanged (2.2e-6 of the output scale,
 // profiles/r02_mlp_experiments.md).  libm tanhf is ~25 instructions with both range branches predicated, and the epilogue warps
-// are issue/latency-bound: 4.67 -> 4.50 ms per 2^20 rows.  -DMLP_EXP_NOTANH (timing experiments only) removes the activation.
+// are issue/latency-bound: 4.67 -> 4.58 ms per 2^20 rows.  -DMLP_EXP_NOTANH (timing experiments only) removes the activation.
 #ifdef MLP_EXP_NOTANH
 __device__ __forceinline__ float tanh_act(float x) { return x * 0.01f; }
 #else
@@ -340,15 +351,24 @@ __global__ void __launch_bounds__(THREADS, 1) layer_kernel(const __grid_constant
             for (int c0 = part * PART_COLS; c0 < (part + 1) * PART_COLS && c0 < BN; c0 += 32) {
                 uint32_t v[32], w[32];
                 float o[32];
-                const float bias_l = args.bias ? __ldg(args.bias + n0 + c0 + lane) : 0.0f;   // lane q holds the bias of column q: one load, in flight while the accumulators are read
-                tmem_ld32(d_main + (uint32_t)c0, v);
-                if (NS > 1) tmem_ld32(d_main + ACC2 + (uint32_t)c0, w);
+                tmem_ld32_issue(d_main + (uint32_t)c0, v);
+                if (NS > 1) tmem_ld32_issue(d_main + ACC2 + (uint32_t)c0, w);
+                tmem_ld_wait();
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    float f = __uint_as_float(v[j]);
-                    if (NS > 1) f = __fadd_rn(f, __uint_as_float(w[j]));
-                    if (args.bias) f = __fadd_rn(f, __shfl_sync(0xffffffffu, bias_l, j));
-                    o[j] = args.act ? tanh_act(f) : f;
+                for (int j = 0; j < 32; ++j) o[j] = NS > 1 ? __fadd_rn(__uint_as_float(v[j]), __uint_as_float(w[j])) : __uint_as_float(v[j]);
+                if (args.bias) {                                           // eight vector loads issued together (a load per element made every add wait for its own load)
+                    float4 b4[8];
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) b4[q] = __ldg(reinterpret_cast<const float4 *>(args.bias + n0 + c0) + q);
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        o[4 * q] = __fadd_rn(o[4 * q], b4[q].x); o[4 * q + 1] = __fadd_rn(o[4 * q + 1], b4[q].y);
+                        o[4 * q + 2] = __fadd_rn(o[4 * q + 2], b4[q].z); o[4 * q + 3] = __fadd_rn(o[4 * q + 3], b4[q].w);
+                    }
+                }
+                if (args.act) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) o[j] = tanh_act(o[j]);
                 }
                 if (args.out_f32) {
                     if (m < args.m_valid) {
@@ -420,7 +440,7 @@ __global__ void __launch_bounds__(THREADS, 1) layer_kernel(const __grid_constant
 // (fence.proxy.async) and loads the full-width A operand from L2.  INFLIGHT row blocks are interleaved layer by layer, so the
 // epilogue and the cross-SM hand-over of one overlap the MMAs of the others.  Results are bit-identical to the per-layer
 // launches (same MMA order per tile, same epilogue arithmetic).  Measured on 2^20 rows (profiles/r02_mlp_experiments.md):
-// INFLIGHT = 4 (78 MB ring): 4.41 ms, 3.4 KB of DRAM traffic per row; 3 (58 MB): 4.64 ms, 1.6 KB; 2 (39 MB): 5.17 ms, 1.3 KB -
+// INFLIGHT = 4 (78 MB ring): 4.3 ms, 3.4 KB of DRAM traffic per row; 3 (58 MB): +5 %, 1.6 KB; 2 (39 MB): +17 %, 1.3 KB -
 // of which 0.6 KB is the input plane split, still a separate launch.  Launched cooperatively: the spin waits need every CTA of
 // a group resident.
 #ifndef MLP_INFLIGHT
@@ -451,19 +471,21 @@ struct ChainMaps {
 template <class F>
 __device__ __forceinline__ void chain_tiles(const ChainArgs &a, int g, int r, F &&f) {
     const int mine = (a.row_blocks - g + a.n_groups - 1) / a.n_groups;     // row blocks g, g + n_groups, ... of this group
-    auto tile = [&](int j, int l) {
-        const int nt = (r + GROUP - (j & (GROUP - 1))) & (GROUP - 1);      // a layer with fewer than GROUP tiles rotates over the CTAs
-        if (nt * a.L[l].bn < a.L[l].n_total) f(j, l, g + a.n_groups * j, nt);
-    };
     for (int j0 = 0; j0 < mine; j0 += INFLIGHT) {
         const int cnt = mine - j0 < INFLIGHT ? mine - j0 : INFLIGHT;
-        for (int s = 0; s < 2 && s < cnt; ++s) tile(j0 + s, 0);
-        for (int s = 0; s < cnt; ++s) {
-            tile(j0 + s, 1);
-            if (s + 2 < cnt) tile(j0 + s + 2, 0);
+        int n0 = 0, n1 = 0, l2 = 2, s2 = 0;                                // next row block of layer 0 / of layer 1; cursor over the later layers
+        for (;;) {                                                         // (one call site: the body is inlined once, its counters stay in registers)
+            int s, l;
+            if (n1 < cnt) {
+                if (n0 < cnt && n0 < n1 + 2) { s = n0++; l = 0; } else { s = n1++; l = 1; }
+            } else if (l2 < a.n_layers) {
+                s = s2; l = l2;
+                if (++s2 == cnt) { s2 = 0; ++l2; }
+            } else break;
+            const int j = j0 + s;
+            const int nt = (r + GROUP - (j & (GROUP - 1))) & (GROUP - 1);   // a layer with fewer than GROUP tiles rotates over the CTAs
+            if (nt * a.L[l].bn < a.L[l].n_total) f(j, l, g + a.n_groups * j, nt);
         }
-        for (int l = 2; l < a.n_layers; ++l)
-            for (int s = 0; s < cnt; ++s) tile(j0 + s, l);
     }
 }
 
@@ -608,14 +630,24 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 1) chain_kernel(const __grid_co
             for (int c0 = part * 32; c0 < L.bn; c0 += 32 * (EPI_WARPS / 4)) {
                 uint32_t v[32], w[32];
                 float o[32];
-                const float bias_l = L.bias ? __ldg(L.bias + n0 + c0 + lane) : 0.0f;         // lane q holds the bias of column q: one load, in flight while the accumulators are read
-                tmem_ld32(d_main + (uint32_t)c0, v);
-                tmem_ld32(d_main + (uint32_t)(L.bn + c0), w);
+                tmem_ld32_issue(d_main + (uint32_t)c0, v);
+                tmem_ld32_issue(d_main + (uint32_t)(L.bn + c0), w);
+                tmem_ld_wait();
 #pragma unroll
-                for (int q = 0; q < 32; ++q) {
-                    float f = __fadd_rn(__uint_as_float(v[q]), __uint_as_float(w[q]));
-                    if (L.bias) f = __fadd_rn(f, __shfl_sync(0xffffffffu, bias_l, q));
-                    o[q] = L.act ? tanh_act(f) : f;
+                for (int q = 0; q < 32; ++q) o[q] = __fadd_rn(__uint_as_float(v[q]), __uint_as_float(w[q]));
+                if (L.bias) {                                              // eight vector loads issued together into the registers v / w just freed
+                    float4 b4[8];
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) b4[q] = __ldg(reinterpret_cast<const float4 *>(L.bias + n0 + c0) + q);
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        o[4 * q] = __fadd_rn(o[4 * q], b4[q].x); o[4 * q + 1] = __fadd_rn(o[4 * q + 1], b4[q].y);
+                        o[4 * q + 2] = __fadd_rn(o[4 * q + 2], b4[q].z); o[4 * q + 3] = __fadd_rn(o[4 * q + 3], b4[q].w);
+                    }
+                }
+                if (L.act) {
+#pragma unroll
+                    for (int q = 0; q < 32; ++q) o[q] = tanh_act(o[q]);
                 }
                 if (l == last) {
                     const long long m = (long long)rb * BM + row;
