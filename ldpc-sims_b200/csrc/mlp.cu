@@ -706,6 +706,276 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 1) chain_kernel(const __grid_co
     }
 }
 
+// ---- the chain on CTA PAIRS (cta_group::2) -----------------------------------------------------------------------------
+// A single-SM tcgen05.mma fetches its shared-memory operands at ~64 B/clk, and the plane-split products need 20 KB per k-slice
+// (profiles/r02_mlp_experiments.md): 320 clk against 192 clk of math.  Here two SMs (a cluster of 2) issue ONE M = 256
+// instruction: each CTA holds the A planes of its own 128 rows and HALF of the B operand (for A0 [W0;W1]^T: CTA 0 stages the W0
+// tile, CTA 1 the W1 tile; for A1 W0^T each stages half of the W0 rows): 14 KB per SM and k-slice.  A group is two pairs and
+// carries a block of 256 rows; pair p computes two of the four column tiles of every layer; CTA c of both pairs depends only on
+// rows c*128.. of the previous layer (written by CTA c of both pairs).  Only the leader (cluster rank 0) issues MMAs; both CTAs
+// run a TMA producer (transaction bytes on the LEADER's full barrier), epilogue warps and a signaller; tcgen05.commit multicasts
+// the "stage free" / "accumulator full" arrivals to both CTAs, the peer's epilogue warps arrive remotely on the leader's
+// "accumulator empty" barrier.
+#ifndef MLP_PAIR_LEAD
+#define MLP_PAIR_LEAD 4
+#endif
+constexpr int INFLIGHT2 = 2;                         // 256-row blocks in flight per group
+constexpr uint32_t PEER_MASK = 0xFEFFFFFFu;          // shared::cluster address of the same offset in the pair's even CTA
+
+struct Chain2Maps {
+    CUtensorMap a[MAX_CHAIN], w[MAX_CHAIN], w2[MAX_CHAIN];   // w: box [64 x BN] of one plane; w2: box [64 x BN/2]
+};
+
+__device__ __forceinline__ void tma_load_3d_pair(uint32_t dst, const CUtensorMap *map, uint32_t leader_bar, int c0, int c1, int c2, uint64_t policy) {
+    asm volatile("cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4, %5}], [%2], %6;"
+                 ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(leader_bar), "r"(c0), "r"(c1), "r"(c2), "l"(policy) : "memory");
+}
+__device__ __forceinline__ void umma_f16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n}"
+                 ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tc_commit_pair(uint32_t bar) {          // arrives on `bar` of BOTH CTAs once the MMAs issued so far are done
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_leader(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(bar & PEER_MASK) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+// Tiles of CTA (pair p, rank c) of group g: the scheduler of chain_tiles over "virtual row blocks" v = 2 * (256-row block) + u,
+// u = which of the pair's two column tiles.
+template <class F>
+__device__ __forceinline__ void chain2_tiles(const ChainArgs &a, int g, int p, F &&f) {
+    const int mine = (a.row_blocks - g + a.n_groups - 1) / a.n_groups;     // 256-row blocks g, g + n_groups, ... of this group
+    for (int j0 = 0; j0 < mine; j0 += INFLIGHT2) {
+        const int cnt = 2 * (mine - j0 < INFLIGHT2 ? mine - j0 : INFLIGHT2);
+        int n0 = 0, n1 = 0, l2 = 2, s2 = 0;
+        for (;;) {
+            int v, l;
+            if (n1 < cnt) {
+                if (n0 < cnt && n0 < n1 + MLP_PAIR_LEAD) { v = n0++; l = 0; } else { v = n1++; l = 1; }   // a layer-1 tile needs BOTH layer-0 tiles of its block from both pairs
+            } else if (l2 < a.n_layers) {
+                v = s2; l = l2;
+                if (++s2 == cnt) { s2 = 0; ++l2; }
+            } else break;
+            const int j = j0 + (v >> 1);
+            const int nt = 2 * (v & 1) + ((p ^ j) & 1);                    // a layer with fewer than 4 tiles alternates between the pairs
+            if (nt * a.L[l].bn < a.L[l].n_total) f(j, l, g + a.n_groups * j, nt);
+        }
+    }
+}
+
+template <int NS>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CHAIN_THREADS, 1) chain2_kernel(const __grid_constant__ Chain2Maps maps, const ChainArgs args) {
+    static_assert(NS == 2, "two-plane path");
+    constexpr int A_BYTES = BM * BK * 2, STAGE_MAX = NS * A_BYTES + 128 * BK * 2 + 64 * BK * 2, STAGES = 3;
+    constexpr uint32_t ACC_COLS = 256, TMEM_COLS = 512;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t bars = base + STAGES * STAGE_MAX;
+    auto full_bar = [&](int s) { return bars + 8u * s; };                  // leader's copy is the live one
+    auto empty_bar = [&](int s) { return bars + 8u * (STAGES + s); };
+    auto tfull_bar = [&](int a) { return bars + 8u * (2 * STAGES + a); };
+    auto tempty_bar = [&](int a) { return bars + 8u * (2 * STAGES + 2 + a); };   // leader's copy is the live one (2 * EPI_WARPS arrivals)
+    const uint32_t tmem_slot = bars + 8u * (2 * STAGES + 4);
+    auto stored_bar = [&](uint32_t t) { return bars + 8u * (2 * STAGES + 5 + (t & 3)); };
+    const uint32_t store_staging = bars + 128u;
+    volatile uint32_t *tmem_slot_ptr = reinterpret_cast<volatile uint32_t *>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint32_t c;                                                            // rank in the pair: 0 = leader
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(c));
+    const int g = blockIdx.x / 4, p = (blockIdx.x >> 1) & 1;
+    const int last = args.n_layers - 1;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 2 * EPI_WARPS); }
+        for (uint32_t t = 0; t < 4; ++t) mbar_init(stored_bar(t), EPI_WARPS);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();                                                    // both CTAs' barriers initialised before any remote arrival
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+    auto flag_of = [&](int slot, int l) { return args.flags + ((slot * 2 + (int)c) * MAX_CHAIN + l); };
+
+    if (warp == 2 + EPI_WARPS) {                                           // ===== signaller =====
+        if (lane == 0) {
+            uint32_t ti = 0;
+            chain2_tiles(args, g, p, [&](int j, int l, int, int) {
+                mbar_wait(stored_bar(ti), (ti >> 2) & 1);
+                ++ti;
+                __threadfence();
+                atomicAdd(flag_of(g * INFLIGHT2 + (j % INFLIGHT2), l), (unsigned)EPI_WARPS);
+            });
+        }
+    } else if (warp == 0) {
+        if (lane == 0) {                                                   // ===== TMA producer (both CTAs) =====
+            uint32_t it = 0;
+            chain2_tiles(args, g, p, [&](int j, int l, int rb, int nt) {
+                const ChainLayer &L = args.L[l];
+                const int slot = g * INFLIGHT2 + (j % INFLIGHT2);
+                const unsigned use = (unsigned)(j / INFLIGHT2);
+                int arow;
+                if (l == 0) {
+                    arow = rb * 2 * BM + (int)c * BM;
+                    if (use) wait_counter(flag_of(slot, last), (unsigned)EPI_WARPS * (unsigned)(args.L[last].n_total / args.L[last].bn) * use);
+                } else {
+                    arow = slot * 2 * BM + (int)c * BM;
+                    wait_counter(flag_of(slot, l - 1), (unsigned)EPI_WARPS * (unsigned)(args.L[l - 1].n_total / args.L[l - 1].bn) * (use + 1));
+                }
+                const uint32_t b1_bytes = (uint32_t)L.bn * BK * 2, b2_bytes = b1_bytes / 2;
+                const uint32_t stage_bytes = NS * A_BYTES + b1_bytes + b2_bytes;
+                TRACE(0);
+                for (int kb = 0; kb < L.k_blocks; ++kb, ++it) {
+                    const int s = it % STAGES;
+                    mbar_wait(empty_bar(s), ((it / STAGES) & 1) ^ 1);
+                    if (c == 0) mbar_expect_tx(full_bar(s), 2 * stage_bytes);     // the bytes of both CTAs land on the leader's barrier
+                    const uint32_t st = base + s * STAGE_MAX, fb = full_bar(s) & PEER_MASK;
+                    const uint64_t pa = l == 0 ? L2_EVICT_FIRST : L2_EVICT_LAST;
+                    tma_load_3d_pair(st, &maps.a[l], fb, kb * BK, arow, 0, pa);
+                    tma_load_3d_pair(st + A_BYTES, &maps.a[l], fb, kb * BK, arow, 1, pa);
+                    tma_load_3d_pair(st + NS * A_BYTES, &maps.w[l], fb, kb * BK, nt * L.bn, (int)c, L2_EVICT_LAST);                       // W0 tile | W1 tile
+                    tma_load_3d_pair(st + NS * A_BYTES + b1_bytes, &maps.w2[l], fb, kb * BK, nt * L.bn + (int)c * (L.bn / 2), 0, L2_EVICT_LAST);   // half of the W0 rows
+                }
+            });
+        }
+    } else if (warp == 1) {
+        if (c == 0) {                                                      // ===== MMA issuer (leader only) =====
+            uint32_t it = 0, ti = 0;
+            chain2_tiles(args, g, p, [&](int, int l, int, int) {
+                const ChainLayer &L = args.L[l];
+                const uint32_t acc = ti & 1, acc_ph = (ti >> 1) & 1;
+                ++ti;
+                mbar_wait(tempty_bar(acc), acc_ph ^ 1);
+                tc_fence_after();
+                if (lane == 0) TRACE(1);
+                const uint32_t d_main = tmem_base + acc * ACC_COLS;
+                const uint32_t idesc = (1u << 4) | ((uint32_t)(L.bn >> 3) << 17) | ((uint32_t)((2 * BM) >> 4) << 24);
+                const uint32_t idesc2 = (1u << 4) | ((uint32_t)((2 * L.bn) >> 3) << 17) | ((uint32_t)((2 * BM) >> 4) << 24);
+                const uint32_t b1_bytes = (uint32_t)L.bn * BK * 2;
+                for (int kb = 0; kb < L.k_blocks; ++kb, ++it) {
+                    const int s = it % STAGES;
+                    mbar_wait(full_bar(s), (it / STAGES) & 1);
+                    tc_fence_after();
+                    if (lane == 0) {
+                        const uint32_t st = base + s * STAGE_MAX;
+#pragma unroll
+                        for (int k = 0; k < BK / UMMA_K; ++k) {
+                            const uint64_t a0 = umma_desc_sw128(st + k * UMMA_K * 2), a1 = umma_desc_sw128(st + A_BYTES + k * UMMA_K * 2);
+                            const uint64_t b1 = umma_desc_sw128(st + NS * A_BYTES + k * UMMA_K * 2), b2 = umma_desc_sw128(st + NS * A_BYTES + b1_bytes + k * UMMA_K * 2);
+                            umma_f16_pair(d_main, a0, b1, idesc2, (kb | k) ? 1u : 0u);          // [256 x 2 BN]: pairs (0,0) | (0,1)
+                            umma_f16_pair(d_main + (uint32_t)L.bn, a1, b2, idesc, 1u);            // [256 x BN]: pair (1,0)
+                        }
+                        tc_commit_pair(empty_bar(s));
+                        if (kb == L.k_blocks - 1) { tc_commit_pair(tfull_bar(acc)); TRACE(1); }
+                    }
+                    __syncwarp();
+                }
+            });
+        }
+    } else {                                                               // ===== epilogue warps (both CTAs: their own 128 rows) =====
+        const int quad = warp & 3, part = (warp - 2) >> 2;
+        const int row = quad * 32 + lane;
+        uint32_t ti = 0;
+        chain2_tiles(args, g, p, [&](int j, int l, int rb, int nt) {
+            const ChainLayer &L = args.L[l];
+            const int slot = g * INFLIGHT2 + (j % INFLIGHT2);
+            const int n0 = nt * L.bn;
+            const uint32_t acc = ti & 1, acc_ph = (ti >> 1) & 1;
+            ++ti;
+            mbar_wait(tfull_bar(acc), acc_ph);
+            tc_fence_after();
+            if (warp == 2 && lane == 0) TRACE(2);
+            const uint32_t d_main = tmem_base + acc * ACC_COLS + ((uint32_t)(quad * 32) << 16);
+#pragma unroll 1
+            for (int c0 = part * 32; c0 < L.bn; c0 += 32 * (EPI_WARPS / 4)) {
+                uint32_t v[32], w[32];
+                float o[32];
+                tmem_ld32_issue(d_main + (uint32_t)c0, v);
+                tmem_ld32_issue(d_main + (uint32_t)(L.bn + c0), w);
+                tmem_ld_wait();
+#pragma unroll
+                for (int q = 0; q < 32; ++q) o[q] = __fadd_rn(__uint_as_float(v[q]), __uint_as_float(w[q]));
+                if (L.bias) {
+                    float4 b4[8];
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) b4[q] = __ldg(reinterpret_cast<const float4 *>(L.bias + n0 + c0) + q);
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        o[4 * q] = __fadd_rn(o[4 * q], b4[q].x); o[4 * q + 1] = __fadd_rn(o[4 * q + 1], b4[q].y);
+                        o[4 * q + 2] = __fadd_rn(o[4 * q + 2], b4[q].z); o[4 * q + 3] = __fadd_rn(o[4 * q + 3], b4[q].w);
+                    }
+                }
+                if (L.act) {
+#pragma unroll
+                    for (int q = 0; q < 32; ++q) o[q] = tanh_act(o[q]);
+                }
+                if (l == last) {
+                    const long long m = ((long long)rb * 2 + c) * BM + row;
+                    if (m < args.m_valid) {
+                        float4 *dst = reinterpret_cast<float4 *>(args.out_f32 + m * L.n_total + n0 + c0);
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) __stcs(dst + q, make_float4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]));
+                    }
+                } else {
+                    const uint32_t stg = store_staging + (uint32_t)(warp - 2) * 2048u;
+#pragma unroll
+                    for (int s = 0; s < NS; ++s) {
+                        uint32_t pk[16];
+#pragma unroll
+                        for (int q = 0; q < 16; ++q) {
+                            const __half2 h = __floats2half2_rn(o[2 * q], o[2 * q + 1]);
+                            pk[q] = *reinterpret_cast<const uint32_t *>(&h);
+                            if (s + 1 < NS) {
+                                const float2 hf = __half22float2(h);
+                                o[2 * q] = __fsub_rn(o[2 * q], hf.x);
+                                o[2 * q + 1] = __fsub_rn(o[2 * q + 1], hf.y);
+                            }
+                        }
+#pragma unroll
+                        for (int q = 0; q < 4; ++q)
+                            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg + (uint32_t)lane * 64u + (uint32_t)((q ^ ((lane >> 1) & 3)) << 4)),
+                                         "r"(pk[4 * q]), "r"(pk[4 * q + 1]), "r"(pk[4 * q + 2]), "r"(pk[4 * q + 3]) : "memory");
+                        __syncwarp();
+                        __half *const plane = args.ring[(l + 1) & 1] + ((long long)s * args.ring_rows + ((long long)slot * 2 + c) * BM + quad * 32) * args.ring_pitch + n0 + c0;
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const int R = 8 * i + (lane >> 2), C = lane & 3;
+                            uint4 u;
+                            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(u.x), "=r"(u.y), "=r"(u.z), "=r"(u.w)
+                                         : "r"(stg + (uint32_t)R * 64u + (uint32_t)((C ^ ((R >> 1) & 3)) << 4)) : "memory");
+                            st_global_v4_hint(plane + (long long)R * args.ring_pitch + C * 8, u, L2_EVICT_LAST);
+                        }
+                        __syncwarp();
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+                mbar_arrive_leader(tempty_bar(acc));                       // the MMA issuer waits for the epilogues of BOTH CTAs
+                mbar_arrive(stored_bar(ti - 1));
+                if (warp == 2) TRACE(2);
+            }
+        });
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();                                                    // no CTA of the pair leaves while the other may still signal it
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    }
+}
+
 // ---- host side -----------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
                                   const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -762,6 +1032,8 @@ struct ldpc_mlp {
     __half *d_x = nullptr, *d_ring[2] = {nullptr, nullptr};
     unsigned int *d_flags = nullptr;
     ldpc::mlp::ChainMaps cmaps;
+    ldpc::mlp::Chain2Maps cmaps2;
+    bool pairs_ok = false;     // cluster launch of CTA pairs available too
     std::mutex mu;             // ldpc_mlp_forward grows and reuses the activation buffers: one call at a time per handle
 };
 
@@ -909,10 +1181,14 @@ static int ensure_chain_buffers(ldpc_mlp *h, long long rows, cudaStream_t s) {
         const long long ring_rows = (long long)h->n_groups * INFLIGHT * BM;
         for (int b = 0; b < 2; ++b)
             if (cudaMalloc(&h->d_ring[b], (size_t)h->ns * ring_rows * h->maxw * sizeof(__half)) != cudaSuccess) { set_error("ldpc_mlp_forward: out of device memory (activation ring)"); return LDPC_ENOMEM; }
-        if (cudaMalloc(&h->d_flags, (size_t)h->n_groups * INFLIGHT * MAX_CHAIN * sizeof(unsigned int)) != cudaSuccess) { set_error("ldpc_mlp_forward: out of device memory"); return LDPC_ENOMEM; }
+        if (cudaMalloc(&h->d_flags, (size_t)h->n_groups * INFLIGHT * 2 * MAX_CHAIN * sizeof(unsigned int)) != cudaSuccess) { set_error("ldpc_mlp_forward: out of device memory"); return LDPC_ENOMEM; }
         for (size_t l = 0; l < h->layers.size(); ++l) {
-            h->cmaps.w[l] = h->layers[l].map_w;
-            if (l) { const int rc = make_map(&h->cmaps.a[l], h->d_ring[l & 1], h->layers[l].Kp, ring_rows, h->ns, BM, h->maxw); if (rc) return rc; }
+            Layer &L = h->layers[l];
+            h->cmaps.w[l] = L.map_w;
+            if (l) { const int rc = make_map(&h->cmaps.a[l], h->d_ring[l & 1], L.Kp, ring_rows, h->ns, BM, h->maxw); if (rc) return rc; }
+            h->cmaps2.w[l] = L.map_w;
+            h->cmaps2.a[l] = h->cmaps.a[l];
+            { const int rc = make_map(&h->cmaps2.w2[l], L.d_w, L.Kp, L.N, h->ns, L.BN / 2); if (rc) return rc; }
         }
     }
     const long long want = std::min<long long>(h->chain_chunk_max, ((rows + BM - 1) / BM) * BM);
@@ -924,33 +1200,42 @@ static int ensure_chain_buffers(ldpc_mlp *h, long long rows, cudaStream_t s) {
         h->x_rows = want;
         const int rc = make_map(&h->cmaps.a[0], h->d_x, L0.Kp, h->x_rows, h->ns, BM);
         if (rc) return rc;
+        h->cmaps2.a[0] = h->cmaps.a[0];
     }
     return LDPC_OK;
 }
 
-static int forward_chain(ldpc_mlp *h, const float *x, long long B, float *y, cudaStream_t s) {
+static int forward_chain(ldpc_mlp *h, const float *x, long long B, float *y, cudaStream_t s, bool pairs) {
     { const int rc = ensure_chain_buffers(h, B, s); if (rc) return rc; }
     const int nl = (int)h->layers.size();
     const Layer &L0 = h->layers[0];
-    auto k = chain_kernel<2>;
-    constexpr int SMEM = 3 * 2 * (BM * BK * 2 + 128 * BK * 2) + 1024 + 128 + EPI_WARPS * 2048;
-    LDPC_CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    constexpr int SMEM1 = 3 * 2 * (BM * BK * 2 + 128 * BK * 2) + 1024 + 128 + EPI_WARPS * 2048;
+    constexpr int SMEM2 = 3 * (2 * BM * BK * 2 + 128 * BK * 2 + 64 * BK * 2) + 1024 + 128 + EPI_WARPS * 2048;
+    if (pairs) LDPC_CUDA_TRY(cudaFuncSetAttribute(chain2_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2));
+    else LDPC_CUDA_TRY(cudaFuncSetAttribute(chain_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM1));
+    const int rows_per_block = pairs ? 2 * BM : BM;
     for (long long done = 0; done < B; done += h->x_rows) {
         const long long rows = std::min<long long>(h->x_rows, B - done);
         { const int rc = launch_split<2>(x + done * L0.K, L0.K, L0.K, rows, L0.Kp, h->d_x, h->x_rows * L0.Kp, s); if (rc) return rc; }
         ChainArgs a;
         memset(&a, 0, sizeof(a));
-        a.n_layers = nl; a.m_valid = (int)rows; a.row_blocks = (int)((rows + BM - 1) / BM);
+        a.n_layers = nl; a.m_valid = (int)rows; a.row_blocks = (int)((rows + rows_per_block - 1) / rows_per_block);
         a.n_groups = std::min(h->n_groups, a.row_blocks);
         for (int l = 0; l < nl; ++l) { const Layer &L = h->layers[l]; a.L[l] = ChainLayer{L.Kp / BK, L.N, L.BN, L.act, L.d_bias}; }
         a.ring[0] = h->d_ring[0]; a.ring[1] = h->d_ring[1];
-        a.ring_rows = (long long)h->n_groups * INFLIGHT * BM;
+        a.ring_rows = (long long)h->n_groups * INFLIGHT * BM;             // = n_groups * INFLIGHT2 * 256 for the pairs
         a.ring_pitch = h->maxw;
         a.out_f32 = y + done * h->layers[nl - 1].N;
         a.flags = h->d_flags;
-        LDPC_CUDA_TRY(cudaMemsetAsync(h->d_flags, 0, (size_t)h->n_groups * INFLIGHT * MAX_CHAIN * sizeof(unsigned int), s));
-        void *params[2] = {(void *)&h->cmaps, (void *)&a};
-        LDPC_CUDA_TRY(cudaLaunchCooperativeKernel((const void *)k, dim3((unsigned)(a.n_groups * GROUP)), dim3(CHAIN_THREADS), params, (size_t)SMEM, s));
+        LDPC_CUDA_TRY(cudaMemsetAsync(h->d_flags, 0, (size_t)h->n_groups * INFLIGHT * 2 * MAX_CHAIN * sizeof(unsigned int), s));
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof(cfg));
+        cfg.gridDim = dim3((unsigned)(a.n_groups * GROUP)); cfg.blockDim = dim3(CHAIN_THREADS); cfg.stream = s;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeCooperative; at[0].val.cooperative = 1;     // every CTA of a group must be resident: the waits spin
+        cfg.attrs = at; cfg.numAttrs = 1;
+        if (pairs) { cfg.dynamicSmemBytes = SMEM2; LDPC_CUDA_TRY(cudaLaunchKernelEx(&cfg, chain2_kernel<2>, h->cmaps2, a)); }
+        else { cfg.dynamicSmemBytes = SMEM1; LDPC_CUDA_TRY(cudaLaunchKernelEx(&cfg, chain_kernel<2>, h->cmaps, a)); }
     }
     return LDPC_OK;
 }
@@ -961,8 +1246,8 @@ int ldpc_mlp_forward(ldpc_mlp_t *h, const float *x, int64_t B, float *y, ldpc_st
     if (B == 0) return LDPC_OK;
     if (reinterpret_cast<uintptr_t>(y) & 15) { set_error("ldpc_mlp_forward: y must be 16-byte aligned"); return LDPC_EINVAL; }
     std::lock_guard<std::mutex> lock(h->mu);   // host-side serialisation; work of different calls is still ordered per stream by the caller
-    if (h->mode == LDPC_MLP_CHAIN && !h->chain_ok) { set_error("ldpc_mlp_forward: the single-launch chain needs splits = 2, 2..%d layers of at most %d column tiles and cooperative launch", MAX_CHAIN, GROUP); return LDPC_EUNSUPPORTED; }
-    if (h->chain_ok && h->mode != LDPC_MLP_PER_LAYER) return forward_chain(h, x, B, y, s);
+    if (h->mode >= LDPC_MLP_CHAIN && !h->chain_ok) { set_error("ldpc_mlp_forward: the single-launch chain needs splits = 2, 2..%d layers of at most %d column tiles and cooperative launch", MAX_CHAIN, GROUP); return LDPC_EUNSUPPORTED; }
+    if (h->chain_ok && h->mode != LDPC_MLP_PER_LAYER) return forward_chain(h, x, B, y, s, h->mode == LDPC_MLP_CHAIN_PAIRS);
     {
         const int rc0 = ensure_activation_buffers(h, B, s);
         if (rc0) return rc0;
@@ -996,8 +1281,8 @@ int ldpc_mlp_forward(ldpc_mlp_t *h, const float *x, int64_t B, float *y, ldpc_st
 }
 
 int ldpc_mlp_set_mode(ldpc_mlp_t *h, int mode) {
-    if (!h || mode < LDPC_MLP_AUTO || mode > LDPC_MLP_CHAIN) { set_error("ldpc_mlp_set_mode: bad arguments"); return LDPC_EINVAL; }
-    if (mode == LDPC_MLP_CHAIN && !h->chain_ok) { set_error("ldpc_mlp_set_mode: this network / device cannot run the single-launch chain"); return LDPC_EUNSUPPORTED; }
+    if (!h || mode < LDPC_MLP_AUTO || mode > LDPC_MLP_CHAIN_PAIRS) { set_error("ldpc_mlp_set_mode: bad arguments"); return LDPC_EINVAL; }
+    if (mode >= LDPC_MLP_CHAIN && !h->chain_ok) { set_error("ldpc_mlp_set_mode: this network / device cannot run the single-launch chain"); return LDPC_EUNSUPPORTED; }
     std::lock_guard<std::mutex> lock(h->mu);
     h->mode = mode;
     return LDPC_OK;

@@ -11,14 +11,15 @@ import torch
 from . import _native as N
 
 
-MODES = {"auto": 0, "per_layer": 1, "chain": 2}       # LDPC_MLP_* of include/ldpc_b200.h
+MODES = {"auto": 0, "per_layer": 1, "chain": 2, "chain_pairs": 3}       # LDPC_MLP_* of include/ldpc_b200.h
 
 
 class NativeMLP:
     """weights[l]: [out_l, in_l] float32 (nn.Linear.weight), biases[l]: [out_l] or None,
     activations[l]: True -> tanh after layer l (default: every layer but the last).
     mode: "auto" (default: the single-launch L2-resident chain where the shape allows it), "per_layer" (one launch per
-    layer) or "chain" (raises if the network cannot run it); the results are bit-identical."""
+    layer), "chain" (raises if the network cannot run it) or "chain_pairs" (the chain on cta_group::2 CTA pairs: measured 2 %
+    slower than "chain", kept as the documented experiment); the results are bit-identical."""
 
     def __init__(self, weights, biases=None, activations=None, splits=2, chunk_rows=0, device=None, mode="auto"):
         N.require_cuda()

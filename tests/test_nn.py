@@ -111,11 +111,13 @@ def test_mlp_single_launch_chain_equals_per_layer_launches():
         for chunk in (0, 384):
             a = NativeMLP(W, Bs, acts, chunk_rows=chunk, mode="chain")
             b = NativeMLP(W, Bs, acts, chunk_rows=chunk, mode="per_layer")
-            for B in ((1, 127, 129, 1000, 150001) if chunk == 0 else (1, 385, 5000)):
+            c = NativeMLP(W, Bs, acts, chunk_rows=chunk, mode="chain_pairs")   # the same chain on cta_group::2 pairs of SMs
+            for B in ((1, 127, 129, 257, 1000, 150001) if chunk == 0 else (1, 385, 5000)):
                 x = torch.tensor(rng.randn(B, dims[0]).astype(np.float32) * 0.7).cuda()
-                ya, yb = a(x), b(x)
+                ya, yb, yc = a(x), b(x), c(x)
                 assert torch.equal(ya, yb), (dims, chunk, B, float((ya - yb).abs().max()))
-                assert torch.equal(a(x), ya)                      # and reproducible run to run (counters restart per launch)
+                assert torch.equal(yc, yb), (dims, chunk, B, float((yc - yb).abs().max()))
+                assert torch.equal(a(x), ya) and torch.equal(c(x), yc)   # reproducible run to run (counters restart per launch)
     # shapes the chain cannot run are refused in "chain" mode and served per layer in "auto"
     W = [(rng.rand(1024, 64).astype(np.float32) - 0.5) / 8, (rng.rand(64, 1024).astype(np.float32) - 0.5) / 32]
     with pytest.raises(RuntimeError, match="single-launch chain"):
