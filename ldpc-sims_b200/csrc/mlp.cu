@@ -1146,6 +1146,15 @@ int ldpc_mlp_create(int n_layers, const int32_t *dims, const float *const *weigh
         h->n_groups = sms / GROUP;
         h->chain_ok = coop && h->ns == 2 && n_layers >= 2 && n_layers <= MAX_CHAIN && h->n_groups > 0;
         for (const Layer &L : h->layers) h->chain_ok = h->chain_ok && L.N / L.BN <= GROUP;
+        if (h->chain_ok) {                                                // what the cooperative launch will check: one CTA per SM must fit
+            constexpr int SMEM1 = 3 * 2 * (BM * BK * 2 + 128 * BK * 2) + 1024 + 128 + EPI_WARPS * 2048;
+            int per_sm = 0;
+            if (cudaFuncSetAttribute(chain_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM1) != cudaSuccess ||
+                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, chain_kernel<2>, CHAIN_THREADS, SMEM1) != cudaSuccess || per_sm < 1) {
+                cudaGetLastError();
+                h->chain_ok = false;                                      // AUTO then runs one launch per layer
+            }
+        }
     }
     *out = h;
     return LDPC_OK;
