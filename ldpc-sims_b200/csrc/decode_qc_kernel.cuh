@@ -148,7 +148,8 @@ __global__ void __launch_bounds__((QcLayout<Code, CW>::THREADS), (QcLayout<Code,
             const LinkConsts kc(lp, SIM);
             const int lane = tid & 31, nsym = N / 2;
             constexpr int S = 1;                                         // OFDM symbols in flight per warp (2 measured no faster)
-            const int total = ncw * lp.n_ofdm_per_cw;
+            constexpr int OFDM_PER_CW = (N / 2 + (SIM > 0 ? SIM : 32) - 1) / (SIM > 0 ? SIM : 32);   // = lp.n_ofdm_per_cw (sim.cu), as a constant divisor
+            const int total = ncw * OFDM_PER_CW;
             for (int o0 = (tid >> 5) * S; o0 < total; o0 += (T >> 5) * S) {
                 int osv[S];
                 unsigned long long gcw[S];
@@ -159,8 +160,8 @@ __global__ void __launch_bounds__((QcLayout<Code, CW>::THREADS), (QcLayout<Code,
                 for (int q = 0; q < S; ++q) {
                     const int o = o0 + q;
                     valid[q] = o < total;
-                    const int c = valid[q] ? o / lp.n_ofdm_per_cw : 0;
-                    osv[q] = valid[q] ? o - c * lp.n_ofdm_per_cw : 0;
+                    const int c = valid[q] ? o / OFDM_PER_CW : 0;
+                    osv[q] = valid[q] ? o - c * OFDM_PER_CW : 0;
                     gcw[q] = (unsigned long long)(lp.cw_first + cw0 + c);
                     brow[q] = hard_s + c * L::HARD_STRIDE;
                     orow[q] = stage + c * N;

@@ -41,6 +41,24 @@ __device__ __forceinline__ void count_errors(const uint8_t *hard_s, int hs_strid
                                              int *scratch /* [3 + ncw] */) {
     const int nbytes = (n + 7) >> 3;
     int unc = 0, inf = 0;
+    if (!ref_packed_g && (n & 3) == 0 && (hs_stride & 3) == 0) {
+        // single-launch simulator: decision (bit 0), uncoded decision (bit 1) and transmitted bit (bit 2) share a byte -
+        // four code bits per 32-bit word, compared with three shifts and counted with popc
+        const int words = n >> 2;
+        for (int cw = 0; cw < ncw; ++cw) {
+            const uint32_t *row = reinterpret_cast<const uint32_t *>(hard_s + cw * hs_stride);
+            unsigned any = 0;
+            for (int w = threadIdx.x; w < words; w += blockDim.x) {
+                const uint32_t hv = row[w], ref = (hv >> 2) & 0x01010101u;
+                const uint32_t e = (hv ^ ref) & 0x01010101u;                   // decoded bit != transmitted bit
+                unc += __popc(((hv >> 1) ^ ref) & 0x01010101u);
+                const int left = k_info - 4 * w;                               // information bits in this word: all four, none, or the first `left`
+                inf += __popc(left >= 4 ? e : (left <= 0 ? 0u : (e & (0xffffffffu >> (32 - 8 * left)))));
+                any |= e;
+            }
+            if (any) scratch[3 + cw] = 1;                                      // benign race: everyone writes 1
+        }
+    } else
     for (int i = threadIdx.x; i < ncw * n; i += blockDim.x) {
         const int cw = i / n, v = i - cw * n;
         const int hv = hard_s[cw * hs_stride + v];
