@@ -106,6 +106,15 @@ __global__ void __launch_bounds__((QcLayout<Code, CW>::THREADS), (QcLayout<Code,
         uint8_t *bits = hard_s + (active ? cw : 0) * L::HARD_STRIDE;       // bit 2 of the byte = transmitted bit
         const uint32_t *u = u_s + (active ? cw : 0) * KWS;
         auto ubit = [&](int i) { return (u[i >> 5] >> (i & 31)) & 1u; };
+        // the information bits as bytes first (bit 2 = transmitted bit): the encoder below then reads one byte per term instead
+        // of extracting a bit from the packed Philox words (word index, shift, mask)
+        if (active) {
+            static_for<KB>([&](auto cc) {
+                constexpr int c = decltype(cc)::value;
+                bits[c * Z + t] = (uint8_t)(ubit(c * Z + t) << 2);
+            });
+        }
+        __syncthreads();
         unsigned lam = 0;                                                  // bit r = lambda_r[t]
         if (active) {
             static_for<MB>([&](auto rr) {
@@ -116,13 +125,9 @@ __global__ void __launch_bounds__((QcLayout<Code, CW>::THREADS), (QcLayout<Code,
                     constexpr int c = kQc<Code>.enc_col[r][j], sh = kQc<Code>.enc_shift[r][j];
                     int z = t + sh;
                     if (z >= Z) z -= Z;
-                    acc ^= ubit(c * Z + z);
+                    acc ^= bits[c * Z + z];                                // bit 2 carries the XOR
                 });
-                lam |= acc << r;
-            });
-            static_for<KB>([&](auto cc) {
-                constexpr int c = decltype(cc)::value;
-                bits[c * Z + t] = (uint8_t)(ubit(c * Z + t) << 2);
+                lam |= ((acc >> 2) & 1u) << r;
             });
             bits[KB * Z + t] = (uint8_t)((__popc(lam) & 1) << 2);          // p0
         }

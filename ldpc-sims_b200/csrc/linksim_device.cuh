@@ -74,7 +74,7 @@ __device__ __forceinline__ void ofdm_symbols_llr(int lane, const int (&os)[S], c
 #pragma unroll
         for (int r = 0; r < P; ++r) {                     // QPSK, null subcarriers past the codeword
             const int sidx = os[s] * N + r * 32 + lane;
-            if (valid[s] && sidx < nsym) x[s][r] = {k.a * (float)(1 - 2 * bit(s, 2 * sidx)), k.a * (float)(1 - 2 * bit(s, 2 * sidx + 1))};
+            if (valid[s] && sidx < nsym) x[s][r] = {bit(s, 2 * sidx) ? -k.a : k.a, bit(s, 2 * sidx + 1) ? -k.a : k.a};   // a (1 - 2 b), exactly
             else x[s][r] = {0.0f, 0.0f};
         }
 #pragma unroll
