@@ -426,7 +426,7 @@ __global__ void __launch_bounds__((QcLayout<Code, CW>::THREADS), (QcLayout<Code,
     if (a.hard_packed) pack_hard(hard_s, L::HARD_STRIDE, ncw, N, a.hard_packed + cw0 * ((N + 7) >> 3));
     if (a.counters) {
         __syncthreads();
-        count_errors(hard_s, L::HARD_STRIDE, ncw, N, a.k_info, SIM ? nullptr : a.ref_packed + cw0 * ((N + 7) >> 3),
+        count_errors<(SIM != 0)>(hard_s, L::HARD_STRIDE, ncw, N, a.k_info, SIM ? nullptr : a.ref_packed + cw0 * ((N + 7) >> 3),
                      a.counters, scratch + 1);
     }
 }

@@ -36,12 +36,14 @@ __device__ __forceinline__ void pack_hard(const uint8_t *hard_s, int hs_stride, 
 // Uncoded decision = bit 1 of hard_s (llr > 0 -> 1, llr == 0 -> 0, i.e. (sign+1)//2);
 // ref_packed_g: transmitted codewords, MSB-first.
 // scratch: 3 ints + ncw ints of shared memory, zeroed by the caller before a barrier.
+// SELF_REF (single-launch simulator): the transmitted bit is bit 2 of the shared byte itself and ref_packed_g is null.
+template <bool SELF_REF = false>
 __device__ __forceinline__ void count_errors(const uint8_t *hard_s, int hs_stride, int ncw, int n, int k_info,
                                              const uint8_t *ref_packed_g, unsigned long long *counters,
                                              int *scratch /* [3 + ncw] */) {
     const int nbytes = (n + 7) >> 3;
     int unc = 0, inf = 0;
-    if (!ref_packed_g && (n & 3) == 0 && (hs_stride & 3) == 0) {
+    if (SELF_REF && (n & 3) == 0 && (hs_stride & 3) == 0) {
         // single-launch simulator: decision (bit 0), uncoded decision (bit 1) and transmitted bit (bit 2) share a byte -
         // four code bits per 32-bit word, compared with three shifts and counted with popc
         const int words = n >> 2;
