@@ -228,7 +228,9 @@ def bench_nn(a, dev, world, barrier, peaks):
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
-    ms_mlp = timed(lambda: net(x), 3)                   # default schedule: the single-launch L2-resident chain
+    ms_mlp = timed(lambda: net(x), 3)                   # default schedule: the single-launch L2-resident chain on CTA pairs
+    net.set_mode("chain")
+    ms_mlp_chain = timed(lambda: net(x), 3)             # the same chain on single SMs (cta_group::1)
     net.set_mode("per_layer")
     ms_mlp_pl = timed(lambda: net(x), 3)                # round-1 schedule: one launch per layer, activations through HBM
     net.set_mode("auto")
@@ -246,10 +248,10 @@ def bench_nn(a, dev, world, barrier, peaks):
     c = counters.cpu().numpy().astype(np.float64)
     return {"workload": "LLRestimator_withSNR(32) 65-512-512-512-64 tanh (reference checkpoint) + (64,32) code, sum-product x10, 15 dB, 3-bit ADC",
             "ofdm_symbols_per_gpu": S, "link_ms": ms_link, "link_symbols_per_s": S * world / (ms_link * 1e-3),
-            "link_info_gbps": S * world * 32 / (ms_link * 1e-3) / 1e9, "mlp_ms": ms_mlp, "mlp_ms_per_layer_launches": ms_mlp_pl,
-            "mlp_schedule": "one cooperative launch per 303 104-row chunk: groups of 4 SMs carry 128-row blocks through all layers, activation "
-                            "planes handed over through L2 (DRAM traffic 3.4 KB/row against 10.6 KB/row of the per-layer launches, ncu: "
-                            "profiles/r02_mlp_experiments.md)",
+            "link_info_gbps": S * world * 32 / (ms_link * 1e-3) / 1e9, "mlp_ms": ms_mlp, "mlp_ms_single_sm_chain": ms_mlp_chain, "mlp_ms_per_layer_launches": ms_mlp_pl,
+            "mlp_schedule": "one cooperative launch per 303 104-row chunk: groups of 4 SMs (two cta_group::2 pairs) carry 256-row blocks through all "
+                            "layers, activation planes handed over through L2 (DRAM traffic 4.6 KB/row on pairs, 3.4 KB/row on single SMs, against "
+                            "10.6 KB/row of the per-layer launches; ncu: profiles/r02_mlp_experiments.md)",
             "mlp_fp32_equivalent_tflops": flops / (ms_mlp * 1e-3) / 1e12,
             "roofline": {"bound": "tensor", "achieved": 3 * flops / (ms_mlp * 1e-3) / 1e12, "peak": tf_peak, "unit": "TFLOP/s",
                          "frac": 3 * flops / (ms_mlp * 1e-3) / 1e12 / tf_peak, "traffic": None,

@@ -94,28 +94,14 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
     d |= (uint64_t)2 << 61;                            // SWIZZLE_128B
     return d;
 }
-__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t (&v)[32]) {
+__device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, uint32_t *v) {
     asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
-        "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
         : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
-          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
-          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
         : "r"(taddr));
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
-        "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
-        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
-          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
-          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-        : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
 
 // tanh(x) = sign(x) (1 - e) / (1 + e) with e = 2^(-2 log2(e) |x|): two MUFU (ex2, rcp) + five ALU instructions, no branch.
 // Absolute error <= ~3e-7 over the whole range (the cancellation in 1 - e near 0 costs relative, not absolute, accuracy, and the
@@ -132,6 +118,42 @@ __device__ __forceinline__ float tanh_act(float x) {
     return copysignf((1.0f - e) * r, x);
 }
 #endif
+
+// Accumulators -> activations for 32 columns of one TMEM lane (= output row): leading (+ correction) accumulator, bias, tanh.
+// The columns go in two halves, the TMEM read of the second in flight while the first is summed, biased and passed through tanh
+// (all epilogue warps start a tile together and queue on the TMEM read port: 3 % of the forward; four quarters were slower);
+// the bias is four vector loads per half issued together (a load per element made every add wait for its own load).
+template <bool CORR>
+__device__ __forceinline__ void acc_to_values(uint32_t t_main, uint32_t corr_off, const float *bias /* of these 32 columns, or null */, bool act, float (&o)[32]) {
+    uint32_t v[32], w[32];
+    tmem_ld16_issue(t_main, v);
+    if (CORR) tmem_ld16_issue(t_main + corr_off, w);
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+        tmem_ld_wait();
+        if (half == 0) {
+            tmem_ld16_issue(t_main + 16, v + 16);
+            if (CORR) tmem_ld16_issue(t_main + corr_off + 16, w + 16);
+        }
+#pragma unroll
+        for (int q = 16 * half; q < 16 * half + 16; ++q) o[q] = CORR ? __fadd_rn(__uint_as_float(v[q]), __uint_as_float(w[q])) : __uint_as_float(v[q]);
+        if (bias) {
+            float4 b4[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) b4[q] = __ldg(reinterpret_cast<const float4 *>(bias + 16 * half) + q);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int e = 16 * half + 4 * q;
+                o[e] = __fadd_rn(o[e], b4[q].x); o[e + 1] = __fadd_rn(o[e + 1], b4[q].y);
+                o[e + 2] = __fadd_rn(o[e + 2], b4[q].z); o[e + 3] = __fadd_rn(o[e + 3], b4[q].w);
+            }
+        }
+        if (act) {
+#pragma unroll
+            for (int q = 16 * half; q < 16 * half + 16; ++q) o[q] = tanh_act(o[q]);
+        }
+    }
+}
 
 // exact split of an fp32 value into binary16 planes
 template <int NS>
@@ -349,27 +371,8 @@ __global__ void __launch_bounds__(THREADS, 1) layer_kernel(const __grid_constant
             const uint32_t d_main = tmem_base + acc * ACC_COLS + ((uint32_t)(quad * 32) << 16);
 #pragma unroll 1
             for (int c0 = part * PART_COLS; c0 < (part + 1) * PART_COLS && c0 < BN; c0 += 32) {
-                uint32_t v[32], w[32];
                 float o[32];
-                tmem_ld32_issue(d_main + (uint32_t)c0, v);
-                if (NS > 1) tmem_ld32_issue(d_main + ACC2 + (uint32_t)c0, w);
-                tmem_ld_wait();
-#pragma unroll
-                for (int j = 0; j < 32; ++j) o[j] = NS > 1 ? __fadd_rn(__uint_as_float(v[j]), __uint_as_float(w[j])) : __uint_as_float(v[j]);
-                if (args.bias) {                                           // eight vector loads issued together (a load per element made every add wait for its own load)
-                    float4 b4[8];
-#pragma unroll
-                    for (int q = 0; q < 8; ++q) b4[q] = __ldg(reinterpret_cast<const float4 *>(args.bias + n0 + c0) + q);
-#pragma unroll
-                    for (int q = 0; q < 8; ++q) {
-                        o[4 * q] = __fadd_rn(o[4 * q], b4[q].x); o[4 * q + 1] = __fadd_rn(o[4 * q + 1], b4[q].y);
-                        o[4 * q + 2] = __fadd_rn(o[4 * q + 2], b4[q].z); o[4 * q + 3] = __fadd_rn(o[4 * q + 3], b4[q].w);
-                    }
-                }
-                if (args.act) {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) o[j] = tanh_act(o[j]);
-                }
+                acc_to_values<(NS > 1)>(d_main + (uint32_t)c0, ACC2, args.bias ? args.bias + n0 + c0 : nullptr, args.act != 0, o);
                 if (args.out_f32) {
                     if (m < args.m_valid) {
                         float4 *dst = reinterpret_cast<float4 *>(args.out_f32 + m * args.n_total + n0 + c0);
@@ -628,27 +631,8 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 1) chain_kernel(const __grid_co
             const uint32_t d_main = tmem_base + acc * ACC_COLS + ((uint32_t)(quad * 32) << 16);
 #pragma unroll 1
             for (int c0 = part * 32; c0 < L.bn; c0 += 32 * (EPI_WARPS / 4)) {
-                uint32_t v[32], w[32];
                 float o[32];
-                tmem_ld32_issue(d_main + (uint32_t)c0, v);
-                tmem_ld32_issue(d_main + (uint32_t)(L.bn + c0), w);
-                tmem_ld_wait();
-#pragma unroll
-                for (int q = 0; q < 32; ++q) o[q] = __fadd_rn(__uint_as_float(v[q]), __uint_as_float(w[q]));
-                if (L.bias) {                                              // eight vector loads issued together into the registers v / w just freed
-                    float4 b4[8];
-#pragma unroll
-                    for (int q = 0; q < 8; ++q) b4[q] = __ldg(reinterpret_cast<const float4 *>(L.bias + n0 + c0) + q);
-#pragma unroll
-                    for (int q = 0; q < 8; ++q) {
-                        o[4 * q] = __fadd_rn(o[4 * q], b4[q].x); o[4 * q + 1] = __fadd_rn(o[4 * q + 1], b4[q].y);
-                        o[4 * q + 2] = __fadd_rn(o[4 * q + 2], b4[q].z); o[4 * q + 3] = __fadd_rn(o[4 * q + 3], b4[q].w);
-                    }
-                }
-                if (L.act) {
-#pragma unroll
-                    for (int q = 0; q < 32; ++q) o[q] = tanh_act(o[q]);
-                }
+                acc_to_values<true>(d_main + (uint32_t)c0, (uint32_t)L.bn, L.bias ? L.bias + n0 + c0 : nullptr, L.act != 0, o);
                 if (l == last) {
                     const long long m = (long long)rb * BM + row;
                     if (m < args.m_valid) {
@@ -897,27 +881,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CHAIN_THREADS, 1) ch
             const uint32_t d_main = tmem_base + acc * ACC_COLS + ((uint32_t)(quad * 32) << 16);
 #pragma unroll 1
             for (int c0 = part * 32; c0 < L.bn; c0 += 32 * (EPI_WARPS / 4)) {
-                uint32_t v[32], w[32];
                 float o[32];
-                tmem_ld32_issue(d_main + (uint32_t)c0, v);
-                tmem_ld32_issue(d_main + (uint32_t)(L.bn + c0), w);
-                tmem_ld_wait();
-#pragma unroll
-                for (int q = 0; q < 32; ++q) o[q] = __fadd_rn(__uint_as_float(v[q]), __uint_as_float(w[q]));
-                if (L.bias) {
-                    float4 b4[8];
-#pragma unroll
-                    for (int q = 0; q < 8; ++q) b4[q] = __ldg(reinterpret_cast<const float4 *>(L.bias + n0 + c0) + q);
-#pragma unroll
-                    for (int q = 0; q < 8; ++q) {
-                        o[4 * q] = __fadd_rn(o[4 * q], b4[q].x); o[4 * q + 1] = __fadd_rn(o[4 * q + 1], b4[q].y);
-                        o[4 * q + 2] = __fadd_rn(o[4 * q + 2], b4[q].z); o[4 * q + 3] = __fadd_rn(o[4 * q + 3], b4[q].w);
-                    }
-                }
-                if (L.act) {
-#pragma unroll
-                    for (int q = 0; q < 32; ++q) o[q] = tanh_act(o[q]);
-                }
+                acc_to_values<true>(d_main + (uint32_t)c0, (uint32_t)L.bn, L.bias ? L.bias + n0 + c0 : nullptr, L.act != 0, o);
                 if (l == last) {
                     const long long m = ((long long)rb * 2 + c) * BM + row;
                     if (m < args.m_valid) {
@@ -1155,6 +1120,19 @@ int ldpc_mlp_create(int n_layers, const int32_t *dims, const float *const *weigh
                 h->chain_ok = false;                                      // AUTO then runs one launch per layer
             }
         }
+        if (h->chain_ok) {                                                // and the pair kernel: every cluster of 2 must be resident at once
+            constexpr int SMEM2 = 3 * (2 * BM * BK * 2 + 128 * BK * 2 + 64 * BK * 2) + 1024 + 128 + EPI_WARPS * 2048;
+            cudaLaunchConfig_t cfg;
+            memset(&cfg, 0, sizeof(cfg));
+            cfg.gridDim = dim3((unsigned)(h->n_groups * GROUP)); cfg.blockDim = dim3(CHAIN_THREADS); cfg.dynamicSmemBytes = SMEM2;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+            cfg.attrs = at; cfg.numAttrs = 1;
+            int clusters = 0;
+            h->pairs_ok = cudaFuncSetAttribute(chain2_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2) == cudaSuccess &&
+                          cudaOccupancyMaxActiveClusters(&clusters, chain2_kernel<2>, &cfg) == cudaSuccess && clusters * 2 >= h->n_groups * GROUP;
+            if (!h->pairs_ok) cudaGetLastError();
+        }
     }
     *out = h;
     return LDPC_OK;
@@ -1256,7 +1234,9 @@ int ldpc_mlp_forward(ldpc_mlp_t *h, const float *x, int64_t B, float *y, ldpc_st
     if (reinterpret_cast<uintptr_t>(y) & 15) { set_error("ldpc_mlp_forward: y must be 16-byte aligned"); return LDPC_EINVAL; }
     std::lock_guard<std::mutex> lock(h->mu);   // host-side serialisation; work of different calls is still ordered per stream by the caller
     if (h->mode >= LDPC_MLP_CHAIN && !h->chain_ok) { set_error("ldpc_mlp_forward: the single-launch chain needs splits = 2, 2..%d layers of at most %d column tiles and cooperative launch", MAX_CHAIN, GROUP); return LDPC_EUNSUPPORTED; }
-    if (h->chain_ok && h->mode != LDPC_MLP_PER_LAYER) return forward_chain(h, x, B, y, s, h->mode == LDPC_MLP_CHAIN_PAIRS);
+    if (h->mode == LDPC_MLP_CHAIN_PAIRS && !h->pairs_ok) { set_error("ldpc_mlp_forward: the single-launch chain on CTA pairs needs every cluster of 2 resident at once on this device"); return LDPC_EUNSUPPORTED; }
+    if (h->chain_ok && h->mode != LDPC_MLP_PER_LAYER)                     // AUTO: pairs (fastest), else the single-SM chain
+        return forward_chain(h, x, B, y, s, h->mode == LDPC_MLP_CHAIN_PAIRS || (h->mode == LDPC_MLP_AUTO && h->pairs_ok));
     {
         const int rc0 = ensure_activation_buffers(h, B, s);
         if (rc0) return rc0;
@@ -1291,7 +1271,7 @@ int ldpc_mlp_forward(ldpc_mlp_t *h, const float *x, int64_t B, float *y, ldpc_st
 
 int ldpc_mlp_set_mode(ldpc_mlp_t *h, int mode) {
     if (!h || mode < LDPC_MLP_AUTO || mode > LDPC_MLP_CHAIN_PAIRS) { set_error("ldpc_mlp_set_mode: bad arguments"); return LDPC_EINVAL; }
-    if (mode >= LDPC_MLP_CHAIN && !h->chain_ok) { set_error("ldpc_mlp_set_mode: this network / device cannot run the single-launch chain"); return LDPC_EUNSUPPORTED; }
+    if ((mode >= LDPC_MLP_CHAIN && !h->chain_ok) || (mode == LDPC_MLP_CHAIN_PAIRS && !h->pairs_ok)) { set_error("ldpc_mlp_set_mode: this network / device cannot run the single-launch chain"); return LDPC_EUNSUPPORTED; }
     std::lock_guard<std::mutex> lock(h->mu);
     h->mode = mode;
     return LDPC_OK;

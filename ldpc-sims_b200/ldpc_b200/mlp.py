@@ -17,9 +17,9 @@ MODES = {"auto": 0, "per_layer": 1, "chain": 2, "chain_pairs": 3}       # LDPC_M
 class NativeMLP:
     """weights[l]: [out_l, in_l] float32 (nn.Linear.weight), biases[l]: [out_l] or None,
     activations[l]: True -> tanh after layer l (default: every layer but the last).
-    mode: "auto" (default: the single-launch L2-resident chain where the shape allows it), "per_layer" (one launch per
-    layer), "chain" (raises if the network cannot run it) or "chain_pairs" (the chain on cta_group::2 CTA pairs: measured
-    1.7 % faster than "chain" with 1.4x its DRAM traffic); the results are bit-identical."""
+    mode: "auto" (default: the single-launch L2-resident chain where the shape allows it - on cta_group::2 CTA pairs if the
+    device can hold every cluster, else on single SMs), "per_layer" (one launch per layer), "chain" (single SMs; raises if the
+    network cannot run it) or "chain_pairs" (4 % faster than "chain", 1.4x its DRAM traffic); the results are bit-identical."""
 
     def __init__(self, weights, biases=None, activations=None, splits=2, chunk_rows=0, device=None, mode="auto"):
         N.require_cuda()
