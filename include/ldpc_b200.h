@@ -353,7 +353,8 @@ void ldpc_mlp_destroy(ldpc_mlp_t *mlp);
  *                      LDPC_EUNSUPPORTED otherwise);
  * LDPC_MLP_CHAIN_PAIRS - the chain on pairs of SMs (clusters of 2, cta_group::2 MMAs of M = 256, each SM staging half of every
  *                      weight operand): 4 % faster than LDPC_MLP_CHAIN on B200 with 1.4x its DRAM traffic;
- * LDPC_MLP_AUTO      - LDPC_MLP_CHAIN_PAIRS where it applies, else LDPC_MLP_CHAIN, else LDPC_MLP_PER_LAYER (default). */
+ * LDPC_MLP_AUTO      - LDPC_MLP_CHAIN_PAIRS where it applies and the batch has at least 32 768 rows, else LDPC_MLP_CHAIN, else
+ *                      LDPC_MLP_PER_LAYER (default). */
 enum { LDPC_MLP_AUTO = 0, LDPC_MLP_PER_LAYER = 1, LDPC_MLP_CHAIN = 2, LDPC_MLP_CHAIN_PAIRS = 3 };
 int ldpc_mlp_set_mode(ldpc_mlp_t *mlp, int mode);
 

@@ -1235,8 +1235,10 @@ int ldpc_mlp_forward(ldpc_mlp_t *h, const float *x, int64_t B, float *y, ldpc_st
     std::lock_guard<std::mutex> lock(h->mu);   // host-side serialisation; work of different calls is still ordered per stream by the caller
     if (h->mode >= LDPC_MLP_CHAIN && !h->chain_ok) { set_error("ldpc_mlp_forward: the single-launch chain needs splits = 2, 2..%d layers of at most %d column tiles and cooperative launch", MAX_CHAIN, GROUP); return LDPC_EUNSUPPORTED; }
     if (h->mode == LDPC_MLP_CHAIN_PAIRS && !h->pairs_ok) { set_error("ldpc_mlp_forward: the single-launch chain on CTA pairs needs every cluster of 2 resident at once on this device"); return LDPC_EUNSUPPORTED; }
-    if (h->chain_ok && h->mode != LDPC_MLP_PER_LAYER)                     // AUTO: pairs (fastest), else the single-SM chain
-        return forward_chain(h, x, B, y, s, h->mode == LDPC_MLP_CHAIN_PAIRS || (h->mode == LDPC_MLP_AUTO && h->pairs_ok));
+    // AUTO: the chain on CTA pairs for large batches (4 % faster from ~64 K rows), on single SMs for small ones (the pairs'
+    // longer hand-over chain costs 59 against 45 us at the reference's 1 024-row batches, evaluate_quantized_snr.py:150-157)
+    if (h->chain_ok && h->mode != LDPC_MLP_PER_LAYER)
+        return forward_chain(h, x, B, y, s, h->mode == LDPC_MLP_CHAIN_PAIRS || (h->mode == LDPC_MLP_AUTO && h->pairs_ok && B >= 32768));
     {
         const int rc0 = ensure_activation_buffers(h, B, s);
         if (rc0) return rc0;
