@@ -250,7 +250,7 @@ def bench_nn(a, dev, world, barrier, peaks):
             "ofdm_symbols_per_gpu": S, "link_ms": ms_link, "link_symbols_per_s": S * world / (ms_link * 1e-3),
             "link_info_gbps": S * world * 32 / (ms_link * 1e-3) / 1e9, "mlp_ms": ms_mlp, "mlp_ms_single_sm_chain": ms_mlp_chain, "mlp_ms_per_layer_launches": ms_mlp_pl,
             "mlp_schedule": "one cooperative launch per 303 104-row chunk: groups of 4 SMs (two cta_group::2 pairs) carry 256-row blocks through all "
-                            "layers, activation planes handed over through L2 (DRAM traffic 4.6 KB/row on pairs, 3.4 KB/row on single SMs, against "
+                            "layers, activation planes handed over through L2 (DRAM traffic 3.8 KB/row on pairs against "
                             "10.6 KB/row of the per-layer launches; ncu: profiles/r02_mlp_experiments.md)",
             "mlp_fp32_equivalent_tflops": flops / (ms_mlp * 1e-3) / 1e12,
             "roofline": {"bound": "tensor", "achieved": 3 * flops / (ms_mlp * 1e-3) / 1e12, "peak": tf_peak, "unit": "TFLOP/s",

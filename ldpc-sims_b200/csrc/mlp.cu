@@ -171,7 +171,7 @@ __device__ __forceinline__ void split_f16(float v, __half (&p)[NS]) {
 template <int NS>
 __global__ void __launch_bounds__(256) split_rows_kernel(const float *x, long long ld, int K, long long M, int Kp,
                                                          __half *planes, long long plane_stride) {
-    const int groups = Kp >> 3;                                           // Kp is a multiple of 64
+    const int groups = Kp >> 3;                                           // Kp is a multiple of 8
     const long long total = M * groups;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         const long long m = i / groups;
@@ -1183,9 +1183,12 @@ static int ensure_chain_buffers(ldpc_mlp *h, long long rows, cudaStream_t s) {
         if (h->x_rows) LDPC_CUDA_TRY(cudaStreamSynchronize(s));
         cudaFree(h->d_x);
         h->d_x = nullptr; h->x_rows = 0;
-        if (cudaMalloc(&h->d_x, (size_t)h->ns * want * L0.Kp * sizeof(__half)) != cudaSuccess) { set_error("ldpc_mlp_forward: out of device memory (%lld input rows)", want); return LDPC_ENOMEM; }
+        // the input planes keep only ceil(K / 8) * 8 columns (65 -> 72, not 128): the TMA box of the last k-block runs past the tensor's
+        // inner extent and is zero-filled there, which is what the zero-padded weight planes expect
+        const int kx = ((L0.K + 7) / 8) * 8;
+        if (cudaMalloc(&h->d_x, (size_t)h->ns * want * kx * sizeof(__half)) != cudaSuccess) { set_error("ldpc_mlp_forward: out of device memory (%lld input rows)", want); return LDPC_ENOMEM; }
         h->x_rows = want;
-        const int rc = make_map(&h->cmaps.a[0], h->d_x, L0.Kp, h->x_rows, h->ns, BM);
+        const int rc = make_map(&h->cmaps.a[0], h->d_x, kx, h->x_rows, h->ns, BM);
         if (rc) return rc;
         h->cmaps2.a[0] = h->cmaps.a[0];
     }
@@ -1203,7 +1206,8 @@ static int forward_chain(ldpc_mlp *h, const float *x, long long B, float *y, cud
     const int rows_per_block = pairs ? 2 * BM : BM;
     for (long long done = 0; done < B; done += h->x_rows) {
         const long long rows = std::min<long long>(h->x_rows, B - done);
-        { const int rc = launch_split<2>(x + done * L0.K, L0.K, L0.K, rows, L0.Kp, h->d_x, h->x_rows * L0.Kp, s); if (rc) return rc; }
+        const int kx = ((L0.K + 7) / 8) * 8;
+        { const int rc = launch_split<2>(x + done * L0.K, L0.K, L0.K, rows, kx, h->d_x, h->x_rows * kx, s); if (rc) return rc; }
         ChainArgs a;
         memset(&a, 0, sizeof(a));
         a.n_layers = nl; a.m_valid = (int)rows; a.row_blocks = (int)((rows + rows_per_block - 1) / rows_per_block);
