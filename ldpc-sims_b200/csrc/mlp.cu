@@ -996,6 +996,7 @@ struct ldpc_mlp {
     long long x_rows = 0;
     __half *d_x = nullptr, *d_ring[2] = {nullptr, nullptr};
     unsigned int *d_flags = nullptr;
+    size_t ring_bytes = 0;
     ldpc::mlp::ChainMaps cmaps;
     ldpc::mlp::Chain2Maps cmaps2;
     bool pairs_ok = false;     // cluster launch of CTA pairs available too
@@ -1049,7 +1050,7 @@ void ldpc_mlp_destroy(ldpc_mlp_t *h) {
     if (!h) return;
     for (auto &L : h->layers) { cudaFree(L.d_bias); cudaFree(L.d_w); }
     cudaFree(h->d_act[0]); cudaFree(h->d_act[1]);
-    cudaFree(h->d_x); cudaFree(h->d_ring[0]); cudaFree(h->d_ring[1]); cudaFree(h->d_flags);
+    cudaFree(h->d_x); cudaFree(h->d_ring[0]); cudaFree(h->d_flags);
     delete h;
 }
 
@@ -1166,8 +1167,10 @@ static int ensure_chain_buffers(ldpc_mlp *h, long long rows, cudaStream_t s) {
     const Layer &L0 = h->layers[0];
     if (!h->d_ring[0]) {
         const long long ring_rows = (long long)h->n_groups * INFLIGHT * BM;
-        for (int b = 0; b < 2; ++b)
-            if (cudaMalloc(&h->d_ring[b], (size_t)h->ns * ring_rows * h->maxw * sizeof(__half)) != cudaSuccess) { set_error("ldpc_mlp_forward: out of device memory (activation ring)"); return LDPC_ENOMEM; }
+        const size_t ring_elems = (size_t)h->ns * ring_rows * h->maxw;    // one allocation: the two buffers form ONE L2 persistence window
+        if (cudaMalloc(&h->d_ring[0], 2 * ring_elems * sizeof(__half)) != cudaSuccess) { set_error("ldpc_mlp_forward: out of device memory (activation ring)"); return LDPC_ENOMEM; }
+        h->d_ring[1] = h->d_ring[0] + ring_elems;
+        h->ring_bytes = 2 * ring_elems * sizeof(__half);
         if (cudaMalloc(&h->d_flags, (size_t)h->n_groups * INFLIGHT * 2 * MAX_CHAIN * sizeof(unsigned int)) != cudaSuccess) { set_error("ldpc_mlp_forward: out of device memory"); return LDPC_ENOMEM; }
         for (size_t l = 0; l < h->layers.size(); ++l) {
             Layer &L = h->layers[l];
@@ -1222,9 +1225,18 @@ static int forward_chain(ldpc_mlp *h, const float *x, long long B, float *y, cud
         cudaLaunchConfig_t cfg;
         memset(&cfg, 0, sizeof(cfg));
         cfg.gridDim = dim3((unsigned)(a.n_groups * GROUP)); cfg.blockDim = dim3(CHAIN_THREADS); cfg.stream = s;
-        cudaLaunchAttribute at[1];
+        cudaLaunchAttribute at[2];
         at[0].id = cudaLaunchAttributeCooperative; at[0].val.cooperative = 1;     // every CTA of a group must be resident: the waits spin
         cfg.attrs = at; cfg.numAttrs = 1;
+#ifdef MLP_EXP_PERSIST
+        at[1].id = cudaLaunchAttributeAccessPolicyWindow;
+        at[1].val.accessPolicyWindow.base_ptr = h->d_ring[0];
+        at[1].val.accessPolicyWindow.num_bytes = h->ring_bytes;
+        at[1].val.accessPolicyWindow.hitRatio = 1.0f;
+        at[1].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+        at[1].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+        cfg.numAttrs = 2;
+#endif
         if (pairs) { cfg.dynamicSmemBytes = SMEM2; LDPC_CUDA_TRY(cudaLaunchKernelEx(&cfg, chain2_kernel<2>, h->cmaps2, a)); }
         else { cfg.dynamicSmemBytes = SMEM1; LDPC_CUDA_TRY(cudaLaunchKernelEx(&cfg, chain_kernel<2>, h->cmaps, a)); }
     }

@@ -45,6 +45,13 @@ int main(int argc, char **argv) {
     float *dx, *dy;
     CK(cudaMalloc(&dx, x.size() * 4)); CK(cudaMalloc(&dy, (size_t)B * 64 * 4));
     CK(cudaMemcpy(dx, x.data(), x.size() * 4, cudaMemcpyHostToDevice));
+#ifdef MLP_EXP_PERSIST
+    {   // experiment: set the persisting L2 carve-out to its maximum
+        cudaDeviceProp pr; CK(cudaGetDeviceProperties(&pr, 0));
+        printf("L2 %d MB, persisting max %d MB, window max %d MB\n", pr.l2CacheSize >> 20, pr.persistingL2CacheMaxSize >> 20, pr.accessPolicyMaxWindowSize >> 20);
+        CK(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, pr.persistingL2CacheMaxSize));
+    }
+#endif
     ldpc_mlp_t *h = nullptr;
     if (ldpc_mlp_create(4, dims, wp, bp, nullptr, 2, chunk, &h)) return 1;
     if (ldpc_mlp_set_mode(h, mode)) return 1;
