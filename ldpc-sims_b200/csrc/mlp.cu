@@ -1168,10 +1168,15 @@ static int ensure_chain_buffers(ldpc_mlp *h, long long rows, cudaStream_t s) {
     if (!h->d_ring[0]) {
         const long long ring_rows = (long long)h->n_groups * INFLIGHT * BM;
         const size_t ring_elems = (size_t)h->ns * ring_rows * h->maxw;    // one allocation: the two buffers form ONE L2 persistence window
-        if (cudaMalloc(&h->d_ring[0], 2 * ring_elems * sizeof(__half)) != cudaSuccess) { set_error("ldpc_mlp_forward: out of device memory (activation ring)"); return LDPC_ENOMEM; }
+        if (cudaMalloc(&h->d_ring[0], 2 * ring_elems * sizeof(__half)) != cudaSuccess) { h->d_ring[0] = nullptr; set_error("ldpc_mlp_forward: out of device memory (activation ring)"); return LDPC_ENOMEM; }
         h->d_ring[1] = h->d_ring[0] + ring_elems;
         h->ring_bytes = 2 * ring_elems * sizeof(__half);
-        if (cudaMalloc(&h->d_flags, (size_t)h->n_groups * INFLIGHT * 2 * MAX_CHAIN * sizeof(unsigned int)) != cudaSuccess) { set_error("ldpc_mlp_forward: out of device memory"); return LDPC_ENOMEM; }
+        if (cudaMalloc(&h->d_flags, (size_t)h->n_groups * INFLIGHT * 2 * MAX_CHAIN * sizeof(unsigned int)) != cudaSuccess) {
+            cudaFree(h->d_ring[0]);                                           // all or nothing: the next call starts over
+            h->d_ring[0] = h->d_ring[1] = nullptr;
+            set_error("ldpc_mlp_forward: out of device memory");
+            return LDPC_ENOMEM;
+        }
         for (size_t l = 0; l < h->layers.size(); ++l) {
             Layer &L = h->layers[l];
             h->cmaps.w[l] = L.map_w;
@@ -1189,7 +1194,7 @@ static int ensure_chain_buffers(ldpc_mlp *h, long long rows, cudaStream_t s) {
         // the input planes keep only ceil(K / 8) * 8 columns (65 -> 72, not 128): the TMA box of the last k-block runs past the tensor's
         // inner extent and is zero-filled there, which is what the zero-padded weight planes expect
         const int kx = ((L0.K + 7) / 8) * 8;
-        if (cudaMalloc(&h->d_x, (size_t)h->ns * want * kx * sizeof(__half)) != cudaSuccess) { set_error("ldpc_mlp_forward: out of device memory (%lld input rows)", want); return LDPC_ENOMEM; }
+        if (cudaMalloc(&h->d_x, (size_t)h->ns * want * kx * sizeof(__half)) != cudaSuccess) { h->d_x = nullptr; set_error("ldpc_mlp_forward: out of device memory (%lld input rows)", want); return LDPC_ENOMEM; }
         h->x_rows = want;
         const int rc = make_map(&h->cmaps.a[0], h->d_x, kx, h->x_rows, h->ns, BM);
         if (rc) return rc;
